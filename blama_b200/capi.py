@@ -1,0 +1,250 @@
+"""ctypes view of the C ABI in include/blama_b200.h (the library a blama maintainer would bind).
+
+This module is the thin Python harness the tests and bench.py drive the product through.  It loads
+blama_b200/lib/libblama_b200.so and fails loudly if the library is missing or no CUDA device is present:
+there is no CPU fallback and nothing under oracle/ is ever imported from here."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libblama_b200.so")
+
+TD_DTYPE = np.dtype([("token", np.int32), ("logit", np.float32)])
+
+# every symbol include/blama_b200.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _f32p = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
+LOG_CB = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
+PROGRESS_CB = C.CFUNCTYPE(C.c_int32, C.c_float, C.c_void_p)
+SYMBOLS = {
+    "blk_init": (_i32, []),
+    "blk_set_log_callback": (None, [LOG_CB, _vp]),
+    "blk_last_error": (C.c_char_p, []),
+    "blk_device_count": (_i32, []),
+    "blk_version": (C.c_char_p, []),
+    "blk_model_load": (_vp, [C.c_char_p, _i32, PROGRESS_CB, _vp]),
+    "blk_model_free": (None, [_vp]),
+    "blk_model_n_vocab": (_i32, [_vp]),
+    "blk_model_n_ctx_train": (_i32, [_vp]),
+    "blk_model_n_embd": (_i32, [_vp]),
+    "blk_model_n_layer": (_i32, [_vp]),
+    "blk_model_token_bos": (_i32, [_vp]),
+    "blk_model_token_eos": (_i32, [_vp]),
+    "blk_model_is_eog": (_i32, [_vp, _i32]),
+    "blk_model_add_bos": (_i32, [_vp]),
+    "blk_model_device": (_i32, [_vp]),
+    "blk_model_weight_bytes_per_token": (_i64, [_vp]),
+    "blk_model_kv_bytes_per_token": (_i64, [_vp]),
+    "blk_model_token_text": (_i32, [_vp, _i32, C.c_char_p, _i32]),
+    "blk_model_meta_str": (_i32, [_vp, C.c_char_p, C.c_char_p, _i32]),
+    "blk_ctx_create": (_vp, [_vp, _i32, _i32]),
+    "blk_ctx_free": (None, [_vp]),
+    "blk_ctx_n_ctx": (_i32, [_vp]),
+    "blk_ctx_n_batch": (_i32, [_vp]),
+    "blk_ctx_n_past": (_i32, [_vp]),
+    "blk_kv_clear": (_i32, [_vp]),
+    "blk_sync": (_i32, [_vp]),
+    "blk_decode": (_i32, [_vp, _vp, _i32]),
+    "blk_topk_last": (_i32, [_vp, _i32, _vp]),
+    "blk_gather_last": (_i32, [_vp, _vp, _i32, _vp]),
+    "blk_get_logits_last": (_i32, [_vp, _vp]),
+    "blk_decode_topk": (_i32, [_vp, _i32, _i32, _vp]),
+    "blk_verify_prefill": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "blk_ctx_set_verify_mode": (_i32, [_vp, _i32]),
+    "blk_timer_start": (_i32, [_vp]),
+    "blk_timer_stop": (_i32, [_vp, _f32p]),
+    "blk_ctx_kernel_launches": (_i64, [_vp]),
+    "blk_flush_l2": (_i32, [_vp]),
+    "blk_bench_kernel": (_i32, [_vp, _i32, _i32, _f32p, C.POINTER(C.c_int64)]),
+    "blk_test_gemv": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _vp]),
+    "blk_test_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "blk_test_dequant": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class BlkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[blk status {code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA engine.  Raises if it has not been built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(blama_b200 has no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise BlkError(rc, (lib().blk_last_error() or b"").decode(errors="replace"))
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def init() -> None:
+    _check(lib().blk_init())
+
+
+def device_count() -> int:
+    return int(lib().blk_device_count())
+
+
+class Model:
+    """blk_model handle (reference: bl::llama::Model, Model.hpp:26-58)."""
+
+    def __init__(self, path: str, device: int = 0, progress=None):
+        init()
+        cb = PROGRESS_CB(lambda p, u: 1 if progress is None else int(bool(progress(p) is not False)))
+        self._cb = cb
+        self.h = lib().blk_model_load(path.encode(), device, cb, None)
+        if not self.h:
+            raise BlkError(-1, (lib().blk_last_error() or b"").decode(errors="replace"))
+        L = lib()
+        self.n_vocab = L.blk_model_n_vocab(self.h)
+        self.n_ctx_train = L.blk_model_n_ctx_train(self.h)
+        self.n_embd = L.blk_model_n_embd(self.h)
+        self.n_layer = L.blk_model_n_layer(self.h)
+        self.bos = L.blk_model_token_bos(self.h)
+        self.eos = L.blk_model_token_eos(self.h)
+        self.weight_bytes_per_token = int(L.blk_model_weight_bytes_per_token(self.h))
+        self.kv_bytes_per_token = int(L.blk_model_kv_bytes_per_token(self.h))
+
+    def is_eog(self, tok: int) -> bool:
+        return bool(lib().blk_model_is_eog(self.h, int(tok)))
+
+    def token_text(self, tok: int) -> str:
+        buf = C.create_string_buffer(256)
+        n = lib().blk_model_token_text(self.h, int(tok), buf, 256)
+        return buf.raw[: min(n, 256)].decode(errors="replace")
+
+    def close(self):
+        if self.h:
+            lib().blk_model_free(self.h)
+            self.h = None
+
+
+class Ctx:
+    """blk_ctx handle (reference: bl::llama::Instance + llama_context, Instance.hpp:21-50)."""
+
+    def __init__(self, model: Model, n_ctx: int = 4096, n_batch: int = 2048):
+        self.m = model
+        self.h = lib().blk_ctx_create(model.h, n_ctx, n_batch)
+        if not self.h:
+            raise BlkError(-1, (lib().blk_last_error() or b"").decode(errors="replace"))
+
+    @property
+    def n_past(self) -> int:
+        return int(lib().blk_ctx_n_past(self.h))
+
+    def clear(self):
+        _check(lib().blk_kv_clear(self.h))
+
+    def sync(self):
+        _check(lib().blk_sync(self.h))
+
+    def decode(self, tokens: Sequence[int]):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        _check(lib().blk_decode(self.h, _p(t), len(t)))
+
+    def topk(self, k: int = 10) -> np.ndarray:
+        out = np.zeros(k, dtype=TD_DTYPE)
+        _check(lib().blk_topk_last(self.h, k, _p(out)))
+        return out
+
+    def decode_topk(self, token: int, k: int = 40) -> np.ndarray:
+        out = np.zeros(k, dtype=TD_DTYPE)
+        _check(lib().blk_decode_topk(self.h, int(token), k, _p(out)))
+        return out
+
+    def gather(self, ids: Sequence[int]) -> np.ndarray:
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        out = np.zeros(len(i), dtype=np.float32)
+        _check(lib().blk_gather_last(self.h, _p(i), len(i), _p(out)))
+        return out
+
+    def logits(self) -> np.ndarray:
+        out = np.zeros(self.m.n_vocab, dtype=np.float32)
+        _check(lib().blk_get_logits_last(self.h, _p(out)))
+        return out
+
+    def set_verify_mode(self, mode: int):
+        _check(lib().blk_ctx_set_verify_mode(self.h, mode))
+
+    def verify_prefill(self, tokens: Sequence[int], claimed: np.ndarray, n_claimed: Optional[np.ndarray] = None, want_top: bool = True):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = len(t)
+        cl = np.ascontiguousarray(claimed, dtype=np.int32).reshape(n, 10)
+        nc = np.full(n, 10, dtype=np.int32) if n_claimed is None else np.ascontiguousarray(n_claimed, dtype=np.int32)
+        g = np.zeros((n, 10), dtype=np.float32)
+        top = np.zeros((n, 10), dtype=TD_DTYPE) if want_top else None
+        _check(lib().blk_verify_prefill(self.h, _p(t), n, _p(cl), _p(nc), _p(g), _p(top) if want_top else None))
+        return g, top
+
+    def timer_start(self):
+        _check(lib().blk_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().blk_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def bench_kernel(self, which: int, iters: int = 64) -> Tuple[float, int]:
+        """(average ms per launch, algorithmic bytes per launch) of one decode kernel timed alone"""
+        ms = C.c_float(0)
+        b = C.c_int64(0)
+        _check(lib().blk_bench_kernel(self.h, which, iters, C.byref(ms), C.byref(b)))
+        return float(ms.value), int(b.value)
+
+    def flush_l2(self):
+        _check(lib().blk_flush_l2(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().blk_ctx_kernel_launches(self.h))
+
+    def close(self):
+        if self.h:
+            lib().blk_ctx_free(self.h)
+            self.h = None
+
+
+def test_gemv(gtype: int, blocks: np.ndarray, rows: int, k: int, x: np.ndarray, device: int = 0) -> np.ndarray:
+    b = np.ascontiguousarray(blocks, dtype=np.uint8)
+    xx = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros(rows, dtype=np.float32)
+    _check(lib().blk_test_gemv(device, gtype, _p(b), rows, k, _p(xx), _p(y)))
+    return y
+
+
+def test_gemm(gtype: int, blocks: np.ndarray, rows: int, k: int, x: np.ndarray, device: int = 0) -> np.ndarray:
+    b = np.ascontiguousarray(blocks, dtype=np.uint8)
+    xx = np.ascontiguousarray(x, dtype=np.float32)
+    n_tok = xx.shape[0]
+    y = np.zeros((n_tok, rows), dtype=np.float32)
+    _check(lib().blk_test_gemm(device, gtype, _p(b), rows, k, _p(xx), n_tok, _p(y)))
+    return y
+
+
+def test_dequant(gtype: int, blocks: np.ndarray, rows: int, k: int, device: int = 0) -> np.ndarray:
+    b = np.ascontiguousarray(blocks, dtype=np.uint8)
+    out = np.zeros((rows, k), dtype=np.float32)
+    _check(lib().blk_test_dequant(device, gtype, _p(b), rows, k, _p(out)))
+    return out

@@ -1,0 +1,748 @@
+// engine.cu -- model loading, context, decode step and the C ABI (include/blama_b200.h).
+//
+// Replaces, for blama's hot path, what llama.cpp does under llama_model_load_from_file / llama_init_from_model /
+// llama_decode / llama_get_logits_ith (reference call sites: Model.cpp:50-53, Instance.cpp:34-48, Session.cpp:388,
+// Session.cpp:24).  There is no CPU fallback anywhere in this file: without a device every entry point fails.
+#include "engine.hpp"
+#include "gguf.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+using namespace blk;
+
+// ------------------------------------------------------------------------------------------------------------------
+// logging / errors
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_last_error;
+blk_log_cb g_log_cb = nullptr;
+void* g_log_user = nullptr;
+std::once_flag g_init_once;
+int g_device_count = 0;
+
+blk_status fail(blk_status code, const std::string& msg) {
+    g_last_error = msg;
+    log_msg(3, msg);
+    return code;
+}
+template <class F> blk_status guarded(F&& f) {
+    try { f(); return BLK_OK; }
+    catch (const BlkError& e) { return fail(e.code, e.what()); }
+    catch (const std::bad_alloc&) { return fail(BLK_ERR_OOM, "host allocation failed"); }
+    catch (const std::exception& e) { return fail(BLK_ERR_FORMAT, e.what()); }
+}
+} // namespace
+
+void blk::log_msg(int level, const std::string& s) {
+    if (g_log_cb) g_log_cb(level, s.c_str(), g_log_user);
+    else if (level >= 2) fprintf(stderr, "[blama_b200] %s\n", s.c_str());
+}
+
+extern "C" blk_status blk_init(void) {
+    std::call_once(g_init_once, [] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+        g_device_count = n;
+    });
+    if (g_device_count <= 0) return fail(BLK_ERR_NO_DEVICE, "no CUDA device available (blama_b200 has no CPU fallback)");
+    return BLK_OK;
+}
+extern "C" void blk_set_log_callback(blk_log_cb cb, void* user) { g_log_cb = cb; g_log_user = user; }
+extern "C" const char* blk_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t blk_device_count(void) { blk_init(); return g_device_count; }
+extern "C" const char* blk_version(void) { return "blama_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------------------------
+blk_model::~blk_model() {
+    cudaSetDevice(device);
+    for (void* p : allocs) cudaFree(p);
+}
+
+namespace {
+
+struct Uploader {
+    blk_model* m;
+    uint8_t* staging = nullptr; size_t staging_bytes = 0;
+    uint8_t* arena = nullptr; size_t arena_off = 0, arena_bytes = 0;
+    cudaStream_t stream = nullptr;
+
+    uint8_t* take(size_t n) {
+        uint8_t* p = arena + arena_off;
+        arena_off += (n + 255) & ~size_t(255);
+        if (arena_off > arena_bytes) throw BlkError(BLK_ERR_OOM, "weight arena overflow");
+        return p;
+    }
+    static size_t planes_bytes(const GgufTensor& t) {
+        // split planes are padded to 256 B each; worst case 4 planes
+        return t.nbytes + 4 * 256;
+    }
+    QMat upload_matrix(const GgufTensor& t) {
+        QMat W; W.type = t.type; W.K = (int)t.ne[0]; W.N = (int)t.n_rows(); W.bytes = t.nbytes;
+        const int64_t K = W.K, N = W.N;
+        if (t.type == GT_F32 || t.type == GT_F16) {
+            uint8_t* dst = take(t.nbytes);
+            BLK_CUDA(cudaMemcpyAsync(dst, t.data, t.nbytes, cudaMemcpyHostToDevice, stream));
+            W.p0 = dst;
+            if (K % 8) throw BlkError(BLK_ERR_FORMAT, "row length must be a multiple of 8: " + t.name);
+            return W;
+        }
+        BLK_CUDA(cudaMemcpyAsync(staging, t.data, t.nbytes, cudaMemcpyHostToDevice, stream));
+        const int threads = 128;
+        if (t.type == GT_Q4_K) {
+            const int64_t nb = N * (K / 256);
+            uint8_t* qs = take(nb * 128); uint8_t* hdr = take(nb * 16);
+            retile_q4k_kernel<<<(unsigned)((nb + threads - 1) / threads), threads, 0, stream>>>(staging, qs, hdr, nb);
+            W.p0 = qs; W.p1 = hdr;
+        } else if (t.type == GT_Q5_K) {
+            const int64_t nb = N * (K / 256);
+            uint8_t* qs = take(nb * 128); uint8_t* hdr = take(nb * 16); uint8_t* qh = take(nb * 32);
+            retile_q5k_kernel<<<(unsigned)((nb + threads - 1) / threads), threads, 0, stream>>>(staging, qs, hdr, qh, nb);
+            W.p0 = qs; W.p1 = hdr; W.p2 = qh;
+        } else if (t.type == GT_Q6_K) {
+            const int64_t nb = N * (K / 256);
+            uint8_t* ql = take(nb * 128); uint8_t* qh = take(nb * 64); uint8_t* sc = take(nb * 16); uint8_t* d = take(nb * 2);
+            retile_q6k_kernel<<<(unsigned)((nb + threads - 1) / threads), threads, 0, stream>>>(staging, ql, qh, sc, d, nb);
+            W.p0 = ql; W.p1 = qh; W.p2 = sc; W.p3 = d;
+        } else if (t.type == GT_Q8_0) {
+            const int64_t nb = N * (K / 32);
+            uint8_t* qs = take(nb * 32); uint8_t* d = take(nb * 2);
+            retile_q80_kernel<<<(unsigned)((nb + threads - 1) / threads), threads, 0, stream>>>(staging, qs, d, nb);
+            W.p0 = qs; W.p1 = d;
+        } else {
+            throw BlkError(BLK_ERR_FORMAT, "unsupported tensor type for " + t.name);
+        }
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(cudaStreamSynchronize(stream));      // staging is reused by the next tensor
+        return W;
+    }
+    const float* upload_f32(const GgufTensor& t) {
+        if (t.type != GT_F32) throw BlkError(BLK_ERR_FORMAT, "expected F32 tensor: " + t.name);
+        uint8_t* dst = take(t.nbytes);
+        BLK_CUDA(cudaMemcpyAsync(dst, t.data, t.nbytes, cudaMemcpyHostToDevice, stream));
+        return reinterpret_cast<const float*>(dst);
+    }
+};
+
+} // namespace
+
+extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progress_cb cb, void* user) {
+    if (blk_init() != BLK_OK) return nullptr;
+    if (device < 0 || device >= g_device_count) { fail(BLK_ERR_ARG, "bad device index"); return nullptr; }
+    std::unique_ptr<blk_model> m(new blk_model());
+    m->device = device;
+    blk_status st = guarded([&] {
+        std::unique_ptr<GgufFile> fp;
+        try { fp.reset(new GgufFile(path)); }
+        catch (const std::exception& e) {
+            const std::string w = e.what();
+            throw BlkError(w.rfind("gguf:", 0) == 0 ? BLK_ERR_FORMAT : BLK_ERR_IO, w);
+        }
+        GgufFile& f = *fp;
+        const std::string* arch = f.str("general.architecture");
+        if (!arch) throw BlkError(BLK_ERR_FORMAT, "gguf: no general.architecture");
+        m->arch = *arch;
+        if (m->arch != "llama" && m->arch != "qwen2") throw BlkError(BLK_ERR_FORMAT, "unsupported architecture: " + m->arch);
+        auto hp = [&](const char* k) { return f.num_required(m->arch + "." + k); };
+        auto hpd = [&](const char* k, double d) { return f.num(m->arch + "." + k, d); };
+        m->n_embd = (int)hp("embedding_length");
+        m->n_layer = (int)hp("block_count");
+        m->n_ff = (int)hp("feed_forward_length");
+        m->n_head = (int)hp("attention.head_count");
+        m->n_head_kv = (int)hpd("attention.head_count_kv", m->n_head);
+        m->n_ctx_train = (int)hp("context_length");
+        m->rms_eps = (float)hpd("attention.layer_norm_rms_epsilon", 1e-5);
+        m->rope_theta = (float)hpd("rope.freq_base", 10000.0);
+        m->d_head = m->n_embd / m->n_head;
+        m->n_rot = (int)hpd("rope.dimension_count", m->d_head);
+        m->neox = (m->arch == "qwen2");
+        m->theta_scale = powf(m->rope_theta, -2.0f / (float)m->n_rot);
+        if (m->n_rot != m->d_head) throw BlkError(BLK_ERR_FORMAT, "partial rotary dimensions are not supported");
+        if (m->d_head != 64 && m->d_head != 128) throw BlkError(BLK_ERR_FORMAT, "head size must be 64 or 128");
+        if (m->n_head % m->n_head_kv || m->n_head / m->n_head_kv > MAX_GQ) throw BlkError(BLK_ERR_FORMAT, "unsupported GQA ratio");
+        if ((m->n_head * m->d_head) % 256 || m->n_embd % 256 || m->n_ff % 256) throw BlkError(BLK_ERR_FORMAT, "model widths must be multiples of 256");
+        m->tok_bos = (int)f.num("tokenizer.ggml.bos_token_id", -1);
+        m->tok_eos = (int)f.num("tokenizer.ggml.eos_token_id", -1);
+        m->tok_eot = (int)f.num("tokenizer.ggml.eot_token_id", -1);
+        m->tok_eom = (int)f.num("tokenizer.ggml.eom_token_id", -1);
+        m->add_bos = f.num("tokenizer.ggml.add_bos_token", 0) != 0;
+        if (const auto* v = f.str_array("tokenizer.ggml.tokens")) m->vocab = *v;
+        for (const char* k : {"general.name", "general.architecture", "tokenizer.chat_template", "tokenizer.ggml.model", "tokenizer.ggml.pre"})
+            if (const std::string* s = f.str(k)) m->meta[k] = *s;
+
+        BLK_CUDA(cudaSetDevice(device));
+        Uploader up; up.m = m.get();
+        BLK_CUDA(cudaStreamCreateWithFlags(&up.stream, cudaStreamNonBlocking));
+        size_t total = 0, biggest = 0;
+        for (const GgufTensor& t : f.tensors()) { total += Uploader::planes_bytes(t); biggest = std::max(biggest, t.nbytes); }
+        up.arena_bytes = total;
+        BLK_CUDA(cudaMalloc(&up.arena, up.arena_bytes)); m->allocs.push_back(up.arena);
+        BLK_CUDA(cudaMalloc(&up.staging, biggest)); up.staging_bytes = biggest;
+        struct StagingGuard { uint8_t* p; cudaStream_t s; ~StagingGuard() { cudaFree(p); cudaStreamDestroy(s); } } sg{up.staging, up.stream};
+
+        const size_t n_t = f.tensors().size(); size_t done = 0;
+        auto progress = [&]() { done++; if (cb && !cb((float)done / (float)n_t, user)) throw BlkError(BLK_ERR_IO, "model load aborted by the progress callback"); };
+        auto need = [&](const std::string& n) -> const GgufTensor& { const GgufTensor* t = f.find(n); if (!t) throw BlkError(BLK_ERR_FORMAT, "gguf: missing tensor " + n); return *t; };
+        auto mat = [&](const std::string& n, int K, int N) {
+            const GgufTensor& t = need(n);
+            if (t.ne[0] != K || t.n_rows() != N) throw BlkError(BLK_ERR_FORMAT, "gguf: unexpected shape for " + n);
+            QMat W = up.upload_matrix(t); progress(); return W;
+        };
+        auto vec = [&](const std::string& n, int len, bool required) -> const float* {
+            const GgufTensor* t = f.find(n);
+            if (!t) { if (required) throw BlkError(BLK_ERR_FORMAT, "gguf: missing tensor " + n); return nullptr; }
+            if (t->ne[0] != len) throw BlkError(BLK_ERR_FORMAT, "gguf: unexpected shape for " + n);
+            const float* p = up.upload_f32(*t); progress(); return p;
+        };
+        const int d = m->n_embd, dq = m->n_head * m->d_head, dkv = m->n_head_kv * m->d_head, ff = m->n_ff;
+        {
+            const GgufTensor& te = need("token_embd.weight");
+            if (te.ne[0] != d) throw BlkError(BLK_ERR_FORMAT, "gguf: unexpected shape for token_embd.weight");
+            m->n_vocab = (int)te.n_rows();
+            m->tok_embd = up.upload_matrix(te); progress();
+        }
+        m->layers.resize(m->n_layer);
+        int64_t wb = 0;
+        for (int l = 0; l < m->n_layer; l++) {
+            const std::string p = "blk." + std::to_string(l) + ".";
+            LayerWeights& L = m->layers[l];
+            L.attn_norm = vec(p + "attn_norm.weight", d, true);
+            L.wq = mat(p + "attn_q.weight", d, dq); L.wk = mat(p + "attn_k.weight", d, dkv); L.wv = mat(p + "attn_v.weight", d, dkv);
+            L.bq = vec(p + "attn_q.bias", dq, false); L.bk = vec(p + "attn_k.bias", dkv, false); L.bv = vec(p + "attn_v.bias", dkv, false);
+            L.wo = mat(p + "attn_output.weight", dq, d);
+            L.ffn_norm = vec(p + "ffn_norm.weight", d, true);
+            L.gate = mat(p + "ffn_gate.weight", d, ff); L.up = mat(p + "ffn_up.weight", d, ff); L.down = mat(p + "ffn_down.weight", ff, d);
+            if (L.gate.type != L.up.type) throw BlkError(BLK_ERR_FORMAT, "ffn_gate / ffn_up must share a type");
+            const int fam = act_format_for(L.wq.type);
+            for (const QMat* W : {&L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down})
+                if (act_format_for(W->type) != fam) throw BlkError(BLK_ERR_FORMAT, "mixed quantisation families within a model are not supported");
+            if (l == 0) m->act_fmt = fam; else if (fam != m->act_fmt) throw BlkError(BLK_ERR_FORMAT, "mixed quantisation families across layers");
+            wb += (int64_t)(L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.gate.bytes + L.up.bytes + L.down.bytes) + 2 * 4 * d;
+            if (L.bq) wb += 4 * (dq + 2 * dkv);
+        }
+        m->out_norm = vec("output_norm.weight", d, true);
+        if (f.find("output.weight")) m->output = mat("output.weight", d, m->n_vocab); else m->output = m->tok_embd;
+        m->act_fmt_out = act_format_for(m->output.type);
+        m->rope_freqs = vec("rope_freqs.weight", m->d_head / 2, false);
+        wb += (int64_t)m->output.bytes + 4 * d;
+        m->weight_bytes_per_token = wb;
+        BLK_CUDA(cudaStreamSynchronize(up.stream));
+        if ((int)m->vocab.size() != m->n_vocab) m->vocab.clear();
+    });
+    if (st != BLK_OK) return nullptr;
+    return m.release();
+}
+
+extern "C" void blk_model_free(blk_model* m) { delete m; }
+extern "C" int32_t blk_model_n_vocab(const blk_model* m) { return m->n_vocab; }
+extern "C" int32_t blk_model_n_ctx_train(const blk_model* m) { return m->n_ctx_train; }
+extern "C" int32_t blk_model_n_embd(const blk_model* m) { return m->n_embd; }
+extern "C" int32_t blk_model_n_layer(const blk_model* m) { return m->n_layer; }
+extern "C" int32_t blk_model_token_bos(const blk_model* m) { return m->tok_bos; }
+extern "C" int32_t blk_model_token_eos(const blk_model* m) { return m->tok_eos; }
+extern "C" int32_t blk_model_is_eog(const blk_model* m, int32_t t) { return t >= 0 && (t == m->tok_eos || t == m->tok_eot || t == m->tok_eom); }
+extern "C" int32_t blk_model_add_bos(const blk_model* m) { return m->add_bos ? 1 : 0; }
+extern "C" int32_t blk_model_device(const blk_model* m) { return m->device; }
+extern "C" int64_t blk_model_weight_bytes_per_token(const blk_model* m) { return m->weight_bytes_per_token; }
+extern "C" int64_t blk_model_kv_bytes_per_token(const blk_model* m) { return (int64_t)m->n_layer * m->n_head_kv * m->d_head * 2 * 2; }
+extern "C" int32_t blk_model_token_text(const blk_model* m, int32_t tok, char* buf, int32_t cap) {
+    if (tok < 0 || tok >= (int)m->vocab.size()) return 0;
+    const std::string& s = m->vocab[tok];
+    const int n = (int)s.size();
+    if (buf && cap > 0) memcpy(buf, s.data(), (size_t)std::min(n, cap));
+    return n;
+}
+extern "C" int32_t blk_model_meta_str(const blk_model* m, const char* key, char* buf, int32_t cap) {
+    auto it = m->meta.find(key);
+    if (it == m->meta.end()) return -1;
+    const int n = (int)it->second.size();
+    if (buf && cap > 0) memcpy(buf, it->second.data(), (size_t)std::min(n, cap));
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------------
+blk_ctx::~blk_ctx() {
+    if (m) cudaSetDevice(m->device);
+    if (g_full) cudaGraphExecDestroy(g_full);
+    if (g_body) cudaGraphExecDestroy(g_body);
+    for (void* p : allocs) cudaFree(p);
+    for (void* p : host_allocs) cudaFreeHost(p);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+namespace {
+
+template <class T> T* dalloc(blk_ctx* c, size_t n) {
+    void* p = nullptr;
+    BLK_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    c->allocs.push_back(p);
+    return reinterpret_cast<T*>(p);
+}
+template <class T> T* halloc(blk_ctx* c, size_t n) {
+    void* p = nullptr;
+    BLK_CUDA(cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    c->host_allocs.push_back(p);
+    return reinterpret_cast<T*>(p);
+}
+ActBuf make_act(blk_ctx* c, int K) {
+    ActBuf a;
+    a.f32 = dalloc<float>(c, K); a.q = dalloc<int8_t>(c, K); a.d = dalloc<float>(c, K / 32 + 8); a.bs = dalloc<int16_t>(c, K / 16 + 8);
+    return a;
+}
+
+// opt-in shared memory sizes; per device, outside any stream capture
+void ensure_kernel_attrs(int device) {
+    static std::mutex mu; static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64 || done[device]) return;
+    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    BLK_CUDA(cudaFuncSetAttribute(act_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    BLK_CUDA(cudaFuncSetAttribute(act_prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    done[device] = true;
+}
+
+template <int EPI>
+void launch_gemv(blk_ctx* c, GemvArgs& a) {
+    const int K = a.seg[0].W.K;
+    const size_t smem = gemv_smem_bytes(K, a.act_fmt);
+    if (smem > 64 * 1024) throw BlkError(BLK_ERR_ARG, "row length too large for the decode mat-vec");
+    // grid: one warp per row pair, capped at one full wave of resident CTAs (multiple of the SM count)
+    static int resident = 0;            // per instantiation; CTAs per SM x SMs
+    if (!resident) {
+        int per_sm = 0, sms = 0, dev = 0;
+        BLK_CUDA(cudaGetDevice(&dev));
+        BLK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_pairs_kernel<EPI>, GEMV_THREADS, 16 * 1024));
+        resident = std::max(1, per_sm) * std::max(1, sms);
+    }
+    int ctas = (a.total_pairs + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
+    if (ctas > resident) ctas = resident;
+    gemv_pairs_kernel<EPI><<<ctas, GEMV_THREADS, smem, c->stream>>>(a);
+    BLK_CUDA(cudaGetLastError());
+    c->launches++;
+}
+
+void launch_act_prepare(blk_ctx* c, const float* x, const float* w, int K, int fmt, const ActBuf& out, bool norm) {
+    const size_t smem = (size_t)K * 4;
+    if (smem > 160 * 1024) throw BlkError(BLK_ERR_ARG, "row too long for act_prepare");
+    if (norm) act_prepare_kernel<true><<<1, 512, smem, c->stream>>>(x, w, K, c->m->rms_eps, fmt, out, 0, 0, 0);
+    else act_prepare_kernel<false><<<1, 512, smem, c->stream>>>(x, w, K, c->m->rms_eps, fmt, out, 0, 0, 0);
+    BLK_CUDA(cudaGetLastError());
+    c->launches++;
+}
+
+// one decode step on c->stream: token id in c->d_tok, position in c->d_pos
+void enqueue_step(blk_ctx* c, bool with_head) {
+    blk_model* m = c->m;
+    const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+    embed_kernel<<<1, 256, 0, c->stream>>>(m->tok_embd, c->d_tok, c->d_pos, c->x, c->rope_cs, dh / 2, m->theta_scale, m->rope_freqs);
+    BLK_CUDA(cudaGetLastError()); c->launches++;
+    for (int l = 0; l < m->n_layer; l++) {
+        const LayerWeights& L = m->layers[l];
+        launch_act_prepare(c, c->x, L.attn_norm, d, m->act_fmt, c->act_d, true);
+        {
+            GemvArgs a{};
+            a.nseg = 3;
+            a.seg[0] = {L.wq, L.bq, 0, 0};
+            a.seg[1] = {L.wk, L.bk, dq / 2, 1};
+            a.seg[2] = {L.wv, L.bv, dq / 2 + dkv / 2, 2};
+            a.total_pairs = dq / 2 + dkv;
+            a.act = c->act_d; a.act_fmt = m->act_fmt; a.out = c->qbuf;
+            a.d_head = dh; a.neox = m->neox ? 1 : 0; a.rope_cs = c->rope_cs; a.pos = c->d_pos;
+            a.k_pool = c->k_pool[l]; a.v_pool = c->v_pool[l]; a.page_table = c->page_table; a.kv_dim = dkv;
+            launch_gemv<EPI_QKV>(c, a);
+        }
+        {
+            AttnArgs at{};
+            at.q = c->qbuf; at.k_pool = c->k_pool[l]; at.v_pool = c->v_pool[l]; at.page_table = c->page_table; at.pos = c->d_pos;
+            at.n_head = m->n_head; at.n_head_kv = m->n_head_kv; at.d_head = dh; at.kv_dim = dkv; at.n_split = c->n_split;
+            at.scale = 1.0f / sqrtf((float)dh); at.scores = c->scores; at.score_stride = c->n_pages * KV_PAGE; at.part_o = c->part_o;
+            dim3 grid(m->n_head_kv, c->n_split);
+            if (dh == 128) { attn_scores_kernel<128><<<grid, 128, 0, c->stream>>>(at); attn_pv_kernel<128><<<grid, 128, 0, c->stream>>>(at); }
+            else { attn_scores_kernel<64><<<grid, 64, 0, c->stream>>>(at); attn_pv_kernel<64><<<grid, 64, 0, c->stream>>>(at); }
+            BLK_CUDA(cudaGetLastError()); c->launches += 2;
+            attn_combine_kernel<<<dq / 256, 256, 0, c->stream>>>(c->part_o, dh, c->n_split, m->act_fmt, c->act_q);
+            BLK_CUDA(cudaGetLastError()); c->launches++;
+        }
+        {
+            GemvArgs a{};
+            a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2;
+            a.act = c->act_q; a.act_fmt = m->act_fmt; a.out = c->x;
+            launch_gemv<EPI_RESID>(c, a);
+        }
+        launch_act_prepare(c, c->x, L.ffn_norm, d, m->act_fmt, c->act_d, true);
+        {
+            GemvArgs a{};
+            a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff;
+            a.act = c->act_d; a.act_fmt = m->act_fmt; a.out = c->hbuf;
+            launch_gemv<EPI_SWIGLU>(c, a);
+        }
+        if (m->act_fmt != ACT_F32) {
+            act_quant_kernel<<<(ff / 256 + 7) / 8, 256, 0, c->stream>>>(c->hbuf, ff, m->act_fmt, c->act_ff);
+            BLK_CUDA(cudaGetLastError()); c->launches++;
+        }
+        {
+            GemvArgs a{};
+            a.nseg = 1; a.seg[0] = {L.down, nullptr, 0, 0}; a.total_pairs = d / 2;
+            a.act = c->act_ff; a.act_fmt = m->act_fmt; a.out = c->x;
+            if (m->act_fmt == ACT_F32) a.act.f32 = c->hbuf;
+            launch_gemv<EPI_RESID>(c, a);
+        }
+    }
+    if (with_head) {
+        launch_act_prepare(c, c->x, m->out_norm, d, m->act_fmt_out, c->act_d, true);
+        GemvArgs a{};
+        a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = m->n_vocab / 2;
+        a.act = c->act_d; a.act_fmt = m->act_fmt_out; a.out = c->logits;
+        launch_gemv<EPI_STORE>(c, a);
+        topk_stage1_kernel<<<c->n_chunks, 256, 0, c->stream>>>(c->logits, m->n_vocab, c->cand_l, c->cand_i);
+        BLK_CUDA(cudaGetLastError()); c->launches++;
+        topk_stage2_kernel<<<1, 1024, 0, c->stream>>>(c->cand_l, c->cand_i, c->n_chunks * TOPK_MAX, TOPK_MAX, c->top_ids, c->top_logits);
+        BLK_CUDA(cudaGetLastError()); c->launches++;
+    }
+    advance_pos_kernel<<<1, 32, 0, c->stream>>>(c->d_pos, 1);
+    BLK_CUDA(cudaGetLastError()); c->launches++;
+    if (with_head) {
+        BLK_CUDA(cudaMemcpyAsync(c->h_top_ids, c->top_ids, TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+}
+
+void build_graphs(blk_ctx* c) {
+    for (int which = 0; which < 2; which++) {
+        const bool head = (which == 0);
+        cudaGraph_t g = nullptr;
+        const int64_t before = c->launches;
+        BLK_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        try { enqueue_step(c, head); }
+        catch (...) { cudaGraph_t tmp = nullptr; cudaStreamEndCapture(c->stream, &tmp); if (tmp) cudaGraphDestroy(tmp); throw; }
+        BLK_CUDA(cudaStreamEndCapture(c->stream, &g));
+        cudaGraphExec_t ge = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        BLK_CUDA(e);
+        (head ? c->g_full : c->g_body) = ge;
+        (head ? c->launches_full : c->launches_body) = c->launches - before;
+        c->launches = before;
+    }
+}
+
+void step(blk_ctx* c, int32_t tok, bool with_head) {
+    blk_model* m = c->m;
+    if (tok < 0 || tok >= m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
+    if (c->n_past + 1 > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+    // pinned ring of token slots: a slot is only rewritten after the stream has drained once per lap
+    if (c->tok_slot == 0) BLK_CUDA(cudaStreamSynchronize(c->stream));
+    int32_t* slot = c->h_tok + c->tok_slot;
+    c->tok_slot = (c->tok_slot + 1) % blk_ctx::TOK_RING;
+    *slot = tok;
+    BLK_CUDA(cudaMemcpyAsync(c->d_tok, slot, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    BLK_CUDA(cudaGraphLaunch(with_head ? c->g_full : c->g_body, c->stream));
+    c->launches += with_head ? c->launches_full : c->launches_body;
+    c->n_past++;
+    c->have_logits = with_head;
+}
+
+} // namespace
+
+extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch) {
+    if (!m) { fail(BLK_ERR_ARG, "null model"); return nullptr; }
+    std::unique_ptr<blk_ctx> c(new blk_ctx());
+    c->m = m;
+    blk_status st = guarded([&] {
+        BLK_CUDA(cudaSetDevice(m->device));
+        ensure_kernel_attrs(m->device);
+        c->n_ctx = n_ctx > 0 ? n_ctx : m->n_ctx_train;
+        c->n_batch = n_batch > 0 ? n_batch : 2048;
+        BLK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        BLK_CUDA(cudaEventCreate(&c->ev0)); BLK_CUDA(cudaEventCreate(&c->ev1));
+        const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+        c->n_pages = (c->n_ctx + KV_PAGE - 1) / KV_PAGE;
+        c->k_pool.resize(m->n_layer); c->v_pool.resize(m->n_layer);
+        const size_t pool_elems = (size_t)c->n_pages * KV_PAGE * dkv;
+        for (int l = 0; l < m->n_layer; l++) { c->k_pool[l] = dalloc<__half>(c.get(), pool_elems); c->v_pool[l] = dalloc<__half>(c.get(), pool_elems); }
+        c->page_table = dalloc<int32_t>(c.get(), c->n_pages);
+        {   // identity mapping today; every kernel goes through the table so pages can be shared / remapped later
+            std::vector<int32_t> pt(c->n_pages);
+            for (int i = 0; i < c->n_pages; i++) pt[i] = i;
+            BLK_CUDA(cudaMemcpy(c->page_table, pt.data(), pt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        c->d_tok = dalloc<int32_t>(c.get(), 1); c->d_pos = dalloc<int32_t>(c.get(), 1);
+        BLK_CUDA(cudaMemset(c->d_pos, 0, sizeof(int32_t)));
+        c->h_tok = halloc<int32_t>(c.get(), blk_ctx::TOK_RING);
+        c->x = dalloc<float>(c.get(), d); c->qbuf = dalloc<float>(c.get(), dq); c->hbuf = dalloc<float>(c.get(), ff);
+        c->rope_cs = dalloc<float2>(c.get(), dh / 2);
+        c->act_d = make_act(c.get(), d); c->act_q = make_act(c.get(), dq); c->act_ff = make_act(c.get(), ff);
+        c->n_split = std::max(1, std::min(32, (2 * 148) / m->n_head_kv));
+        c->part_o = dalloc<float>(c.get(), (size_t)m->n_head * c->n_split * dh);
+        c->scores = dalloc<float>(c.get(), (size_t)m->n_head * c->n_pages * KV_PAGE);
+        c->logits = dalloc<float>(c.get(), m->n_vocab);
+        c->n_chunks = (m->n_vocab + TOPK_CHUNK - 1) / TOPK_CHUNK;
+        c->cand_l = dalloc<float>(c.get(), (size_t)c->n_chunks * TOPK_MAX); c->cand_i = dalloc<int>(c.get(), (size_t)c->n_chunks * TOPK_MAX);
+        c->top_ids = dalloc<int32_t>(c.get(), TOPK_MAX); c->top_logits = dalloc<float>(c.get(), TOPK_MAX);
+        c->h_top_ids = halloc<int32_t>(c.get(), TOPK_MAX); c->h_top_logits = halloc<float>(c.get(), TOPK_MAX);
+        c->ids_cap = 4096;
+        c->d_ids = dalloc<int32_t>(c.get(), c->ids_cap); c->d_gath = dalloc<float>(c.get(), c->ids_cap);
+        if (m->n_vocab % 2) throw BlkError(BLK_ERR_FORMAT, "vocabulary size must be even");
+        build_graphs(c.get());
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+    });
+    if (st != BLK_OK) { fail(st == BLK_ERR_OOM ? BLK_ERR_OOM : st, std::string("Failed to create context: ") + g_last_error); return nullptr; }
+    return c.release();
+}
+extern "C" void blk_ctx_free(blk_ctx* c) { delete c; }
+extern "C" int32_t blk_ctx_n_ctx(const blk_ctx* c) { return c->n_ctx; }
+extern "C" int32_t blk_ctx_n_batch(const blk_ctx* c) { return c->n_batch; }
+extern "C" int32_t blk_ctx_n_past(const blk_ctx* c) { return c->n_past; }
+extern "C" int64_t blk_ctx_kernel_launches(const blk_ctx* c) { return c->launches; }
+
+extern "C" blk_status blk_ctx_set_verify_mode(blk_ctx* c, int32_t mode) {
+    if (!c || mode < 0 || mode > 1) return fail(BLK_ERR_ARG, "blk_ctx_set_verify_mode: bad arguments");
+    c->verify_mode = mode; return BLK_OK;
+}
+
+extern "C" blk_status blk_kv_clear(blk_ctx* c) {
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, sizeof(int32_t), c->stream));
+        c->n_past = 0; c->have_logits = false;
+    });
+}
+extern "C" blk_status blk_sync(blk_ctx* c) {
+    return guarded([&] { BLK_CUDA(cudaSetDevice(c->m->device)); BLK_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
+    if (!c || !tokens || n <= 0) return fail(BLK_ERR_ARG, "blk_decode: bad arguments");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (c->n_past + n > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+        for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= c->m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
+        for (int i = 0; i < n; i++) step(c, tokens[i], i == n - 1);
+    });
+}
+
+extern "C" blk_status blk_topk_last(blk_ctx* c, int32_t k, blk_token_data* out) {
+    if (!c || !out || k <= 0 || k > TOPK_MAX) return fail(BLK_ERR_ARG, "blk_topk_last: bad arguments");
+    return guarded([&] {
+        if (!c->have_logits) throw BlkError(BLK_ERR_ARG, "no logits available: decode first");
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < k; i++) { out[i].token = c->h_top_ids[i]; out[i].logit = c->h_top_logits[i]; }
+    });
+}
+
+extern "C" blk_status blk_decode_topk(blk_ctx* c, int32_t token, int32_t k, blk_token_data* out) {
+    if (!c || !out || k <= 0 || k > TOPK_MAX) return fail(BLK_ERR_ARG, "blk_decode_topk: bad arguments");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        step(c, token, true);
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < k; i++) { out[i].token = c->h_top_ids[i]; out[i].logit = c->h_top_logits[i]; }
+    });
+}
+
+extern "C" blk_status blk_gather_last(blk_ctx* c, const int32_t* ids, int32_t n, float* out) {
+    if (!c || !ids || !out || n <= 0 || n > 4096) return fail(BLK_ERR_ARG, "blk_gather_last: bad arguments");
+    return guarded([&] {
+        if (!c->have_logits) throw BlkError(BLK_ERR_ARG, "no logits available: decode first");
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        BLK_CUDA(cudaMemcpyAsync(c->d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        gather_logits_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->logits, c->m->n_vocab, c->d_ids, n, c->d_gath);
+        BLK_CUDA(cudaGetLastError()); c->launches++;
+        BLK_CUDA(cudaMemcpyAsync(out, c->d_gath, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+extern "C" blk_status blk_get_logits_last(blk_ctx* c, float* out) {
+    if (!c || !out) return fail(BLK_ERR_ARG, "blk_get_logits_last: bad arguments");
+    return guarded([&] {
+        if (!c->have_logits) throw BlkError(BLK_ERR_ARG, "no logits available: decode first");
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        BLK_CUDA(cudaMemcpyAsync(out, c->logits, (size_t)c->m->n_vocab * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+extern "C" blk_status blk_verify_prefill(blk_ctx* c, const int32_t* tokens, int32_t n, const int32_t* claimed, const int32_t* n_claimed,
+                                         float* gathered, blk_token_data* top) {
+    if (!c || !tokens || n <= 0 || !claimed || !n_claimed || !gathered) return fail(BLK_ERR_ARG, "blk_verify_prefill: bad arguments");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (c->n_past + n > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+        for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= c->m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
+        // sequential form of the context fill: one batch-1 decode per response token (Session.cpp:235-241), logits gathered
+        // on the device at the claimed ids.  Bit-identical to what blk_decode_topk produced for the prover.
+        for (int i = 0; i < n; i++) {
+            step(c, tokens[i], true);
+            const int nc = std::max(0, std::min(10, n_claimed[i]));
+            if (nc > 0) {
+                BLK_CUDA(cudaMemcpyAsync(c->d_ids, claimed + (size_t)i * 10, nc * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+                gather_logits_kernel<<<1, 32, 0, c->stream>>>(c->logits, c->m->n_vocab, c->d_ids, nc, c->d_gath);
+                BLK_CUDA(cudaGetLastError()); c->launches++;
+                BLK_CUDA(cudaMemcpyAsync(gathered + (size_t)i * 10, c->d_gath, nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            }
+            BLK_CUDA(cudaStreamSynchronize(c->stream));
+            if (top) for (int j = 0; j < 10; j++) { top[(size_t)i * 10 + j].token = c->h_top_ids[j]; top[(size_t)i * 10 + j].logit = c->h_top_logits[j]; }
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// measurement
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" blk_status blk_timer_start(blk_ctx* c) {
+    return guarded([&] { BLK_CUDA(cudaSetDevice(c->m->device)); BLK_CUDA(cudaEventRecord(c->ev0, c->stream)); });
+}
+extern "C" blk_status blk_timer_stop(blk_ctx* c, float* ms) {
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        BLK_CUDA(cudaEventRecord(c->ev1, c->stream));
+        BLK_CUDA(cudaEventSynchronize(c->ev1));
+        BLK_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    });
+}
+extern "C" blk_status blk_bench_kernel(blk_ctx* c, int32_t which, int32_t iters, float* avg_ms, int64_t* bytes_per_launch) {
+    if (!c || iters <= 0 || !avg_ms || !bytes_per_launch || which < 0 || which > 4) return fail(BLK_ERR_ARG, "blk_bench_kernel: bad arguments");
+    return guarded([&] {
+        blk_model* m = c->m;
+        BLK_CUDA(cudaSetDevice(m->device));
+        const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+        // make the activation buffers hold something sane
+        BLK_CUDA(cudaMemsetAsync(c->x, 0, d * sizeof(float), c->stream));
+        BLK_CUDA(cudaMemsetAsync(c->hbuf, 0, ff * sizeof(float), c->stream));
+        launch_act_prepare(c, c->x, m->layers[0].attn_norm, d, m->act_fmt, c->act_d, true);
+        act_quant_kernel<<<(ff / 256 + 7) / 8, 256, 0, c->stream>>>(c->hbuf, ff, m->act_fmt == ACT_F32 ? ACT_Q8_0 : m->act_fmt, c->act_ff);
+        act_quant_kernel<<<(dq / 256 + 7) / 8, 256, 0, c->stream>>>(c->hbuf, dq, m->act_fmt == ACT_F32 ? ACT_Q8_0 : m->act_fmt, c->act_q);
+        int64_t bytes = 0;
+        auto one = [&](int it, bool count) {
+            const LayerWeights& L = m->layers[it % m->n_layer];
+            GemvArgs a{};
+            a.act_fmt = m->act_fmt;
+            switch (which) {
+            case 0:
+                a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff; a.act = c->act_d; a.out = c->hbuf;
+                if (count) bytes += (int64_t)L.gate.bytes + (int64_t)L.up.bytes + d + ff * 4;
+                launch_gemv<EPI_SWIGLU>(c, a); break;
+            case 1:
+                a.nseg = 1; a.seg[0] = {L.down, nullptr, 0, 0}; a.total_pairs = d / 2; a.act = c->act_ff; a.out = c->x;
+                if (m->act_fmt == ACT_F32) a.act.f32 = c->hbuf;
+                if (count) bytes += (int64_t)L.down.bytes + ff + d * 8;
+                launch_gemv<EPI_RESID>(c, a); break;
+            case 2:
+                a.nseg = 3; a.seg[0] = {L.wq, L.bq, 0, 0}; a.seg[1] = {L.wk, L.bk, dq / 2, 1}; a.seg[2] = {L.wv, L.bv, dq / 2 + dkv / 2, 2};
+                a.total_pairs = dq / 2 + dkv; a.act = c->act_d; a.out = c->qbuf;
+                a.d_head = dh; a.neox = m->neox ? 1 : 0; a.rope_cs = c->rope_cs; a.pos = c->d_pos;
+                a.k_pool = c->k_pool[it % m->n_layer]; a.v_pool = c->v_pool[it % m->n_layer]; a.page_table = c->page_table; a.kv_dim = dkv;
+                if (count) bytes += (int64_t)(L.wq.bytes + L.wk.bytes + L.wv.bytes) + d + dq * 4 + dkv * 4;
+                launch_gemv<EPI_QKV>(c, a); break;
+            case 3:
+                a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2; a.act = c->act_q; a.out = c->x;
+                if (count) bytes += (int64_t)L.wo.bytes + dq + d * 8;
+                launch_gemv<EPI_RESID>(c, a); break;
+            default:
+                a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = m->n_vocab / 2; a.act = c->act_d; a.act_fmt = m->act_fmt_out; a.out = c->logits;
+                if (count) bytes += (int64_t)m->output.bytes + d + (int64_t)m->n_vocab * 4;
+                launch_gemv<EPI_STORE>(c, a); break;
+            }
+        };
+        for (int i = 0; i < std::min(iters, 8); i++) one(i, false);          // warm-up
+        BLK_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < iters; i++) one(i, true);
+        BLK_CUDA(cudaEventRecord(c->ev1, c->stream));
+        BLK_CUDA(cudaEventSynchronize(c->ev1));
+        float ms = 0.0f;
+        BLK_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *avg_ms = ms / (float)iters;
+        *bytes_per_launch = bytes / iters;
+        BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, sizeof(int32_t), c->stream));
+        c->n_past = 0; c->have_logits = false;
+    });
+}
+
+extern "C" blk_status blk_flush_l2(blk_ctx* c) {
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (!c->flush_buf) { c->flush_bytes = 256u << 20; BLK_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes)); c->allocs.push_back(c->flush_buf); }
+        BLK_CUDA(cudaMemsetAsync(c->flush_buf, 0x5a, c->flush_bytes, c->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// unit-level entry points
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct TestMat {
+    blk_model holder;       // owns device allocations
+    QMat W;
+};
+void test_upload(TestMat& tm, int device, int type, const void* blocks, int64_t rows, int64_t k) {
+    if (blk_init() != BLK_OK) throw BlkError(BLK_ERR_NO_DEVICE, g_last_error);
+    BLK_CUDA(cudaSetDevice(device));
+    tm.holder.device = device;
+    GgufTensor t; t.name = "test"; t.type = type; t.n_dims = 2; t.ne[0] = k; t.ne[1] = rows;
+    int blck = 0, bytes = 0;
+    if (!ggml_type_geometry(type, blck, bytes) || k % blck) throw BlkError(BLK_ERR_ARG, "bad type / row length");
+    if (type != GT_F32 && type != GT_F16 && (k % 256) && type != GT_Q8_0) throw BlkError(BLK_ERR_ARG, "row length must be a multiple of 256");
+    t.nbytes = (size_t)(k / blck) * bytes * (size_t)rows; t.data = (const uint8_t*)blocks;
+    Uploader up; up.m = &tm.holder;
+    BLK_CUDA(cudaStreamCreateWithFlags(&up.stream, cudaStreamNonBlocking));
+    up.arena_bytes = Uploader::planes_bytes(t);
+    BLK_CUDA(cudaMalloc(&up.arena, up.arena_bytes)); tm.holder.allocs.push_back(up.arena);
+    BLK_CUDA(cudaMalloc(&up.staging, t.nbytes)); tm.holder.allocs.push_back(up.staging);
+    tm.W = up.upload_matrix(t);
+    BLK_CUDA(cudaStreamSynchronize(up.stream));
+    cudaStreamDestroy(up.stream);
+}
+__global__ void test_dequant_kernel(QMat W, float* out) { dequant_row_cta(W, blockIdx.x, out + (size_t)blockIdx.x * W.K); }
+} // namespace
+
+extern "C" blk_status blk_test_dequant(int32_t device, int32_t type, const void* blocks, int64_t rows, int64_t k, float* out) {
+    return guarded([&] {
+        TestMat tm; test_upload(tm, device, type, blocks, rows, k);
+        float* d_out = nullptr;
+        BLK_CUDA(cudaMalloc(&d_out, (size_t)rows * k * 4)); tm.holder.allocs.push_back(d_out);
+        test_dequant_kernel<<<(unsigned)rows, 128>>>(tm.W, d_out);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(cudaMemcpy(out, d_out, (size_t)rows * k * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+extern "C" blk_status blk_test_gemv(int32_t device, int32_t type, const void* blocks, int64_t rows, int64_t k, const float* x, float* y) {
+    return guarded([&] {
+        if (rows % 2) throw BlkError(BLK_ERR_ARG, "rows must be even");
+        TestMat tm; test_upload(tm, device, type, blocks, rows, k);
+        blk_ctx c; c.m = &tm.holder;
+        ensure_kernel_attrs(device);
+        BLK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        float* d_x = dalloc<float>(&c, k); float* d_y = dalloc<float>(&c, rows);
+        ActBuf act = make_act(&c, (int)k);
+        BLK_CUDA(cudaMemcpyAsync(d_x, x, k * 4, cudaMemcpyHostToDevice, c.stream));
+        const int fmt = act_format_for(type);
+        launch_act_prepare(&c, d_x, nullptr, (int)k, fmt, act, false);
+        GemvArgs a{};
+        a.nseg = 1; a.seg[0] = {tm.W, nullptr, 0, 0}; a.total_pairs = (int)(rows / 2);
+        a.act = act; a.act_fmt = fmt; a.out = d_y;
+        launch_gemv<EPI_STORE>(&c, a);
+        BLK_CUDA(cudaMemcpyAsync(y, d_y, rows * 4, cudaMemcpyDeviceToHost, c.stream));
+        BLK_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+extern "C" blk_status blk_test_gemm(int32_t, int32_t, const void*, int64_t, int64_t, const float*, int64_t, float*) {
+    return fail(BLK_ERR_ARG, "blk_test_gemm: prefill GEMM not built in this revision");
+}

@@ -1,0 +1,99 @@
+// engine.hpp -- model / context objects behind the C ABI (include/blama_b200.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/blama_b200.h"
+#include "decode_kernels.cuh"
+
+namespace blk {
+
+struct BlkError : std::runtime_error {
+    blk_status code;
+    BlkError(blk_status c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define BLK_CUDA(expr)                                                                                              \
+    do {                                                                                                            \
+        cudaError_t e__ = (expr);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+            throw ::blk::BlkError(e__ == cudaErrorMemoryAllocation ? BLK_ERR_OOM : BLK_ERR_CUDA,                    \
+                                  std::string(#expr) + ": " + cudaGetErrorString(e__));                             \
+    } while (0)
+
+void log_msg(int level, const std::string& s);
+
+struct LayerWeights {
+    QMat wq, wk, wv, wo, gate, up, down;
+    const float* attn_norm = nullptr;
+    const float* ffn_norm = nullptr;
+    const float* bq = nullptr;
+    const float* bk = nullptr;
+    const float* bv = nullptr;
+};
+
+} // namespace blk
+
+struct blk_model {
+    int device = 0;
+    std::string arch;
+    int n_vocab = 0, n_embd = 0, n_layer = 0, n_head = 0, n_head_kv = 0, d_head = 0, n_ff = 0, n_ctx_train = 0, n_rot = 0;
+    float rms_eps = 1e-5f, rope_theta = 10000.0f, theta_scale = 1.0f;
+    bool neox = false;
+    int tok_bos = -1, tok_eos = -1, tok_eot = -1, tok_eom = -1;
+    bool add_bos = false;
+    std::vector<blk::LayerWeights> layers;
+    blk::QMat tok_embd, output;
+    const float* out_norm = nullptr;
+    const float* rope_freqs = nullptr;
+    std::vector<void*> allocs;
+    std::vector<std::string> vocab;
+    std::map<std::string, std::string> meta;
+    int64_t weight_bytes_per_token = 0;
+    int act_fmt = blk::ACT_F32;       // activation format of the layer mat-vecs
+    int act_fmt_out = blk::ACT_F32;   // ... of the lm_head
+    ~blk_model();
+};
+
+struct blk_ctx {
+    blk_model* m = nullptr;
+    int n_ctx = 0, n_batch = 0, n_past = 0;
+    int n_pages = 0, n_split = 1;
+    int verify_mode = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> allocs;
+    std::vector<void*> host_allocs;
+    // KV pages
+    std::vector<__half*> k_pool, v_pool;
+    int32_t* page_table = nullptr;
+    // decode-step state
+    int32_t* d_tok = nullptr; int32_t* d_pos = nullptr;
+    static constexpr int TOK_RING = 256;
+    int32_t* h_tok = nullptr;             // pinned ring [TOK_RING]
+    int tok_slot = 0;
+    float* x = nullptr;                   // residual stream [d]
+    float* qbuf = nullptr;                // [n_head*d_head]
+    float* hbuf = nullptr;                // [n_ff]
+    float2* rope_cs = nullptr;            // [d_head/2]
+    blk::ActBuf act_d, act_q, act_ff;
+    float* part_o = nullptr; float* scores = nullptr;
+    float* logits = nullptr;              // [n_vocab] of the last decoded token
+    float* cand_l = nullptr; int* cand_i = nullptr; int n_chunks = 0;
+    int32_t* top_ids = nullptr; float* top_logits = nullptr;           // device [TOPK_MAX]
+    int32_t* h_top_ids = nullptr; float* h_top_logits = nullptr;       // pinned
+    bool have_logits = false;
+    cudaGraphExec_t g_full = nullptr, g_body = nullptr;
+    int64_t launches_full = 0, launches_body = 0;
+    int64_t launches = 0;
+    // scratch for gather / verify
+    int32_t* d_ids = nullptr; float* d_gath = nullptr; int ids_cap = 0;
+    void* flush_buf = nullptr; size_t flush_bytes = 0;
+    ~blk_ctx();
+};

@@ -119,9 +119,9 @@ def random_blocks(rng: np.random.Generator, gtype: int, n_elems: int, sigma: flo
     assert n_elems % bs == 0
     nb = n_elems // bs
     if gtype == F32:
-        return (rng.standard_normal(n_elems, dtype=np.float32) * sigma).view(np.uint8)
+        return (rng.standard_normal(n_elems, dtype=np.float32) * np.float32(sigma)).astype(np.float32).view(np.uint8)
     if gtype == F16:
-        return (rng.standard_normal(n_elems, dtype=np.float32) * sigma).astype(np.float16).view(np.uint8)
+        return (rng.standard_normal(n_elems, dtype=np.float32) * np.float32(sigma)).astype(np.float16).view(np.uint8)
     raw = rng.integers(0, 256, size=(nb, nbytes), dtype=np.uint8)
     jitter = np.exp(0.25 * rng.standard_normal(nb, dtype=np.float32))
     if gtype == Q8_0:

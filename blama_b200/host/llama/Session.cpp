@@ -1,0 +1,302 @@
+// Session.cpp -- blama's per-request control loop (reference inference/code/llama/Session.cpp) on the CUDA engine.
+//
+// What stays: phases, error strings, the "logits attached to token t are those AFTER t was decoded" rule
+// (reference :186-189 + :252), EOG handling (:181-184), sampler accept/reset points.
+// What changes: one blk_decode_topk per generated token replaces llama_decode + a 513 KB logits copy + two host
+// passes + a full std::sort (:23-39, :254-260); fillCtx is one causal prefill instead of N decodes (:235-241).
+#include "Session.hpp"
+#include "Errors.hpp"
+#include "Init.hpp"
+#include "Instance.hpp"
+#include "Model.hpp"
+
+#include <blama_b200.h>
+
+#include <algorithm>
+
+namespace bl::llama {
+namespace {
+constexpr int32_t kReportedTop = 10;       // TokenPrediction carries the 10 best logits (Session.cpp:188)
+}
+
+Session::Session(Instance& instance, blk_ctx* ctx, InitParams params)
+    : m_instance(instance)
+    , m_ctx(ctx)
+    , m_sampler(new Sampler(instance.model(), [&] {
+          Sampler::Params sp;
+          sp.rngSeed = params.seed;
+          sp.topP = params.topP;
+          sp.temp = params.temperature;
+          sp.grammar = params.grammar;
+          return sp;
+      }()))
+    , m_params(std::move(params)) {
+    throwIfFailed(blk_kv_clear(m_ctx), "kv clear");
+    throwIfFailed(blk_sync(m_ctx), "synchronize");
+    m_maxTokens = unsigned(blk_ctx_n_ctx(m_ctx)) - 4;   // (#16)
+}
+
+Session::~Session() {
+    try { flushPendingState(); } catch (...) {}
+}
+
+void Session::requireStarted(bool allowStreaming) const {
+    if (m_phase == Phase::Generating) return;
+    if (allowStreaming && m_phase == Phase::Streaming) return;
+    Raise{} << "Session hasn't started yet";
+}
+
+void Session::setInitialPrompt(std::span<const Token> initialPrompt) {
+    if (m_phase != Phase::Initial) Raise{} << "Session already started";
+
+    Token single;
+    const auto ctxLen = blk_ctx_n_ctx(m_ctx);
+    m_numKeep = std::min(uint32_t(initialPrompt.size()), m_maxTokens);
+    if (initialPrompt.empty()) {
+        single = blk_model_token_bos(m_instance.model().lmodel());
+        initialPrompt = {&single, 1};
+    }
+    if (initialPrompt.size() > m_maxTokens)
+        Raise{} << "Initial prompt too long. Got " << initialPrompt.size() << " tokens, max: " << ctxLen - 4;
+    if (m_params.gaFactor != 1) {
+        if (m_params.gaWidth % m_params.gaFactor != 0)
+            Raise{} << "Group-attention width " << m_params.gaWidth << " must be a multiple of group-attention factor " << m_params.gaFactor;
+        Raise{} << "Self-Extend (gaFactor != 1) is not supported by this build";
+    }
+    doDecode(initialPrompt, Source::InitialPrompt);
+    m_phase = Phase::Generating;
+}
+
+void Session::pushPrompt(std::span<const Token> prompt, std::span<const Token> postfix) {
+    requireStarted(false);
+    flushPendingState();
+    if (prompt.empty() && postfix.empty()) Raise{} << "Prompt and postfix are empty";
+    if (!postfix.empty()) Raise{} << "fill-in-the-middle prompts are not supported by this build";
+
+    auto& model = m_instance.model();
+    m_sampler->reset();     // previous inputs must not influence the generation
+
+    std::vector<Token> tokens;
+    tokens.reserve(prompt.size() + 1);
+    if (model.prefixInputsWithBos()) tokens.push_back(blk_model_token_bos(model.lmodel()));
+    tokens.insert(tokens.end(), prompt.begin(), prompt.end());
+    if (tokens.size() > m_maxTokens)
+        Raise{} << "Prompt too long. Got " << tokens.size() << " tokens, max: " << blk_ctx_n_ctx(m_ctx) - 4;
+    doDecode(tokens, Source::InteractivePrompt);
+}
+
+TokenPrediction Session::getToken() {
+    requireStarted(true);
+    flushPendingState();
+
+    // sample from the distribution left by the last decode; the chain only ever looks at its top-k
+    const int32_t need = m_sampler->candidatesNeeded();
+    if (need > 0) {
+        m_currToken = m_sampler->sample({m_candidates.data(), std::min<size_t>(m_candidates.size(), size_t(need))}, true);
+    } else {
+        // top-k disabled or wider than the device list: the whole row is needed (reference behaviour, slow path)
+        const int32_t nVocab = blk_model_n_vocab(m_instance.model().lmodel());
+        std::vector<float> row(static_cast<size_t>(nVocab));
+        throwIfFailed(blk_get_logits_last(m_ctx, row.data()), "get logits");
+        TokenDataVector all(static_cast<size_t>(nVocab));
+        for (int32_t i = 0; i < nVocab; ++i) all[size_t(i)] = {i, row[size_t(i)]};
+        m_currToken = m_sampler->sample(all, false);
+    }
+
+    if (m_instance.model().vocab().isEog(m_currToken)) m_currToken = Token_Invalid;   // EOG is never decoded
+    TokenPrediction out;
+    out.token = m_currToken;
+    out.logits = getLogitsFromCtx(kReportedTop);
+    return out;
+}
+
+std::vector<TokenPrediction> Session::complete(CompleteParams params) {
+    requireStarted(false);
+    flushPendingState();
+    if (params.prompt.size() || params.suffix.size()) pushPrompt(params.prompt, params.suffix);
+
+    std::vector<TokenPrediction> predictions;
+    for (int32_t i = 0; i < params.maxTokens; i++) {
+        auto p = getToken();
+        if (p.token == Token_Invalid) break;
+        predictions.push_back(std::move(p));
+    }
+    return predictions;
+}
+
+Session::StreamGenerator Session::completeStream(CompleteParams params) {
+    requireStarted(false);
+    flushPendingState();
+    if (params.prompt.size() || params.suffix.size()) pushPrompt(params.prompt, params.suffix);
+    m_phase = Phase::Streaming;
+    return StreamGenerator(*this, params);
+}
+
+std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens) {
+    std::vector<TokenPrediction> result;
+    result.reserve(tokens.size());
+    if (tokens.empty()) return result;
+
+    if (m_instance.model().prefixInputsWithBos()) {
+        // every pushPrompt would insert a BOS before its token (reference :129-132): keep the literal per-token loop
+        for (const auto& token : tokens) {
+            pushPrompt({&token.token, 1}, {});
+            result.push_back({token.token, getLogitsFromCtx(token.logits)});
+        }
+        return result;
+    }
+
+    requireStarted(false);
+    flushPendingState();
+    m_sampler->reset();
+
+    const size_t n = tokens.size();
+    if (m_numPast + n >= uint32_t(blk_ctx_n_ctx(m_ctx))) Raise{} << "context limit of " << blk_ctx_n_ctx(m_ctx) << " reached";
+    std::vector<Token> ids(n);
+    std::vector<int32_t> claimed(n * 10, 0), nClaimed(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        ids[i] = tokens[i].token;
+        m_sampler->accept(ids[i], false);
+        // distinct claimed ids in ascending order: what the reference's vocabulary walk would visit (:271-275)
+        std::vector<Token> uniq;
+        for (const auto& td : tokens[i].logits) uniq.push_back(td.token);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        const int32_t nVocab = blk_model_n_vocab(m_instance.model().lmodel());
+        uniq.erase(std::remove_if(uniq.begin(), uniq.end(), [&](Token t) { return t < 0 || t >= nVocab; }), uniq.end());
+        if (uniq.size() > 10) Raise{} << "at most 10 claimed logits per token are supported";
+        nClaimed[i] = int32_t(uniq.size());
+        std::copy(uniq.begin(), uniq.end(), claimed.begin() + long(i * 10));
+    }
+    std::vector<float> gathered(n * 10, 0.0f);
+    std::vector<blk_token_data> top(n * 10);
+    throwIfFailed(blk_ctx_set_verify_mode(m_ctx, m_params.sequentialVerify ? 1 : 0), "verify mode");
+    const int st = blk_verify_prefill(m_ctx, ids.data(), int32_t(n), claimed.data(), nClaimed.data(), gathered.data(), top.data());
+    if (st != BLK_OK) Raise{} << "Failed to decode tokens";
+    m_numPast += uint32_t(n);
+
+    for (size_t i = 0; i < n; ++i) {
+        TokenDataVector v(size_t(nClaimed[i]));
+        for (int32_t j = 0; j < nClaimed[i]; ++j) v[size_t(j)] = {claimed[i * 10 + size_t(j)], gathered[i * 10 + size_t(j)]};
+        std::sort(v.begin(), v.end(), [](const TokenData& a, const TokenData& b) { return a.logit > b.logit; });
+        result.push_back({ids[i], std::move(v)});
+    }
+    // the verifier's own candidates for whoever continues generating after the fill
+    m_candidates.resize(10);
+    for (size_t j = 0; j < 10; ++j) m_candidates[j] = {top[(n - 1) * 10 + j].token, top[(n - 1) * 10 + j].logit};
+    refreshCandidates();
+    return result;
+}
+
+void Session::refreshCandidates() {
+    m_candidates.resize(size_t(Sampler::MaxDeviceCandidates));
+    static_assert(sizeof(TokenData) == sizeof(blk_token_data));
+    throwIfFailed(blk_topk_last(m_ctx, Sampler::MaxDeviceCandidates, reinterpret_cast<blk_token_data*>(m_candidates.data())), "top-k");
+}
+
+TokenDataVector Session::getLogitsFromCtx(int32_t topK) {
+    requireStarted(true);
+    flushPendingState();
+    if (topK < 0) topK = 0;
+    if (size_t(topK) <= m_candidates.size()) return TokenDataVector(m_candidates.begin(), m_candidates.begin() + topK);
+    // more than the device list holds: fetch the row and sort on the host exactly like the reference (:254-260)
+    const int32_t nVocab = blk_model_n_vocab(m_instance.model().lmodel());
+    std::vector<float> row(static_cast<size_t>(nVocab));
+    throwIfFailed(blk_get_logits_last(m_ctx, row.data()), "get logits");
+    TokenDataVector all(static_cast<size_t>(nVocab));
+    for (int32_t i = 0; i < nVocab; ++i) all[size_t(i)] = {i, row[size_t(i)]};
+    std::sort(all.begin(), all.end(), [](const TokenData& a, const TokenData& b) { return a.logit > b.logit; });
+    all.resize(size_t(std::min(topK, nVocab)));
+    return all;
+}
+
+TokenDataVector Session::getLogitsFromCtx(TokenDataVector tokens) {
+    requireStarted(true);
+    flushPendingState();
+    std::vector<Token> uniq;
+    for (const auto& td : tokens) uniq.push_back(td.token);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    const int32_t nVocab = blk_model_n_vocab(m_instance.model().lmodel());
+    uniq.erase(std::remove_if(uniq.begin(), uniq.end(), [&](Token t) { return t < 0 || t >= nVocab; }), uniq.end());
+    TokenDataVector res(uniq.size());
+    if (uniq.empty()) return res;
+    std::vector<float> vals(uniq.size());
+    throwIfFailed(blk_gather_last(m_ctx, uniq.data(), int32_t(uniq.size()), vals.data()), "gather logits");
+    for (size_t i = 0; i < uniq.size(); ++i) res[i] = {uniq[i], vals[i]};
+    std::sort(res.begin(), res.end(), [](const TokenData& a, const TokenData& b) { return a.logit > b.logit; });
+    return res;
+}
+
+std::vector<uint8_t> Session::getState() {
+    requireStarted(false);
+    flushPendingState();
+    Raise{} << "Failed to get state";       // state save / restore is outside this build's scope
+    return {};
+}
+
+bool Session::setState(std::span<uint8_t>) {
+    if (m_phase != Phase::Initial) Raise{} << "Session already started";
+    Raise{} << "Failed to set state";
+    return false;
+}
+
+void Session::doDecode(std::span<const Token> tokens, Source src) {
+    if (tokens.size() > m_maxTokens) {
+        const auto skipped = tokens.size() - m_maxTokens;
+        tokens = tokens.first(m_maxTokens);
+        logLine(LogLevel::Warning, "Input too long. Skipping " + std::to_string(skipped) + " tokens");
+    }
+    const auto ctxLen = uint32_t(blk_ctx_n_ctx(m_ctx));
+    if (m_numPast + tokens.size() >= ctxLen) {
+        // the reference would shift the context here (:324-347); K-shift on the paged cache is not built yet
+        Raise{} << "context limit of " << ctxLen << " reached";
+    }
+    for (auto t : tokens) m_sampler->accept(t, src == Source::Generated);
+
+    if (tokens.size() == 1) {
+        m_candidates.resize(size_t(Sampler::MaxDeviceCandidates));
+        const int st = blk_decode_topk(m_ctx, tokens[0], Sampler::MaxDeviceCandidates, reinterpret_cast<blk_token_data*>(m_candidates.data()));
+        if (st != BLK_OK) Raise{} << "Failed to decode tokens";
+        m_numPast += 1;
+        return;
+    }
+    const auto batchSize = size_t(blk_ctx_n_batch(m_ctx));
+    while (!tokens.empty()) {
+        auto batch = tokens.size() > batchSize ? tokens.first(batchSize) : tokens;
+        tokens = tokens.subspan(batch.size());
+        if (blk_decode(m_ctx, batch.data(), int32_t(batch.size())) != BLK_OK) Raise{} << "Failed to decode tokens";
+        m_numPast += uint32_t(batch.size());
+    }
+    refreshCandidates();
+}
+
+void Session::flushPendingState() {
+    if (m_currToken != Token_Invalid) {
+        const Token t = m_currToken;
+        m_currToken = Token_Invalid;
+        doDecode({&t, 1}, Source::Generated);
+    }
+}
+
+void Session::resetSampler(const Sampler::Params& params) { m_sampler.reset(new Sampler(m_instance.model(), params)); }
+
+TokenPrediction Session::StreamGenerator::complete() {
+    if (m_session.m_phase != Session::Phase::Streaming || m_status != Status::InProgress) return {Token_Invalid, {}};
+    auto p = m_session.getToken();
+    if (p.token == Token_Invalid) {
+        m_session.m_phase = Session::Phase::Generating;
+        m_status = Status::Completed;
+        return p;
+    }
+    m_genTokens++;
+    if (m_genTokens >= m_params.maxTokens) {
+        m_session.m_phase = Session::Phase::Generating;
+        m_status = Status::Completed;
+    }
+    return p;
+}
+
+void Session::StreamGenerator::abort() { m_status = Status::Aborted; }
+
+} // namespace bl::llama

@@ -1,0 +1,58 @@
+// Server.hpp -- request-level façade (mirror of reference server/code/server/Server.hpp:17-69).
+//
+// The reference owns ONE Instance and ONE inference thread (Server.cpp:23-43): requests are serialised.  Requests are
+// independent (fresh session + KV clear each), so this build partitions them across GPUs: one full model replica,
+// one Instance and one worker thread per GPU, all pulling whole requests from a shared queue.  No collective is
+// involved.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace bl::llama {
+class Model;
+namespace server {
+
+class Server {
+public:
+    explicit Server(std::shared_ptr<Model> model);                      // reference signature: one replica
+    explicit Server(std::vector<std::shared_ptr<Model>> replicas);      // one replica per GPU
+    ~Server();
+    Server(const Server&) = delete;
+    Server& operator=(const Server&) = delete;
+
+    struct CompleteRequestParams {
+        std::string prompt;
+        uint32_t maxTokens = 0;
+        uint32_t seed = 0;
+        std::string suffix;           // parsed by the HTTP layer but never forwarded (reference Server.cpp:53-56)
+        float temperature = 0.8f;
+        float topP = 0.95f;
+    };
+    struct TokenData {
+        std::string tokenStr;
+        uint32_t tokenId = 0;
+        struct LogitData { uint32_t tokenId = 0; float logit = 0; };
+        std::vector<LogitData> logits;
+    };
+    using CompleteReponse = std::vector<TokenData>;
+
+    void completeText(CompleteRequestParams params, std::function<void(CompleteReponse)> cb);
+    void verify(CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb);
+
+    // extension used by the benchmark harness: prompts given as token ids (no tokenizer on the path)
+    void completeTokens(std::vector<int32_t> prompt, CompleteRequestParams params, std::function<void(CompleteReponse)> cb);
+    void verifyTokens(std::vector<int32_t> prompt, CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb);
+
+    size_t workerCount() const noexcept;
+    void drain();     // blocks until every queued request has run
+
+private:
+    struct Impl;
+    std::unique_ptr<Impl> m_impl;
+};
+
+} // namespace server
+} // namespace bl::llama

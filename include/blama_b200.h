@@ -1,0 +1,152 @@
+/*
+ * blama_b200.h -- C ABI of the B200-native engine behind blama's inference hot path.
+ *
+ * blama has no plugin registry: the seam its hot path sits behind is the llama.cpp C API called from
+ * bl::llama::{Model,Instance,Session,Sampler}.  This header is the narrower ABI that
+ * replaces those call sites; each entry point cites the reference interface it stands in for
+ * (paths relative to the reference tree, inference/code/llama/ unless noted).  The C++ classes in
+ * blama_b200/host/llama/ re-implement bl::llama::* over exactly these functions, and INTEGRATION.md shows the
+ * binding a blama maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a blk_status (0 = ok) unless it returns a
+ * handle (NULL on failure) or a value; no exceptions cross the boundary; blk_last_error() gives the message of the
+ * last failure on the calling thread.  One thread drives one blk_ctx at a time (Server.cpp:36); several contexts may
+ * share one blk_model (t-integration.cpp:220-224).  There is NO CPU fallback: without a CUDA device every call
+ * that needs one fails with BLK_ERR_NO_DEVICE.
+ */
+#ifndef BLAMA_B200_H
+#define BLAMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLK_API __attribute__((visibility("default")))
+
+typedef int32_t blk_status;
+enum {
+    BLK_OK = 0,
+    BLK_ERR_NO_DEVICE = 1,   /* no CUDA device / driver (the product never falls back to the CPU) */
+    BLK_ERR_IO = 2,          /* file missing / unreadable */
+    BLK_ERR_FORMAT = 3,      /* not a GGUF v2/v3 file, unsupported arch or tensor type */
+    BLK_ERR_ARG = 4,         /* bad argument (token id out of range, n <= 0, ...) */
+    BLK_ERR_CTX_FULL = 5,    /* n_past + n > n_ctx            (llama_decode != 0, Session.cpp:388-390) */
+    BLK_ERR_CUDA = 6,        /* CUDA runtime error */
+    BLK_ERR_OOM = 7
+};
+
+typedef struct blk_model blk_model;
+typedef struct blk_ctx blk_ctx;
+
+/* TokenData of the reference (Token.hpp:12-15): 8 bytes, {int32 token; float logit} */
+typedef struct { int32_t token; float logit; } blk_token_data;
+
+/* ---- library -------------------------------------------------------------------------------------------- */
+/* llama_backend_init + llama_log_set (Init.cpp:34-38).  Idempotent. */
+BLK_API blk_status blk_init(void);
+typedef void (*blk_log_cb)(int level, const char* text, void* user);      /* level: 0 debug 1 info 2 warn 3 error */
+BLK_API void blk_set_log_callback(blk_log_cb cb, void* user);              /* Init.cpp:11-30 llamaLogCb */
+BLK_API const char* blk_last_error(void);
+BLK_API int32_t blk_device_count(void);                                   /* ggml_backend_dev_by_type(GPU), Model.cpp:14-19 */
+BLK_API const char* blk_version(void);
+
+/* ---- model (Model.cpp:50-53 llama_model_load_from_file, llama_model_free) -------------------------------- */
+typedef int32_t (*blk_progress_cb)(float progress, void* user);           /* Model.cpp:37-43; return 0 to abort */
+/* Parses the GGUF, uploads every tensor to `device` as device-resident quant blocks (Q4_K/Q5_K/Q6_K/Q8_0/F16/F32),
+ * re-tiled on the device into the split layout the kernels stream (DESIGN.md "Data layout"). */
+BLK_API blk_model* blk_model_load(const char* gguf_path, int32_t device, blk_progress_cb cb, void* user);
+BLK_API void       blk_model_free(blk_model*);
+BLK_API int32_t blk_model_n_vocab(const blk_model*);        /* llama_vocab_n_tokens    Session.cpp:27 */
+BLK_API int32_t blk_model_n_ctx_train(const blk_model*);    /* llama_model_n_ctx_train Model.cpp:59 */
+BLK_API int32_t blk_model_n_embd(const blk_model*);         /* llama_model_n_embd */
+BLK_API int32_t blk_model_n_layer(const blk_model*);        /* llama_model_n_layer */
+BLK_API int32_t blk_model_token_bos(const blk_model*);      /* llama_vocab_bos         Session.cpp:73 */
+BLK_API int32_t blk_model_token_eos(const blk_model*);      /* llama_vocab_eos         Instance.cpp:94 */
+BLK_API int32_t blk_model_is_eog(const blk_model*, int32_t token);   /* llama_vocab_is_eog Vocab.cpp:30 */
+BLK_API int32_t blk_model_add_bos(const blk_model*);        /* llama_vocab_get_add_bos Model.cpp:63 */
+BLK_API int32_t blk_model_device(const blk_model*);
+/* bytes of weights one decoded token streams from HBM (all matmul tensors once + lm_head) */
+BLK_API int64_t blk_model_weight_bytes_per_token(const blk_model*);
+/* KV bytes per context token (K+V, all layers, f16) */
+BLK_API int64_t blk_model_kv_bytes_per_token(const blk_model*);
+/* token text (tokenizer.ggml.tokens[token]); returns length, copies at most cap bytes (llama_token_to_piece, Vocab.cpp:57) */
+BLK_API int32_t blk_model_token_text(const blk_model*, int32_t token, char* buf, int32_t cap);
+/* metadata string lookup (llama_model_meta_val_str, Model.cpp:77); returns length or -1 */
+BLK_API int32_t blk_model_meta_str(const blk_model*, const char* key, char* buf, int32_t cap);
+
+/* ---- context (Instance.cpp:34-48 llama_init_from_model, llama_free) -------------------------------------- */
+/* n_ctx = 0 -> training context (Instance.hpp:22).  n_batch = logical prefill batch (Instance.hpp:23). */
+BLK_API blk_ctx*   blk_ctx_create(blk_model*, int32_t n_ctx, int32_t n_batch);
+BLK_API void       blk_ctx_free(blk_ctx*);
+BLK_API int32_t    blk_ctx_n_ctx(const blk_ctx*);           /* llama_n_ctx   Session.cpp:57 */
+BLK_API int32_t    blk_ctx_n_batch(const blk_ctx*);         /* llama_n_batch Session.cpp:381 */
+BLK_API int32_t    blk_ctx_n_past(const blk_ctx*);
+BLK_API blk_status blk_kv_clear(blk_ctx*);                  /* llama_kv_self_clear Session.cpp:53 */
+BLK_API blk_status blk_sync(blk_ctx*);                      /* llama_synchronize   Session.cpp:54 */
+
+/* ---- decode (Session.cpp:388 llama_decode on a llama_batch_get_one batch) -------------------------------- */
+/* Appends n tokens at positions n_past.. ; afterwards the logits of the LAST token are resident on the device
+ * (the reference's llama_get_logits_ith(-1) row).  n == 1 is the batch-1 decode step (dequant-fused GEMV path,
+ * CUDA graph); n > 1 is prompt prefill (tcgen05 GEMM path). */
+BLK_API blk_status blk_decode(blk_ctx*, const int32_t* tokens, int32_t n);
+
+/* Session::getLogitsFromCtx(topK) (Session.cpp:246-261) without the host sort: top-k (k <= 64) of the last
+ * token's logits, descending (ties: lower id first). */
+BLK_API blk_status blk_topk_last(blk_ctx*, int32_t k, blk_token_data* out);
+/* Session::getLogitsFromCtx(TokenDataVector) (Session.cpp:263-282) without the V-long host loop: logits of the last
+ * token at `ids` (raw, in the order given; the caller applies the reference's de-dup + sort). */
+BLK_API blk_status blk_gather_last(blk_ctx*, const int32_t* ids, int32_t n, float* out);
+/* llama_get_logits_ith(-1) (Session.cpp:24, Sampler.cpp:111): copies all n_vocab logits to the host.  Test / debug
+ * path: the product never needs the full row. */
+BLK_API blk_status blk_get_logits_last(blk_ctx*, float* out);
+
+/* One fused decode step for Session::getToken (Session.cpp:169-190): decode `token`, then return the top-k of the new
+ * distribution in one device->host copy. */
+BLK_API blk_status blk_decode_topk(blk_ctx*, int32_t token, int32_t k, blk_token_data* out);
+
+/* ---- verification context fill (Session::fillCtx, Session.cpp:231-244) ----------------------------------- */
+/* Appends the n response tokens as ONE causal prefill (chunked by n_batch) instead of n single-token decodes, and for
+ * every position i returns
+ *   gathered[i*10 + j] = verifier logit at claimed[i*10 + j]  (j < n_claimed[i]; raw, unsorted), and
+ *   top[i*10 .. i*10+9] = the verifier's own top-10 (descending),
+ * without ever materialising the n x n_vocab logits.  `top` may be NULL. */
+BLK_API blk_status blk_verify_prefill(blk_ctx*, const int32_t* tokens, int32_t n,
+                                      const int32_t* claimed /* [n][10] */, const int32_t* n_claimed /* [n] */,
+                                      float* gathered /* [n][10] */, blk_token_data* top /* [n][10] or NULL */);
+
+/* 0 (default) = batched prefill (tcgen05 GEMM path; results within the stated fp tolerance of the decode path);
+ * 1 = sequential: n batch-1 decodes, exactly the reference's algorithm, logits bit-identical to blk_decode_topk. */
+BLK_API blk_status blk_ctx_set_verify_mode(blk_ctx*, int32_t mode);
+
+/* ---- measurement ------------------------------------------------------------------------------------------ */
+/* CUDA-event timing on the context's own stream (torch.cuda.Event cannot see it). */
+BLK_API blk_status blk_timer_start(blk_ctx*);
+BLK_API blk_status blk_timer_stop(blk_ctx*, float* ms);     /* synchronises the stream */
+/* number of kernels this context has launched since creation (graph replays count their kernel nodes) */
+BLK_API int64_t    blk_ctx_kernel_launches(const blk_ctx*);
+/* Times ONE kernel of the decode path in isolation, for the roofline line of bench.py: launches it `iters` times back to
+ * back, cycling through the layers so consecutive launches stream different weights (working set >> L2), bracketed by
+ * CUDA events on the context's stream.  which: 0 = gate/up + SwiGLU mat-vec, 1 = down-proj mat-vec, 2 = QKV mat-vec,
+ * 3 = attention-output mat-vec, 4 = lm_head mat-vec.  Returns the average launch duration and the algorithmic bytes one
+ * launch must move (quantised weight planes + activations + outputs). */
+BLK_API blk_status blk_bench_kernel(blk_ctx*, int32_t which, int32_t iters, float* avg_ms, int64_t* bytes_per_launch);
+/* writes >= bytes of device memory to evict L2 between timed iterations */
+BLK_API blk_status blk_flush_l2(blk_ctx*);
+
+/* ---- unit-level entry points (kernel parity tests) --------------------------------------------------------- */
+/* y[r] = W[r,:] . x through the decode GEMV kernel of ggml type `type` (raw ggml blocks in, host buffers) */
+BLK_API blk_status blk_test_gemv(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k,
+                                 const float* x, float* y);
+/* Y[t][r] = W[r,:] . X[t,:] through the prefill tcgen05 GEMM (bf16 operands, f32 accumulate) */
+BLK_API blk_status blk_test_gemm(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k,
+                                 const float* x, int64_t n_tok, float* y);
+/* dequantise through the device re-tile + dequant kernels */
+BLK_API blk_status blk_test_dequant(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLAMA_B200_H */

@@ -1,0 +1,123 @@
+"""End-to-end decode parity on random-init GGUFs: CUDA engine (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from blama_b200 import gguf_synth as gs
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["tiny-llama-q4km", "tiny-llama-q8", "tiny-qwen2-q8", "tiny-llama-f32", "small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km"]
+# Two implementations of ggml's arithmetic agree on every integer partial sum but not on the ORDER of the fp32
+# additions.  A 1e-7 difference occasionally flips one Q8_K / f16 rounding, and the requantise-matmul chain amplifies a
+# flip into ~0.1 logit differences that then persist through the KV cache (measured: the oracle against itself with a
+# different lane count shows the same, tests/test_oracle.py::test_summation_order_noise_floor).  So steps are either
+# CLEAN (fp32 noise only) or FLIPPED (bounded by the quantisation noise of the reference's own arithmetic).
+CLEAN_TOL = 1e-4          # absolute, logits have std ~2
+FLIP_TOL = 0.45           # ~ the Q8_K activation-quantisation noise of the reference arithmetic itself (see test_oracle)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_decode_logits_match_oracle(name, gguf_path, oracle):
+    from blama_b200 import capi
+
+    path = gguf_path(name)
+    om = oracle.Model(path)
+    oc = oracle.Ctx(om, 256, oracle.MODE_GGML, 4)
+    m = capi.Model(path)
+    c = capi.Ctx(m, 256)
+    assert m.n_vocab == om.n_vocab and m.weight_bytes_per_token == om.weight_bytes_per_token()
+    clean = total = 0
+    for seq in range(6):                      # independent short sequences: a flip only taints its own sequence
+        toks = gs.synth_prompt(name, 6, 100 + seq)
+        oc.clear(); c.clear()
+        for i, t in enumerate(toks):
+            want = oc.decode([t])[0]
+            c.decode([int(t)])
+            got = c.logits()
+            err = float(np.abs(got - want).max())
+            total += 1
+            assert err <= FLIP_TOL, (seq, i, err)
+            top_want, top_got = oracle.topk(want, 10), c.topk(10)
+            assert np.array_equal(c.topk(10)["logit"], np.sort(got)[::-1][:10])          # device top-k == sort of device logits
+            ids = np.array([0, m.n_vocab - 1, int(top_want["token"][3]), 7], dtype=np.int32)
+            assert np.array_equal(c.gather(ids), got[ids])
+            if err <= CLEAN_TOL:
+                clean += 1
+                assert np.array_equal(top_got["token"], top_want["token"]), (seq, i, top_got, top_want)
+                assert np.abs(top_got["logit"] - top_want["logit"]).max() <= CLEAN_TOL
+            else:
+                assert top_got["token"][0] == top_want["token"][0] or (top_want["logit"][0] - top_want["logit"][1]) < 2 * err
+                assert len(set(top_got["token"]) & set(top_want["token"])) >= 7
+    assert clean >= 0.4 * total, (clean, total)
+    c.close(); m.close(); oc.close(); om.close()
+
+
+@pytest.mark.parametrize("name", ["tiny-llama-q4km", "small-qwen2-q8"])
+def test_batch_decode_equals_single_steps(name, gguf_path):
+    """blk_decode(n tokens) leaves the same state as n single decodes (reference: llama_decode batches, Session.cpp:381-392)"""
+    from blama_b200 import capi
+
+    path = gguf_path(name)
+    toks = gs.synth_prompt(name, 33, 5)
+    m = capi.Model(path)
+    a, b = capi.Ctx(m, 128), capi.Ctx(m, 128)
+    a.decode(toks)
+    for t in toks:
+        b.decode([int(t)])
+    la, lb = a.logits(), b.logits()
+    assert np.array_equal(la, lb)        # the batch path of this revision IS n single steps
+    assert np.array_equal(a.topk(10)["token"], b.topk(10)["token"])
+    a.close(); b.close(); m.close()
+
+
+def test_sequential_verify_is_bit_equal_to_complete(gguf_path):
+    """reference t-integration.cpp:219-248 "filling ctx": complete on one instance, fillCtx on another -> equal ids and
+    logits (CHECK(l.logit == l2.logit))"""
+    from blama_b200 import capi
+
+    name = "small-llama-q4km"
+    path = gguf_path(name)
+    prompt = gs.synth_prompt(name, 12, 9)
+    m = capi.Model(path)
+    prover, verifier = capi.Ctx(m, 256), capi.Ctx(m, 256)
+    prover.decode(prompt)
+    toks, tops = [], []
+    cur = prover.topk(40)
+    for i in range(16):
+        tok = int(cur["token"][i % 3])          # any deterministic choice among the candidates
+        cur = prover.decode_topk(tok, 40)
+        toks.append(tok); tops.append(cur[:10].copy())
+    verifier.set_verify_mode(1)
+    verifier.decode(prompt)
+    claimed = np.stack([t["token"] for t in tops])
+    g, top = verifier.verify_prefill(toks, claimed)
+    for i in range(len(toks)):
+        assert np.array_equal(top[i]["token"], tops[i]["token"])
+        assert np.array_equal(top[i]["logit"], tops[i]["logit"])
+        assert np.array_equal(g[i], tops[i]["logit"])
+    prover.close(); verifier.close(); m.close()
+
+
+def test_errors(gguf_path, tmp_path):
+    from blama_b200 import capi
+
+    with pytest.raises(capi.BlkError):
+        capi.Model(str(tmp_path / "missing.gguf"))
+    bad = tmp_path / "bad.gguf"
+    bad.write_bytes(b"NOTGGUF" * 10)
+    with pytest.raises(capi.BlkError):
+        capi.Model(str(bad))
+    m = capi.Model(gguf_path("tiny-llama-q4km"))
+    c = capi.Ctx(m, 64)
+    with pytest.raises(capi.BlkError):
+        c.decode([m.n_vocab])                   # token id out of range
+    with pytest.raises(capi.BlkError):
+        c.topk(10)                              # no logits yet
+    c.decode(list(range(1, 61)))
+    with pytest.raises(capi.BlkError) as e:
+        c.decode(list(range(1, 9)))             # 60 + 8 > 64
+    assert e.value.code == 5
+    c.clear()
+    c.decode([1, 2, 3])
+    assert c.n_past == 3
+    c.close(); m.close()

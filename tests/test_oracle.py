@@ -1,0 +1,143 @@
+"""Pins the CPU oracle (oracle/oracle.cpp) before anything is compared against it:
+  * block dequantisation           == gguf-py's numpy dequantisers, bit for bit
+  * Q8_K / Q8_0 quantisers         == the published ggml algorithms restated in numpy
+  * integer dot products           == exact integer arithmetic in numpy, fp32 scales
+  * whole forward (llama / qwen2)  == an independent float64 numpy model on dequantised weights (tests/np_forward.py)
+  * top-k / gather semantics of Session.cpp:246-282"""
+import numpy as np
+import pytest
+
+from blama_b200 import gguf_synth as gs
+
+TYPES = [(gs.Q8_0, "Q8_0"), (gs.Q4_K, "Q4_K"), (gs.Q5_K, "Q5_K"), (gs.Q6_K, "Q6_K")]
+
+
+@pytest.mark.parametrize("gtype,name", TYPES)
+def test_dequantize_matches_gguf_py(gtype, name, oracle):
+    import gguf
+
+    rng = np.random.default_rng(3)
+    n = 256 * 40
+    raw = rng.integers(0, 256, size=(n // gs.BLOCK[gtype][0], gs.BLOCK[gtype][1]), dtype=np.uint8)
+    # fully random bytes, only the fp16 scale fields made finite
+    blk = gs.random_blocks(rng, gtype, n, 0.3).reshape(raw.shape)
+    mix = np.where(rng.random(raw.shape) < 0.5, raw, blk)
+    if gtype == gs.Q8_0:
+        mix[:, 0:2] = blk[:, 0:2]
+    elif gtype == gs.Q6_K:
+        mix[:, 208:210] = blk[:, 208:210]
+    else:
+        mix[:, 0:4] = blk[:, 0:4]
+    got = oracle.dequantize(gtype, mix.reshape(-1), n)
+    want = gguf.quants.dequantize(mix, gguf.GGMLQuantizationType(gtype)).reshape(-1)
+    assert np.array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
+
+
+def test_quantize_q8_K_algorithm(oracle):
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal(256 * 6) * 3).astype(np.float32)
+    x[256:512] = 0.0                       # all-zero block -> d = 0
+    x[700] = -x[600]                       # equal magnitudes, opposite sign: the FIRST one decides the sign
+    x[600] = np.float32(50.0); x[700] = np.float32(-50.0)
+    qs, d, bs = oracle.quantize_q8_K(x)
+    for b in range(6):
+        xb = x[b * 256:(b + 1) * 256]
+        amax_i = int(np.argmax(np.abs(xb)))
+        if xb[amax_i] == 0:
+            assert d[b] == 0 and not qs[b * 256:(b + 1) * 256].any()
+            continue
+        iscale = np.float32(-127.0) / xb[amax_i]
+        want = np.minimum(127, np.rint(iscale * xb)).astype(np.int8)
+        assert np.array_equal(qs[b * 256:(b + 1) * 256], want)
+        assert d[b] == np.float32(1.0) / iscale
+        assert np.array_equal(bs[b * 16:(b + 1) * 16], want.astype(np.int32).reshape(16, 16).sum(1).astype(np.int16))
+    assert qs[600] == -127 and qs[700] == 127
+
+
+def test_quantize_q8_0_algorithm(oracle):
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(32 * 20) * 2).astype(np.float32)
+    qs, d = oracle.quantize_q8_0(x)
+    for b in range(20):
+        xb = x[b * 32:(b + 1) * 32]
+        dd = np.float32(np.abs(xb).max() / np.float32(127))
+        idd = np.float32(1.0) / dd
+        want = np.where(xb * idd >= 0, np.floor(xb * idd + np.float32(0.5)), np.ceil(xb * idd - np.float32(0.5))).astype(np.int8)
+        assert np.array_equal(qs[b * 32:(b + 1) * 32], want)
+        assert d[b] == np.float32(np.float16(dd))
+
+
+@pytest.mark.parametrize("gtype,name", TYPES)
+def test_integer_dot_against_exact_arithmetic(gtype, name, oracle):
+    """the GGML-mode mat-vec equals  sum_blocks scale_w * scale_a * (exact integer dot)  computed in float64 from the
+    dequantised weights and the quantised activations: checks every bit-field path of the vec_dot restatements"""
+    rng = np.random.default_rng(6)
+    rows, k = 16, 1024
+    blk = gs.random_blocks(rng, gtype, rows * k, 0.05)
+    x = rng.standard_normal(k).astype(np.float32)
+    w = oracle.dequantize(gtype, blk, rows * k).reshape(rows, k).astype(np.float64)
+    if gtype == gs.Q8_0:
+        qs, d = oracle.quantize_q8_0(x)
+        xa = qs.astype(np.float64) * np.repeat(d.astype(np.float64), 32)
+    else:
+        qs, d, _ = oracle.quantize_q8_K(x)
+        xa = qs.astype(np.float64) * np.repeat(d.astype(np.float64), 256)
+    want = w @ xa
+    got = oracle.matvec(gtype, blk, rows, k, x, oracle.MODE_GGML)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-6
+    # and the float modes are what they say
+    f32 = oracle.matvec(gtype, blk, rows, k, x, oracle.MODE_F32)
+    assert np.abs(f32 - w @ x.astype(np.float64)).max() <= 1e-6 * np.abs(want).max() + 1e-7
+
+
+@pytest.mark.parametrize("name", ["tiny-llama-q4km", "tiny-qwen2-q8", "tiny-llama-q8", "small-llama70-q4km"])
+def test_forward_structure_against_numpy(name, gguf_path, oracle):
+    import np_forward
+
+    path = gguf_path(name)
+    toks = gs.synth_prompt(name, 12, 1)
+    W, f = np_forward.load_weights(path)
+    ref = np_forward.forward(W, f, toks)
+    m = oracle.Model(path)
+    c = oracle.Ctx(m, 64, oracle.MODE_F32, 2)
+    lg = c.decode(toks, all_logits=True)
+    assert np.abs(lg - ref).max() <= 2e-2                     # only the f16 KV / f16 attention operands differ
+    # batch == token-by-token (ggml-cpu is batch invariant), in the reference arithmetic
+    cg = oracle.Ctx(m, 64, oracle.MODE_GGML, 2)
+    batch = cg.decode(toks, all_logits=True)
+    cg.clear()
+    seq = np.stack([cg.decode([t])[0] for t in toks])
+    assert np.array_equal(batch, seq)
+    assert np.abs(batch - ref).max() <= 0.6                   # Q8 activation quantisation noise, logits std ~2
+    c.close(); cg.close(); m.close()
+
+
+def test_topk_and_gather_semantics(oracle):
+    rng = np.random.default_rng(8)
+    lg = rng.standard_normal(1000).astype(np.float32)
+    lg[10] = lg[20] = 9.0                                     # tie -> lower id first
+    top = oracle.topk(lg, 10)
+    order = np.lexsort((np.arange(1000), -lg))[:10]
+    assert np.array_equal(top["token"], order) and np.array_equal(top["logit"], lg[order])
+    g = oracle.gather_sorted(lg, [5, 999, 5, 20, -1, 1000])   # duplicates once, out-of-range dropped, sorted desc
+    assert sorted(g["token"].tolist()) == [5, 20, 999]
+    assert np.all(np.diff(g["logit"]) <= 0)
+
+
+def test_session_round_trip_same_backend_is_exact(gguf_path, oracle):
+    """reference t-integration.cpp:219-248: complete then fillCtx on the same backend -> identical ids and logits,
+    hence LogitComparer score 1 (config 1 of BASELINE.json in miniature)"""
+    name = "tiny-llama-q8"
+    path = gguf_path(name)
+    m = oracle.Model(path)
+    prover, verifier = oracle.Ctx(m, 128, oracle.MODE_GGML, 2), oracle.Ctx(m, 128, oracle.MODE_GGML, 2)
+    prompt = gs.synth_prompt(name, 8, 2)
+    toks, top = prover.complete(prompt, 24)
+    assert len(toks) > 0
+    out, out_n = verifier.fill_ctx(prompt, toks, top["token"])
+    metrics = []
+    for i in range(len(toks)):
+        assert np.array_equal(out[i][: out_n[i]], top[i])
+        metrics.append(oracle.lc_compare(top[i], out[i][: out_n[i]]))
+    assert oracle.lc_score(metrics) == 1.0
+    prover.close(); verifier.close(); m.close()
