@@ -53,12 +53,14 @@ SYMBOLS = {
     "blk_gather_last": (_i32, [_vp, _vp, _i32, _vp]),
     "blk_get_logits_last": (_i32, [_vp, _vp]),
     "blk_decode_topk": (_i32, [_vp, _i32, _i32, _vp]),
+    "blk_decode_loop": (_i32, [_vp, _i32, _i32, C.POINTER(_i32)]),
     "blk_verify_prefill": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "blk_ctx_set_verify_mode": (_i32, [_vp, _i32]),
     "blk_timer_start": (_i32, [_vp]),
     "blk_timer_stop": (_i32, [_vp, _f32p]),
     "blk_ctx_kernel_launches": (_i64, [_vp]),
     "blk_flush_l2": (_i32, [_vp]),
+    "blk_profile_step": (_i32, [_vp, _i32, C.c_char_p, _i32]),
     "blk_bench_kernel": (_i32, [_vp, _i32, _i32, _f32p, C.POINTER(C.c_int64)]),
     "blk_test_gemv": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _vp]),
     "blk_test_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
@@ -174,6 +176,11 @@ class Ctx:
         _check(lib().blk_decode_topk(self.h, int(token), k, _p(out)))
         return out
 
+    def decode_loop(self, first_token: int, n_steps: int, wait: bool = True) -> int:
+        last = _i32(-1)
+        _check(lib().blk_decode_loop(self.h, int(first_token), n_steps, C.byref(last) if wait else None))
+        return int(last.value)
+
     def gather(self, ids: Sequence[int]) -> np.ndarray:
         i = np.ascontiguousarray(ids, dtype=np.int32)
         out = np.zeros(len(i), dtype=np.float32)
@@ -212,6 +219,11 @@ class Ctx:
         b = C.c_int64(0)
         _check(lib().blk_bench_kernel(self.h, which, iters, C.byref(ms), C.byref(b)))
         return float(ms.value), int(b.value)
+
+    def profile_step(self, token: int) -> str:
+        buf = C.create_string_buffer(8192)
+        _check(lib().blk_profile_step(self.h, int(token), buf, 8192))
+        return buf.value.decode()
 
     def flush_l2(self):
         _check(lib().blk_flush_l2(self.h))

@@ -9,39 +9,10 @@
 // All kernels here are HBM-bound byte/integer work: coalesced 128-bit loads (two per lane per step), warp-shuffle
 // reductions, grids sized in multiples of the SM count.  No tensor cores (decode -> HBM roofline).
 #pragma once
-#include "qweights.cuh"
+#include <cooperative_groups.h>
+#include "gemv_kernels.cuh"
 
 namespace blk {
-
-constexpr int KV_PAGE = 64;          // tokens per KV page
-constexpr int GEMV_THREADS = 256;    // 8 warps per CTA
-constexpr int MAX_GQ = 8;            // query heads per KV head (70B: 8, Qwen2.5-7B: 7)
-constexpr int TOPK_MAX = 64;
-constexpr int TOPK_CHUNK = 1024;     // logits per CTA in the first top-k stage
-
-// activations prepared for a quantised mat-vec
-struct ActBuf {
-    float* f32 = nullptr;     // [K]   (always written: residual / debug / F32 weights)
-    int8_t* q = nullptr;      // [K]
-    float* d = nullptr;       // [K/256] (Q8_K) or [K/32] (Q8_0; value already rounded through fp16)
-    int16_t* bs = nullptr;    // [K/16]  (Q8_K only)
-};
-
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 // =================================================================================================================
 // weight re-tiling (load time): ggml blocks -> split planes (qweights.cuh)
@@ -97,6 +68,7 @@ __device__ inline void rope_table_fill(float2* cs, int half_rot, int pos, float 
 // grid = n_tok CTAs.  x[t] = dequant(token_embd[tok[t]]); CTA 0.. also fill the rope table rows for their token
 __global__ void embed_kernel(QMat E, const int32_t* __restrict__ tokens, const int32_t* __restrict__ pos0, float* x,
                              float2* rope_cs, int half_rot, float theta_scale, const float* freq_factors) {
+    pdl_launch_dependents(); pdl_wait();
     const int t = blockIdx.x;
     dequant_row_cta(E, tokens[t], x + (size_t)t * E.K);
     rope_table_fill(rope_cs + (size_t)t * half_rot, half_rot, pos0[0] + t, theta_scale, freq_factors);
@@ -109,66 +81,10 @@ __global__ void embed_kernel(QMat E, const int32_t* __restrict__ tokens, const i
 //   Q8_0    : upstream ggml-quants.c quantize_row_q8_0_ref   (d = amax/127 stored as f16, roundf)
 // grid = n_rows (tokens), block = 512.  K % 32 == 0.
 // =================================================================================================================
-__device__ __forceinline__ void quantize_256_warp(const float* y /*smem or global, 256-aligned block*/, int valid, int fmt,
-                                                   int8_t* q, float* dq, int16_t* bs, int blk_index) {
-    const int lane = threadIdx.x & 31;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = (lane * 8 + i < valid) ? y[lane * 8 + i] : 0.0f;
-    int qi[8];
-    if (fmt == ACT_Q8_K) {
-        // first element attaining the max |x| decides the sign of the scale
-        float amax = 0.0f; int idx = 0x7fffffff;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { const float ax = fabsf(v[i]); if (ax > amax) { amax = ax; idx = lane * 8 + i; } }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (oa > amax || (oa == amax && oi < idx)) { amax = oa; idx = oi; }
-        }
-        float mx = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) if (lane * 8 + i == idx) mx = v[i];
-        mx = __shfl_sync(0xffffffffu, mx, (idx == 0x7fffffff ? 0 : idx) >> 3);
-        if (amax == 0.0f) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) qi[i] = 0;
-            if (lane == 0) dq[blk_index] = 0.0f;
-        } else {
-            const float iscale = __fdiv_rn(-127.0f, mx);
-#pragma unroll
-            for (int i = 0; i < 8; i++) qi[i] = min(127, __float2int_rn(__fmul_rn(iscale, v[i])));
-            if (lane == 0) dq[blk_index] = __fdiv_rn(1.0f, iscale);
-        }
-        int s = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) s += qi[i];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if ((lane & 1) == 0) bs[blk_index * 16 + (lane >> 1)] = (int16_t)s;
-    } else {   // ACT_Q8_0: 32-element blocks = 4 lanes
-        float amax = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-        const float d = __fdiv_rn(amax, 127.0f);
-        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) qi[i] = (int)roundf(__fmul_rn(v[i], id));
-        if ((lane & 3) == 0 && lane * 8 < valid) dq[blk_index * 8 + (lane >> 2)] = __half2float(__float2half_rn(d));
-    }
-    if (lane * 8 < valid) {
-        uint2 pk;
-        pk.x = (uint32_t)(qi[0] & 0xff) | ((uint32_t)(qi[1] & 0xff) << 8) | ((uint32_t)(qi[2] & 0xff) << 16) | ((uint32_t)(qi[3] & 0xff) << 24);
-        pk.y = (uint32_t)(qi[4] & 0xff) | ((uint32_t)(qi[5] & 0xff) << 8) | ((uint32_t)(qi[6] & 0xff) << 16) | ((uint32_t)(qi[7] & 0xff) << 24);
-        *reinterpret_cast<uint2*>(q + lane * 8) = pk;
-    }
-}
-
 template <bool NORM>
 __global__ void __launch_bounds__(512) act_prepare_kernel(const float* __restrict__ x, const float* __restrict__ w, int K, float eps,
                                                           int fmt, ActBuf out, int64_t row_stride_q, int64_t row_stride_d, int64_t row_stride_bs) {
+    pdl_launch_dependents(); pdl_wait();
     // row-strided outputs so the same kernel serves the batch (prefill) case: row = blockIdx.x
     const int row = blockIdx.x;
     x += (size_t)row * K;
@@ -211,297 +127,6 @@ __global__ void __launch_bounds__(512) act_prepare_kernel(const float* __restric
 }
 
 // =================================================================================================================
-// dequant-fused mat-vec: one warp owns a PAIR of rows at a time; each lane streams 2 x 128 bit of quantised weights
-// per row per step and multiplies them with the int8 activations held in shared memory.
-// =================================================================================================================
-struct ActView { const int8_t* q; const float* d; const int16_t* bs; const float* f32; };
-
-template <int TYPE> struct RowUnit;
-template <> struct RowUnit<QT_Q4_K> {
-    uint4 q0, q1, hdr;
-    __device__ __forceinline__ void load(const QMat& W, int64_t row, int u) {
-        const uint8_t* q = W.p0 + (size_t)row * (W.K >> 1) + (size_t)u * 32;
-        q0 = ldg_stream(q); q1 = ldg_stream(q + 16);
-        hdr = __ldg(reinterpret_cast<const uint4*>(W.p1 + ((size_t)row * (W.K >> 8) + (u >> 2)) * 16));
-    }
-    __device__ __forceinline__ float dot(const ActView& A, int u) const {
-        const int4* a = reinterpret_cast<const int4*>(A.q + (size_t)u * 64);
-        const int4 l0 = a[0], l1 = a[1], h0 = a[2], h1 = a[3];
-        int ilo = 0, ihi = 0;
-        const uint32_t M = 0x0F0F0F0Fu;
-        ilo = __dp4a((int)(q0.x & M), l0.x, ilo); ihi = __dp4a((int)((q0.x >> 4) & M), h0.x, ihi);
-        ilo = __dp4a((int)(q0.y & M), l0.y, ilo); ihi = __dp4a((int)((q0.y >> 4) & M), h0.y, ihi);
-        ilo = __dp4a((int)(q0.z & M), l0.z, ilo); ihi = __dp4a((int)((q0.z >> 4) & M), h0.z, ihi);
-        ilo = __dp4a((int)(q0.w & M), l0.w, ilo); ihi = __dp4a((int)((q0.w >> 4) & M), h0.w, ihi);
-        ilo = __dp4a((int)(q1.x & M), l1.x, ilo); ihi = __dp4a((int)((q1.x >> 4) & M), h1.x, ihi);
-        ilo = __dp4a((int)(q1.y & M), l1.y, ilo); ihi = __dp4a((int)((q1.y >> 4) & M), h1.y, ihi);
-        ilo = __dp4a((int)(q1.z & M), l1.z, ilo); ihi = __dp4a((int)((q1.z >> 4) & M), h1.z, ihi);
-        ilo = __dp4a((int)(q1.w & M), l1.w, ilo); ihi = __dp4a((int)((q1.w >> 4) & M), h1.w, ihi);
-        uint32_t sc2, mn2; k4_scale_min_pair(hdr, u & 3, sc2, mn2);
-        const uint2 bsw = *reinterpret_cast<const uint2*>(A.bs + (size_t)u * 4);   // 4 x int16 sums of 16
-        const int blo = (int)(int16_t)(bsw.x & 0xffff) + (int)(int16_t)(bsw.x >> 16);
-        const int bhi = (int)(int16_t)(bsw.y & 0xffff) + (int)(int16_t)(bsw.y >> 16);
-        const int p = (int)(sc2 & 0xff) * ilo + (int)(sc2 >> 8) * ihi;
-        const int pm = (int)(mn2 & 0xff) * blo + (int)(mn2 >> 8) * bhi;
-        const float2 dm = hdr_d_dmin(hdr);
-        const float ad = A.d[u >> 2];
-        return (dm.x * ad) * (float)p - (dm.y * ad) * (float)pm;
-    }
-};
-template <> struct RowUnit<QT_Q5_K> {
-    uint4 q0, q1, hdr, h0, h1;
-    __device__ __forceinline__ void load(const QMat& W, int64_t row, int u) {
-        const uint8_t* q = W.p0 + (size_t)row * (W.K >> 1) + (size_t)u * 32;
-        q0 = ldg_stream(q); q1 = ldg_stream(q + 16);
-        const size_t sb = (size_t)row * (W.K >> 8) + (u >> 2);
-        hdr = __ldg(reinterpret_cast<const uint4*>(W.p1 + sb * 16));
-        h0 = __ldg(reinterpret_cast<const uint4*>(W.p2 + sb * 32));
-        h1 = __ldg(reinterpret_cast<const uint4*>(W.p2 + sb * 32 + 16));
-    }
-    __device__ __forceinline__ float dot(const ActView& A, int u) const {
-        const int4* a = reinterpret_cast<const int4*>(A.q + (size_t)u * 64);
-        const int4 l0 = a[0], l1 = a[1], g0 = a[2], g1 = a[3];
-        const int j = u & 3;
-        const uint32_t M = 0x0F0F0F0Fu, B = 0x01010101u;
-        int ilo = 0, ihi = 0;
-#define BLK_Q5_STEP(QW, HW, AL, AH)                                                                  \
-        ilo = __dp4a((int)(((QW) & M) | ((((HW) >> (2 * j)) & B) << 4)), (AL), ilo);                 \
-        ihi = __dp4a((int)((((QW) >> 4) & M) | ((((HW) >> (2 * j + 1)) & B) << 4)), (AH), ihi);
-        BLK_Q5_STEP(q0.x, h0.x, l0.x, g0.x) BLK_Q5_STEP(q0.y, h0.y, l0.y, g0.y)
-        BLK_Q5_STEP(q0.z, h0.z, l0.z, g0.z) BLK_Q5_STEP(q0.w, h0.w, l0.w, g0.w)
-        BLK_Q5_STEP(q1.x, h1.x, l1.x, g1.x) BLK_Q5_STEP(q1.y, h1.y, l1.y, g1.y)
-        BLK_Q5_STEP(q1.z, h1.z, l1.z, g1.z) BLK_Q5_STEP(q1.w, h1.w, l1.w, g1.w)
-#undef BLK_Q5_STEP
-        uint32_t sc2, mn2; k4_scale_min_pair(hdr, j, sc2, mn2);
-        const uint2 bsw = *reinterpret_cast<const uint2*>(A.bs + (size_t)u * 4);
-        const int blo = (int)(int16_t)(bsw.x & 0xffff) + (int)(int16_t)(bsw.x >> 16);
-        const int bhi = (int)(int16_t)(bsw.y & 0xffff) + (int)(int16_t)(bsw.y >> 16);
-        const int p = (int)(sc2 & 0xff) * ilo + (int)(sc2 >> 8) * ihi;
-        const int pm = (int)(mn2 & 0xff) * blo + (int)(mn2 >> 8) * bhi;
-        const float2 dm = hdr_d_dmin(hdr);
-        const float ad = A.d[u >> 2];
-        return (dm.x * ad) * (float)p - (dm.y * ad) * (float)pm;
-    }
-};
-template <> struct RowUnit<QT_Q6_K> {
-    uint4 l0, l1, h; uint2 sc; uint16_t dh;
-    __device__ __forceinline__ void load(const QMat& W, int64_t row, int u) {
-        const int s = u >> 2, hh = (u >> 1) & 1, t = u & 1;
-        const uint8_t* ql = W.p0 + (size_t)row * (W.K >> 1) + (size_t)s * 128 + hh * 64 + t * 16;
-        l0 = ldg_stream(ql); l1 = ldg_stream(ql + 32);
-        h = ldg_stream(W.p1 + (size_t)row * (W.K >> 2) + (size_t)s * 64 + hh * 32 + t * 16);
-        sc = __ldg(reinterpret_cast<const uint2*>(W.p2 + (size_t)row * (W.K >> 4) + s * 16 + hh * 8));
-        dh = __ldg(reinterpret_cast<const uint16_t*>(W.p3) + (size_t)row * (W.K >> 8) + s);
-    }
-    __device__ __forceinline__ float dot(const ActView& A, int u) const {
-        const int s = u >> 2, hh = (u >> 1) & 1, t = u & 1;
-        const int e0 = 256 * s + 128 * hh + 16 * t;
-        const int4 a0 = *reinterpret_cast<const int4*>(A.q + e0);
-        const int4 a1 = *reinterpret_cast<const int4*>(A.q + e0 + 32);
-        const int4 a2 = *reinterpret_cast<const int4*>(A.q + e0 + 64);
-        const int4 a3 = *reinterpret_cast<const int4*>(A.q + e0 + 96);
-        const uint32_t M = 0x0F0F0F0Fu, H = 0x30303030u;
-        int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-#define BLK_Q6_STEP(LA, LB, HW, A0, A1, A2, A3)                                     \
-        i0 = __dp4a((int)(((LA) & M) | (((HW) << 4) & H)), (A0), i0);               \
-        i1 = __dp4a((int)(((LB) & M) | (((HW) << 2) & H)), (A1), i1);               \
-        i2 = __dp4a((int)((((LA) >> 4) & M) | ((HW) & H)), (A2), i2);               \
-        i3 = __dp4a((int)((((LB) >> 4) & M) | (((HW) >> 2) & H)), (A3), i3);
-        BLK_Q6_STEP(l0.x, l1.x, h.x, a0.x, a1.x, a2.x, a3.x)
-        BLK_Q6_STEP(l0.y, l1.y, h.y, a0.y, a1.y, a2.y, a3.y)
-        BLK_Q6_STEP(l0.z, l1.z, h.z, a0.z, a1.z, a2.z, a3.z)
-        BLK_Q6_STEP(l0.w, l1.w, h.w, a0.w, a1.w, a2.w, a3.w)
-#undef BLK_Q6_STEP
-        // 16-element sums of the activations give the "-32" offset: sum (q-32) a = sum q a - 32 sum a
-        const int bi = 16 * s + 8 * hh + t;
-        const int b0 = A.bs[bi], b1 = A.bs[bi + 2], b2 = A.bs[bi + 4], b3 = A.bs[bi + 6];
-        const uint32_t sl = t ? (sc.x >> 8) : sc.x, sh = t ? (sc.y >> 8) : sc.y;   // bytes t, t+2 | t+4, t+6
-        const int s0 = (int)(int8_t)(sl & 0xff), s1 = (int)(int8_t)((sl >> 16) & 0xff);
-        const int s2 = (int)(int8_t)(sh & 0xff), s3 = (int)(int8_t)((sh >> 16) & 0xff);
-        const int p = s0 * (i0 - 32 * b0) + s1 * (i1 - 32 * b1) + s2 * (i2 - 32 * b2) + s3 * (i3 - 32 * b3);
-        const float d = __half2float(__ushort_as_half(dh));
-        return (d * A.d[s]) * (float)p;
-    }
-};
-template <> struct RowUnit<QT_Q8_0> {
-    uint4 q0, q1; uint16_t dh;
-    __device__ __forceinline__ void load(const QMat& W, int64_t row, int u) {
-        const uint8_t* q = W.p0 + (size_t)row * W.K + (size_t)u * 32;
-        q0 = ldg_stream(q); q1 = ldg_stream(q + 16);
-        dh = __ldg(reinterpret_cast<const uint16_t*>(W.p1) + (size_t)row * (W.K >> 5) + u);
-    }
-    __device__ __forceinline__ float dot(const ActView& A, int u) const {
-        const int4* a = reinterpret_cast<const int4*>(A.q + (size_t)u * 32);
-        const int4 a0 = a[0], a1 = a[1];
-        int i = 0;
-        i = __dp4a((int)q0.x, a0.x, i); i = __dp4a((int)q0.y, a0.y, i); i = __dp4a((int)q0.z, a0.z, i); i = __dp4a((int)q0.w, a0.w, i);
-        i = __dp4a((int)q1.x, a1.x, i); i = __dp4a((int)q1.y, a1.y, i); i = __dp4a((int)q1.z, a1.z, i); i = __dp4a((int)q1.w, a1.w, i);
-        return (float)i * (__half2float(__ushort_as_half(dh)) * A.d[u]);
-    }
-};
-template <> struct RowUnit<QT_F32> {
-    float4 w0, w1;
-    __device__ __forceinline__ void load(const QMat& W, int64_t row, int u) {
-        const float4* p = reinterpret_cast<const float4*>(W.p0) + ((size_t)row * W.K + (size_t)u * 8) / 4;
-        w0 = __ldg(p); w1 = __ldg(p + 1);
-    }
-    __device__ __forceinline__ float dot(const ActView& A, int u) const {
-        const float4* x = reinterpret_cast<const float4*>(A.f32 + (size_t)u * 8);
-        const float4 x0 = x[0], x1 = x[1];
-        return w0.x * x0.x + w0.y * x0.y + w0.z * x0.z + w0.w * x0.w + w1.x * x1.x + w1.y * x1.y + w1.z * x1.z + w1.w * x1.w;
-    }
-};
-template <> struct RowUnit<QT_F16> {
-    uint4 w;
-    __device__ __forceinline__ void load(const QMat& W, int64_t row, int u) {
-        w = __ldg(reinterpret_cast<const uint4*>(W.p0 + ((size_t)row * W.K + (size_t)u * 8) * 2));
-    }
-    __device__ __forceinline__ float dot(const ActView& A, int u) const {
-        // ggml converts the activations to f16 for F16 weights (vec_dot_type F16) and accumulates in f32
-        const float* x = A.f32 + (size_t)u * 8;
-        const __half2* h = reinterpret_cast<const __half2*>(&w);
-        float acc = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float2 wf = __half22float2(h[i]);
-            acc += wf.x * __half2float(__float2half_rn(x[2 * i])) + wf.y * __half2float(__float2half_rn(x[2 * i + 1]));
-        }
-        return acc;
-    }
-};
-
-// two rows (possibly of two different matrices of the same type) against the same activations
-template <int TYPE>
-__device__ __forceinline__ void dot_pair(const QMat& Wa, int64_t ra, const QMat& Wb, int64_t rb, const ActView& A, float& oa, float& ob) {
-    const int lane = threadIdx.x & 31;
-    const int units = Wa.K / qmat_unit_elems(TYPE);
-    float sa = 0.0f, sb = 0.0f;
-    int u = lane;
-    // two steps in flight: 8 x 128-bit loads per lane outstanding
-    for (; u + 32 < units; u += 64) {
-        RowUnit<TYPE> a0, b0, a1, b1;
-        a0.load(Wa, ra, u); b0.load(Wb, rb, u); a1.load(Wa, ra, u + 32); b1.load(Wb, rb, u + 32);
-        sa += a0.dot(A, u); sb += b0.dot(A, u); sa += a1.dot(A, u + 32); sb += b1.dot(A, u + 32);
-    }
-    if (u < units) {
-        RowUnit<TYPE> a0, b0;
-        a0.load(Wa, ra, u); b0.load(Wb, rb, u);
-        sa += a0.dot(A, u); sb += b0.dot(A, u);
-    }
-    oa = warp_sum(sa); ob = warp_sum(sb);
-}
-
-__device__ __forceinline__ void dot_pair_any(const QMat& Wa, int64_t ra, const QMat& Wb, int64_t rb, const ActView& A, float& oa, float& ob) {
-    switch (Wa.type) {
-        case QT_Q4_K: dot_pair<QT_Q4_K>(Wa, ra, Wb, rb, A, oa, ob); break;
-        case QT_Q6_K: dot_pair<QT_Q6_K>(Wa, ra, Wb, rb, A, oa, ob); break;
-        case QT_Q8_0: dot_pair<QT_Q8_0>(Wa, ra, Wb, rb, A, oa, ob); break;
-        case QT_Q5_K: dot_pair<QT_Q5_K>(Wa, ra, Wb, rb, A, oa, ob); break;
-        case QT_F32: dot_pair<QT_F32>(Wa, ra, Wb, rb, A, oa, ob); break;
-        default: dot_pair<QT_F16>(Wa, ra, Wb, rb, A, oa, ob); break;
-    }
-}
-
-enum : int { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SWIGLU = 3 };
-
-struct GemvSeg {
-    QMat W;                 // rows of this segment
-    const float* bias;      // optional [N]
-    int pair0;              // first pair index of this segment
-    int kind;               // EPI_QKV only: 0 = q, 1 = k, 2 = v
-};
-
-struct GemvArgs {
-    GemvSeg seg[3];
-    int nseg;
-    int total_pairs;
-    ActBuf act;             // global-memory activations (prepared by act_prepare_kernel)
-    int act_fmt;
-    float* out;             // EPI_STORE / EPI_RESID / EPI_SWIGLU destination; EPI_QKV: q vector [n_head*d_head] f32
-    // EPI_QKV
-    int d_head, neox;
-    const float2* rope_cs;  // [d_head/2] {cos, sin} of this step's position
-    const int32_t* pos;     // device scalar: position of the token being decoded
-    __half* k_pool; __half* v_pool;   // this layer's KV pages [n_pages][KV_PAGE][n_kv*d_head]
-    const int32_t* page_table;
-    int kv_dim;             // n_head_kv * d_head
-};
-
-// stage the prepared activations into shared memory (int8 + scales + 16-sums); F32 activations stay in global
-__device__ __forceinline__ ActView stage_activations(const GemvArgs& a, int K, unsigned char* smem) {
-    ActView v{nullptr, nullptr, nullptr, a.act.f32};
-    if (a.act_fmt == ACT_F32) return v;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int8_t* sq = reinterpret_cast<int8_t*>(smem);
-    const int nd = (a.act_fmt == ACT_Q8_K) ? (K >> 8) : (K >> 5);
-    float* sd = reinterpret_cast<float*>(smem + K);
-    int16_t* sb = reinterpret_cast<int16_t*>(smem + K + ((nd * 4 + 15) & ~15));
-    for (int i = tid; i < (K >> 4); i += nt) reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(a.act.q)[i];
-    for (int i = tid; i < nd; i += nt) sd[i] = a.act.d[i];
-    if (a.act_fmt == ACT_Q8_K) for (int i = tid; i < (K >> 5); i += nt) reinterpret_cast<uint32_t*>(sb)[i] = reinterpret_cast<const uint32_t*>(a.act.bs)[i];
-    v.q = sq; v.d = sd; v.bs = sb;
-    return v;
-}
-__host__ __device__ inline size_t gemv_smem_bytes(int K, int fmt) {
-    if (fmt == ACT_F32) return 0;
-    const int nd = (fmt == ACT_Q8_K) ? (K >> 8) : (K >> 5);
-    return (size_t)K + (size_t)((nd * 4 + 15) & ~15) + (fmt == ACT_Q8_K ? (size_t)(K >> 4) * 2 : 0) + 16;
-}
-
-template <int EPI>
-__global__ void __launch_bounds__(GEMV_THREADS) gemv_pairs_kernel(const GemvArgs a) {
-    extern __shared__ __align__(16) unsigned char gemv_smem[];
-    const int K = a.seg[0].W.K;
-    const ActView A = stage_activations(a, K, gemv_smem);
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * GEMV_THREADS + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * GEMV_THREADS) >> 5;
-    for (int pair = warp; pair < a.total_pairs; pair += nwarps) {
-        if (EPI == EPI_SWIGLU) {
-            // seg[0] = gate, seg[1] = up: pair p = (gate row p, up row p)
-            float g, u;
-            dot_pair_any(a.seg[0].W, pair, a.seg[1].W, pair, A, g, u);
-            if (lane == 0) a.out[pair] = (g / (1.0f + expf(-g))) * u;     // ggml_silu_f32 then ggml_mul
-            continue;
-        }
-        int si = 0;
-        if (a.nseg > 1 && pair >= a.seg[1].pair0) si = 1;
-        if (a.nseg > 2 && pair >= a.seg[2].pair0) si = 2;
-        const GemvSeg& S = a.seg[si];
-        const int p = pair - S.pair0;
-        int r0 = 2 * p, r1 = 2 * p + 1;
-        if (EPI == EPI_QKV && a.neox && S.kind != 2) {
-            const int hd = a.d_head >> 1;
-            r0 = (p / hd) * a.d_head + (p % hd); r1 = r0 + hd;
-        }
-        float v0, v1;
-        dot_pair_any(S.W, r0, S.W, r1, A, v0, v1);
-        if (lane != 0) continue;
-        if (S.bias) { v0 += S.bias[r0]; v1 += S.bias[r1]; }
-        if (EPI == EPI_STORE) { a.out[r0] = v0; a.out[r1] = v1; }
-        else if (EPI == EPI_RESID) { a.out[r0] += v0; a.out[r1] += v1; }
-        else if (EPI == EPI_QKV) {
-            if (S.kind != 2) {     // rotary embedding on the (r0, r1) pair: ggml rope NORM / NEOX
-                const int i = a.neox ? (r0 % a.d_head) : ((r0 % a.d_head) >> 1);
-                const float2 cs = a.rope_cs[i];
-                const float x0 = v0, x1 = v1;
-                v0 = x0 * cs.x - x1 * cs.y;
-                v1 = x0 * cs.y + x1 * cs.x;
-            }
-            if (S.kind == 0) { a.out[r0] = v0; a.out[r1] = v1; }
-            else {
-                const int pos = a.pos[0];
-                const size_t base = ((size_t)a.page_table[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * a.kv_dim;
-                __half* dst = (S.kind == 1) ? a.k_pool : a.v_pool;
-                dst[base + r0] = __float2half_rn(v0);      // ggml_cpy f32 -> f16 into the cache
-                dst[base + r1] = __float2half_rn(v1);
-            }
-        }
-    }
-}
-
-// =================================================================================================================
 // decode attention over the paged f16 KV cache, split along the context.
 //   follows llama-graph.cpp build_attn_mha with flash_attn = false, in ggml's own order of operations:
 //     kq = K.q (q rounded to f16, f32 accumulate) * scale ; soft_max_ext: max, expf, sum in double, p = e * (1/sum) ;
@@ -526,6 +151,7 @@ struct AttnArgs {
 
 template <int DH>
 __global__ void __launch_bounds__(DH) attn_scores_kernel(const AttnArgs a) {
+    pdl_launch_dependents(); pdl_wait();
     const int hk = blockIdx.x, split = blockIdx.y, tid = threadIdx.x;
     const int gq = a.n_head / a.n_head_kv;
     const int n_kv = a.pos[0] + 1;
@@ -561,6 +187,7 @@ __global__ void __launch_bounds__(DH) attn_scores_kernel(const AttnArgs a) {
 
 template <int DH>
 __global__ void __launch_bounds__(DH) attn_pv_kernel(const AttnArgs a) {
+    pdl_launch_dependents(); pdl_wait();
     const int hk = blockIdx.x, split = blockIdx.y, tid = threadIdx.x;
     const int gq = a.n_head / a.n_head_kv;
     const int n_kv = a.pos[0] + 1;
@@ -637,9 +264,208 @@ __global__ void __launch_bounds__(DH) attn_pv_kernel(const AttnArgs a) {
     for (int g = 0; g < MAX_GQ; g++) if (g < gq) po[(size_t)g * a.n_split * DH + tid] = acc[g];
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Single-kernel decode attention: one thread-block CLUSTER per KV head, the context split across the cluster's CTAs,
+// the cross-CTA reductions (row max, row sum, output) done through distributed shared memory.  Same arithmetic order as
+// the three-kernel path above (max -> expf -> sum in double -> p = e * (1/sum) -> f16 -> V.p), but the scores never leave
+// shared memory and there is one launch instead of three.
+//   grid = n_head_kv * CS CTAs (cluster dims (CS,1,1)), block = 128 threads, dynamic smem = gq * cap * 4 bytes (scores)
+// -----------------------------------------------------------------------------------------------------------------
+struct AttnClusterArgs {
+    const float* q; const __half* k_pool; const __half* v_pool; const int32_t* page_table; const int32_t* pos;
+    int n_head, n_head_kv, kv_dim, cap;      // cap = tokens of the context one CTA can hold scores for
+    float scale;
+    float* out;                              // [n_head * d_head] f32 attention output
+};
+
+constexpr int ATTN_THREADS = 512;
+
+template <int DH, int GQ>      // GQ = compile-time bound on query heads per KV head (4 or 8)
+__global__ void __launch_bounds__(ATTN_THREADS) attn_cluster_kernel(const AttnClusterArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_launch_dependents(); pdl_wait();
+    constexpr int NW = ATTN_THREADS / 32;
+    extern __shared__ float s_sc[];                  // [gq][cap] scores, then [NW][gq][DH] per-warp partial outputs
+    __shared__ __half sq[GQ * DH];
+    __shared__ float c_max[GQ];                      // read by the other CTAs of the cluster
+    __shared__ double c_sum[GQ];                     //   "
+    __shared__ float c_out[GQ * DH];                 //   "   this CTA's partial V.p
+    __shared__ float s_M[GQ], s_inv[GQ];
+    __shared__ float red_f[GQ][NW];
+    __shared__ double red_d[GQ][NW];
+    __shared__ int s_page[512];
+
+    const int CS = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    const int hk = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gq = a.n_head / a.n_head_kv;
+    float* red_o = s_sc + (size_t)gq * a.cap;        // [NW][gq][DH]
+    const int n_kv = a.pos[0] + 1;
+    const int per = (n_kv + CS - 1) / CS;
+    const int t0 = r * per, t1 = min(n_kv, t0 + per);
+    const int nt = max(0, t1 - t0);
+    for (int i = tid; i < gq * DH; i += ATTN_THREADS) sq[i] = __float2half_rn(a.q[(size_t)(hk * gq) * DH + i]);
+    // physical pages of this CTA's token slice (removes a dependent global load from every K / V row address)
+    const int pg0 = t0 / KV_PAGE;
+    const int npg = nt > 0 ? (t1 - 1) / KV_PAGE - pg0 + 1 : 0;
+    for (int i = tid; i < npg && i < 512; i += ATTN_THREADS) s_page[i] = a.page_table[pg0 + i];
+    __syncthreads();
+    auto row_off = [&](int t) -> size_t { return ((size_t)s_page[t / KV_PAGE - pg0] * KV_PAGE + (t % KV_PAGE)) * a.kv_dim + (size_t)hk * DH; };
+
+    // ---- 1. scores: 4 lanes per token, each a quarter of the head dim; local row max ----
+    constexpr int QD = DH / 4;                       // dims per lane
+    float lmax[GQ];
+#pragma unroll
+    for (int g = 0; g < GQ; g++) lmax[g] = -INFINITY;
+    const int qd = tid & 3;
+    for (int tl0 = 0; tl0 < nt; tl0 += ATTN_THREADS / 4) {
+        const int tl = tl0 + (tid >> 2);
+        float s[GQ];
+#pragma unroll
+        for (int g = 0; g < GQ; g++) s[g] = 0.0f;
+        if (tl < nt) {
+            const uint4* kr = reinterpret_cast<const uint4*>(a.k_pool + row_off(t0 + tl) + qd * QD);
+            uint4 kreg[QD / 8];
+#pragma unroll
+            for (int c = 0; c < QD / 8; c++) kreg[c] = kr[c];
+#pragma unroll
+            for (int c = 0; c < QD / 8; c++) {
+                const __half2* kh = reinterpret_cast<const __half2*>(&kreg[c]);
+                float kf[8];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const float2 f = __half22float2(kh[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
+#pragma unroll
+                for (int g = 0; g < GQ; g++) if (g < gq) {
+                    const __half2* qh = reinterpret_cast<const __half2*>(sq + g * DH + qd * QD + c * 8);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(qh[i]); s[g] += kf[2 * i] * f.x; s[g] += kf[2 * i + 1] * f.y; }
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < GQ; g++) if (g < gq) {
+            float v = s[g];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v = __fmul_rn(v, a.scale);
+            if (tl < nt) { if (qd == 0) s_sc[g * a.cap + tl] = v; lmax[g] = fmaxf(lmax[g], v); }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < GQ; g++) if (g < gq) { const float m = warp_max(lmax[g]); if (lane == 0) red_f[g][wid] = m; }
+    __syncthreads();
+    if (tid < gq) { float m = red_f[tid][0]; for (int k = 1; k < NW; k++) m = fmaxf(m, red_f[tid][k]); c_max[tid] = m; }
+    cluster.sync();                                                                   // [1] every CTA's c_max is final
+    if (tid < gq) {
+        float M = -INFINITY;
+        for (int rr = 0; rr < CS; rr++) M = fmaxf(M, *cluster.map_shared_rank(&c_max[tid], rr));
+        s_M[tid] = M;
+    }
+    __syncthreads();
+
+    // ---- 2. e = expf(s - max), row sum in double ----
+    double lsum[GQ];
+#pragma unroll
+    for (int g = 0; g < GQ; g++) lsum[g] = 0.0;
+    for (int i = tid; i < nt * gq; i += ATTN_THREADS) {
+        const int g = i / nt, tl = i - g * nt;
+        const float e = expf(s_sc[g * a.cap + tl] - s_M[g]);
+        s_sc[g * a.cap + tl] = e;
+#pragma unroll
+        for (int gg = 0; gg < GQ; gg++) if (gg == g) lsum[gg] += (double)e;
+    }
+#pragma unroll
+    for (int g = 0; g < GQ; g++) if (g < gq) {
+        double v = lsum[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red_d[g][wid] = v;
+    }
+    __syncthreads();
+    if (tid < gq) { double v = 0.0; for (int k = 0; k < NW; k++) v += red_d[tid][k]; c_sum[tid] = v; }
+    cluster.sync();                                                                   // [2] every CTA's c_sum is final
+    if (tid < gq) {
+        double S = 0.0;
+        for (int rr = 0; rr < CS; rr++) S += *cluster.map_shared_rank(&c_sum[tid], rr);
+        s_inv[tid] = (float)(1.0 / S);
+    }
+    __syncthreads();
+    // p = e * (1/sum), rounded to f16 (ggml converts the probabilities to f16 for the V product)
+    for (int i = tid; i < nt * gq; i += ATTN_THREADS) {
+        const int g = i / nt, tl = i - g * nt;
+        s_sc[g * a.cap + tl] = __half2float(__float2half_rn(__fmul_rn(s_sc[g * a.cap + tl], s_inv[g])));
+    }
+    __syncthreads();
+
+    // ---- 3. partial V.p over this CTA's tokens: thread = (8 head dims) x (token group) ----
+    constexpr int DG = DH / 8;                       // threads across the head dim (one 128-bit load each)
+    constexpr int TG = ATTN_THREADS / DG;            // token groups
+    constexpr int TGW = 32 / DG;                     // token groups inside one warp
+    const int dg = tid % DG, tg = tid / DG;
+    float acc[GQ][8];
+#pragma unroll
+    for (int g = 0; g < GQ; g++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[g][i] = 0.0f;
+    for (int tl = tg; tl < nt; tl += 2 * TG) {          // two V rows in flight per thread
+        uint4 vv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int tj = tl + j * TG;
+            vv[j] = (tj < nt) ? *reinterpret_cast<const uint4*>(a.v_pool + row_off(t0 + tj) + dg * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int tj = tl + j * TG;
+            if (tj >= nt) break;
+            const __half2* vh = reinterpret_cast<const __half2*>(&vv[j]);
+            float vf[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float2 f = __half22float2(vh[i]); vf[2 * i] = f.x; vf[2 * i + 1] = f.y; }
+#pragma unroll
+            for (int g = 0; g < GQ; g++) if (g < gq) {
+                const float p = s_sc[g * a.cap + tj];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[g][i] += p * vf[i];
+            }
+        }
+    }
+    // token groups of one warp meet by shuffle, warps meet in shared memory; both in fixed order
+#pragma unroll
+    for (int g = 0; g < GQ; g++) if (g < gq) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float v = acc[g][i];
+#pragma unroll
+            for (int o = DG; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < DG) red_o[((size_t)wid * gq + g) * DH + dg * 8 + i] = v;
+        }
+    }
+    (void)TGW;
+    __syncthreads();
+    for (int e = tid; e < gq * DH; e += ATTN_THREADS) {
+        const int g = e / DH, dd = e - g * DH;
+        float o = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NW; k++) o += red_o[((size_t)k * gq + g) * DH + dd];
+        c_out[e] = o;
+    }
+    cluster.sync();                                                                   // [3] every CTA's c_out is final
+    // ---- 4. sum the CTAs' partials in rank order; CTA r finishes its share of the gq*DH outputs ----
+    const int E = gq * DH;
+    const int share = (E + CS - 1) / CS;
+    for (int e = r * share + tid; e < min(E, (r + 1) * share); e += ATTN_THREADS) {
+        float o = 0.0f;
+        for (int rr = 0; rr < CS; rr++) o += *cluster.map_shared_rank(&c_out[e], rr);
+        a.out[(size_t)hk * E + e] = o;
+    }
+    cluster.sync();                                                                   // [4] remote reads done before any CTA exits
+}
+
 // sum the split partials (fixed order) and quantise the attention output for the Wo mat-vec.
 // grid = n_head*d_head/256 CTAs, block = 256 (one Q8_K super-block of the output each)
 __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ part_o, int d_head, int n_split, int fmt, ActBuf out) {
+    pdl_launch_dependents(); pdl_wait();
     const int e = blockIdx.x * 256 + threadIdx.x;
     const int h = e / d_head, dd = e % d_head;
     float o = 0.0f;
@@ -654,6 +480,7 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restri
 
 // quantise an f32 vector (no norm): grid = ceil(K/256/8), block = 256 (8 warps, one super-block each)
 __global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict__ x, int K, int fmt, ActBuf out) {
+    pdl_launch_dependents(); pdl_wait();
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b * 256 >= K) return;
     quantize_256_warp(x + (size_t)b * 256, min(256, K - b * 256), fmt, out.q + (size_t)b * 256, out.d, out.bs, b);
@@ -685,6 +512,7 @@ __device__ inline void bitonic_sort_desc(float* key, int* idx) {
 }
 
 __global__ void __launch_bounds__(256) topk_stage1_kernel(const float* __restrict__ logits, int n, float* cand_l, int* cand_i) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ float key[TOPK_CHUNK];
     __shared__ int idx[TOPK_CHUNK];
     const int base = blockIdx.x * TOPK_CHUNK;
@@ -701,6 +529,7 @@ __global__ void __launch_bounds__(256) topk_stage1_kernel(const float* __restric
 // one CTA, 1024 threads; n_cand <= 16384 candidates processed in rounds of 2048 keeping the best TOPK_MAX
 __global__ void __launch_bounds__(1024) topk_stage2_kernel(const float* __restrict__ cand_l, const int* __restrict__ cand_i, int n_cand,
                                                           int k, int32_t* out_ids, float* out_logits) {
+    pdl_launch_dependents(); pdl_wait();
     __shared__ float key[2048];
     __shared__ int idx[2048];
     for (int i = threadIdx.x; i < TOPK_MAX; i += 1024) { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
@@ -716,11 +545,119 @@ __global__ void __launch_bounds__(1024) topk_stage2_kernel(const float* __restri
     for (int i = threadIdx.x; i < k; i += 1024) { out_ids[i] = idx[i]; out_logits[i] = key[i]; }
 }
 
+// runtime-size variant (n a power of two <= 2048)
+template <int THREADS>
+__device__ inline void bitonic_sort_desc_n(float* key, int* idx, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool up = ((i & k) == 0);
+                    const float a = key[i], b = key[p]; const int ia = idx[i], ib = idx[p];
+                    const bool a_first = td_before(a, ia, b, ib);
+                    if (up ? !a_first : a_first) { key[i] = b; key[p] = a; idx[i] = ib; idx[p] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Threshold top-k (replaces the two sort stages on the decode path).  The lm_head mat-vec leaves the maximum logit of
+// every vocabulary chunk in chunk_max (atomicMax in its epilogue).  With C >= 64 chunks, the 64th largest chunk maximum
+// tau is a lower bound of the 64th largest logit, so only logits >= tau can be in the top 64: a few hundred survivors
+// out of 128k.  Every CTA derives tau, scans its share of the row and appends survivors; the last CTA to finish sorts
+// them (logit descending, ties by lower id -> deterministic whatever the append order) and resets the scratch state.
+struct TopkArgs {
+    const float* logits; int n;
+    int* chunk_max; int n_chunks;
+    float* cand_l; int* cand_i; int cap;
+    unsigned int* count; unsigned int* done;
+    int32_t* out_ids; float* out_logits;
+};
+
+__global__ void __launch_bounds__(1024) topk_select_kernel(const TopkArgs a) {
+    pdl_launch_dependents(); pdl_wait();
+    __shared__ float key[2048];
+    __shared__ int idx[2048];
+    __shared__ unsigned int s_last, s_n;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // 1. tau from the chunk maxima
+    for (int i = tid; i < 256; i += 1024) { key[i] = i < a.n_chunks ? float_from_order_key(a.chunk_max[i]) : -INFINITY; idx[i] = i; }
+    __syncthreads();
+    bitonic_sort_desc_n<1024>(key, idx, 256);
+    const float tau = (a.n_chunks >= TOPK_MAX) ? key[TOPK_MAX - 1] : -INFINITY;
+    __syncthreads();
+    // 2. scan this CTA's share, append survivors
+    const int per = (a.n + gridDim.x - 1) / gridDim.x;
+    const int begin = blockIdx.x * per, end = min(a.n, begin + per);
+    for (int i0 = begin; i0 < end; i0 += 1024) {
+        const int i = i0 + tid;
+        const float v = i < end ? a.logits[i] : -INFINITY;
+        const bool keep = (i < end) && (v >= tau);
+        const unsigned int m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(a.count, (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const unsigned int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < (unsigned int)a.cap) { a.cand_l[slot] = v; a.cand_i[slot] = i; }
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int old = atomicAdd(a.done, 1u);
+        s_last = (old == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) s_n = *reinterpret_cast<volatile unsigned int*>(a.count);
+    __syncthreads();
+    const unsigned int total = s_n;
+    if (total <= (unsigned int)a.cap) {
+        int n2 = 64;
+        while (n2 < (int)total) n2 <<= 1;
+        for (int i = tid; i < n2; i += 1024) {
+            const bool ok = i < (int)total;
+            key[i] = ok ? __ldcg(a.cand_l + i) : -INFINITY;
+            idx[i] = ok ? __ldcg(a.cand_i + i) : 0x7fffffff;
+        }
+        __syncthreads();
+        bitonic_sort_desc_n<1024>(key, idx, n2);
+    } else {
+        // degenerate row (e.g. thousands of equal logits): exact fallback over the whole row, 1984 at a time
+        for (int i = tid; i < TOPK_MAX; i += 1024) { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
+        for (int base = 0; base < a.n; base += 2048 - TOPK_MAX) {
+            for (int i = tid; i < 2048 - TOPK_MAX; i += 1024) {
+                const int g = base + i;
+                key[TOPK_MAX + i] = g < a.n ? a.logits[g] : -INFINITY;
+                idx[TOPK_MAX + i] = g < a.n ? g : 0x7fffffff;
+            }
+            __syncthreads();
+            bitonic_sort_desc_n<1024>(key, idx, 2048);
+        }
+    }
+    for (int i = tid; i < TOPK_MAX; i += 1024) { a.out_ids[i] = idx[i]; a.out_logits[i] = key[i]; }
+    for (int i = tid; i < a.n_chunks; i += 1024) a.chunk_max[i] = (int)0x80000000;
+    if (tid == 0) { *a.count = 0u; *a.done = 0u; }
+}
+
 __global__ void gather_logits_kernel(const float* __restrict__ logits, int n_vocab, const int32_t* __restrict__ ids, int n, float* out) {
+    pdl_launch_dependents(); pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const int id = ids[i]; out[i] = (id >= 0 && id < n_vocab) ? logits[id] : -INFINITY; }
 }
 
-__global__ void advance_pos_kernel(int32_t* pos, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) pos[0] += n; }
+// greedy on-device feedback for the device-resident decode loop (bench): next token = arg-max of the step just computed
+__global__ void feed_top1_kernel(const int32_t* top_ids, int32_t* tok) {
+    pdl_launch_dependents(); pdl_wait(); if (threadIdx.x == 0 && blockIdx.x == 0) tok[0] = top_ids[0]; }
+
+__global__ void advance_pos_kernel(int32_t* pos, int n) {
+    pdl_launch_dependents(); pdl_wait(); if (threadIdx.x == 0 && blockIdx.x == 0) pos[0] += n; }
 
 } // namespace blk

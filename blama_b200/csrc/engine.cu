@@ -4,6 +4,7 @@
 // llama_decode / llama_get_logits_ith (reference call sites: Model.cpp:50-53, Instance.cpp:34-48, Session.cpp:388,
 // Session.cpp:24).  There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include "engine.hpp"
+#include "gemv_ring.cuh"
 #include "gguf.hpp"
 
 #include <algorithm>
@@ -273,6 +274,7 @@ blk_ctx::~blk_ctx() {
     if (m) cudaSetDevice(m->device);
     if (g_full) cudaGraphExecDestroy(g_full);
     if (g_body) cudaGraphExecDestroy(g_body);
+    if (g_loop) cudaGraphExecDestroy(g_loop);
     for (void* p : allocs) cudaFree(p);
     for (void* p : host_allocs) cudaFreeHost(p);
     if (ev0) cudaEventDestroy(ev0);
@@ -300,15 +302,10 @@ ActBuf make_act(blk_ctx* c, int K) {
     return a;
 }
 
-// opt-in shared memory sizes; per device, outside any stream capture
 void ensure_kernel_attrs(int device) {
     static std::mutex mu; static bool done[64] = {false};
     std::lock_guard<std::mutex> lk(mu);
     if (device < 0 || device >= 64 || done[device]) return;
-    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    BLK_CUDA(cudaFuncSetAttribute(gemv_pairs_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     BLK_CUDA(cudaFuncSetAttribute(act_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     BLK_CUDA(cudaFuncSetAttribute(act_prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     done[device] = true;
@@ -316,43 +313,72 @@ void ensure_kernel_attrs(int device) {
 
 template <int EPI>
 void launch_gemv(blk_ctx* c, GemvArgs& a) {
-    const int K = a.seg[0].W.K;
-    const size_t smem = gemv_smem_bytes(K, a.act_fmt);
-    if (smem > 64 * 1024) throw BlkError(BLK_ERR_ARG, "row length too large for the decode mat-vec");
-    // grid: one warp per row pair, capped at one full wave of resident CTAs (multiple of the SM count)
-    static int resident = 0;            // per instantiation; CTAs per SM x SMs
-    if (!resident) {
-        int per_sm = 0, sms = 0, dev = 0;
-        BLK_CUDA(cudaGetDevice(&dev));
-        BLK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        BLK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemv_pairs_kernel<EPI>, GEMV_THREADS, 16 * 1024));
-        resident = std::max(1, per_sm) * std::max(1, sms);
-    }
-    int ctas = (a.total_pairs + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
-    if (ctas > resident) ctas = resident;
-    gemv_pairs_kernel<EPI><<<ctas, GEMV_THREADS, smem, c->stream>>>(a);
-    BLK_CUDA(cudaGetLastError());
+    cudaError_t e;
+    if (EPI == EPI_STORE) e = launch_gemv_store(a, c->stream);
+    else if (EPI == EPI_RESID) e = launch_gemv_resid(a, c->stream);
+    else if (EPI == EPI_QKV) e = launch_gemv_qkv(a, c->stream);
+    else e = launch_gemv_swiglu(a, c->stream);
+    if (e == cudaErrorInvalidValue) throw BlkError(BLK_ERR_FORMAT, "no mat-vec kernel for this weight type / row length");
+    BLK_CUDA(e);
     c->launches++;
 }
 
 void launch_act_prepare(blk_ctx* c, const float* x, const float* w, int K, int fmt, const ActBuf& out, bool norm) {
     const size_t smem = (size_t)K * 4;
     if (smem > 160 * 1024) throw BlkError(BLK_ERR_ARG, "row too long for act_prepare");
-    if (norm) act_prepare_kernel<true><<<1, 512, smem, c->stream>>>(x, w, K, c->m->rms_eps, fmt, out, 0, 0, 0);
-    else act_prepare_kernel<false><<<1, 512, smem, c->stream>>>(x, w, K, c->m->rms_eps, fmt, out, 0, 0, 0);
+    if (norm) BLK_CUDA(launch_pdl(act_prepare_kernel<true>, dim3(1), dim3(512), smem, c->stream, x, w, K, c->m->rms_eps, fmt, out, 0, 0, 0));
+    else BLK_CUDA(launch_pdl(act_prepare_kernel<false>, dim3(1), dim3(512), smem, c->stream, x, w, K, c->m->rms_eps, fmt, out, 0, 0, 0));
     BLK_CUDA(cudaGetLastError());
     c->launches++;
 }
 
-// one decode step on c->stream: token id in c->d_tok, position in c->d_pos
-void enqueue_step(blk_ctx* c, bool with_head) {
+void prof_mark(blk_ctx* c, const char* name) {
+    if (!c->profiling) return;
+    cudaEvent_t e; BLK_CUDA(cudaEventCreate(&e));
+    BLK_CUDA(cudaEventRecord(e, c->stream));
+    c->prof_marks.emplace_back(name, e);
+}
+
+// A mat-vec of the decode step: y = epilogue(W . act(in)) where act = (optional RMSNorm * norm_w) then the quantisation the
+// weight type needs.  Production shapes run the persistent TMA-ring kernel, whose prologue prepares the activations per CTA;
+// shapes the ring cannot take (rows that are not a whole number of 16 B-aligned super-block planes: the tiny test models)
+// run a separate act_prepare kernel followed by the register-staged kernel of gemv_kernels.cuh.
+template <int EPI>
+void matvec(blk_ctx* c, GemvArgs& a, const float* in, const float* norm_w, const ActBuf& scratch, const char* name) {
+    const int K = a.seg[0].W.K;
+    const int ta = a.seg[0].W.type, tb = (a.nseg > 2) ? a.seg[2].W.type : ta;
+    const int fmt = act_format_for(ta);
+    a.act_fmt = fmt;
+    RingPlan plan = c->use_ring ? ring_plan(K, ta, tb, a.total_pairs, c->n_sms) : RingPlan{};
+    if (plan.ok) {
+        RingArgs ra{};
+        ra.g = a; ra.in = in; ra.norm_w = norm_w; ra.eps = c->m->rms_eps; ra.plan = plan;
+        cudaError_t e;
+        if (EPI == EPI_STORE) e = launch_ring_store(ra, c->stream);
+        else if (EPI == EPI_RESID) e = launch_ring_resid(ra, c->stream);
+        else if (EPI == EPI_QKV) e = launch_ring_qkv(ra, c->stream);
+        else e = launch_ring_swiglu(ra, c->stream);
+        if (e != cudaErrorInvalidValue) { BLK_CUDA(e); c->launches++; prof_mark(c, name); return; }
+        (void)cudaGetLastError();
+    }
+    launch_act_prepare(c, in, norm_w, K, fmt, scratch, norm_w != nullptr);
+    prof_mark(c, "act_prepare");
+    a.act = scratch;
+    launch_gemv<EPI>(c, a);
+    prof_mark(c, name);
+}
+
+// one decode step on c->stream: token id in c->d_tok, position in c->d_pos.
+// Per layer: QKV mat-vec (RMSNorm prologue; +bias, RoPE, KV-page write) | attention | Wo mat-vec (+residual) |
+// gate/up mat-vec (RMSNorm prologue; SwiGLU) | down mat-vec (+residual); then final norm + lm_head mat-vec + top-k.
+void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
     blk_model* m = c->m;
     const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
-    embed_kernel<<<1, 256, 0, c->stream>>>(m->tok_embd, c->d_tok, c->d_pos, c->x, c->rope_cs, dh / 2, m->theta_scale, m->rope_freqs);
-    BLK_CUDA(cudaGetLastError()); c->launches++;
+    BLK_CUDA(launch_pdl(embed_kernel, dim3(1), dim3(256), 0, c->stream, m->tok_embd, c->d_tok, c->d_pos, c->x, c->rope_cs, dh / 2, m->theta_scale, m->rope_freqs));
+    c->launches++;
+    prof_mark(c, "embed");
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
-        launch_act_prepare(c, c->x, L.attn_norm, d, m->act_fmt, c->act_d, true);
         {
             GemvArgs a{};
             a.nseg = 3;
@@ -360,82 +386,104 @@ void enqueue_step(blk_ctx* c, bool with_head) {
             a.seg[1] = {L.wk, L.bk, dq / 2, 1};
             a.seg[2] = {L.wv, L.bv, dq / 2 + dkv / 2, 2};
             a.total_pairs = dq / 2 + dkv;
-            a.act = c->act_d; a.act_fmt = m->act_fmt; a.out = c->qbuf;
+            a.out = c->qbuf;
             a.d_head = dh; a.neox = m->neox ? 1 : 0; a.rope_cs = c->rope_cs; a.pos = c->d_pos;
             a.k_pool = c->k_pool[l]; a.v_pool = c->v_pool[l]; a.page_table = c->page_table; a.kv_dim = dkv;
-            launch_gemv<EPI_QKV>(c, a);
+            matvec<EPI_QKV>(c, a, c->x, L.attn_norm, c->act_d, "gemv_qkv");
         }
         {
+            if (c->attn_cluster > 0) {
+                AttnClusterArgs ac{};
+                ac.q = c->qbuf; ac.k_pool = c->k_pool[l]; ac.v_pool = c->v_pool[l]; ac.page_table = c->page_table; ac.pos = c->d_pos;
+                ac.n_head = m->n_head; ac.n_head_kv = m->n_head_kv; ac.kv_dim = dkv; ac.cap = c->attn_cap;
+                ac.scale = 1.0f / sqrtf((float)dh); ac.out = c->act_q.f32;
+                const size_t smem = (size_t)(m->n_head / m->n_head_kv) * (c->attn_cap + (ATTN_THREADS / 32) * dh) * sizeof(float);
+                const dim3 grid(m->n_head_kv * c->attn_cluster), block(ATTN_THREADS);
+                const bool g4 = (m->n_head / m->n_head_kv) <= 4;
+                if (dh == 128 && g4) BLK_CUDA(launch_pdl_cluster(attn_cluster_kernel<128, 4>, grid, block, smem, c->attn_cluster, c->stream, ac));
+                else if (dh == 128) BLK_CUDA(launch_pdl_cluster(attn_cluster_kernel<128, 8>, grid, block, smem, c->attn_cluster, c->stream, ac));
+                else if (g4) BLK_CUDA(launch_pdl_cluster(attn_cluster_kernel<64, 4>, grid, block, smem, c->attn_cluster, c->stream, ac));
+                else BLK_CUDA(launch_pdl_cluster(attn_cluster_kernel<64, 8>, grid, block, smem, c->attn_cluster, c->stream, ac));
+                c->launches++;
+                prof_mark(c, "attn_cluster");
+            } else {
             AttnArgs at{};
             at.q = c->qbuf; at.k_pool = c->k_pool[l]; at.v_pool = c->v_pool[l]; at.page_table = c->page_table; at.pos = c->d_pos;
             at.n_head = m->n_head; at.n_head_kv = m->n_head_kv; at.d_head = dh; at.kv_dim = dkv; at.n_split = c->n_split;
             at.scale = 1.0f / sqrtf((float)dh); at.scores = c->scores; at.score_stride = c->n_pages * KV_PAGE; at.part_o = c->part_o;
             dim3 grid(m->n_head_kv, c->n_split);
-            if (dh == 128) { attn_scores_kernel<128><<<grid, 128, 0, c->stream>>>(at); attn_pv_kernel<128><<<grid, 128, 0, c->stream>>>(at); }
-            else { attn_scores_kernel<64><<<grid, 64, 0, c->stream>>>(at); attn_pv_kernel<64><<<grid, 64, 0, c->stream>>>(at); }
-            BLK_CUDA(cudaGetLastError()); c->launches += 2;
-            attn_combine_kernel<<<dq / 256, 256, 0, c->stream>>>(c->part_o, dh, c->n_split, m->act_fmt, c->act_q);
-            BLK_CUDA(cudaGetLastError()); c->launches++;
+            if (dh == 128) {
+                BLK_CUDA(launch_pdl(attn_scores_kernel<128>, grid, dim3(128), 0, c->stream, at));
+                prof_mark(c, "attn_scores");
+                BLK_CUDA(launch_pdl(attn_pv_kernel<128>, grid, dim3(128), 0, c->stream, at));
+                prof_mark(c, "attn_pv");
+            } else {
+                BLK_CUDA(launch_pdl(attn_scores_kernel<64>, grid, dim3(64), 0, c->stream, at));
+                prof_mark(c, "attn_scores");
+                BLK_CUDA(launch_pdl(attn_pv_kernel<64>, grid, dim3(64), 0, c->stream, at));
+                prof_mark(c, "attn_pv");
+            }
+            c->launches += 2;
+            BLK_CUDA(launch_pdl(attn_combine_kernel, dim3(dq / 256), dim3(256), 0, c->stream, c->part_o, dh, c->n_split, (int)ACT_F32, c->act_q));
+            c->launches++;
+            prof_mark(c, "attn_combine");
+            }
         }
         {
             GemvArgs a{};
-            a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2;
-            a.act = c->act_q; a.act_fmt = m->act_fmt; a.out = c->x;
-            launch_gemv<EPI_RESID>(c, a);
-        }
-        launch_act_prepare(c, c->x, L.ffn_norm, d, m->act_fmt, c->act_d, true);
-        {
-            GemvArgs a{};
-            a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff;
-            a.act = c->act_d; a.act_fmt = m->act_fmt; a.out = c->hbuf;
-            launch_gemv<EPI_SWIGLU>(c, a);
-        }
-        if (m->act_fmt != ACT_F32) {
-            act_quant_kernel<<<(ff / 256 + 7) / 8, 256, 0, c->stream>>>(c->hbuf, ff, m->act_fmt, c->act_ff);
-            BLK_CUDA(cudaGetLastError()); c->launches++;
+            a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2; a.out = c->x;
+            matvec<EPI_RESID>(c, a, c->act_q.f32, nullptr, c->act_q2, "gemv_wo");
         }
         {
             GemvArgs a{};
-            a.nseg = 1; a.seg[0] = {L.down, nullptr, 0, 0}; a.total_pairs = d / 2;
-            a.act = c->act_ff; a.act_fmt = m->act_fmt; a.out = c->x;
-            if (m->act_fmt == ACT_F32) a.act.f32 = c->hbuf;
-            launch_gemv<EPI_RESID>(c, a);
+            a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff; a.out = c->hbuf;
+            matvec<EPI_SWIGLU>(c, a, c->x, L.ffn_norm, c->act_d, "gemv_gate_up");
+        }
+        {
+            GemvArgs a{};
+            a.nseg = 1; a.seg[0] = {L.down, nullptr, 0, 0}; a.total_pairs = d / 2; a.out = c->x;
+            matvec<EPI_RESID>(c, a, c->hbuf, nullptr, c->act_ff, "gemv_down");
         }
     }
     if (with_head) {
-        launch_act_prepare(c, c->x, m->out_norm, d, m->act_fmt_out, c->act_d, true);
         GemvArgs a{};
-        a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = m->n_vocab / 2;
-        a.act = c->act_d; a.act_fmt = m->act_fmt_out; a.out = c->logits;
-        launch_gemv<EPI_STORE>(c, a);
-        topk_stage1_kernel<<<c->n_chunks, 256, 0, c->stream>>>(c->logits, m->n_vocab, c->cand_l, c->cand_i);
-        BLK_CUDA(cudaGetLastError()); c->launches++;
-        topk_stage2_kernel<<<1, 1024, 0, c->stream>>>(c->cand_l, c->cand_i, c->n_chunks * TOPK_MAX, TOPK_MAX, c->top_ids, c->top_logits);
-        BLK_CUDA(cudaGetLastError()); c->launches++;
+        a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = m->n_vocab / 2; a.out = c->logits;
+        a.tail.kind = TAIL_CHUNKMAX; a.tail.chunk_max = c->chunk_max; a.tail.chunk_shift = c->chunk_shift;
+        matvec<EPI_STORE>(c, a, c->x, m->out_norm, c->act_d, "gemv_lm_head");
+        TopkArgs tk{};
+        tk.logits = c->logits; tk.n = m->n_vocab; tk.chunk_max = c->chunk_max; tk.n_chunks = c->n_chunks;
+        tk.cand_l = c->cand_l; tk.cand_i = c->cand_i; tk.cap = c->cand_cap; tk.count = c->counters + 1; tk.done = c->counters + 2;
+        tk.out_ids = c->top_ids; tk.out_logits = c->top_logits;
+        BLK_CUDA(launch_pdl(topk_select_kernel, dim3(16), dim3(1024), 0, c->stream, tk));
+        c->launches++;
+        prof_mark(c, "topk_select");
     }
-    advance_pos_kernel<<<1, 32, 0, c->stream>>>(c->d_pos, 1);
-    BLK_CUDA(cudaGetLastError()); c->launches++;
-    if (with_head) {
+    BLK_CUDA(launch_pdl(advance_pos_kernel, dim3(1), dim3(32), 0, c->stream, c->d_pos, 1));
+    c->launches++;
+    if (feedback) {
+        BLK_CUDA(launch_pdl(feed_top1_kernel, dim3(1), dim3(32), 0, c->stream, (const int32_t*)c->top_ids, c->d_tok));
+        c->launches++;
+    } else if (with_head) {
         BLK_CUDA(cudaMemcpyAsync(c->h_top_ids, c->top_ids, TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
 }
 
 void build_graphs(blk_ctx* c) {
-    for (int which = 0; which < 2; which++) {
-        const bool head = (which == 0);
+    for (int which = 0; which < 3; which++) {
+        const bool head = (which != 1);
         cudaGraph_t g = nullptr;
         const int64_t before = c->launches;
         BLK_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        try { enqueue_step(c, head); }
+        try { enqueue_step(c, head, which == 2); }
         catch (...) { cudaGraph_t tmp = nullptr; cudaStreamEndCapture(c->stream, &tmp); if (tmp) cudaGraphDestroy(tmp); throw; }
         BLK_CUDA(cudaStreamEndCapture(c->stream, &g));
         cudaGraphExec_t ge = nullptr;
         cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
         BLK_CUDA(e);
-        (head ? c->g_full : c->g_body) = ge;
-        (head ? c->launches_full : c->launches_body) = c->launches - before;
+        (which == 0 ? c->g_full : which == 1 ? c->g_body : c->g_loop) = ge;
+        (which == 0 ? c->launches_full : which == 1 ? c->launches_body : c->launches_loop) = c->launches - before;
         c->launches = before;
     }
 }
@@ -485,18 +533,50 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         c->h_tok = halloc<int32_t>(c.get(), blk_ctx::TOK_RING);
         c->x = dalloc<float>(c.get(), d); c->qbuf = dalloc<float>(c.get(), dq); c->hbuf = dalloc<float>(c.get(), ff);
         c->rope_cs = dalloc<float2>(c.get(), dh / 2);
-        c->act_d = make_act(c.get(), d); c->act_q = make_act(c.get(), dq); c->act_ff = make_act(c.get(), ff);
+        c->act_d = make_act(c.get(), d); c->act_q = make_act(c.get(), dq); c->act_q2 = make_act(c.get(), dq); c->act_ff = make_act(c.get(), ff);
+        BLK_CUDA(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, m->device));
+        { const char* e = getenv("BLK_RING"); c->use_ring = (e && e[0] == '1'); }     // the TMA-ring mat-vec is opt-in (measured slower)
+        {   // single-kernel cluster attention when one CTA's share of the scores fits in shared memory
+            const int gq = m->n_head / m->n_head_kv;
+            c->attn_cluster = 8;
+            c->attn_cap = (c->n_pages * KV_PAGE + c->attn_cluster - 1) / c->attn_cluster;
+            const size_t smem = (size_t)gq * (c->attn_cap + (ATTN_THREADS / 32) * m->d_head) * sizeof(float);
+            const char* e = getenv("BLK_NO_CLUSTER_ATTN");
+            if (smem > 160 * 1024 || (e && e[0] == '1')) c->attn_cluster = 0;
+            else {
+                BLK_CUDA(cudaFuncSetAttribute(attn_cluster_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
+                BLK_CUDA(cudaFuncSetAttribute(attn_cluster_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
+                BLK_CUDA(cudaFuncSetAttribute(attn_cluster_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
+                BLK_CUDA(cudaFuncSetAttribute(attn_cluster_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
+            }
+        }
         c->n_split = std::max(1, std::min(32, (2 * 148) / m->n_head_kv));
         c->part_o = dalloc<float>(c.get(), (size_t)m->n_head * c->n_split * dh);
         c->scores = dalloc<float>(c.get(), (size_t)m->n_head * c->n_pages * KV_PAGE);
         c->logits = dalloc<float>(c.get(), m->n_vocab);
-        c->n_chunks = (m->n_vocab + TOPK_CHUNK - 1) / TOPK_CHUNK;
-        c->cand_l = dalloc<float>(c.get(), (size_t)c->n_chunks * TOPK_MAX); c->cand_i = dalloc<int>(c.get(), (size_t)c->n_chunks * TOPK_MAX);
+        c->chunk_shift = 6;
+        while (((m->n_vocab + (1 << c->chunk_shift) - 1) >> c->chunk_shift) > 256) c->chunk_shift++;
+        c->n_chunks = (m->n_vocab + (1 << c->chunk_shift) - 1) >> c->chunk_shift;
+        c->cand_l = dalloc<float>(c.get(), c->cand_cap); c->cand_i = dalloc<int>(c.get(), c->cand_cap);
+        c->chunk_max = dalloc<int>(c.get(), 256);
+        {
+            std::vector<int> init(256, (int)0x80000000);
+            BLK_CUDA(cudaMemcpy(c->chunk_max, init.data(), 256 * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        c->counters = dalloc<unsigned int>(c.get(), 8 + ff / 256 + 8);
+        BLK_CUDA(cudaMemset(c->counters, 0, (8 + ff / 256 + 8) * sizeof(unsigned int)));
         c->top_ids = dalloc<int32_t>(c.get(), TOPK_MAX); c->top_logits = dalloc<float>(c.get(), TOPK_MAX);
         c->h_top_ids = halloc<int32_t>(c.get(), TOPK_MAX); c->h_top_logits = halloc<float>(c.get(), TOPK_MAX);
         c->ids_cap = 4096;
         c->d_ids = dalloc<int32_t>(c.get(), c->ids_cap); c->d_gath = dalloc<float>(c.get(), c->ids_cap);
         if (m->n_vocab % 2) throw BlkError(BLK_ERR_FORMAT, "vocabulary size must be even");
+        {   // one eager step: loads modules and sets per-function attributes outside of stream capture
+            BLK_CUDA(cudaMemsetAsync(c->d_tok, 0, sizeof(int32_t), c->stream));
+            enqueue_step(c.get(), true, false);
+            BLK_CUDA(cudaStreamSynchronize(c->stream));
+            BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, sizeof(int32_t), c->stream));
+            c->launches = 0;
+        }
         build_graphs(c.get());
         BLK_CUDA(cudaStreamSynchronize(c->stream));
     });
@@ -535,6 +615,26 @@ extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
     });
 }
 
+extern "C" blk_status blk_decode_loop(blk_ctx* c, int32_t first_token, int32_t n_steps, int32_t* last_token) {
+    if (!c || n_steps <= 0) return fail(BLK_ERR_ARG, "blk_decode_loop: bad arguments");
+    return guarded([&] {
+        blk_model* m = c->m;
+        BLK_CUDA(cudaSetDevice(m->device));
+        if (first_token < 0 || first_token >= m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
+        if (c->n_past + n_steps > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        c->h_tok[0] = first_token; c->tok_slot = 1;
+        BLK_CUDA(cudaMemcpyAsync(c->d_tok, c->h_tok, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        for (int i = 0; i < n_steps; i++) BLK_CUDA(cudaGraphLaunch(c->g_loop, c->stream));
+        c->launches += c->launches_loop * n_steps;
+        c->n_past += n_steps;
+        BLK_CUDA(cudaMemcpyAsync(c->h_top_ids, c->top_ids, TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        c->have_logits = true;
+        if (last_token) { BLK_CUDA(cudaStreamSynchronize(c->stream)); *last_token = c->h_top_ids[0]; }
+    });
+}
+
 extern "C" blk_status blk_topk_last(blk_ctx* c, int32_t k, blk_token_data* out) {
     if (!c || !out || k <= 0 || k > TOPK_MAX) return fail(BLK_ERR_ARG, "blk_topk_last: bad arguments");
     return guarded([&] {
@@ -561,7 +661,7 @@ extern "C" blk_status blk_gather_last(blk_ctx* c, const int32_t* ids, int32_t n,
         if (!c->have_logits) throw BlkError(BLK_ERR_ARG, "no logits available: decode first");
         BLK_CUDA(cudaSetDevice(c->m->device));
         BLK_CUDA(cudaMemcpyAsync(c->d_ids, ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        gather_logits_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->logits, c->m->n_vocab, c->d_ids, n, c->d_gath);
+        BLK_CUDA(launch_pdl(gather_logits_kernel, dim3((n + 127) / 128), dim3(128), 0, c->stream, c->logits, c->m->n_vocab, c->d_ids, n, c->d_gath));
         BLK_CUDA(cudaGetLastError()); c->launches++;
         BLK_CUDA(cudaMemcpyAsync(out, c->d_gath, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         BLK_CUDA(cudaStreamSynchronize(c->stream));
@@ -592,7 +692,7 @@ extern "C" blk_status blk_verify_prefill(blk_ctx* c, const int32_t* tokens, int3
             const int nc = std::max(0, std::min(10, n_claimed[i]));
             if (nc > 0) {
                 BLK_CUDA(cudaMemcpyAsync(c->d_ids, claimed + (size_t)i * 10, nc * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-                gather_logits_kernel<<<1, 32, 0, c->stream>>>(c->logits, c->m->n_vocab, c->d_ids, nc, c->d_gath);
+                BLK_CUDA(launch_pdl(gather_logits_kernel, dim3(1), dim3(32), 0, c->stream, c->logits, c->m->n_vocab, c->d_ids, nc, c->d_gath));
                 BLK_CUDA(cudaGetLastError()); c->launches++;
                 BLK_CUDA(cudaMemcpyAsync(gathered + (size_t)i * 10, c->d_gath, nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
             }
@@ -625,39 +725,35 @@ extern "C" blk_status blk_bench_kernel(blk_ctx* c, int32_t which, int32_t iters,
         // make the activation buffers hold something sane
         BLK_CUDA(cudaMemsetAsync(c->x, 0, d * sizeof(float), c->stream));
         BLK_CUDA(cudaMemsetAsync(c->hbuf, 0, ff * sizeof(float), c->stream));
-        launch_act_prepare(c, c->x, m->layers[0].attn_norm, d, m->act_fmt, c->act_d, true);
-        act_quant_kernel<<<(ff / 256 + 7) / 8, 256, 0, c->stream>>>(c->hbuf, ff, m->act_fmt == ACT_F32 ? ACT_Q8_0 : m->act_fmt, c->act_ff);
-        act_quant_kernel<<<(dq / 256 + 7) / 8, 256, 0, c->stream>>>(c->hbuf, dq, m->act_fmt == ACT_F32 ? ACT_Q8_0 : m->act_fmt, c->act_q);
+        BLK_CUDA(cudaMemsetAsync(c->act_q.f32, 0, dq * sizeof(float), c->stream));
         int64_t bytes = 0;
         auto one = [&](int it, bool count) {
             const LayerWeights& L = m->layers[it % m->n_layer];
             GemvArgs a{};
-            a.act_fmt = m->act_fmt;
             switch (which) {
             case 0:
-                a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff; a.act = c->act_d; a.out = c->hbuf;
-                if (count) bytes += (int64_t)L.gate.bytes + (int64_t)L.up.bytes + d + ff * 4;
-                launch_gemv<EPI_SWIGLU>(c, a); break;
+                a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff; a.out = c->hbuf;
+                if (count) bytes += (int64_t)L.gate.bytes + (int64_t)L.up.bytes + d * 8 + ff * 4;
+                matvec<EPI_SWIGLU>(c, a, c->x, L.ffn_norm, c->act_d, "bench"); break;
             case 1:
-                a.nseg = 1; a.seg[0] = {L.down, nullptr, 0, 0}; a.total_pairs = d / 2; a.act = c->act_ff; a.out = c->x;
-                if (m->act_fmt == ACT_F32) a.act.f32 = c->hbuf;
-                if (count) bytes += (int64_t)L.down.bytes + ff + d * 8;
-                launch_gemv<EPI_RESID>(c, a); break;
+                a.nseg = 1; a.seg[0] = {L.down, nullptr, 0, 0}; a.total_pairs = d / 2; a.out = c->x;
+                if (count) bytes += (int64_t)L.down.bytes + ff * 4 + d * 8;
+                matvec<EPI_RESID>(c, a, c->hbuf, nullptr, c->act_ff, "bench"); break;
             case 2:
                 a.nseg = 3; a.seg[0] = {L.wq, L.bq, 0, 0}; a.seg[1] = {L.wk, L.bk, dq / 2, 1}; a.seg[2] = {L.wv, L.bv, dq / 2 + dkv / 2, 2};
-                a.total_pairs = dq / 2 + dkv; a.act = c->act_d; a.out = c->qbuf;
+                a.total_pairs = dq / 2 + dkv; a.out = c->qbuf;
                 a.d_head = dh; a.neox = m->neox ? 1 : 0; a.rope_cs = c->rope_cs; a.pos = c->d_pos;
                 a.k_pool = c->k_pool[it % m->n_layer]; a.v_pool = c->v_pool[it % m->n_layer]; a.page_table = c->page_table; a.kv_dim = dkv;
-                if (count) bytes += (int64_t)(L.wq.bytes + L.wk.bytes + L.wv.bytes) + d + dq * 4 + dkv * 4;
-                launch_gemv<EPI_QKV>(c, a); break;
+                if (count) bytes += (int64_t)(L.wq.bytes + L.wk.bytes + L.wv.bytes) + d * 8 + dq * 4 + dkv * 4;
+                matvec<EPI_QKV>(c, a, c->x, L.attn_norm, c->act_d, "bench"); break;
             case 3:
-                a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2; a.act = c->act_q; a.out = c->x;
-                if (count) bytes += (int64_t)L.wo.bytes + dq + d * 8;
-                launch_gemv<EPI_RESID>(c, a); break;
+                a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2; a.out = c->x;
+                if (count) bytes += (int64_t)L.wo.bytes + dq * 4 + d * 8;
+                matvec<EPI_RESID>(c, a, c->act_q.f32, nullptr, c->act_q2, "bench"); break;
             default:
-                a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = m->n_vocab / 2; a.act = c->act_d; a.act_fmt = m->act_fmt_out; a.out = c->logits;
-                if (count) bytes += (int64_t)m->output.bytes + d + (int64_t)m->n_vocab * 4;
-                launch_gemv<EPI_STORE>(c, a); break;
+                a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = m->n_vocab / 2; a.out = c->logits;
+                if (count) bytes += (int64_t)m->output.bytes + d * 8 + (int64_t)m->n_vocab * 4;
+                matvec<EPI_STORE>(c, a, c->x, m->out_norm, c->act_d, "bench"); break;
             }
         };
         for (int i = 0; i < std::min(iters, 8); i++) one(i, false);          // warm-up
@@ -671,6 +767,42 @@ extern "C" blk_status blk_bench_kernel(blk_ctx* c, int32_t which, int32_t iters,
         *bytes_per_launch = bytes / iters;
         BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, sizeof(int32_t), c->stream));
         c->n_past = 0; c->have_logits = false;
+    });
+}
+
+extern "C" blk_status blk_profile_step(blk_ctx* c, int32_t token, char* report, int32_t cap) {
+    if (!c || !report || cap <= 0) return fail(BLK_ERR_ARG, "blk_profile_step: bad arguments");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (c->n_past + 1 > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        c->h_tok[0] = token; c->tok_slot = 1;
+        BLK_CUDA(cudaMemcpyAsync(c->d_tok, c->h_tok, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        c->profiling = true; c->prof_marks.clear();
+        prof_mark(c, "start");
+        enqueue_step(c, true, false);
+        c->profiling = false;
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        c->n_past++; c->have_logits = true;
+        std::map<std::string, std::pair<int, float>> agg;
+        float total = 0.0f;
+        for (size_t i = 1; i < c->prof_marks.size(); i++) {
+            float ms = 0.0f;
+            BLK_CUDA(cudaEventElapsedTime(&ms, c->prof_marks[i - 1].second, c->prof_marks[i].second));
+            auto& a = agg[c->prof_marks[i].first]; a.first++; a.second += ms; total += ms;
+        }
+        for (auto& p : c->prof_marks) cudaEventDestroy(p.second);
+        c->prof_marks.clear();
+        std::string out = "kernel,launches,total_us,avg_us,share\n";
+        char line[256];
+        for (auto& kv : agg) {
+            snprintf(line, sizeof(line), "%s,%d,%.1f,%.2f,%.3f\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e3f,
+                     kv.second.second * 1e3f / kv.second.first, kv.second.second / total);
+            out += line;
+        }
+        snprintf(line, sizeof(line), "TOTAL,,%.1f,,1.0\n", total * 1e3f);
+        out += line;
+        snprintf(report, (size_t)cap, "%s", out.c_str());
     });
 }
 
@@ -732,12 +864,11 @@ extern "C" blk_status blk_test_gemv(int32_t device, int32_t type, const void* bl
         float* d_x = dalloc<float>(&c, k); float* d_y = dalloc<float>(&c, rows);
         ActBuf act = make_act(&c, (int)k);
         BLK_CUDA(cudaMemcpyAsync(d_x, x, k * 4, cudaMemcpyHostToDevice, c.stream));
-        const int fmt = act_format_for(type);
-        launch_act_prepare(&c, d_x, nullptr, (int)k, fmt, act, false);
         GemvArgs a{};
-        a.nseg = 1; a.seg[0] = {tm.W, nullptr, 0, 0}; a.total_pairs = (int)(rows / 2);
-        a.act = act; a.act_fmt = fmt; a.out = d_y;
-        launch_gemv<EPI_STORE>(&c, a);
+        a.nseg = 1; a.seg[0] = {tm.W, nullptr, 0, 0}; a.total_pairs = (int)(rows / 2); a.out = d_y;
+        BLK_CUDA(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, device));
+        { const char* e = getenv("BLK_RING"); c.use_ring = (e && e[0] == '1'); }
+        matvec<EPI_STORE>(&c, a, d_x, nullptr, act, "test");
         BLK_CUDA(cudaMemcpyAsync(y, d_y, rows * 4, cudaMemcpyDeviceToHost, c.stream));
         BLK_CUDA(cudaStreamSynchronize(c.stream));
     });

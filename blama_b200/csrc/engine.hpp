@@ -82,16 +82,23 @@ struct blk_ctx {
     float* qbuf = nullptr;                // [n_head*d_head]
     float* hbuf = nullptr;                // [n_ff]
     float2* rope_cs = nullptr;            // [d_head/2]
-    blk::ActBuf act_d, act_q, act_ff;
+    blk::ActBuf act_d, act_q, act_q2, act_ff;
+    int n_sms = 148; bool use_ring = false;
+    int attn_cluster = 0, attn_cap = 0;   // cluster size (0 = three-kernel fallback) and tokens per CTA
     float* part_o = nullptr; float* scores = nullptr;
     float* logits = nullptr;              // [n_vocab] of the last decoded token
-    float* cand_l = nullptr; int* cand_i = nullptr; int n_chunks = 0;
+    float* cand_l = nullptr; int* cand_i = nullptr; int n_chunks = 0; int chunk_shift = 10; int cand_cap = 2048;
+    int* chunk_max = nullptr;
+    unsigned int* counters = nullptr;      // [0] residual-norm tail, [1] top-k count, [2] top-k done, [8..] per-block quant tails
     int32_t* top_ids = nullptr; float* top_logits = nullptr;           // device [TOPK_MAX]
     int32_t* h_top_ids = nullptr; float* h_top_logits = nullptr;       // pinned
     bool have_logits = false;
-    cudaGraphExec_t g_full = nullptr, g_body = nullptr;
-    int64_t launches_full = 0, launches_body = 0;
+    cudaGraphExec_t g_full = nullptr, g_body = nullptr, g_loop = nullptr;
+    int64_t launches_full = 0, launches_body = 0, launches_loop = 0;
     int64_t launches = 0;
+    // per-kernel event timing of one eagerly launched step (blk_profile_step)
+    bool profiling = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
     // scratch for gather / verify
     int32_t* d_ids = nullptr; float* d_gath = nullptr; int ids_cap = 0;
     void* flush_buf = nullptr; size_t flush_bytes = 0;

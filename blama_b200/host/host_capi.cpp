@@ -68,6 +68,8 @@ BLK_API int blh_instance_create(void* model, uint32_t ctx_size, uint32_t batch_s
     });
 }
 BLK_API void blh_instance_free(void* i) { delete static_cast<InstanceBox*>(i); }
+// the C-ABI context behind an Instance (bench.py times it with blk_timer_* / counts its launches)
+BLK_API void* blh_instance_ctx(void* i) { return static_cast<InstanceBox*>(i)->inst->lctx(); }
 BLK_API int blh_instance_warmup(void* i) { return guard([&] { static_cast<InstanceBox*>(i)->inst->warmup(); }); }
 
 BLK_API int blh_session_start(void* i, uint32_t seed, float temp, float top_p, int sequential_verify) {

@@ -28,6 +28,7 @@ public:
     Session& startSession(const Session::InitParams params);   // only one live session per instance
     void stopSession() noexcept;
     Model& model() const noexcept { return m_model; }
+    blk_ctx* lctx() noexcept { return m_ctx.get(); }
 
 private:
     Model& m_model;

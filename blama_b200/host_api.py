@@ -24,6 +24,7 @@ HOST_SYMBOLS = {
     "blh_instance_create": (C.c_int, [_vp, _u32, _u32, C.POINTER(_vp)]),
     "blh_instance_free": (None, [_vp]),
     "blh_instance_warmup": (C.c_int, [_vp]),
+    "blh_instance_ctx": (_vp, [_vp]),
     "blh_session_start": (C.c_int, [_vp, _u32, _f32, _f32, C.c_int]),
     "blh_session_stop": (None, [_vp]),
     "blh_session_set_initial_prompt": (C.c_int, [_vp, _vp, C.c_int]),
@@ -111,6 +112,14 @@ class Instance:
 
     def warmup(self):
         _check(lib().blh_instance_warmup(self.h))
+
+    def raw_ctx(self) -> "capi.Ctx":
+        """non-owning capi.Ctx view of this instance's C-ABI context (timers, launch counters)"""
+        c = capi.Ctx.__new__(capi.Ctx)
+        c.m = None
+        c.h = lib().blh_instance_ctx(self.h)
+        c.close = lambda: None
+        return c
 
     def start_session(self, seed: int = 0, temperature: float = 0.8, top_p: float = 0.95, sequential_verify: bool = False):
         _check(lib().blh_session_start(self.h, seed, temperature, top_p, int(sequential_verify)))

@@ -107,6 +107,10 @@ BLK_API blk_status blk_get_logits_last(blk_ctx*, float* out);
  * distribution in one device->host copy. */
 BLK_API blk_status blk_decode_topk(blk_ctx*, int32_t token, int32_t k, blk_token_data* out);
 
+/* Device-resident greedy decode loop (measurement aid for bench.py's `value`): n_steps decode steps back to back with the
+ * arg-max token fed back ON THE DEVICE, no host round trip inside the loop.  Asynchronous unless last_token != NULL. */
+BLK_API blk_status blk_decode_loop(blk_ctx*, int32_t first_token, int32_t n_steps, int32_t* last_token);
+
 /* ---- verification context fill (Session::fillCtx, Session.cpp:231-244) ----------------------------------- */
 /* Appends the n response tokens as ONE causal prefill (chunked by n_batch) instead of n single-token decodes, and for
  * every position i returns
@@ -133,6 +137,9 @@ BLK_API int64_t    blk_ctx_kernel_launches(const blk_ctx*);
  * 3 = attention-output mat-vec, 4 = lm_head mat-vec.  Returns the average launch duration and the algorithmic bytes one
  * launch must move (quantised weight planes + activations + outputs). */
 BLK_API blk_status blk_bench_kernel(blk_ctx*, int32_t which, int32_t iters, float* avg_ms, int64_t* bytes_per_launch);
+/* Decodes `token` with the step's kernels launched eagerly and a CUDA event between every pair of launches (so without
+ * the cross-kernel overlap of the graph), and writes a CSV breakdown (kernel, launches, total_us, avg_us, share). */
+BLK_API blk_status blk_profile_step(blk_ctx*, int32_t token, char* report, int32_t cap);
 /* writes >= bytes of device memory to evict L2 between timed iterations */
 BLK_API blk_status blk_flush_l2(blk_ctx*);
 

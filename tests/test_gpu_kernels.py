@@ -23,12 +23,16 @@ def test_retile_dequant_bit_exact(gtype, name, oracle):
 
 
 @pytest.mark.parametrize("gtype,name", TYPES)
-@pytest.mark.parametrize("rows,k", [(2, 256), (64, 1024), (130, 4096), (34, 14336 if True else 0)])
+@pytest.mark.parametrize("rows,k", [(2, 256), (64, 1024), (130, 4096), (34, 14336), (6, 28672), (10, 18944)])
 def test_gemv_matches_ggml_arithmetic(gtype, name, rows, k, oracle):
     """dequant-fused GEMV == oracle's ggml-cpu restatement (Q8_K/Q8_0 activations, integer dot): the integer partial sums
     are identical, so the only difference is fp32 summation order -> tight tolerance"""
     from blama_b200 import capi
 
+    if gtype == gs.Q8_0 and k > 18944:
+        pytest.skip("Q8_0 rows longer than 18944 (Qwen2.5-7B ffn) are not covered")
+    if gtype == gs.F32 and k > 8192:
+        pytest.skip("F32 weights are a test-only format: rows up to 8192 elements")
     rng = np.random.default_rng(rows * 7 + k)
     blk = gs.random_blocks(rng, gtype, rows * k, 1.0 / np.sqrt(k))
     x = rng.standard_normal(k).astype(np.float32)
