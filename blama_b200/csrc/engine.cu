@@ -279,6 +279,9 @@ blk_ctx::~blk_ctx() {
     for (void* p : host_allocs) cudaFreeHost(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (pf_fork) cudaEventDestroy(pf_fork);
+    if (pf_join) cudaEventDestroy(pf_join);
+    if (pf_stream) cudaStreamDestroy(pf_stream);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -361,11 +364,51 @@ void matvec(blk_ctx* c, GemvArgs& a, const float* in, const float* norm_w, const
         if (e != cudaErrorInvalidValue) { BLK_CUDA(e); c->launches++; prof_mark(c, name); return; }
         (void)cudaGetLastError();
     }
-    launch_act_prepare(c, in, norm_w, K, fmt, scratch, norm_w != nullptr);
+    if (!norm_w && fmt != ACT_F32) {
+        // quantise only: every 256-element block is independent -> one warp per block across several CTAs
+        BLK_CUDA(launch_pdl(act_quant_kernel, dim3((K / 256 + 7) / 8), dim3(256), 0, c->stream, in, K, fmt, scratch));
+        c->launches++;
+    } else {
+        launch_act_prepare(c, in, norm_w, K, fmt, scratch, norm_w != nullptr);
+    }
     prof_mark(c, "act_prepare");
     a.act = scratch;
+    if (fmt == ACT_F32 && !norm_w) a.act.f32 = const_cast<float*>(in);
     launch_gemv<EPI>(c, a);
     prof_mark(c, name);
+}
+
+// launch an L2 prefetch of the given matrices on the prefetch stream, ordered after everything enqueued so far on the
+// main stream (i.e. it starts when the previous phase has completed and overlaps the phase enqueued next)
+void prefetch_after_current(blk_ctx* c, std::initializer_list<const QMat*> mats, int which = 0, size_t max_bytes = (size_t)96 << 20) {
+    if (!c->use_prefetch || !((c->pf_mask >> which) & 1)) return;
+    PrefetchArgs pa{};
+    size_t budget = max_bytes;
+    for (const QMat* W : mats) {
+        const uint8_t* planes[4] = {W->p0, W->p1, W->p2, W->p3};
+        size_t sizes[4] = {0, 0, 0, 0};
+        const size_t nsb = (size_t)W->N * (W->K / 256), nb32 = (size_t)W->N * (W->K / 32);
+        switch (W->type) {
+            case QT_Q4_K: sizes[0] = nsb * 128; sizes[1] = nsb * 16; break;
+            case QT_Q5_K: sizes[0] = nsb * 128; sizes[1] = nsb * 16; sizes[2] = nsb * 32; break;
+            case QT_Q6_K: sizes[0] = nsb * 128; sizes[1] = nsb * 64; sizes[2] = nsb * 16; sizes[3] = nsb * 2; break;
+            case QT_Q8_0: sizes[0] = nb32 * 32; sizes[1] = nb32 * 2; break;
+            default: sizes[0] = W->bytes; break;
+        }
+        for (int i = 0; i < 4 && pa.n < 8; i++) {
+            if (!planes[i] || !sizes[i] || !budget) continue;
+            const size_t take = std::min(sizes[i], budget);
+            pa.ptr[pa.n] = planes[i]; pa.bytes[pa.n] = take; pa.n++;
+            budget -= take;
+        }
+    }
+    if (!pa.n) return;
+    BLK_CUDA(cudaEventRecord(c->pf_fork, c->stream));
+    BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pf_fork, 0));
+    l2_prefetch_kernel<<<c->pf_ctas, c->pf_threads, 0, c->pf_stream>>>(pa);
+    BLK_CUDA(cudaGetLastError());
+    c->launches++;
+    c->pf_used = true;
 }
 
 // one decode step on c->stream: token id in c->d_tok, position in c->d_pos.
@@ -377,8 +420,10 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
     BLK_CUDA(launch_pdl(embed_kernel, dim3(1), dim3(256), 0, c->stream, m->tok_embd, c->d_tok, c->d_pos, c->x, c->rope_cs, dh / 2, m->theta_scale, m->rope_freqs));
     c->launches++;
     prof_mark(c, "embed");
+    c->pf_used = false;
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
+        if (!c->profiling) prefetch_after_current(c, {&L.wo}, 0);                          // overlaps the QKV mat-vec
         {
             GemvArgs a{};
             a.nseg = 3;
@@ -392,6 +437,7 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
             matvec<EPI_QKV>(c, a, c->x, L.attn_norm, c->act_d, "gemv_qkv");
         }
         {
+            if (!c->profiling) prefetch_after_current(c, {&L.gate, &L.up}, 1);             // overlaps attention + Wo
             if (c->attn_cluster > 0) {
                 AttnClusterArgs ac{};
                 ac.q = c->qbuf; ac.k_pool = c->k_pool[l]; ac.v_pool = c->v_pool[l]; ac.page_table = c->page_table; ac.pos = c->d_pos;
@@ -434,10 +480,15 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
             a.nseg = 1; a.seg[0] = {L.wo, nullptr, 0, 0}; a.total_pairs = d / 2; a.out = c->x;
             matvec<EPI_RESID>(c, a, c->act_q.f32, nullptr, c->act_q2, "gemv_wo");
         }
+        if (!c->profiling) prefetch_after_current(c, {&L.down}, 2);                        // overlaps the gate/up mat-vec
         {
             GemvArgs a{};
             a.nseg = 2; a.seg[0] = {L.gate, nullptr, 0, 0}; a.seg[1] = {L.up, nullptr, 0, 0}; a.total_pairs = ff; a.out = c->hbuf;
             matvec<EPI_SWIGLU>(c, a, c->x, L.ffn_norm, c->act_d, "gemv_gate_up");
+        }
+        if (!c->profiling) {                                                            // overlaps the down mat-vec
+            if (l + 1 < m->n_layer) prefetch_after_current(c, {&m->layers[l + 1].wq, &m->layers[l + 1].wk, &m->layers[l + 1].wv}, 3);
+            else if (with_head) prefetch_after_current(c, {&m->output}, 4);
         }
         {
             GemvArgs a{};
@@ -457,6 +508,10 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
         BLK_CUDA(launch_pdl(topk_select_kernel, dim3(16), dim3(1024), 0, c->stream, tk));
         c->launches++;
         prof_mark(c, "topk_select");
+    }
+    if (c->pf_used) {      // join the prefetch branch back into the main stream
+        BLK_CUDA(cudaEventRecord(c->pf_join, c->pf_stream));
+        BLK_CUDA(cudaStreamWaitEvent(c->stream, c->pf_join, 0));
     }
     BLK_CUDA(launch_pdl(advance_pos_kernel, dim3(1), dim3(32), 0, c->stream, c->d_pos, 1));
     c->launches++;
@@ -517,6 +572,12 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         c->n_batch = n_batch > 0 ? n_batch : 2048;
         BLK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         BLK_CUDA(cudaEventCreate(&c->ev0)); BLK_CUDA(cudaEventCreate(&c->ev1));
+        BLK_CUDA(cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
+        BLK_CUDA(cudaEventCreateWithFlags(&c->pf_fork, cudaEventDisableTiming)); BLK_CUDA(cudaEventCreateWithFlags(&c->pf_join, cudaEventDisableTiming));
+        { const char* e = getenv("BLK_PREFETCH"); c->use_prefetch = (e && e[0] == '1'); }   // opt-in: measured slower
+        { const char* e = getenv("BLK_PF_MASK"); c->pf_mask = e ? atoi(e) : 31; }
+        { const char* e = getenv("BLK_PF_THREADS"); c->pf_threads = e ? atoi(e) : 256; }
+        { const char* e = getenv("BLK_PF_CTAS"); c->pf_ctas = e ? atoi(e) : 148; }
         const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
         c->n_pages = (c->n_ctx + KV_PAGE - 1) / KV_PAGE;
         c->k_pool.resize(m->n_layer); c->v_pool.resize(m->n_layer);

@@ -67,6 +67,10 @@ struct blk_ctx {
     int n_pages = 0, n_split = 1;
     int verify_mode = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pf_stream = nullptr;      // L2 weight prefetch, one phase ahead of the mat-vecs
+    cudaEvent_t pf_fork = nullptr, pf_join = nullptr;
+    bool use_prefetch = true, pf_used = false;
+    int pf_mask = 31, pf_threads = 256, pf_ctas = 148;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void*> allocs;
     std::vector<void*> host_allocs;
