@@ -6,6 +6,7 @@
 #include "engine.hpp"
 #include "gemv_ring.cuh"
 #include "gguf.hpp"
+#include "prefill.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -935,6 +936,19 @@ extern "C" blk_status blk_test_gemv(int32_t device, int32_t type, const void* bl
     });
 }
 
-extern "C" blk_status blk_test_gemm(int32_t, int32_t, const void*, int64_t, int64_t, const float*, int64_t, float*) {
-    return fail(BLK_ERR_ARG, "blk_test_gemm: prefill GEMM not built in this revision");
+extern "C" blk_status blk_test_gemm(int32_t device, int32_t type, const void* blocks, int64_t rows, int64_t k, const float* x, int64_t n_tok, float* y) {
+    return guarded([&] {
+        if (n_tok <= 0) throw BlkError(BLK_ERR_ARG, "n_tok must be positive");
+        TestMat tm; test_upload(tm, device, type, blocks, rows, k);
+        blk_ctx c; c.m = &tm.holder;
+        BLK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        float* d_x = dalloc<float>(&c, (size_t)n_tok * k);
+        __nv_bfloat16* d_xb = dalloc<__nv_bfloat16>(&c, (size_t)n_tok * k);
+        float* d_y = dalloc<float>(&c, (size_t)n_tok * rows);
+        BLK_CUDA(cudaMemcpyAsync(d_x, x, (size_t)n_tok * k * 4, cudaMemcpyHostToDevice, c.stream));
+        BLK_CUDA(convert_f32_to_bf16(d_x, d_xb, (size_t)n_tok * k, c.stream));
+        BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream));
+        BLK_CUDA(cudaMemcpyAsync(y, d_y, (size_t)n_tok * rows * 4, cudaMemcpyDeviceToHost, c.stream));
+        BLK_CUDA(cudaStreamSynchronize(c.stream));
+    });
 }

@@ -1,0 +1,280 @@
+// prefill_gemm.cuh -- dequant-fused tcgen05 / TMEM GEMM for multi-token prefill (the /verify_completion context fill,
+// reference Session::fillCtx, Session.cpp:231-244, done as ONE causal prefill instead of N single-token decodes).
+//
+//   C[T][N] (f32) (+)= X[T][K] (bf16) . W[N][K]^T      W = device-resident quant blocks (Q4_K / Q5_K / Q6_K / Q8_0 / F32)
+//
+// Per CTA tile: 256 tokens x 256 weight rows, K walked in steps of 64.
+//   warp 8  (1 thread)  : TMA producer -- two 128x64 bf16 boxes of X per stage (cp.async.bulk.tensor, SWIZZLE_128B)
+//   warps 0-7 (256 thr) : dequant producers -- thread r turns 64 K-elements of weight row n0+r into bf16 and writes them
+//                         as one 128-byte row of the canonical K-major SWIZZLE_128B tile the UMMA descriptor describes
+//                         (weights are dequantised once per 256 tokens and never touch HBM in bf16)
+//   warp 9  (1 thread)  : MMA issuer -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16; two accumulators
+//                         (token rows 0-127 / 128-255) x 256 f32 columns = all 512 TMEM columns
+//   warps 4-7 double as the epilogue after the main loop of a tile: tcgen05.ld 32x32b -> registers -> global
+// Operands are bf16 (weights: bf16(dequantised f32), activations: bf16), accumulation is f32 in TMEM: this is the
+// ORC_MODE_BF16 arithmetic of the oracle; tolerance against the reference's int8 path is stated in the tests.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "gemv_ring.cuh"   // mbarrier / bulk-copy wrappers, QMat
+
+namespace blk {
+
+constexpr int PG_BM = 256, PG_BN = 256, PG_BK = 64;
+constexpr int PG_STAGES = 3;
+constexpr int PG_PRODUCER_THREADS = 256;
+constexpr int PG_THREADS = PG_PRODUCER_THREADS + 64;      // + TMA warp + MMA warp
+constexpr int PG_A_BYTES = PG_BM * PG_BK * 2;             // 32 KB (two 128-row boxes)
+constexpr int PG_B_BYTES = PG_BN * PG_BK * 2;             // 32 KB
+constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
+constexpr int PG_SMEM_BYTES = PG_STAGES * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+enum : int { PG_STORE = 0, PG_ACCUM = 1 };
+
+struct PrefillGemmArgs {
+    QMat W;
+    const float* bias;          // optional [N], added in PG_STORE mode
+    float* C; long long ldc;    // f32 output, row stride in elements
+    int T, N, K;
+    int mode;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, bf16 x bf16 -> f32
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 | SBO(1024 B >>4)<<32 |
+// version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both,
+// n_dim = N>>3 @17, m_dim = M>>4 @24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- 64 consecutive K-elements of one weight row, dequantised (f32) -----------------------------------------------------
+// kb = index of the 64-element block inside the row.  Same float expressions as ggml's dequantize_row_* (no FMA).
+__device__ __forceinline__ void dequant_k64(const QMat& W, int64_t row, int kb, float* out) {
+    if (W.type == QT_Q4_K) { dequant_unit_q4k(W, row, kb, out); return; }
+    if (W.type == QT_Q5_K) { dequant_unit_q5k(W, row, kb, out); return; }
+    if (W.type == QT_Q8_0) { dequant_unit_q80(W, row, 2 * kb, out); dequant_unit_q80(W, row, 2 * kb + 1, out + 32); return; }
+    if (W.type == QT_Q6_K) {
+        const int s = kb >> 2, hh = (kb >> 1) & 1, hi = kb & 1;           // quarters (2*hi, 2*hi+1) of half hh
+        const uint8_t* ql = W.p0 + (size_t)row * (W.K >> 1) + (size_t)s * 128 + hh * 64;
+        const uint8_t* qh = W.p1 + (size_t)row * (W.K >> 2) + (size_t)s * 64 + hh * 32;
+        const int8_t* sc = reinterpret_cast<const int8_t*>(W.p2) + (size_t)row * (W.K >> 4) + s * 16 + hh * 8 + hi * 4;
+        const float d = __half2float(reinterpret_cast<const __half*>(W.p3)[(size_t)row * (W.K >> 8) + s]);
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            const uint8_t a = ql[l], b = ql[l + 32], h = qh[l];
+            const int qa = (int)(((hi ? (a >> 4) : (a & 0xF))) | (((h >> (4 * hi)) & 3) << 4)) - 32;
+            const int qb = (int)(((hi ? (b >> 4) : (b & 0xF))) | (((h >> (4 * hi + 2)) & 3) << 4)) - 32;
+            out[l] = d * (float)sc[l >> 4] * (float)qa;
+            out[32 + l] = d * (float)sc[2 + (l >> 4)] * (float)qb;
+        }
+        return;
+    }
+    if (W.type == QT_F32) {
+        const float* src = reinterpret_cast<const float*>(W.p0) + (size_t)row * W.K + (size_t)kb * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i++) out[i] = src[i];
+        return;
+    }
+    const __half* src = reinterpret_cast<const __half*>(W.p0) + (size_t)row * W.K + (size_t)kb * 64;
+#pragma unroll
+    for (int i = 0; i < 64; i++) out[i] = __half2float(src[i]);
+}
+
+__global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const PrefillGemmArgs a) {
+    extern __shared__ unsigned char pg_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PG_STAGES * PG_STAGE_BYTES);
+    uint64_t* full = bars;                          // [PG_STAGES]  TMA bytes + 8 producer-warp arrivals
+    uint64_t* empty = bars + PG_STAGES;             // [PG_STAGES]  tcgen05.commit
+    uint64_t* tmem_full = bars + 2 * PG_STAGES;     // accumulators complete
+    uint64_t* tmem_empty = bars + 2 * PG_STAGES + 1;    // epilogue drained them (4 warps)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * PG_STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PG_STAGES; s++) { mbar_init(full + s, 1 + PG_PRODUCER_THREADS / 32); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 9) {    // one warp allocates all 512 TMEM columns (two 128 x 256 f32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = (a.N + PG_BN - 1) / PG_BN;
+    const int k_blocks = a.K / PG_BK;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 8) {
+        // ===================== TMA producer (activations) =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile % m_tiles) * PG_BM;
+                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                    const int s = it % PG_STAGES;
+                    mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
+                    unsigned char* sa = smem + s * PG_STAGE_BYTES;
+                    mbar_expect_tx(full + s, PG_A_BYTES);
+                    tma_load_2d(sa, &tmap_x, kb * PG_BK, m0, full + s);
+                    tma_load_2d(sa + PG_A_BYTES / 2, &tmap_x, kb * PG_BK, m0 + 128, full + s);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, PG_BN);
+            int it = 0, tile_i = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_i++) {
+                mbar_wait(tmem_empty, (tile_i & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
+                tc_fence_after();
+                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                    const int s = it % PG_STAGES;
+                    mbar_wait(full + s, (it / PG_STAGES) & 1);
+                    tc_fence_after();
+                    unsigned char* sa = smem + s * PG_STAGE_BYTES;
+                    unsigned char* sb = sa + PG_A_BYTES;
+                    const uint64_t da0 = umma_desc_sw128(sa), da1 = umma_desc_sw128(sa + PG_A_BYTES / 2), db = umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < PG_BK / 16; k++) {
+                        const uint64_t koff = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 B along K inside the swizzle atom
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        tc_mma_bf16(tmem_base, da0 + koff, db + koff, idesc, acc);
+                        tc_mma_bf16(tmem_base + PG_BN, da1 + koff, db + koff, idesc, acc);
+                    }
+                    tc_commit(empty + s);                         // frees the stage when these MMAs have read it
+                }
+                tc_commit(tmem_full);                             // accumulators of this tile are final
+            }
+        }
+    } else {
+        // ===================== dequant producers (warps 0-7); warps 4-7 also run the epilogue =====================
+        const int r = threadIdx.x;                                // B-tile row handled by this thread
+        int it = 0, tile_i = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_i++) {
+            const int m0 = (tile % m_tiles) * PG_BM, n0 = (tile / m_tiles) * PG_BN;
+            const int64_t row = (int64_t)n0 + r;
+            const bool row_ok = row < a.N;
+            for (int kb = 0; kb < k_blocks; kb++, it++) {
+                const int s = it % PG_STAGES;
+                float w[64];
+                if (row_ok) dequant_k64(a.W, row, kb, w);          // global loads issued before waiting for the slot
+                else {
+#pragma unroll
+                    for (int i = 0; i < 64; i++) w[i] = 0.0f;
+                }
+                mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
+                unsigned char* srow = smem + s * PG_STAGE_BYTES + PG_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint4 v;
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(w[c * 8 + 0], w[c * 8 + 1]);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(w[c * 8 + 2], w[c * 8 + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(w[c * 8 + 4], w[c * 8 + 5]);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(w[c * 8 + 6], w[c * 8 + 7]);
+                    v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+                    v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(srow + ((c ^ (r & 7)) << 4)) = v;      // SWIZZLE_128B: 16 B chunk index XOR (row % 8)
+                }
+                fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + s);
+            }
+            if (warp >= 4) {
+                // ---- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 of both accumulators ----
+                const int q = warp & 3;
+                mbar_wait(tmem_full, tile_i & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    const int trow = m0 + h * 128 + q * 32 + lane;
+#pragma unroll 1
+                    for (int cc = 0; cc < PG_BN / 32; cc++) {
+                        uint32_t v[32];
+                        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * PG_BN + cc * 32), v);
+                        tc_wait_ld();
+                        if (trow < a.T) {
+                            float* dst = a.C + (size_t)trow * a.ldc + n0 + cc * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const int n = n0 + cc * 32 + j;
+                                if (n + 3 < a.N) {
+                                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                    if (a.mode == PG_ACCUM) { const float4 c0 = *reinterpret_cast<const float4*>(dst + j); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
+                                    else if (a.bias) { o.x += a.bias[n]; o.y += a.bias[n + 1]; o.z += a.bias[n + 2]; o.w += a.bias[n + 3]; }
+                                    *reinterpret_cast<float4*>(dst + j) = o;
+                                } else {
+                                    for (int jj = 0; jj < 4; jj++) if (n + jj < a.N) {
+                                        float o = __uint_as_float(v[j + jj]);
+                                        if (a.mode == PG_ACCUM) o += dst[j + jj]; else if (a.bias) o += a.bias[n + jj];
+                                        dst[j + jj] = o;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+} // namespace blk
