@@ -64,6 +64,7 @@ SYMBOLS = {
     "blk_bench_kernel": (_i32, [_vp, _i32, _i32, _f32p, C.POINTER(C.c_int64)]),
     "blk_test_gemv": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _vp]),
     "blk_test_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "blk_bench_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _i64, _i32, _f32p]),
     "blk_test_dequant": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp]),
 }
 
@@ -260,3 +261,11 @@ def test_dequant(gtype: int, blocks: np.ndarray, rows: int, k: int, device: int 
     out = np.zeros((rows, k), dtype=np.float32)
     _check(lib().blk_test_dequant(device, gtype, _p(b), rows, k, _p(out)))
     return out
+
+
+def bench_gemm(gtype: int, blocks: np.ndarray, rows: int, k: int, n_tok: int, iters: int = 10, device: int = 0) -> float:
+    """average ms of one prefill GEMM [n_tok x k] . [rows x k]^T"""
+    b = np.ascontiguousarray(blocks, dtype=np.uint8)
+    ms = C.c_float(0)
+    _check(lib().blk_bench_gemm(device, gtype, _p(b), rows, k, n_tok, iters, C.byref(ms)))
+    return float(ms.value)

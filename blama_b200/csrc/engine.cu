@@ -952,3 +952,24 @@ extern "C" blk_status blk_test_gemm(int32_t device, int32_t type, const void* bl
         BLK_CUDA(cudaStreamSynchronize(c.stream));
     });
 }
+
+extern "C" blk_status blk_bench_gemm(int32_t device, int32_t type, const void* blocks, int64_t rows, int64_t k, int64_t n_tok, int32_t iters, float* avg_ms) {
+    return guarded([&] {
+        if (n_tok <= 0 || iters <= 0 || !avg_ms) throw BlkError(BLK_ERR_ARG, "blk_bench_gemm: bad arguments");
+        TestMat tm; test_upload(tm, device, type, blocks, rows, k);
+        blk_ctx c; c.m = &tm.holder;
+        BLK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        BLK_CUDA(cudaEventCreate(&c.ev0)); BLK_CUDA(cudaEventCreate(&c.ev1));
+        __nv_bfloat16* d_xb = dalloc<__nv_bfloat16>(&c, (size_t)n_tok * k);
+        float* d_y = dalloc<float>(&c, (size_t)n_tok * rows);
+        BLK_CUDA(cudaMemsetAsync(d_xb, 0x3c, (size_t)n_tok * k * 2, c.stream));
+        for (int i = 0; i < 3; i++) BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream));
+        BLK_CUDA(cudaEventRecord(c.ev0, c.stream));
+        for (int i = 0; i < iters; i++) BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream));
+        BLK_CUDA(cudaEventRecord(c.ev1, c.stream));
+        BLK_CUDA(cudaEventSynchronize(c.ev1));
+        float ms = 0.0f;
+        BLK_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+        *avg_ms = ms / (float)iters;
+    });
+}

@@ -57,21 +57,27 @@ cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    static unsigned long long attr_done = 0;
+    void (*kernel)(const CUtensorMap, const PrefillGemmArgs) = nullptr;
+    switch (W.type) {
+        case QT_Q4_K: kernel = prefill_gemm_kernel<QT_Q4_K>; break;
+        case QT_Q5_K: kernel = prefill_gemm_kernel<QT_Q5_K>; break;
+        case QT_Q6_K: kernel = prefill_gemm_kernel<QT_Q6_K>; break;
+        case QT_Q8_0: kernel = prefill_gemm_kernel<QT_Q8_0>; break;
+        case QT_F32: kernel = prefill_gemm_kernel<QT_F32>; break;
+        case QT_F16: kernel = prefill_gemm_kernel<QT_F16>; break;
+        default: return cudaErrorInvalidValue;
+    }
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (!((attr_done >> (dev & 63)) & 1ull)) {
-        e = cudaFuncSetAttribute(prefill_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done |= 1ull << (dev & 63);
-    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     PrefillGemmArgs a{};
     a.W = W; a.bias = bias; a.C = C; a.ldc = ldc; a.T = T; a.N = W.N; a.K = W.K; a.mode = mode;
     const int tiles = ((T + PG_BM - 1) / PG_BM) * ((W.N + PG_BN - 1) / PG_BN);
     const int grid = tiles < sms ? tiles : sms;
-    prefill_gemm_kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, a);
+    kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, a);
     return cudaGetLastError();
 }
 

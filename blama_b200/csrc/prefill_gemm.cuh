@@ -124,6 +124,173 @@ __device__ __forceinline__ void dequant_k64(const QMat& W, int64_t row, int kb, 
     for (int i = 0; i < 64; i++) out[i] = __half2float(src[i]);
 }
 
+// ---- optimised producers: raw 64-element slices held in registers (loaded one stage ahead), expanded to bf16 ----------
+// byte -> float without I2F: PRMT drops the byte into the mantissa of 2^23 (0x4B000000), one FADD removes the bias
+__device__ __forceinline__ float byte_to_float(uint32_t word, int i) {      // (float) byte i of word
+    const uint32_t m = __byte_perm(word, 0x4B000000u, 0x7650 + i);          // {byte i, 0x00, 0x00, 0x4B}
+    return __uint_as_float(m) - 8388608.0f;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+// store 8 consecutive K-elements (one 16 B chunk c of the 128 B row) into the SWIZZLE_128B tile
+__device__ __forceinline__ void store_chunk(unsigned char* srow, int r, int c, const float* v) {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(srow + ((c ^ (r & 7)) << 4)) = o;
+}
+
+template <int TYPE> struct RawK64;
+template <> struct RawK64<QT_Q4_K> {
+    uint4 q0, q1, hdr;
+    __device__ __forceinline__ void load(const QMat& W, int64_t row, int kb) {
+        const uint8_t* q = W.p0 + (size_t)row * (W.K >> 1) + (size_t)kb * 32;
+        q0 = ldg_stream(q); q1 = ldg_stream(q + 16);
+        hdr = __ldg(reinterpret_cast<const uint4*>(W.p1 + ((size_t)row * (W.K >> 8) + (kb >> 2)) * 16));
+    }
+    __device__ __forceinline__ void expand(unsigned char* srow, int r, int kb) const {
+        uint32_t sc2, mn2; k4_scale_min_pair(hdr, kb & 3, sc2, mn2);
+        const float2 dm = hdr_d_dmin(hdr);
+        const float d1 = dm.x * (float)(sc2 & 0xFF), m1 = dm.y * (float)(mn2 & 0xFF);
+        const float d2 = dm.x * (float)(sc2 >> 8), m2 = dm.y * (float)(mn2 >> 8);
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {           // chunk c: low nibbles of bytes 8c..8c+7; chunk c+4: their high nibbles
+            float lo[8], hi[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t wl = w[2 * c + h] & 0x0F0F0F0Fu, wh = (w[2 * c + h] >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lo[4 * h + i] = __fmaf_rn(d1, byte_to_float(wl, i), -m1);
+                    hi[4 * h + i] = __fmaf_rn(d2, byte_to_float(wh, i), -m2);
+                }
+            }
+            store_chunk(srow, r, c, lo);
+            store_chunk(srow, r, c + 4, hi);
+        }
+    }
+};
+template <> struct RawK64<QT_Q5_K> {
+    uint4 q0, q1, hdr, h0, h1;
+    __device__ __forceinline__ void load(const QMat& W, int64_t row, int kb) {
+        const uint8_t* q = W.p0 + (size_t)row * (W.K >> 1) + (size_t)kb * 32;
+        q0 = ldg_stream(q); q1 = ldg_stream(q + 16);
+        const size_t sb = (size_t)row * (W.K >> 8) + (kb >> 2);
+        hdr = __ldg(reinterpret_cast<const uint4*>(W.p1 + sb * 16));
+        h0 = __ldg(reinterpret_cast<const uint4*>(W.p2 + sb * 32));
+        h1 = __ldg(reinterpret_cast<const uint4*>(W.p2 + sb * 32 + 16));
+    }
+    __device__ __forceinline__ void expand(unsigned char* srow, int r, int kb) const {
+        const int j = kb & 3;
+        uint32_t sc2, mn2; k4_scale_min_pair(hdr, j, sc2, mn2);
+        const float2 dm = hdr_d_dmin(hdr);
+        const float d1 = dm.x * (float)(sc2 & 0xFF), m1 = dm.y * (float)(mn2 & 0xFF);
+        const float d2 = dm.x * (float)(sc2 >> 8), m2 = dm.y * (float)(mn2 >> 8);
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const uint32_t hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float lo[8], hi[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t hw = hb[2 * c + h];
+                const uint32_t wl = (w[2 * c + h] & 0x0F0F0F0Fu) | (((hw >> (2 * j)) & 0x01010101u) << 4);
+                const uint32_t wh = ((w[2 * c + h] >> 4) & 0x0F0F0F0Fu) | (((hw >> (2 * j + 1)) & 0x01010101u) << 4);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lo[4 * h + i] = __fmaf_rn(d1, byte_to_float(wl, i), -m1);
+                    hi[4 * h + i] = __fmaf_rn(d2, byte_to_float(wh, i), -m2);
+                }
+            }
+            store_chunk(srow, r, c, lo);
+            store_chunk(srow, r, c + 4, hi);
+        }
+    }
+};
+template <> struct RawK64<QT_Q6_K> {
+    uint4 l0, l1, l2, l3, h0, h1; uint32_t sc4; uint16_t dh;      // 64 B of ql, 32 B of qh, 4 scales, d
+    __device__ __forceinline__ void load(const QMat& W, int64_t row, int kb) {
+        const int s = kb >> 2, hh = (kb >> 1) & 1, hi = kb & 1;
+        const uint8_t* ql = W.p0 + (size_t)row * (W.K >> 1) + (size_t)s * 128 + hh * 64;
+        l0 = ldg_stream(ql); l1 = ldg_stream(ql + 16); l2 = ldg_stream(ql + 32); l3 = ldg_stream(ql + 48);
+        const uint8_t* qh = W.p1 + (size_t)row * (W.K >> 2) + (size_t)s * 64 + hh * 32;
+        h0 = ldg_stream(qh); h1 = ldg_stream(qh + 16);
+        sc4 = __ldg(reinterpret_cast<const uint32_t*>(W.p2 + (size_t)row * (W.K >> 4) + s * 16 + hh * 8 + hi * 4));
+        dh = __ldg(reinterpret_cast<const uint16_t*>(W.p3) + (size_t)row * (W.K >> 8) + s);
+    }
+    __device__ __forceinline__ void expand(unsigned char* srow, int r, int kb) const {
+        const int hi = kb & 1;
+        const float d = __half2float(__ushort_as_half(dh));
+        float dsc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) dsc[i] = d * (float)(int)(int8_t)((sc4 >> (8 * i)) & 0xFF);
+        const uint32_t la[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};      // ql[0..31]
+        const uint32_t lb[8] = {l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};      // ql[32..63]
+        const uint32_t hq[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};      // qh[0..31]
+        // elements 0..31: quarter 2*hi (ql[l], qh bits 4*hi..), elements 32..63: quarter 2*hi+1 (ql[32+l], qh bits 4*hi+2..)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float qa[8], qb[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int wi = 2 * c + h;
+                const uint32_t na = hi ? ((la[wi] >> 4) & 0x0F0F0F0Fu) : (la[wi] & 0x0F0F0F0Fu);
+                const uint32_t nb = hi ? ((lb[wi] >> 4) & 0x0F0F0F0Fu) : (lb[wi] & 0x0F0F0F0Fu);
+                const uint32_t ha = hi ? (hq[wi] & 0x30303030u) : ((hq[wi] << 4) & 0x30303030u);
+                const uint32_t hbq = hi ? ((hq[wi] >> 2) & 0x30303030u) : ((hq[wi] << 2) & 0x30303030u);
+                const uint32_t wa = na | ha, wb = nb | hbq;
+                // scale index: 16 elements per scale -> word wi covers elements 4wi..4wi+3 -> scale (4wi)/16 = wi/4
+                const float sa = dsc[wi >> 2], sb = dsc[2 + (wi >> 2)];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    qa[4 * h + i] = sa * (byte_to_float(wa, i) - 32.0f);
+                    qb[4 * h + i] = sb * (byte_to_float(wb, i) - 32.0f);
+                }
+            }
+            store_chunk(srow, r, c, qa);
+            store_chunk(srow, r, c + 4, qb);
+        }
+    }
+};
+template <> struct RawK64<QT_Q8_0> {
+    uint4 q0, q1, q2, q3; uint32_t d2;
+    __device__ __forceinline__ void load(const QMat& W, int64_t row, int kb) {
+        const uint8_t* q = W.p0 + (size_t)row * W.K + (size_t)kb * 64;
+        q0 = ldg_stream(q); q1 = ldg_stream(q + 16); q2 = ldg_stream(q + 32); q3 = ldg_stream(q + 48);
+        d2 = __ldg(reinterpret_cast<const uint32_t*>(W.p1 + ((size_t)row * (W.K >> 5) + 2 * kb) * 2));
+    }
+    __device__ __forceinline__ void expand(unsigned char* srow, int r, int) const {
+        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&d2));
+        const uint32_t w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float dd = c < 4 ? d.x : d.y;
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t u = w[2 * c + h] ^ 0x80808080u;          // int8 -> biased uint8
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[4 * h + i] = (byte_to_float(u, i) - 128.0f) * dd;
+            }
+            store_chunk(srow, r, c, v);
+        }
+    }
+};
+// generic (test-only formats F32 / F16): plain loads at expand time
+template <int TYPE> struct RawK64 {
+    const QMat* W; int64_t row;
+    __device__ __forceinline__ void load(const QMat& w, int64_t r, int) { W = &w; row = r; }
+    __device__ __forceinline__ void expand(unsigned char* srow, int r, int kb) const {
+        float v[64];
+        dequant_k64(*W, row, kb, v);
+#pragma unroll
+        for (int c = 0; c < 8; c++) store_chunk(srow, r, c, v + 8 * c);
+    }
+};
+
+template <int TYPE>
 __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const PrefillGemmArgs a) {
     extern __shared__ unsigned char pg_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -205,30 +372,22 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
             const int m0 = (tile % m_tiles) * PG_BM, n0 = (tile / m_tiles) * PG_BN;
             const int64_t row = (int64_t)n0 + r;
             const bool row_ok = row < a.N;
+            RawK64<TYPE> cur, nxt;
+            if (row_ok) cur.load(a.W, row, 0);
             for (int kb = 0; kb < k_blocks; kb++, it++) {
                 const int s = it % PG_STAGES;
-                float w[64];
-                if (row_ok) dequant_k64(a.W, row, kb, w);          // global loads issued before waiting for the slot
-                else {
-#pragma unroll
-                    for (int i = 0; i < 64; i++) w[i] = 0.0f;
-                }
+                if (row_ok && kb + 1 < k_blocks) nxt.load(a.W, row, kb + 1);      // next slice's loads fly while this one is expanded
                 mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
                 unsigned char* srow = smem + s * PG_STAGE_BYTES + PG_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                if (row_ok) cur.expand(srow, r, kb);
+                else {
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint4 v;
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(w[c * 8 + 0], w[c * 8 + 1]);
-                    __nv_bfloat162 p1 = __floats2bfloat162_rn(w[c * 8 + 2], w[c * 8 + 3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(w[c * 8 + 4], w[c * 8 + 5]);
-                    __nv_bfloat162 p3 = __floats2bfloat162_rn(w[c * 8 + 6], w[c * 8 + 7]);
-                    v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
-                    v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
-                    *reinterpret_cast<uint4*>(srow + ((c ^ (r & 7)) << 4)) = v;      // SWIZZLE_128B: 16 B chunk index XOR (row % 8)
+                    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(srow + (c << 4)) = make_uint4(0, 0, 0, 0);
                 }
                 fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + s);
+                cur = nxt;
             }
             if (warp >= 4) {
                 // ---- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 of both accumulators ----

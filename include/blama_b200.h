@@ -150,6 +150,8 @@ BLK_API blk_status blk_test_gemv(int32_t device, int32_t type, const void* w_blo
 /* Y[t][r] = W[r,:] . X[t,:] through the prefill tcgen05 GEMM (bf16 operands, f32 accumulate) */
 BLK_API blk_status blk_test_gemm(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k,
                                  const float* x, int64_t n_tok, float* y);
+/* average duration of the prefill GEMM on the given weights with n_tok resident bf16 activations (CUDA events) */
+BLK_API blk_status blk_bench_gemm(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k, int64_t n_tok, int32_t iters, float* avg_ms);
 /* dequantise through the device re-tile + dequant kernels */
 BLK_API blk_status blk_test_dequant(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k, float* out);
 
