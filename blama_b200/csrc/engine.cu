@@ -7,6 +7,7 @@
 #include "gemv_ring.cuh"
 #include "gguf.hpp"
 #include "prefill.hpp"
+#include "prefill_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -525,6 +526,131 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// multi-token prefill (tcgen05 GEMM path)
+// ------------------------------------------------------------------------------------------------------------------
+void ensure_prefill_bufs(blk_ctx* c, int T) {
+    if (T <= c->pf_cap) return;
+    blk_model* m = c->m;
+    const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+    const int cap = std::max(T, std::min(c->n_batch, c->n_ctx));
+    const size_t t = (size_t)cap;
+    c->pf_tokens = dalloc<int32_t>(c, t); c->pf_rope = dalloc<float2>(c, t * (dh / 2));
+    c->pf_x = dalloc<float>(c, t * d);
+    c->pf_xn = dalloc<__nv_bfloat16>(c, t * std::max(d, dq));
+    c->pf_qkv = dalloc<float>(c, t * (dq + 2 * dkv));
+    c->pf_q = dalloc<__half>(c, t * dq);
+    c->pf_ao = dalloc<__nv_bfloat16>(c, t * dq);
+    c->pf_g = dalloc<float>(c, t * ff); c->pf_u = dalloc<float>(c, t * ff);
+    c->pf_h = dalloc<__nv_bfloat16>(c, t * ff);
+    c->pf_logit_rows = 256;
+    c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
+    c->pf_claimed = dalloc<int32_t>(c, t * 10); c->pf_nclaimed = dalloc<int32_t>(c, t);
+    c->pf_gath = dalloc<float>(c, t * 10); c->pf_topi = dalloc<int32_t>(c, t * 10); c->pf_topl = dalloc<float>(c, t * 10);
+    c->pf_cap = cap;
+    BLK_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * (128 + 8) * 2));
+    BLK_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * (64 + 8) * 2));
+}
+
+// top-64 of c->logits through the threshold selector (the row did not come from the decode lm_head mat-vec)
+void topk_of_logits(blk_ctx* c) {
+    blk_model* m = c->m;
+    chunk_max_kernel<<<c->n_chunks, 256, 0, c->stream>>>(c->logits, m->n_vocab, c->chunk_shift, c->chunk_max);
+    BLK_CUDA(cudaGetLastError()); c->launches++;
+    TopkArgs tk{};
+    tk.logits = c->logits; tk.n = m->n_vocab; tk.chunk_max = c->chunk_max; tk.n_chunks = c->n_chunks;
+    tk.cand_l = c->cand_l; tk.cand_i = c->cand_i; tk.cap = c->cand_cap; tk.count = c->counters + 1; tk.done = c->counters + 2;
+    tk.out_ids = c->top_ids; tk.out_logits = c->top_logits;
+    topk_select_kernel<<<16, 1024, 0, c->stream>>>(tk);
+    BLK_CUDA(cudaGetLastError()); c->launches++;
+    BLK_CUDA(cudaMemcpyAsync(c->h_top_ids, c->top_ids, TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+}
+
+// One causal prefill of n tokens at positions n_past.. .  verify != nullptr: logits of EVERY position go through the
+// per-row top-10 + claimed-id gather (never stored beyond a 256-row chunk); otherwise only the last position's logits are
+// produced (decode mat-vec on the last row).
+struct VerifyIo { const int32_t* claimed; const int32_t* n_claimed; float* gathered; blk_token_data* top; };
+
+void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* verify, int verify_row0) {
+    blk_model* m = c->m;
+    const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff, V = m->n_vocab;
+    ensure_prefill_bufs(c, n);
+    cudaStream_t st = c->stream;
+    BLK_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    embed_kernel<<<n, 256, 0, st>>>(m->tok_embd, c->pf_tokens, c->d_pos, c->pf_x, c->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
+    BLK_CUDA(cudaGetLastError()); c->launches++;
+    const long long ldq = dq + 2 * dkv;
+    for (int l = 0; l < m->n_layer; l++) {
+        const LayerWeights& L = m->layers[l];
+        rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(prefill_gemm(L.wq, c->pf_xn, n, c->pf_qkv, ldq, L.bq, 0, st));
+        BLK_CUDA(prefill_gemm(L.wk, c->pf_xn, n, c->pf_qkv + dq, ldq, L.bk, 0, st));
+        BLK_CUDA(prefill_gemm(L.wv, c->pf_xn, n, c->pf_qkv + dq + dkv, ldq, L.bv, 0, st));
+        QkvPostArgs qa{};
+        qa.qkv = c->pf_qkv; qa.ld = ldq; qa.rope_cs = c->pf_rope; qa.pos0 = c->d_pos; qa.q_out = c->pf_q;
+        qa.k_pool = c->k_pool[l]; qa.v_pool = c->v_pool[l]; qa.page_table = c->page_table;
+        qa.dq = dq; qa.dkv = dkv; qa.d_head = dh; qa.neox = m->neox ? 1 : 0;
+        qkv_post_kernel<<<n, 256, 0, st>>>(qa);
+        BLK_CUDA(cudaGetLastError());
+        PrefillAttnArgs pa{};
+        pa.q = c->pf_q; pa.k_pool = c->k_pool[l]; pa.v_pool = c->v_pool[l]; pa.page_table = c->page_table; pa.pos0 = c->d_pos;
+        pa.out = c->pf_ao; pa.T = n; pa.n_head = m->n_head; pa.n_head_kv = m->n_head_kv; pa.kv_dim = dkv; pa.scale = 1.0f / sqrtf((float)dh);
+        const dim3 agrid((n + 63) / 64, m->n_head);
+        if (dh == 128) prefill_attn_kernel<128><<<agrid, 128, 3 * 64 * (128 + 8) * 2, st>>>(pa);
+        else prefill_attn_kernel<64><<<agrid, 128, 3 * 64 * (64 + 8) * 2, st>>>(pa);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st));
+        rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(prefill_gemm(L.gate, c->pf_xn, n, c->pf_g, ff, nullptr, 0, st));
+        BLK_CUDA(prefill_gemm(L.up, c->pf_xn, n, c->pf_u, ff, nullptr, 0, st));
+        const size_t nh = (size_t)n * ff;
+        swiglu_bf16_kernel<<<(unsigned)((nh / 4 + 255) / 256), 256, 0, st>>>(c->pf_g, c->pf_u, nh, c->pf_h);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st));
+        c->launches += 12;
+    }
+    BLK_CUDA(launch_pdl(advance_pos_kernel, dim3(1), dim3(32), 0, st, c->d_pos, n));
+    c->launches++;
+    if (verify) {
+        BLK_CUDA(cudaMemcpyAsync(c->pf_claimed, verify->claimed + (size_t)verify_row0 * 10, (size_t)n * 10 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        BLK_CUDA(cudaMemcpyAsync(c->pf_nclaimed, verify->n_claimed + verify_row0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn);
+        BLK_CUDA(cudaGetLastError()); c->launches++;
+        for (int r0 = 0; r0 < n; r0 += c->pf_logit_rows) {
+            const int rows = std::min(c->pf_logit_rows, n - r0);
+            BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st));
+            RowTopkArgs ta{};
+            ta.logits = c->pf_logits; ta.ld = V; ta.n_vocab = V; ta.row0 = r0;
+            ta.claimed = c->pf_claimed; ta.n_claimed = c->pf_nclaimed; ta.gathered = c->pf_gath;
+            ta.top_ids = verify->top ? c->pf_topi : nullptr; ta.top_logits = c->pf_topl;
+            row_topk_gather_kernel<<<rows, 256, 0, st>>>(ta);
+            BLK_CUDA(cudaGetLastError()); c->launches += 2;
+            if (r0 + rows == n)     // keep the last position's full row for top-k / gather / sampling after the fill
+                BLK_CUDA(cudaMemcpyAsync(c->logits, c->pf_logits + (size_t)(rows - 1) * V, (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        BLK_CUDA(cudaMemcpyAsync(verify->gathered + (size_t)verify_row0 * 10, c->pf_gath, (size_t)n * 10 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        topk_of_logits(c);
+        BLK_CUDA(cudaStreamSynchronize(st));
+        if (verify->top) {
+            std::vector<int32_t> ti((size_t)n * 10); std::vector<float> tl((size_t)n * 10);
+            BLK_CUDA(cudaMemcpy(ti.data(), c->pf_topi, ti.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            BLK_CUDA(cudaMemcpy(tl.data(), c->pf_topl, tl.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < ti.size(); i++) { verify->top[(size_t)verify_row0 * 10 + i].token = ti[i]; verify->top[(size_t)verify_row0 * 10 + i].logit = tl[i]; }
+        }
+    } else {
+        // only the last position's distribution is needed (llama_get_logits_ith(-1)): decode mat-vec on the last row
+        GemvArgs a{};
+        a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = V / 2; a.out = c->logits;
+        matvec<EPI_STORE>(c, a, c->pf_x + (size_t)(n - 1) * d, m->out_norm, c->act_d, "gemv_lm_head");
+        topk_of_logits(c);
+    }
+    c->n_past += n;
+    c->have_logits = true;
+}
+
 void build_graphs(blk_ctx* c) {
     for (int which = 0; which < 3; which++) {
         const bool head = (which != 1);
@@ -571,6 +697,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         ensure_kernel_attrs(m->device);
         c->n_ctx = n_ctx > 0 ? n_ctx : m->n_ctx_train;
         c->n_batch = n_batch > 0 ? n_batch : 2048;
+        { const char* e = getenv("BLK_PREFILL_MIN"); if (e) c->prefill_min = std::max(2, atoi(e)); }
         BLK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         BLK_CUDA(cudaEventCreate(&c->ev0)); BLK_CUDA(cudaEventCreate(&c->ev1));
         BLK_CUDA(cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
@@ -673,6 +800,10 @@ extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
         BLK_CUDA(cudaSetDevice(c->m->device));
         if (c->n_past + n > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
         for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= c->m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
+        if (n >= c->prefill_min) {
+            for (int off = 0; off < n; off += c->n_batch) prefill_chunk(c, tokens + off, std::min(c->n_batch, n - off), nullptr, 0);
+            return;
+        }
         for (int i = 0; i < n; i++) step(c, tokens[i], i == n - 1);
     });
 }
@@ -747,6 +878,11 @@ extern "C" blk_status blk_verify_prefill(blk_ctx* c, const int32_t* tokens, int3
         BLK_CUDA(cudaSetDevice(c->m->device));
         if (c->n_past + n > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
         for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= c->m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
+        if (c->verify_mode == 0 && n >= c->prefill_min) {
+            VerifyIo io{claimed, n_claimed, gathered, top};
+            for (int off = 0; off < n; off += c->n_batch) prefill_chunk(c, tokens + off, std::min(c->n_batch, n - off), &io, off);
+            return;
+        }
         // sequential form of the context fill: one batch-1 decode per response token (Session.cpp:235-241), logits gathered
         // on the device at the claimed ids.  Bit-identical to what blk_decode_topk produced for the prover.
         for (int i = 0; i < n; i++) {

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/blama_b200.h"
+#include <cuda_bf16.h>
 #include "decode_kernels.cuh"
 
 namespace blk {
@@ -103,6 +104,14 @@ struct blk_ctx {
     // per-kernel event timing of one eagerly launched step (blk_profile_step)
     bool profiling = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
+    // multi-token prefill workspaces (allocated on first use, sized for pf_cap tokens)
+    int pf_cap = 0, pf_logit_rows = 0;
+    int32_t* pf_tokens = nullptr; float2* pf_rope = nullptr;
+    float* pf_x = nullptr; __nv_bfloat16* pf_xn = nullptr; float* pf_qkv = nullptr; __half* pf_q = nullptr;
+    __nv_bfloat16* pf_ao = nullptr; float* pf_g = nullptr; float* pf_u = nullptr; __nv_bfloat16* pf_h = nullptr;
+    float* pf_logits = nullptr;
+    int32_t* pf_claimed = nullptr; int32_t* pf_nclaimed = nullptr; float* pf_gath = nullptr; int32_t* pf_topi = nullptr; float* pf_topl = nullptr;
+    int prefill_min = 32;                  // blk_decode / blk_verify_prefill use the tcgen05 path from this many tokens on
     // scratch for gather / verify
     int32_t* d_ids = nullptr; float* d_gath = nullptr; int ids_cap = 0;
     void* flush_buf = nullptr; size_t flush_bytes = 0;

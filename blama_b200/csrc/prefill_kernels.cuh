@@ -1,0 +1,286 @@
+// prefill_kernels.cuh -- the non-GEMM kernels of the multi-token prefill path (verification context fill / prompt
+// prefill): RMSNorm -> bf16, RoPE + KV-page write, causal flash attention over the paged f16 KV cache (mma.sync f16),
+// SwiGLU, and per-row top-10 + claimed-id gather over vocabulary logits.
+// Arithmetic class: bf16 GEMM operands, f16 attention operands, f32 accumulation everywhere (oracle mode ORC_MODE_BF16 for
+// the GEMMs); tolerances against the reference's int8 path are stated in tests/test_gpu_prefill.py.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "decode_kernels.cuh"
+
+namespace blk {
+
+// ---- RMSNorm * weight -> bf16 (one CTA per token row) -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, int K, float eps,
+                                                          __nv_bfloat16* __restrict__ y) {
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    x += (size_t)row * K; y += (size_t)row * K;
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    double sum = 0.0;
+    for (int i = tid; i < K; i += 256) { const float v = x[i]; sum += (double)__fmul_rn(v, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < 8; i++) tot += red[i];
+        s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(tot / (double)K), eps)));
+    }
+    __syncthreads();
+    const float scale = s_scale;
+    for (int i = tid; i < K; i += 256) y[i] = __float2bfloat16_rn(__fmul_rn(__fmul_rn(x[i], scale), w[i]));
+}
+
+// ---- RoPE on q,k; q -> f16 [T][dq]; k,v -> f16 KV pages (one CTA per token) ---------------------------------------------------
+struct QkvPostArgs {
+    const float* qkv; long long ld;            // [T][dq + 2*dkv] f32 (bias already added by the GEMM)
+    const float2* rope_cs;                     // [T][d_head/2]
+    const int32_t* pos0;                       // device scalar: position of token 0
+    __half* q_out;                             // [T][dq]
+    __half* k_pool; __half* v_pool; const int32_t* page_table;
+    int dq, dkv, d_head, neox;
+};
+__global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const float* row = a.qkv + (size_t)t * a.ld;
+    const float2* cs = a.rope_cs + (size_t)t * (a.d_head / 2);
+    const int pos = a.pos0[0] + t;
+    const size_t base = ((size_t)a.page_table[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * a.dkv;
+    const int hd = a.d_head / 2;
+    // rotary pairs of q and k
+    for (int p = tid; p < (a.dq + a.dkv) / 2; p += 256) {
+        const bool is_k = p >= a.dq / 2;
+        const int pp = is_k ? p - a.dq / 2 : p;
+        const int h = pp / hd, i = pp % hd;
+        const int r0 = a.neox ? h * a.d_head + i : h * a.d_head + 2 * i;
+        const int r1 = a.neox ? r0 + hd : r0 + 1;
+        const float* src = row + (is_k ? a.dq : 0);
+        const float x0 = src[r0], x1 = src[r1];
+        const float2 c = cs[i];
+        const float y0 = x0 * c.x - x1 * c.y, y1 = x0 * c.y + x1 * c.x;
+        if (is_k) { a.k_pool[base + r0] = __float2half_rn(y0); a.k_pool[base + r1] = __float2half_rn(y1); }
+        else { a.q_out[(size_t)t * a.dq + r0] = __float2half_rn(y0); a.q_out[(size_t)t * a.dq + r1] = __float2half_rn(y1); }
+    }
+    for (int i = tid; i < a.dkv; i += 256) a.v_pool[base + i] = __float2half_rn(row[a.dq + a.dkv + i]);
+}
+
+// ---- SwiGLU: h = silu(g) * u -> bf16 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) swiglu_bf16_kernel(const float* __restrict__ g, const float* __restrict__ u, size_t n, __nv_bfloat16* __restrict__ h) {
+    const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 a = *reinterpret_cast<const float4*>(g + i), b = *reinterpret_cast<const float4*>(u + i);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn((a.x / (1.0f + expf(-a.x))) * b.x, (a.y / (1.0f + expf(-a.y))) * b.y);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn((a.z / (1.0f + expf(-a.z))) * b.z, (a.w / (1.0f + expf(-a.w))) * b.w);
+        uint2 o; o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(h + i) = o;
+    } else {
+        for (size_t j = i; j < n; j++) h[j] = __float2bfloat16_rn((g[j] / (1.0f + expf(-g[j]))) * u[j]);
+    }
+}
+
+// ---- causal flash attention over the paged KV cache (mma.sync m16n8k16 f16, f32 accumulate) -------------------------------------
+// grid = (ceil(T/64), n_head); block = 128 (4 warps x 16 query rows).  Keys 0 .. pos0+T-1 (the chunk's own K/V are already
+// in the cache).  Output bf16 [T][n_head*DH].
+struct PrefillAttnArgs {
+    const __half* q; const __half* k_pool; const __half* v_pool; const int32_t* page_table; const int32_t* pos0;
+    __nv_bfloat16* out;
+    int T, n_head, n_head_kv, kv_dim;
+    float scale;
+};
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_f16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+
+template <int DH>
+__global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnArgs a) {
+    constexpr int BQ = 64, BKV = 64, LD = DH + 8;        // padded rows: conflict-free ldmatrix
+    extern __shared__ __align__(16) unsigned char pa_smem[];
+    __half* sQ = reinterpret_cast<__half*>(pa_smem);
+    __half* sK = sQ + BQ * LD;
+    __half* sV = sK + BKV * LD;
+    const int qt = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hk = h / (a.n_head / a.n_head_kv);
+    const int pos0 = a.pos0[0];
+    const int q0 = qt * BQ;
+    const int dq = a.n_head * DH;
+    // Q tile -> smem
+    for (int i = tid; i < BQ * (DH / 8); i += 128) {
+        const int r = i / (DH / 8), c = i % (DH / 8);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + r < a.T) v = *reinterpret_cast<const uint4*>(a.q + (size_t)(q0 + r) * dq + (size_t)h * DH + c * 8);
+        *reinterpret_cast<uint4*>(sQ + r * LD + c * 8) = v;
+    }
+    float o[DH / 8][4];
+#pragma unroll
+    for (int i = 0; i < DH / 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
+    const int g = lane >> 2, t4 = lane & 3;
+    const int qrow0 = q0 + warp * 16 + g;                 // this thread's two query rows: qrow0, qrow0 + 8
+    const int kv_end = min(pos0 + a.T, pos0 + q0 + BQ);  // causal: keys up to the last query of the tile
+    const float sl2 = a.scale * 1.4426950408889634f;
+    for (int k0 = 0; k0 < kv_end; k0 += BKV) {
+        __syncthreads();
+        for (int i = tid; i < BKV * (DH / 8); i += 128) {
+            const int r = i / (DH / 8), c = i % (DH / 8);
+            const int key = k0 + r;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (key < kv_end) {
+                const size_t off = ((size_t)a.page_table[key / KV_PAGE] * KV_PAGE + (key % KV_PAGE)) * a.kv_dim + (size_t)hk * DH + c * 8;
+                kv = *reinterpret_cast<const uint4*>(a.k_pool + off);
+                vv = *reinterpret_cast<const uint4*>(a.v_pool + off);
+            }
+            *reinterpret_cast<uint4*>(sK + r * LD + c * 8) = kv;
+            *reinterpret_cast<uint4*>(sV + r * LD + c * 8) = vv;
+        }
+        __syncthreads();
+        // S = Q K^T for this warp's 16 rows x 64 keys
+        float s[BKV / 8][4];
+#pragma unroll
+        for (int i = 0; i < BKV / 8; i++) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f; }
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; kk++) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(a0, a1, a2, a3, sQ + (warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + kk * 16 + 8 * (lane >> 4));
+#pragma unroll
+            for (int nb = 0; nb < BKV / 16; nb++) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(b0, b1, b2, b3, sK + (nb * 16 + (lane & 7) + 8 * (lane >> 4)) * LD + kk * 16 + 8 * ((lane >> 3) & 1));
+                mma_f16(s[2 * nb], a0, a1, a2, a3, b0, b1);
+                mma_f16(s[2 * nb + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+        // scale, causal mask, online softmax
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < BKV / 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int key = k0 + i * 8 + 2 * t4 + (j & 1);
+                const int qr = qrow0 + 8 * (j >> 1);
+                const bool ok = (key <= pos0 + qr) && (qr < a.T);
+                s[i][j] = ok ? s[i][j] * sl2 : -INFINITY;
+                mx[j >> 1] = fmaxf(mx[j >> 1], s[i][j]);
+            }
+        }
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float mn = fmaxf(m_run[r], mx[r]);
+            corr[r] = (m_run[r] == -INFINITY) ? 0.0f : exp2f(m_run[r] - mn);
+            m_run[r] = mn;
+        }
+        float ls[2] = {0.0f, 0.0f};
+        uint32_t pfrag[BKV / 8][2];
+#pragma unroll
+        for (int i = 0; i < BKV / 8; i++) {
+            float p[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                p[j] = (m_run[j >> 1] == -INFINITY) ? 0.0f : exp2f(s[i][j] - m_run[j >> 1]);
+                ls[j >> 1] += p[j];
+            }
+            pfrag[i][0] = pack_f16x2(p[0], p[1]);
+            pfrag[i][1] = pack_f16x2(p[2], p[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            ls[r] += __shfl_xor_sync(0xffffffffu, ls[r], 1);
+            ls[r] += __shfl_xor_sync(0xffffffffu, ls[r], 2);
+            l_run[r] = l_run[r] * corr[r] + ls[r];
+        }
+#pragma unroll
+        for (int i = 0; i < DH / 8; i++) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+        // O += P V
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; kk++) {
+            const uint32_t a0 = pfrag[2 * kk][0], a1 = pfrag[2 * kk][1], a2 = pfrag[2 * kk + 1][0], a3 = pfrag[2 * kk + 1][1];
+#pragma unroll
+            for (int nb = 0; nb < DH / 16; nb++) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(b0, b1, b2, b3, sV + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + nb * 16 + 8 * (lane >> 4));
+                mma_f16(o[2 * nb], a0, a1, a2, a3, b0, b1);
+                mma_f16(o[2 * nb + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+    }
+    // normalise and store bf16
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int qr = qrow0 + 8 * r;
+        if (qr >= a.T) continue;
+        const float inv = l_run[r] > 0.0f ? 1.0f / l_run[r] : 0.0f;
+        __nv_bfloat16* dst = a.out + (size_t)qr * dq + (size_t)h * DH;
+#pragma unroll
+        for (int i = 0; i < DH / 8; i++) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+            *reinterpret_cast<__nv_bfloat162*>(dst + i * 8 + 2 * t4) = p;
+        }
+    }
+}
+
+// ---- per-row top-10 + gather at claimed ids over a chunk of vocabulary logits (one CTA per row) --------------------------------
+// Session::getLogitsFromCtx(10) / getLogitsFromCtx(TokenDataVector) for every position of the verification fill.
+struct RowTopkArgs {
+    const float* logits; long long ld; int n_vocab; int row0;      // logits of rows row0 .. row0+gridDim.x-1
+    const int32_t* claimed; const int32_t* n_claimed;              // [n][10], [n]  (indexed by absolute row)
+    float* gathered;                                               // [n][10]
+    int32_t* top_ids; float* top_logits;                           // [n][10]
+};
+__global__ void __launch_bounds__(256) row_topk_gather_kernel(const RowTopkArgs a) {
+    const int rl = blockIdx.x, row = a.row0 + rl, tid = threadIdx.x;
+    const float* lg = a.logits + (size_t)rl * a.ld;
+    if (a.claimed && tid < 10) {
+        float v = 0.0f;
+        if (tid < a.n_claimed[row]) { const int id = a.claimed[(size_t)row * 10 + tid]; v = (id >= 0 && id < a.n_vocab) ? lg[id] : -INFINITY; }
+        a.gathered[(size_t)row * 10 + tid] = v;
+    }
+    if (!a.top_ids) return;
+    // thread-local top-10 by insertion, then a block-wide merge through shared memory
+    float bl[10]; int bi[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { bl[i] = -INFINITY; bi[i] = 0x7fffffff; }
+    for (int i = tid; i < a.n_vocab; i += 256) {
+        const float v = lg[i];
+        if (td_before(v, i, bl[9], bi[9])) {
+            bl[9] = v; bi[9] = i;
+#pragma unroll
+            for (int j = 9; j > 0; j--) {
+                if (td_before(bl[j], bi[j], bl[j - 1], bi[j - 1])) { const float tv = bl[j]; bl[j] = bl[j - 1]; bl[j - 1] = tv; const int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti; }
+            }
+        }
+    }
+    __shared__ float key[4096];
+    __shared__ int idx[4096];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { key[tid * 10 + i] = bl[i]; idx[tid * 10 + i] = bi[i]; }
+    for (int i = 2560 + tid; i < 4096; i += 256) { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
+    __syncthreads();
+    bitonic_sort_desc_n<256>(key, idx, 4096);
+    if (tid < 10) { a.top_ids[(size_t)row * 10 + tid] = idx[tid]; a.top_logits[(size_t)row * 10 + tid] = key[tid]; }
+}
+
+// per-chunk maxima of a logits row (feeds topk_select_kernel when the row was not produced by the decode lm_head mat-vec)
+__global__ void __launch_bounds__(256) chunk_max_kernel(const float* __restrict__ logits, int n, int chunk_shift, int* chunk_max) {
+    const int c = blockIdx.x, begin = c << chunk_shift, end = min(n, begin + (1 << chunk_shift));
+    float m = -INFINITY;
+    for (int i = begin + threadIdx.x; i < end; i += 256) m = fmaxf(m, logits[i]);
+    m = warp_max(m);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int i = 1; i < 8; i++) m = fmaxf(m, red[i]); chunk_max[c] = float_order_key(m); }
+}
+
+} // namespace blk
