@@ -266,14 +266,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         inst.start_session(seed=1, sequential_verify=args.sequential_verify)
         inst.set_initial_prompt(prompt[:32])
         t0 = time.perf_counter()
-        out, out_n = inst.fill_ctx(vt_l, vtop_l)
-        metrics = [host_api.lc_compare(vtop_l[i], out[i][: out_n[i]]) for i in range(len(vt_l))]
-        score = host_api.lc_score(metrics[: len(vt)])
+        score = inst.verify(vt_l, vtop_l)          # fillCtx + LogitComparer over every position, in C++ (Server::verify)
         dt = time.perf_counter() - t0
         inst.stop_session()
         t_v = max_over_ranks(dt)
         verify = {"tokens": int(args.verify), "tok_s": sum_over_ranks(float(args.verify)) / t_v, "ms": t_v * 1e3,
-                  "score_first_pass": score, "mode": "batched prefill" if not args.sequential_verify else "sequential decode"}
+                  "score": score, "mode": "batched prefill" if not args.sequential_verify else "sequential decode"}
 
     if rank != 0:
         return

@@ -61,6 +61,7 @@ SYMBOLS = {
     "blk_ctx_kernel_launches": (_i64, [_vp]),
     "blk_flush_l2": (_i32, [_vp]),
     "blk_profile_step": (_i32, [_vp, _i32, C.c_char_p, _i32]),
+    "blk_profile_verify": (_i32, [_vp, _vp, _i32, C.c_char_p, _i32]),
     "blk_bench_kernel": (_i32, [_vp, _i32, _i32, _f32p, C.POINTER(C.c_int64)]),
     "blk_test_gemv": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _vp]),
     "blk_test_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
@@ -224,6 +225,12 @@ class Ctx:
     def profile_step(self, token: int) -> str:
         buf = C.create_string_buffer(8192)
         _check(lib().blk_profile_step(self.h, int(token), buf, 8192))
+        return buf.value.decode()
+
+    def profile_verify(self, tokens: Sequence[int]) -> str:
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        buf = C.create_string_buffer(8192)
+        _check(lib().blk_profile_verify(self.h, _p(t), len(t), buf, 8192))
         return buf.value.decode()
 
     def flush_l2(self):

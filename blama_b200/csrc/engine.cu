@@ -580,20 +580,24 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     BLK_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     embed_kernel<<<n, 256, 0, st>>>(m->tok_embd, c->pf_tokens, c->d_pos, c->pf_x, c->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
     BLK_CUDA(cudaGetLastError()); c->launches++;
+    prof_mark(c, "embed");
     const long long ldq = dq + 2 * dkv;
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
+        prof_mark(c, "rmsnorm_bf16");
         BLK_CUDA(prefill_gemm(L.wq, c->pf_xn, n, c->pf_qkv, ldq, L.bq, 0, st));
         BLK_CUDA(prefill_gemm(L.wk, c->pf_xn, n, c->pf_qkv + dq, ldq, L.bk, 0, st));
         BLK_CUDA(prefill_gemm(L.wv, c->pf_xn, n, c->pf_qkv + dq + dkv, ldq, L.bv, 0, st));
+        prof_mark(c, "gemm_qkv");
         QkvPostArgs qa{};
         qa.qkv = c->pf_qkv; qa.ld = ldq; qa.rope_cs = c->pf_rope; qa.pos0 = c->d_pos; qa.q_out = c->pf_q;
         qa.k_pool = c->k_pool[l]; qa.v_pool = c->v_pool[l]; qa.page_table = c->page_table;
         qa.dq = dq; qa.dkv = dkv; qa.d_head = dh; qa.neox = m->neox ? 1 : 0;
         qkv_post_kernel<<<n, 256, 0, st>>>(qa);
         BLK_CUDA(cudaGetLastError());
+        prof_mark(c, "qkv_post(rope+kv)");
         PrefillAttnArgs pa{};
         pa.q = c->pf_q; pa.k_pool = c->k_pool[l]; pa.v_pool = c->v_pool[l]; pa.page_table = c->page_table; pa.pos0 = c->d_pos;
         pa.out = c->pf_ao; pa.T = n; pa.n_head = m->n_head; pa.n_head_kv = m->n_head_kv; pa.kv_dim = dkv; pa.scale = 1.0f / sqrtf((float)dh);
@@ -601,15 +605,21 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         if (dh == 128) prefill_attn_kernel<128><<<agrid, 128, 3 * 64 * (128 + 8) * 2, st>>>(pa);
         else prefill_attn_kernel<64><<<agrid, 128, 3 * 64 * (64 + 8) * 2, st>>>(pa);
         BLK_CUDA(cudaGetLastError());
+        prof_mark(c, "flash_attn");
         BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st));
+        prof_mark(c, "gemm_wo");
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
+        prof_mark(c, "rmsnorm_bf16");
         BLK_CUDA(prefill_gemm(L.gate, c->pf_xn, n, c->pf_g, ff, nullptr, 0, st));
         BLK_CUDA(prefill_gemm(L.up, c->pf_xn, n, c->pf_u, ff, nullptr, 0, st));
+        prof_mark(c, "gemm_gate_up");
         const size_t nh = (size_t)n * ff;
         swiglu_bf16_kernel<<<(unsigned)((nh / 4 + 255) / 256), 256, 0, st>>>(c->pf_g, c->pf_u, nh, c->pf_h);
         BLK_CUDA(cudaGetLastError());
+        prof_mark(c, "swiglu");
         BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st));
+        prof_mark(c, "gemm_down");
         c->launches += 12;
     }
     BLK_CUDA(launch_pdl(advance_pos_kernel, dim3(1), dim3(32), 0, st, c->d_pos, n));
@@ -622,12 +632,14 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         for (int r0 = 0; r0 < n; r0 += c->pf_logit_rows) {
             const int rows = std::min(c->pf_logit_rows, n - r0);
             BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st));
+            prof_mark(c, "gemm_lm_head");
             RowTopkArgs ta{};
             ta.logits = c->pf_logits; ta.ld = V; ta.n_vocab = V; ta.row0 = r0;
             ta.claimed = c->pf_claimed; ta.n_claimed = c->pf_nclaimed; ta.gathered = c->pf_gath;
             ta.top_ids = verify->top ? c->pf_topi : nullptr; ta.top_logits = c->pf_topl;
             row_topk_gather_kernel<<<rows, 256, 0, st>>>(ta);
             BLK_CUDA(cudaGetLastError()); c->launches += 2;
+            prof_mark(c, "row_top10_gather");
             if (r0 + rows == n)     // keep the last position's full row for top-k / gather / sampling after the fill
                 BLK_CUDA(cudaMemcpyAsync(c->logits, c->pf_logits + (size_t)(rows - 1) * V, (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
@@ -968,6 +980,30 @@ extern "C" blk_status blk_bench_kernel(blk_ctx* c, int32_t which, int32_t iters,
     });
 }
 
+namespace {
+void prof_report(blk_ctx* c, char* report, int32_t cap) {
+    std::map<std::string, std::pair<int, float>> agg;
+    float total = 0.0f;
+    for (size_t i = 1; i < c->prof_marks.size(); i++) {
+        float ms = 0.0f;
+        BLK_CUDA(cudaEventElapsedTime(&ms, c->prof_marks[i - 1].second, c->prof_marks[i].second));
+        auto& a = agg[c->prof_marks[i].first]; a.first++; a.second += ms; total += ms;
+    }
+    for (auto& p : c->prof_marks) cudaEventDestroy(p.second);
+    c->prof_marks.clear();
+    std::string out = "kernel,launches,total_us,avg_us,share\n";
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s,%d,%.1f,%.2f,%.3f\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e3f,
+                 kv.second.second * 1e3f / kv.second.first, kv.second.second / total);
+        out += line;
+    }
+    snprintf(line, sizeof(line), "TOTAL,,%.1f,,1.0\n", total * 1e3f);
+    out += line;
+    snprintf(report, (size_t)cap, "%s", out.c_str());
+}
+} // namespace
+
 extern "C" blk_status blk_profile_step(blk_ctx* c, int32_t token, char* report, int32_t cap) {
     if (!c || !report || cap <= 0) return fail(BLK_ERR_ARG, "blk_profile_step: bad arguments");
     return guarded([&] {
@@ -982,25 +1018,26 @@ extern "C" blk_status blk_profile_step(blk_ctx* c, int32_t token, char* report, 
         c->profiling = false;
         BLK_CUDA(cudaStreamSynchronize(c->stream));
         c->n_past++; c->have_logits = true;
-        std::map<std::string, std::pair<int, float>> agg;
-        float total = 0.0f;
-        for (size_t i = 1; i < c->prof_marks.size(); i++) {
-            float ms = 0.0f;
-            BLK_CUDA(cudaEventElapsedTime(&ms, c->prof_marks[i - 1].second, c->prof_marks[i].second));
-            auto& a = agg[c->prof_marks[i].first]; a.first++; a.second += ms; total += ms;
-        }
-        for (auto& p : c->prof_marks) cudaEventDestroy(p.second);
-        c->prof_marks.clear();
-        std::string out = "kernel,launches,total_us,avg_us,share\n";
-        char line[256];
-        for (auto& kv : agg) {
-            snprintf(line, sizeof(line), "%s,%d,%.1f,%.2f,%.3f\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e3f,
-                     kv.second.second * 1e3f / kv.second.first, kv.second.second / total);
-            out += line;
-        }
-        snprintf(line, sizeof(line), "TOTAL,,%.1f,,1.0\n", total * 1e3f);
-        out += line;
-        snprintf(report, (size_t)cap, "%s", out.c_str());
+        prof_report(c, report, cap);
+    });
+}
+
+extern "C" blk_status blk_profile_verify(blk_ctx* c, const int32_t* tokens, int32_t n, char* report, int32_t cap) {
+    if (!c || !tokens || n <= 0 || !report || cap <= 0) return fail(BLK_ERR_ARG, "blk_profile_verify: bad arguments");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (c->n_past + n > c->n_ctx || n > c->n_batch) throw BlkError(BLK_ERR_CTX_FULL, "context is full / chunk too large");
+        std::vector<int32_t> claimed((size_t)n * 10, 0), ncl((size_t)n, 10);
+        std::vector<float> g((size_t)n * 10);
+        std::vector<blk_token_data> top((size_t)n * 10);
+        VerifyIo io{claimed.data(), ncl.data(), g.data(), top.data()};
+        ensure_prefill_bufs(c, n);
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        c->profiling = true; c->prof_marks.clear();
+        prof_mark(c, "start");
+        prefill_chunk(c, tokens, n, &io, 0);
+        c->profiling = false;
+        prof_report(c, report, cap);
     });
 }
 

@@ -120,6 +120,21 @@ BLK_API int blh_session_fill_ctx(void* i, const int32_t* toks, int n, const blk_
         }
     });
 }
+// Server::verify in one call (reference Server.cpp:127-161 after tokenisation): fillCtx + LogitComparer over every position
+BLK_API int blh_session_verify(void* i, const int32_t* toks, int n, const blk_token_data* claimed /*[n][10]*/, const int32_t* n_claimed, float* score) {
+    return guard([&] {
+        std::vector<TokenPrediction> orig(static_cast<size_t>(n));
+        for (int t = 0; t < n; ++t) { orig[size_t(t)].token = toks[t]; orig[size_t(t)].logits = toVec(claimed + size_t(t) * 10, n_claimed[t]); }
+        auto mine = static_cast<InstanceBox*>(i)->session->fillCtx(orig);
+        MetricsAggregator agg;
+        float s = 0;
+        for (size_t t = 0; t < orig.size(); ++t) {
+            auto m = LogitComparer::compare(orig[t].logits, mine[t].logits);
+            s = agg.pushAndVerify({&m, 1});
+        }
+        *score = s;
+    });
+}
 BLK_API int blh_session_get_state(void* i) { return guard([&] { (void)static_cast<InstanceBox*>(i)->session->getState(); }); }
 BLK_API int blh_session_set_state(void* i) { return guard([&] { (void)static_cast<InstanceBox*>(i)->session->setState({}); }); }
 

@@ -31,6 +31,7 @@ HOST_SYMBOLS = {
     "blh_session_complete": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "blh_session_stream": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "blh_session_fill_ctx": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "blh_session_verify": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.POINTER(_f32)]),
     "blh_session_get_state": (C.c_int, [_vp]),
     "blh_session_set_state": (C.c_int, [_vp]),
     "blh_lc_compare": (None, [_vp, _i32, _vp, _i32, _vp]),
@@ -157,6 +158,17 @@ class Instance:
         out_n = np.zeros(n, dtype=np.int32)
         _check(lib().blh_session_fill_ctx(self.h, _p(t), n, _p(cl), _p(nc), _p(out), _p(out_n)))
         return out, out_n
+
+    def verify(self, tokens: Sequence[int], claimed: np.ndarray, n_claimed: Optional[np.ndarray] = None) -> float:
+        """fillCtx + LogitComparer + MetricsAggregator in C++ (what Server::verify runs); returns the score"""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = len(t)
+        cl = np.ascontiguousarray(claimed).reshape(n, 10)
+        assert cl.dtype == TD_DTYPE
+        nc = np.full(n, 10, dtype=np.int32) if n_claimed is None else np.ascontiguousarray(n_claimed, dtype=np.int32)
+        score = _f32(0)
+        _check(lib().blh_session_verify(self.h, _p(t), n, _p(cl), _p(nc), C.byref(score)))
+        return float(score.value)
 
     def get_state(self):
         _check(lib().blh_session_get_state(self.h))

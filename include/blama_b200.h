@@ -140,6 +140,8 @@ BLK_API blk_status blk_bench_kernel(blk_ctx*, int32_t which, int32_t iters, floa
 /* Decodes `token` with the step's kernels launched eagerly and a CUDA event between every pair of launches (so without
  * the cross-kernel overlap of the graph), and writes a CSV breakdown (kernel, launches, total_us, avg_us, share). */
 BLK_API blk_status blk_profile_step(blk_ctx*, int32_t token, char* report, int32_t cap);
+/* same for one verification prefill of n tokens (event between every kernel of the tcgen05 path) */
+BLK_API blk_status blk_profile_verify(blk_ctx*, const int32_t* tokens, int32_t n, char* report, int32_t cap);
 /* writes >= bytes of device memory to evict L2 between timed iterations */
 BLK_API blk_status blk_flush_l2(blk_ctx*);
 
