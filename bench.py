@@ -165,39 +165,65 @@ def run_reference(args, rank: int, world: int):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU plumbing: requests are partitioned, never sharded -- the only collectives are the barrier and the max / sum of
+# the per-rank timings and token counts (NCCL on GPUs; gloo in the CPU tests)
+# ---------------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, rank: int, world: int, local_rank: int, backend=None):
+        self.rank, self.world, self.local_rank, self.pg, self.device = rank, world, local_rank, None, "cpu"
+        if world > 1 and backend:
+            import torch
+            import torch.distributed as td
+
+            if backend == "nccl":
+                torch.cuda.set_device(local_rank)
+                self.device = f"cuda:{local_rank}"
+                td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            else:
+                td.init_process_group(backend)
+            self.pg = td
+
+    def barrier(self):
+        if self.pg is not None:
+            self.pg.barrier()
+
+    def _reduce(self, x: float, op_name: str) -> float:
+        if self.pg is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=self.device)
+        self.pg.all_reduce(t, op=getattr(self.pg.ReduceOp, op_name))
+        return float(t.item())
+
+    def max(self, x: float) -> float:
+        return self._reduce(x, "MAX")
+
+    def sum(self, x: float) -> float:
+        return self._reduce(x, "SUM")
+
+    def close(self):
+        if self.pg is not None:
+            self.pg.destroy_process_group()
+            self.pg = None
+
+
+def aggregate_throughput(dist: "Dist", units_this_rank: float, seconds_this_rank: float) -> float:
+    """whole-job throughput: units all ranks processed / the slowest rank's time (bench contract)"""
+    return dist.sum(units_this_rank) / dist.max(seconds_this_rank)
+
+
+def request_seed(rank: int, step: int) -> int:
+    """independent requests per rank and step (one replica per GPU, no request is split across GPUs)"""
+    return 1 + rank * 100003 + step
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank: int, world: int, local_rank: int):
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-
-        torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist = dist_mod
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    dist = Dist(rank, world, local_rank, backend="nccl" if world > 1 else None)
+    barrier, max_over_ranks, sum_over_ranks = dist.barrier, dist.max, dist.sum
 
     from blama_b200 import capi, gguf_synth, host_api
 
@@ -209,7 +235,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     inst = host_api.Instance(hm, n_ctx)
     inst.warmup()
     ctx = inst.raw_ctx()
-    prompt = gguf_synth.synth_prompt(args.shape, args.prompt, 1 + rank)
+    prompt = gguf_synth.synth_prompt(args.shape, args.prompt, request_seed(rank, 0))
 
     sampler = ClockSampler(local_rank)
     dev_ms, e2e_s, prompt_ms = [], [], []
@@ -247,22 +273,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     launches = ctx.kernel_launches - (launches0 or 0)
 
     # aggregate: value = tokens all ranks produced / max-over-ranks device time
+    value = aggregate_throughput(dist, float(args.new * args.steps), sum(dev_ms) / 1e3)
+    e2e = aggregate_throughput(dist, float(args.new * args.steps), sum(e2e_s))
     t_dev = max_over_ranks(sum(dev_ms) / 1e3)
-    t_e2e = max_over_ranks(sum(e2e_s))
-    tokens_all = sum_over_ranks(float(args.new * args.steps))
-    value = tokens_all / t_dev
-    e2e = tokens_all / t_e2e
 
     # --- verified tok/s (BASELINE configs[2] shape: re-fill `verify` response tokens, top-10 gather + LogitComparer) -------
     verify = None
     if args.verify > 0:
+        # the prover's side of the round trip (not timed): a real /complete of `verify` tokens with its top-10 per token
         inst.start_session(seed=1)
         inst.set_initial_prompt(prompt[:32])
-        vt, vtop = inst.complete(min(args.verify, 64))
+        vt_l, vtop_l = inst.complete(args.verify)
         inst.stop_session()
-        reps = int(np.ceil(args.verify / max(1, len(vt))))
-        vt_l = np.tile(vt, reps)[: args.verify]
-        vtop_l = np.tile(vtop, (reps, 1))[: args.verify]
         inst.start_session(seed=1, sequential_verify=args.sequential_verify)
         inst.set_initial_prompt(prompt[:32])
         t0 = time.perf_counter()
@@ -270,10 +292,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dt = time.perf_counter() - t0
         inst.stop_session()
         t_v = max_over_ranks(dt)
-        verify = {"tokens": int(args.verify), "tok_s": sum_over_ranks(float(args.verify)) / t_v, "ms": t_v * 1e3,
+        verify = {"tokens": int(len(vt_l)), "tok_s": sum_over_ranks(float(len(vt_l))) / t_v, "ms": t_v * 1e3,
                   "score": score, "mode": "batched prefill" if not args.sequential_verify else "sequential decode"}
 
     if rank != 0:
+        dist.close()
         return
 
     # --- roofline of the dominant kernel, timed alone ------------------------------------------------------------------------
@@ -332,8 +355,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
     print(json.dumps(line), flush=True)
     inst.close(); hm.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    dist.close()
 
 
 def main():

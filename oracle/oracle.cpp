@@ -255,6 +255,16 @@ void quantize_q8_0(const float* x, int64_t k, int8_t* qs, float* dout) {
     }
 }
 
+// ORC_MODE_GGML_ALT: identical integer arithmetic, but the eight fp32 lane sums are added in the opposite order.
+// Exists only to measure how far two faithful implementations of the reference arithmetic drift apart
+// (tests/test_oracle.py::test_summation_order_noise_floor).
+static bool g_alt_order = false;
+inline float lane_sum8(const float* sums, float sumf) {
+    if (g_alt_order) { for (int l = 7; l >= 0; l--) sumf += sums[l]; }
+    else { for (int l = 0; l < 8; l++) sumf += sums[l]; }
+    return sumf;
+}
+
 // ------------------------------------------------------------------------------------------------
 // integer dot products (ggml-cpu-quants.c, generic branch: 8 fp32 partial lanes per row)
 // ------------------------------------------------------------------------------------------------
@@ -281,8 +291,7 @@ float vec_dot_q4_K_q8_K(int64_t k, const uint8_t* w, const int8_t* aq, const flo
         const float dmin = h2f(mh) * ad[i];
         sumf -= dmin * sumi;
     }
-    for (int l = 0; l < 8; l++) sumf += sums[l];
-    return sumf;
+    return lane_sum8(sums, sumf);
 }
 
 float vec_dot_q5_K_q8_K(int64_t k, const uint8_t* w, const int8_t* aq, const float* ad, const int16_t* absum) {
@@ -314,8 +323,7 @@ float vec_dot_q5_K_q8_K(int64_t k, const uint8_t* w, const int8_t* aq, const flo
         const float dmin = h2f(mh) * ad[i];
         sumf -= dmin * sumi;
     }
-    for (int l = 0; l < 8; l++) sumf += sums[l];
-    return sumf;
+    return lane_sum8(sums, sumf);
 }
 
 float vec_dot_q6_K_q8_K(int64_t k, const uint8_t* w, const int8_t* aq, const float* ad) {
@@ -346,8 +354,7 @@ float vec_dot_q6_K_q8_K(int64_t k, const uint8_t* w, const int8_t* aq, const flo
         for (int l = 0; l < 8; l++) sums[l] += d * aux32[l];
     }
     float sumf = 0;
-    for (int l = 0; l < 8; l++) sumf += sums[l];
-    return sumf;
+    return lane_sum8(sums, sumf);
 }
 
 float vec_dot_q8_0_q8_0(int64_t k, const uint8_t* w, const int8_t* aq, const float* ad) {
@@ -504,7 +511,8 @@ namespace {
 void matmul(const orc_ctx* c, const Tensor& W, const float* X, int n_tok, float* Y) {
     const int64_t K = W.ne[0], N = W.ne[1];
     const size_t rb = row_bytes(W.type, K);
-    const int mode = c->mode;
+    const int mode = (c->mode == 3) ? ORC_MODE_GGML : c->mode;
+    g_alt_order = (c->mode == 3);
     const bool kq = (W.type == T_Q4_K || W.type == T_Q5_K || W.type == T_Q6_K);
     if (mode == ORC_MODE_GGML && (kq || W.type == T_Q8_0)) {
         const int64_t nblk = kq ? K / QK_K : K / 32;

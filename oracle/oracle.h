@@ -30,7 +30,8 @@ typedef struct orc_ctx orc_ctx;
  *                      F32  = dequantised weights, f32 activations (ideal);
  *                      BF16 = weights and activations rounded to bf16, f32 accumulate
  *                             (what the tcgen05 prefill GEMM computes). */
-enum { ORC_MODE_GGML = 0, ORC_MODE_F32 = 1, ORC_MODE_BF16 = 2 };
+enum { ORC_MODE_GGML = 0, ORC_MODE_F32 = 1, ORC_MODE_BF16 = 2,
+       ORC_MODE_GGML_ALT = 3 /* GGML arithmetic, fp32 lane sums added in reverse order: noise-floor probe */ };
 
 typedef struct { int32_t token; float logit; } orc_token_data;
 

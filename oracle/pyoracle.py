@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-MODE_GGML, MODE_F32, MODE_BF16 = 0, 1, 2
+MODE_GGML, MODE_F32, MODE_BF16, MODE_GGML_ALT = 0, 1, 2, 3
 
 
 class TokenData(C.Structure):

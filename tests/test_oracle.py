@@ -141,3 +141,25 @@ def test_session_round_trip_same_backend_is_exact(gguf_path, oracle):
         metrics.append(oracle.lc_compare(top[i], out[i][: out_n[i]]))
     assert oracle.lc_score(metrics) == 1.0
     prover.close(); verifier.close(); m.close()
+
+
+def test_summation_order_noise_floor(gguf_path, oracle):
+    """The reference arithmetic is chaotic under fp32 re-ordering: the oracle against ITSELF with the eight fp32 lane sums
+    of every dot product added in the opposite order.  Most steps agree to ~1e-6; now and then one Q8_K / f16 rounding
+    flips and the logits move by ~0.1 from then on.  This is the floor any faithful re-implementation (ggml's own AVX2 /
+    AVX-512 / CUDA builds included) sits on, and what tests/test_gpu_model.py's CLEAN / FLIP tolerances encode."""
+    name = "small-llama-q4km"
+    path = gguf_path(name)
+    m = oracle.Model(path)
+    a, b = oracle.Ctx(m, 128, oracle.MODE_GGML, 2), oracle.Ctx(m, 128, oracle.MODE_GGML_ALT, 2)
+    errs = []
+    for seq in range(8):
+        toks = gs.synth_prompt(name, 8, 300 + seq)
+        a.clear(); b.clear()
+        for t in toks:
+            errs.append(float(np.abs(a.decode([t])[0] - b.decode([t])[0]).max()))
+    errs = np.array(errs)
+    assert errs.max() <= 0.45                       # flipped steps stay inside the quantisation noise
+    assert (errs <= 1e-4).mean() >= 0.3             # ... and a good share of steps is clean
+    print("noise floor: clean fraction", (errs <= 1e-4).mean(), "max", errs.max())
+    a.close(); b.close(); m.close()
