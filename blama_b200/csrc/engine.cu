@@ -587,9 +587,8 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
-        BLK_CUDA(prefill_gemm(L.wq, c->pf_xn, n, c->pf_qkv, ldq, L.bq, 0, st));
-        BLK_CUDA(prefill_gemm(L.wk, c->pf_xn, n, c->pf_qkv + dq, ldq, L.bk, 0, st));
-        BLK_CUDA(prefill_gemm(L.wv, c->pf_xn, n, c->pf_qkv + dq + dkv, ldq, L.bv, 0, st));
+        const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
+        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st));
         prof_mark(c, "gemm_qkv");
         QkvPostArgs qa{};
         qa.qkv = c->pf_qkv; qa.ld = ldq; qa.rope_cs = c->pf_rope; qa.pos0 = c->d_pos; qa.q_out = c->pf_q;
@@ -611,13 +610,8 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
-        BLK_CUDA(prefill_gemm(L.gate, c->pf_xn, n, c->pf_g, ff, nullptr, 0, st));
-        BLK_CUDA(prefill_gemm(L.up, c->pf_xn, n, c->pf_u, ff, nullptr, 0, st));
-        prof_mark(c, "gemm_gate_up");
-        const size_t nh = (size_t)n * ff;
-        swiglu_bf16_kernel<<<(unsigned)((nh / 4 + 255) / 256), 256, 0, st>>>(c->pf_g, c->pf_u, nh, c->pf_h);
-        BLK_CUDA(cudaGetLastError());
-        prof_mark(c, "swiglu");
+        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st));
+        prof_mark(c, "gemm_gate_up_swiglu");
         BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st));
         prof_mark(c, "gemm_down");
         c->launches += 12;

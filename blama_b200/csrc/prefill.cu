@@ -44,41 +44,82 @@ cudaError_t convert_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cuda
     return cudaGetLastError();
 }
 
-cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st) {
+namespace {
+using GemmKernel = void (*)(const CUtensorMap, const PrefillGemmArgs);
+
+GemmKernel pick_kernel(int ta, int tb) {
+#define BLK_K(A, B) if (ta == A && tb == B) return prefill_gemm_kernel<A, B>;
+    BLK_K(QT_Q4_K, QT_Q4_K) BLK_K(QT_Q6_K, QT_Q6_K) BLK_K(QT_Q8_0, QT_Q8_0) BLK_K(QT_Q5_K, QT_Q5_K) BLK_K(QT_F32, QT_F32) BLK_K(QT_F16, QT_F16)
+    BLK_K(QT_Q4_K, QT_Q6_K) BLK_K(QT_Q4_K, QT_Q5_K)
+#undef BLK_K
+    return nullptr;
+}
+
+cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16* X, cudaStream_t st) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
-    if (W.K % PG_BK || T <= 0) return cudaErrorInvalidValue;
+    if (a.K % PG_BK || a.T <= 0 || a.n_tiles <= 0) return cudaErrorInvalidValue;
+    GemmKernel kernel = pick_kernel(ta, tb);
+    if (!kernel) return cudaErrorInvalidValue;
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)W.K, (cuuint64_t)T};
-    const cuuint64_t gstride[1] = {(cuuint64_t)W.K * sizeof(__nv_bfloat16)};
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.T};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.K * sizeof(__nv_bfloat16)};
     const cuuint32_t box[2] = {(cuuint32_t)PG_BK, 128u};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(X), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    void (*kernel)(const CUtensorMap, const PrefillGemmArgs) = nullptr;
-    switch (W.type) {
-        case QT_Q4_K: kernel = prefill_gemm_kernel<QT_Q4_K>; break;
-        case QT_Q5_K: kernel = prefill_gemm_kernel<QT_Q5_K>; break;
-        case QT_Q6_K: kernel = prefill_gemm_kernel<QT_Q6_K>; break;
-        case QT_Q8_0: kernel = prefill_gemm_kernel<QT_Q8_0>; break;
-        case QT_F32: kernel = prefill_gemm_kernel<QT_F32>; break;
-        case QT_F16: kernel = prefill_gemm_kernel<QT_F16>; break;
-        default: return cudaErrorInvalidValue;
-    }
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    PrefillGemmArgs a{};
-    a.W = W; a.bias = bias; a.C = C; a.ldc = ldc; a.T = T; a.N = W.N; a.K = W.K; a.mode = mode;
-    const int tiles = ((T + PG_BM - 1) / PG_BM) * ((W.N + PG_BN - 1) / PG_BN);
+    const int tiles = ((a.T + PG_BM - 1) / PG_BM) * a.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
     kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, a);
     return cudaGetLastError();
+}
+} // namespace
+
+cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st) {
+    PrefillGemmArgs a{};
+    a.nseg = 1; a.seg[0] = {W, bias, 0, 0};
+    a.C = C; a.ldc = ldc; a.T = T; a.K = W.K; a.mode = mode;
+    a.n_tiles = (W.N + PG_BN - 1) / PG_BN;
+    return launch_gemm(a, W.type, W.type, X, st);
+}
+
+cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st) {
+    bool fuse = n_parts >= 2 && n_parts <= 3 && parts[0].W->type == parts[1].W->type;
+    for (int i = 0; i < n_parts && fuse; i++) fuse = (parts[i].col0 % 4 == 0) && parts[i].W->K == parts[0].W->K;
+    if (fuse && n_parts == 3 && !pick_kernel(parts[0].W->type, parts[2].W->type)) fuse = false;
+    if (!fuse) {
+        for (int i = 0; i < n_parts; i++) {
+            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    PrefillGemmArgs a{};
+    a.nseg = n_parts; a.C = C; a.ldc = ldc; a.T = T; a.K = parts[0].W->K; a.mode = PG_STORE;
+    int tile0 = 0;
+    for (int i = 0; i < n_parts; i++) {
+        a.seg[i] = {*parts[i].W, parts[i].bias, parts[i].col0, tile0};
+        tile0 += (parts[i].W->N + PG_BN - 1) / PG_BN;
+    }
+    a.n_tiles = tile0;
+    return launch_gemm(a, parts[0].W->type, n_parts == 3 ? parts[2].W->type : parts[0].W->type, X, st);
+}
+
+cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st) {
+    if (gate.type != up.type || gate.N != up.N || gate.K != up.K || ldh % 8) return cudaErrorInvalidValue;
+    PrefillGemmArgs a{};
+    a.nseg = 2; a.seg[0] = {gate, nullptr, 0, 0}; a.seg[1] = {up, nullptr, 0, 0};
+    a.H = H; a.ldh = ldh; a.T = T; a.K = gate.K; a.mode = PG_SWIGLU;
+    a.n_tiles = (gate.N + 127) / 128;
+    return launch_gemm(a, gate.type, gate.type, X, st);
 }
 
 } // namespace blk

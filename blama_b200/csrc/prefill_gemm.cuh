@@ -30,13 +30,20 @@ constexpr int PG_B_BYTES = PG_BN * PG_BK * 2;             // 32 KB
 constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
 constexpr int PG_SMEM_BYTES = PG_STAGES * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-enum : int { PG_STORE = 0, PG_ACCUM = 1 };
+enum : int { PG_STORE = 0, PG_ACCUM = 1, PG_SWIGLU = 2 };
 
+// Up to three weight matrices share one launch (q | k | v, or gate | up): more tiles per launch = less wave-quantisation
+// loss on 148 SMs.  Segment s covers output columns [col0, col0 + W.N); its tiles are 256 rows of W (the last may be
+// partial).  PG_SWIGLU: seg[0] = gate, seg[1] = up; a tile holds 128 gate rows + the 128 matching up rows and the epilogue
+// writes h = silu(g) * u as bf16.
+struct PgSeg { QMat W; const float* bias; int col0; int tile0; };
 struct PrefillGemmArgs {
-    QMat W;
-    const float* bias;          // optional [N], added in PG_STORE mode
-    float* C; long long ldc;    // f32 output, row stride in elements
-    int T, N, K;
+    PgSeg seg[3];
+    int nseg;
+    float* C; long long ldc;    // f32 output (PG_STORE / PG_ACCUM), row stride in elements
+    __nv_bfloat16* H; long long ldh;   // bf16 output (PG_SWIGLU)
+    int T, K;
+    int n_tiles;                // total column tiles over all segments
     int mode;
 };
 
@@ -130,6 +137,10 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int i) {      // (
     const uint32_t m = __byte_perm(word, 0x4B000000u, 0x7650 + i);          // {byte i, 0x00, 0x00, 0x4B}
     return __uint_as_float(m) - 8388608.0f;
 }
+__device__ __forceinline__ float byte_to_float_off(uint32_t word, int i, float off) {      // (float) byte i of word + 2^23 - off
+    const uint32_t m = __byte_perm(word, 0x4B000000u, 0x7650 + i);
+    return __uint_as_float(m) - off;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);
@@ -221,7 +232,10 @@ template <> struct RawK64<QT_Q6_K> {
         dh = __ldg(reinterpret_cast<const uint16_t*>(W.p3) + (size_t)row * (W.K >> 8) + s);
     }
     __device__ __forceinline__ void expand(unsigned char* srow, int r, int kb) const {
-        const int hi = kb & 1;
+        if (kb & 1) expand_half<1>(srow, r); else expand_half<0>(srow, r);      // compile-time nibble / bit selection
+    }
+    template <int HI>
+    __device__ __forceinline__ void expand_half(unsigned char* srow, int r) const {
         const float d = __half2float(__ushort_as_half(dh));
         float dsc[4];
 #pragma unroll
@@ -229,24 +243,23 @@ template <> struct RawK64<QT_Q6_K> {
         const uint32_t la[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};      // ql[0..31]
         const uint32_t lb[8] = {l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};      // ql[32..63]
         const uint32_t hq[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};      // qh[0..31]
-        // elements 0..31: quarter 2*hi (ql[l], qh bits 4*hi..), elements 32..63: quarter 2*hi+1 (ql[32+l], qh bits 4*hi+2..)
+        // elements 0..31: quarter 2*HI (ql[l], qh bits 4*HI..), elements 32..63: quarter 2*HI+1 (ql[32+l], qh bits 4*HI+2..)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             float qa[8], qb[8];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int wi = 2 * c + h;
-                const uint32_t na = hi ? ((la[wi] >> 4) & 0x0F0F0F0Fu) : (la[wi] & 0x0F0F0F0Fu);
-                const uint32_t nb = hi ? ((lb[wi] >> 4) & 0x0F0F0F0Fu) : (lb[wi] & 0x0F0F0F0Fu);
-                const uint32_t ha = hi ? (hq[wi] & 0x30303030u) : ((hq[wi] << 4) & 0x30303030u);
-                const uint32_t hbq = hi ? ((hq[wi] >> 2) & 0x30303030u) : ((hq[wi] << 2) & 0x30303030u);
+                const uint32_t na = HI ? ((la[wi] >> 4) & 0x0F0F0F0Fu) : (la[wi] & 0x0F0F0F0Fu);
+                const uint32_t nb = HI ? ((lb[wi] >> 4) & 0x0F0F0F0Fu) : (lb[wi] & 0x0F0F0F0Fu);
+                const uint32_t ha = HI ? (hq[wi] & 0x30303030u) : ((hq[wi] << 4) & 0x30303030u);
+                const uint32_t hbq = HI ? ((hq[wi] >> 2) & 0x30303030u) : ((hq[wi] << 2) & 0x30303030u);
                 const uint32_t wa = na | ha, wb = nb | hbq;
-                // scale index: 16 elements per scale -> word wi covers elements 4wi..4wi+3 -> scale (4wi)/16 = wi/4
-                const float sa = dsc[wi >> 2], sb = dsc[2 + (wi >> 2)];
+                const float sa = dsc[wi >> 2], sb = dsc[2 + (wi >> 2)];      // 16 elements per scale
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    qa[4 * h + i] = sa * (byte_to_float(wa, i) - 32.0f);
-                    qb[4 * h + i] = sb * (byte_to_float(wb, i) - 32.0f);
+                    qa[4 * h + i] = sa * byte_to_float_off(wa, i, 8388640.0f);      // (2^23 + q) - (2^23 + 32) = q - 32, exact
+                    qb[4 * h + i] = sb * byte_to_float_off(wb, i, 8388640.0f);
                 }
             }
             store_chunk(srow, r, c, qa);
@@ -272,7 +285,7 @@ template <> struct RawK64<QT_Q8_0> {
             for (int h = 0; h < 2; h++) {
                 const uint32_t u = w[2 * c + h] ^ 0x80808080u;          // int8 -> biased uint8
 #pragma unroll
-                for (int i = 0; i < 4; i++) v[4 * h + i] = (byte_to_float(u, i) - 128.0f) * dd;
+                for (int i = 0; i < 4; i++) v[4 * h + i] = byte_to_float_off(u, i, 8388736.0f) * dd;      // biased byte - 128
             }
             store_chunk(srow, r, c, v);
         }
@@ -290,7 +303,7 @@ template <int TYPE> struct RawK64 {
     }
 };
 
-template <int TYPE>
+template <int TA, int TB>
 __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const PrefillGemmArgs a) {
     extern __shared__ unsigned char pg_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -298,14 +311,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     uint64_t* full = bars;                          // [PG_STAGES]  TMA bytes + 8 producer-warp arrivals
     uint64_t* empty = bars + PG_STAGES;             // [PG_STAGES]  tcgen05.commit
     uint64_t* tmem_full = bars + 2 * PG_STAGES;     // accumulators complete
-    uint64_t* tmem_empty = bars + 2 * PG_STAGES + 1;    // epilogue drained them (4 warps)
+    uint64_t* tmem_empty = bars + 2 * PG_STAGES + 1;    // epilogue drained them (8 warps)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * PG_STAGES + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < PG_STAGES; s++) { mbar_init(full + s, 1 + PG_PRODUCER_THREADS / 32); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, 8);
         mbar_fence_init();
     }
     if (warp == 9) {    // one warp allocates all 512 TMEM columns (two 128 x 256 f32 accumulators)
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = (a.N + PG_BN - 1) / PG_BN;
+    const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = a.n_tiles;
     const int k_blocks = a.K / PG_BK;
     const int total_tiles = m_tiles * n_tiles;
 
@@ -369,58 +382,118 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         const int r = threadIdx.x;                                // B-tile row handled by this thread
         int it = 0, tile_i = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_i++) {
-            const int m0 = (tile % m_tiles) * PG_BM, n0 = (tile / m_tiles) * PG_BN;
-            const int64_t row = (int64_t)n0 + r;
-            const bool row_ok = row < a.N;
-            RawK64<TYPE> cur, nxt;
-            if (row_ok) cur.load(a.W, row, 0);
-            for (int kb = 0; kb < k_blocks; kb++, it++) {
-                const int s = it % PG_STAGES;
-                if (row_ok && kb + 1 < k_blocks) nxt.load(a.W, row, kb + 1);      // next slice's loads fly while this one is expanded
-                mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
-                unsigned char* srow = smem + s * PG_STAGE_BYTES + PG_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-                if (row_ok) cur.expand(srow, r, kb);
-                else {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(srow + (c << 4)) = make_uint4(0, 0, 0, 0);
-                }
-                fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full + s);
-                cur = nxt;
+            const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
+            // which matrix / row this thread dequantises, and where the tile's columns land in the output
+            int si = 0;
+            if (a.mode != PG_SWIGLU) {
+                if (a.nseg > 1 && nt >= a.seg[1].tile0) si = 1;
+                if (a.nseg > 2 && nt >= a.seg[2].tile0) si = 2;
+            } else {
+                si = r >> 7;                                      // rows 0-127: gate, 128-255: up
             }
-            if (warp >= 4) {
-                // ---- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 of both accumulators ----
+            const PgSeg& Sg = a.seg[si];
+            const int n_local0 = (a.mode == PG_SWIGLU) ? nt * 128 : (nt - Sg.tile0) * PG_BN;
+            const int64_t row = (a.mode == PG_SWIGLU) ? (int64_t)n_local0 + (r & 127) : (int64_t)n_local0 + r;
+            const bool row_ok = row < Sg.W.N;
+            auto produce = [&](auto raw_tag) {
+                using Raw = decltype(raw_tag);
+                constexpr bool DEEP = sizeof(Raw) <= 64;           // small raw slices (Q4_K): three in flight; large ones: two
+                Raw cur, nxt, nx2;
+                if (row_ok) { cur.load(Sg.W, row, 0); if (DEEP && k_blocks > 1) nxt.load(Sg.W, row, 1); }
+                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                    const int s = it % PG_STAGES;
+                    if (DEEP) { if (row_ok && kb + 2 < k_blocks) nx2.load(Sg.W, row, kb + 2); }      // loads fly while the current slice is expanded
+                    else { if (row_ok && kb + 1 < k_blocks) nxt.load(Sg.W, row, kb + 1); }
+                    mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
+                    unsigned char* srow = smem + s * PG_STAGE_BYTES + PG_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                    if (row_ok) cur.expand(srow, r, kb);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(srow + (c << 4)) = make_uint4(0, 0, 0, 0);
+                    }
+                    fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full + s);
+                    cur = nxt;
+                    if (DEEP) nxt = nx2;
+                }
+            };
+            if (TA != TB && si == 2) produce(RawK64<TB>{}); else produce(RawK64<TA>{});
+            {
+                // ---- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31; warps 0-3 drain the first accumulator
+                //      (token rows 0-127), warps 4-7 the second (rows 128-255) ----
                 const int q = warp & 3;
                 mbar_wait(tmem_full, tile_i & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int h = 0; h < 2; h++) {
+                // tile-level segment (the producer's `si` is per thread in SwiGLU mode)
+                int ts = 0;
+                if (a.mode != PG_SWIGLU) {
+                    if (a.nseg > 1 && nt >= a.seg[1].tile0) ts = 1;
+                    if (a.nseg > 2 && nt >= a.seg[2].tile0) ts = 2;
+                }
+                const PgSeg& Ts = a.seg[ts];
+                const int tn0 = (a.mode == PG_SWIGLU) ? nt * 128 : (nt - Ts.tile0) * PG_BN;     // first row of W in this tile
+                const int n_valid = Ts.W.N - tn0;                                                 // columns of the tile that exist
+                {
+                    const int h = warp >> 2;
                     const int trow = m0 + h * 128 + q * 32 + lane;
+                    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * PG_BN);
+                    if (a.mode == PG_SWIGLU) {
+#pragma unroll 1
+                        for (int cc = 0; cc < 4; cc++) {
+                            uint32_t g[32], u[32];
+                            tc_ld_32x32b_x32(tbase + cc * 32, g);
+                            tc_ld_32x32b_x32(tbase + 128 + cc * 32, u);
+                            tc_wait_ld();
+                            if (trow < a.T) {
+                                __nv_bfloat16* dst = a.H + (size_t)trow * a.ldh + tn0 + cc * 32;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    if (cc * 32 + j + 7 < n_valid) {
+                                        uint4 o;
+                                        uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                                        for (int e = 0; e < 4; e++) {
+                                            const float g0 = __uint_as_float(g[j + 2 * e]), g1 = __uint_as_float(g[j + 2 * e + 1]);
+                                            op[e] = pack_bf16x2(__fdividef(g0, 1.0f + __expf(-g0)) * __uint_as_float(u[j + 2 * e]),
+                                                                __fdividef(g1, 1.0f + __expf(-g1)) * __uint_as_float(u[j + 2 * e + 1]));
+                                        }
+                                        *reinterpret_cast<uint4*>(dst + j) = o;
+                                    } else {
+                                        for (int e = 0; e < 8; e++) if (cc * 32 + j + e < n_valid) {
+                                            const float gg = __uint_as_float(g[j + e]);
+                                            dst[j + e] = __float2bfloat16_rn((gg / (1.0f + expf(-gg))) * __uint_as_float(u[j + e]));
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    } else {
 #pragma unroll 1
                     for (int cc = 0; cc < PG_BN / 32; cc++) {
                         uint32_t v[32];
-                        tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * PG_BN + cc * 32), v);
+                        tc_ld_32x32b_x32(tbase + cc * 32, v);
                         tc_wait_ld();
-                        if (trow < a.T) {
-                            float* dst = a.C + (size_t)trow * a.ldc + n0 + cc * 32;
+                        if (trow < a.T && cc * 32 < n_valid) {
+                            float* dst = a.C + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
+                            const float* bias = Ts.bias ? Ts.bias + tn0 + cc * 32 : nullptr;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const int n = n0 + cc * 32 + j;
-                                if (n + 3 < a.N) {
+                                if (cc * 32 + j + 3 < n_valid) {
                                     float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                                     if (a.mode == PG_ACCUM) { const float4 c0 = *reinterpret_cast<const float4*>(dst + j); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
-                                    else if (a.bias) { o.x += a.bias[n]; o.y += a.bias[n + 1]; o.z += a.bias[n + 2]; o.w += a.bias[n + 3]; }
+                                    else if (bias) { o.x += bias[j]; o.y += bias[j + 1]; o.z += bias[j + 2]; o.w += bias[j + 3]; }
                                     *reinterpret_cast<float4*>(dst + j) = o;
                                 } else {
-                                    for (int jj = 0; jj < 4; jj++) if (n + jj < a.N) {
+                                    for (int jj = 0; jj < 4; jj++) if (cc * 32 + j + jj < n_valid) {
                                         float o = __uint_as_float(v[j + jj]);
-                                        if (a.mode == PG_ACCUM) o += dst[j + jj]; else if (a.bias) o += a.bias[n + jj];
+                                        if (a.mode == PG_ACCUM) o += dst[j + jj]; else if (bias) o += bias[j + jj];
                                         dst[j + jj] = o;
                                     }
                                 }
                             }
                         }
+                    }
                     }
                 }
                 tc_fence_before();
