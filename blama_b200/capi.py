@@ -59,6 +59,8 @@ SYMBOLS = {
     "blk_timer_start": (_i32, [_vp]),
     "blk_timer_stop": (_i32, [_vp, _f32p]),
     "blk_ctx_kernel_launches": (_i64, [_vp]),
+    "blk_ctx_persistent_decode": (_i32, [_vp]),
+    "blk_debug_trace": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "blk_flush_l2": (_i32, [_vp]),
     "blk_profile_step": (_i32, [_vp, _i32, C.c_char_p, _i32]),
     "blk_profile_verify": (_i32, [_vp, _vp, _i32, C.c_char_p, _i32]),
@@ -235,6 +237,16 @@ class Ctx:
 
     def flush_l2(self):
         _check(lib().blk_flush_l2(self.h))
+
+    @property
+    def persistent_decode(self) -> bool:
+        return bool(lib().blk_ctx_persistent_decode(self.h))
+
+    def debug_trace(self) -> np.ndarray:
+        buf = np.zeros(256 * 1024, dtype=np.int64)
+        n_cta, per = C.c_int32(0), C.c_int32(0)
+        _check(lib().blk_debug_trace(self.h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n_cta), C.byref(per)))
+        return buf[: n_cta.value * per.value].reshape(n_cta.value, per.value)
 
     @property
     def kernel_launches(self) -> int:

@@ -52,19 +52,6 @@ __global__ void retile_q80_kernel(const uint8_t* __restrict__ src, uint8_t* qs, 
 // =================================================================================================================
 // embedding gather (get_rows with dequant) + per-step RoPE table
 // =================================================================================================================
-// rope table: cs[i] = {cos(theta_i), sin(theta_i)}, theta_i = pos * theta_scale^i / freq_factor_i, theta built by
-// repeated multiplication exactly as ggml_rope_cache_init does
-__device__ inline void rope_table_fill(float2* cs, int half_rot, int pos, float theta_scale, const float* freq_factors) {
-    for (int i = threadIdx.x; i < half_rot; i += blockDim.x) {
-        float theta = (float)pos;
-        for (int k = 0; k < i; k++) theta *= theta_scale;
-        const float ff = freq_factors ? freq_factors[i] : 1.0f;
-        const float th = theta / ff;
-        float s, c; sincosf(th, &s, &c);
-        cs[i] = make_float2(c, s);
-    }
-}
-
 // grid = n_tok CTAs.  x[t] = dequant(token_embd[tok[t]]); CTA 0.. also fill the rope table rows for their token
 __global__ void embed_kernel(QMat E, const int32_t* __restrict__ tokens, const int32_t* __restrict__ pos0, float* x,
                              float2* rope_cs, int half_rot, float theta_scale, const float* freq_factors) {
@@ -575,6 +562,7 @@ struct TopkArgs {
     float* cand_l; int* cand_i; int cap;
     unsigned int* count; unsigned int* done;
     int32_t* out_ids; float* out_logits;
+    int32_t* feed_tok;          // optional: receives the arg-max (greedy on-device feedback of the decode loop)
 };
 
 __global__ void __launch_bounds__(1024) topk_select_kernel(const TopkArgs a) {
@@ -643,6 +631,7 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(const TopkArgs a) {
         }
     }
     for (int i = tid; i < TOPK_MAX; i += 1024) { a.out_ids[i] = idx[i]; a.out_logits[i] = key[i]; }
+    if (tid == 0 && a.feed_tok) a.feed_tok[0] = idx[0];
     for (int i = tid; i < a.n_chunks; i += 1024) a.chunk_max[i] = (int)0x80000000;
     if (tid == 0) { *a.count = 0u; *a.done = 0u; }
 }

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <tuple>
 
 using namespace blk;
 
@@ -135,6 +136,107 @@ struct Uploader {
 
 } // namespace
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// persistent decode kernel: plan the stream copy (phases, segments, chunk geometry) from the tensor types
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct MegaHook { int phase, seg, rowmap, ab; };       // where (and how) a GGUF tensor lands in the stream copy
+struct MegaPlan {
+    bool ok = false;
+    std::map<std::string, std::vector<MegaHook>> hooks;
+    std::vector<size_t> seg_off[3];                    // arena offsets per phase / segment
+    size_t arena_bytes = 0;
+};
+
+bool mega_type_ok(int t) { return t == QT_Q4_K || t == QT_Q5_K || t == QT_Q6_K || t == QT_Q8_0; }
+
+// K -> (warps per row pair, lanes per slice, row slices per chunk)
+bool mega_geometry(int K, int& W, int& L, int& rpc) {
+    if (K <= 0 || K % 256) return false;
+    const int halfs = K / 128;
+    W = (halfs + 31) / 32;
+    L = (halfs + W - 1) / W; L += L & 1;
+    rpc = (2 * L <= 32) ? 2 : 1;
+    return W <= MG_WARPS;
+}
+
+MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
+    MegaPlan pl;
+    blk_mega_model& mg = m->mega;
+    { const char* e = getenv("BLK_MEGA"); if (e && e[0] == '0') return pl; }
+    const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff, V = m->n_vocab;
+    if (V % 2 || dq % 256 || d % 256 || ff % 256 || n_sms < m->n_head_kv) return pl;
+    auto ttype = [&](const std::string& n) -> int { const GgufTensor* t = f.find(n); return t ? t->type : -1; };
+    const bool tied = f.find("output.weight") == nullptr;
+    mg.n_cta = n_sms;
+    int64_t rot_acc = 0;
+    int max_items = 1, slot = 0, kmax = 0;
+    bool bad = false;
+    auto add_phase = [&](int layer, int K, int src, std::initializer_list<std::tuple<std::string, int, int, int, int>> segs /*tensor, n_pairs, kind, rowmap, ab*/) {
+        MegaPhase ph{};
+        if (!mega_geometry(K, ph.W, ph.L, ph.rpc)) { bad = true; return; }
+        ph.K = K; ph.src = src; ph.layer = layer; ph.nseg = 0;
+        const int NGtot = n_sms * (MG_WARPS / ph.W);
+        int items = 0;
+        const int pi = (int)mg.phases.size();
+        for (auto& sgd : segs) {
+            const std::string& name = std::get<0>(sgd);
+            const int type = ttype(name);
+            if (!mega_type_ok(type)) { bad = true; return; }
+            const int kind = std::get<2>(sgd);
+            const bool new_seg = !(kind == MK_SWIGLU && std::get<4>(sgd) == 1);     // ffn_up shares the gate segment
+            const int si = new_seg ? ph.nseg : ph.nseg - 1;
+            if (new_seg) {
+                MegaSeg& sg = ph.seg[si];
+                sg.type = type; sg.n_pairs = std::get<1>(sgd); sg.kind = kind;
+                sg.slice_bytes = mg_slice_bytes(type, ph.L / 2);
+                sg.rot = (int)(rot_acc % NGtot); rot_acc += sg.n_pairs;
+                sg.bias = nullptr; sg.base = nullptr;
+                pl.seg_off[si].resize(pi + 1, 0);
+                pl.seg_off[si][pi] = pl.arena_bytes;
+                pl.arena_bytes += (size_t)sg.n_pairs * ph.W * 2 * sg.slice_bytes;
+                pl.arena_bytes = (pl.arena_bytes + 255) & ~size_t(255);
+                items += (sg.n_pairs + NGtot - 1) / NGtot;
+                slot = std::max(slot, sg.slice_bytes * ph.rpc);
+                ph.nseg++;
+            } else if (type != ph.seg[si].type) { bad = true; return; }
+            pl.hooks[name].push_back({pi, si, std::get<3>(sgd), std::get<4>(sgd)});
+        }
+        ph.act_fmt = act_format_for(ph.seg[0].type);
+        for (int s = 1; s < ph.nseg; s++) if (act_format_for(ph.seg[s].type) != ph.act_fmt) bad = true;
+        max_items = std::max(max_items, items);
+        kmax = std::max(kmax, K);
+        mg.phases.push_back(ph);
+    };
+    const int qk_map = m->neox ? 1 : 0;
+    for (int l = 0; l < m->n_layer && !bad; l++) {
+        const std::string p = "blk." + std::to_string(l) + ".";
+        add_phase(l, d, MSRC_X, {{p + "attn_q.weight", dq / 2, MK_Q, qk_map, 0}, {p + "attn_k.weight", dkv / 2, MK_K, qk_map, 0}, {p + "attn_v.weight", dkv / 2, MK_V, 0, 0}});
+        add_phase(l, dq, MSRC_ATTN, {{p + "attn_output.weight", d / 2, MK_RESID, 0, 0}});
+        add_phase(l, d, MSRC_X, {{p + "ffn_gate.weight", ff, MK_SWIGLU, 2, 0}, {p + "ffn_up.weight", ff, MK_SWIGLU, 2, 1}});
+        add_phase(l, ff, MSRC_H, {{p + "ffn_down.weight", d / 2, MK_RESID, 0, 0}});
+    }
+    if (!bad) add_phase(m->n_layer, d, MSRC_X, {{tied ? "token_embd.weight" : "output.weight", V / 2, MK_LOGITS, 0, 0}});
+    if (bad) { mg.phases.clear(); return pl; }
+    const int gq = m->n_head / m->n_head_kv;
+    const int act_q = kmax + kmax / 4;
+    const int act_attn = std::max(gq * dh * 2, gq * MG_PCAP * 4 + MG_THREADS * gq * 4);
+    mg.slot_bytes = (slot + 127) / 128 * 128;
+    mg.max_items = max_items;
+    mg.act_bytes = (std::max(act_q, act_attn) + 127) / 128 * 128;
+    MegaParams probe{}; probe.slot_bytes = mg.slot_bytes; probe.max_items = mg.max_items; probe.act_bytes = mg.act_bytes; probe.d_head = dh;
+    int limit = 0;
+    if (mega_setup(mega_smem_bytes(probe), &limit) != cudaSuccess) {
+        (void)cudaGetLastError();
+        log_msg(1, "persistent decode kernel disabled: needs " + std::to_string(mega_smem_bytes(probe)) + " B of shared memory");
+        mg.phases.clear(); return pl;
+    }
+    pl.ok = true;
+    return pl;
+}
+} // namespace
+
 extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progress_cb cb, void* user) {
     if (blk_init() != BLK_OK) return nullptr;
     if (device < 0 || device >= g_device_count) { fail(BLK_ERR_ARG, "bad device index"); return nullptr; }
@@ -192,10 +294,24 @@ extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progr
         const size_t n_t = f.tensors().size(); size_t done = 0;
         auto progress = [&]() { done++; if (cb && !cb((float)done / (float)n_t, user)) throw BlkError(BLK_ERR_IO, "model load aborted by the progress callback"); };
         auto need = [&](const std::string& n) -> const GgufTensor& { const GgufTensor* t = f.find(n); if (!t) throw BlkError(BLK_ERR_FORMAT, "gguf: missing tensor " + n); return *t; };
+        MegaPlan mplan;        // filled once the hyper-parameters are known (below)
+        // scatter the raw tensor still sitting in the staging buffer into the stream copy of the persistent decode kernel
+        auto mega_scatter = [&](const GgufTensor& t) {
+            if (!mplan.ok) return;
+            auto it = mplan.hooks.find(t.name);
+            if (it == mplan.hooks.end()) return;
+            for (const MegaHook& hk : it->second) {
+                const MegaPhase& ph = m->mega.phases[hk.phase];
+                const MegaSeg& sg = ph.seg[hk.seg];
+                BLK_CUDA(mega_build_stream(up.staging, const_cast<uint8_t*>(sg.base), t.type, (int)t.n_rows(), (int)t.ne[0], ph.W, ph.L / 2, sg.slice_bytes,
+                                           hk.rowmap, m->d_head, hk.ab, up.stream));
+            }
+            BLK_CUDA(cudaStreamSynchronize(up.stream));
+        };
         auto mat = [&](const std::string& n, int K, int N) {
             const GgufTensor& t = need(n);
             if (t.ne[0] != K || t.n_rows() != N) throw BlkError(BLK_ERR_FORMAT, "gguf: unexpected shape for " + n);
-            QMat W = up.upload_matrix(t); progress(); return W;
+            QMat W = up.upload_matrix(t); mega_scatter(t); progress(); return W;
         };
         auto vec = [&](const std::string& n, int len, bool required) -> const float* {
             const GgufTensor* t = f.find(n);
@@ -208,7 +324,23 @@ extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progr
             const GgufTensor& te = need("token_embd.weight");
             if (te.ne[0] != d) throw BlkError(BLK_ERR_FORMAT, "gguf: unexpected shape for token_embd.weight");
             m->n_vocab = (int)te.n_rows();
-            m->tok_embd = up.upload_matrix(te); progress();
+            {   // plan the persistent decode kernel's stream copy (second copy of the weights, laid out per warp chunk)
+                int n_sms = 0;
+                BLK_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+                mplan = mega_plan(m.get(), f, n_sms);
+                if (mplan.ok) {
+                    blk_mega_model& mg = m->mega;
+                    mg.arena_bytes = mplan.arena_bytes;
+                    if (cudaMalloc(&mg.arena, mg.arena_bytes) != cudaSuccess) { (void)cudaGetLastError(); mplan.ok = false; mg.phases.clear(); mg.arena = nullptr; }
+                    else {
+                        m->allocs.push_back(mg.arena);
+                        BLK_CUDA(cudaMemsetAsync(mg.arena, 0, mg.arena_bytes, up.stream));
+                        for (size_t pi = 0; pi < mg.phases.size(); pi++)
+                            for (int s = 0; s < mg.phases[pi].nseg; s++) mg.phases[pi].seg[s].base = mg.arena + mplan.seg_off[s][pi];
+                    }
+                }
+            }
+            m->tok_embd = up.upload_matrix(te); mega_scatter(te); progress();
         }
         m->layers.resize(m->n_layer);
         int64_t wb = 0;
@@ -235,6 +367,31 @@ extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progr
         m->rope_freqs = vec("rope_freqs.weight", m->d_head / 2, false);
         wb += (int64_t)m->output.bytes + 4 * d;
         m->weight_bytes_per_token = wb;
+        if (mplan.ok) {   // norms / biases are known now: finish the phase table, upload it, build the per-warp chunk lists
+            blk_mega_model& mg = m->mega;
+            for (MegaPhase& ph : mg.phases) {
+                if (ph.layer < m->n_layer) {
+                    const LayerWeights& L = m->layers[ph.layer];
+                    if (ph.seg[0].kind == MK_Q) { ph.norm_w = L.attn_norm; ph.seg[0].bias = L.bq; ph.seg[1].bias = L.bk; ph.seg[2].bias = L.bv; }
+                    else if (ph.seg[0].kind == MK_SWIGLU) ph.norm_w = L.ffn_norm;
+                } else ph.norm_w = m->out_norm;
+            }
+            BLK_CUDA(cudaMalloc(&mg.d_phases, mg.phases.size() * sizeof(MegaPhase))); m->allocs.push_back(mg.d_phases);
+            BLK_CUDA(cudaMemcpyAsync(mg.d_phases, mg.phases.data(), mg.phases.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice, up.stream));
+            const int n_w = mg.n_cta * MG_WARPS;
+            BLK_CUDA(cudaMalloc(&mg.d_counts, n_w * sizeof(int))); m->allocs.push_back(mg.d_counts);
+            BLK_CUDA(mega_chunk_lists(mg.d_phases, (int)mg.phases.size(), mg.n_cta, nullptr, 0, mg.d_counts, up.stream));
+            std::vector<int> counts(n_w);
+            BLK_CUDA(cudaMemcpyAsync(counts.data(), mg.d_counts, n_w * sizeof(int), cudaMemcpyDeviceToHost, up.stream));
+            BLK_CUDA(cudaStreamSynchronize(up.stream));
+            mg.list_stride = std::max(1, *std::max_element(counts.begin(), counts.end()));
+            BLK_CUDA(cudaMalloc(&mg.d_list, (size_t)n_w * mg.list_stride * sizeof(uint4))); m->allocs.push_back(mg.d_list);
+            BLK_CUDA(mega_chunk_lists(mg.d_phases, (int)mg.phases.size(), mg.n_cta, mg.d_list, mg.list_stride, mg.d_counts, up.stream));
+            // a step without the lm_head (prompt tokens fed one by one) must not prefetch the head's chunks
+            BLK_CUDA(cudaMalloc(&mg.d_counts_body, n_w * sizeof(int))); m->allocs.push_back(mg.d_counts_body);
+            BLK_CUDA(mega_chunk_lists(mg.d_phases, (int)mg.phases.size() - 1, mg.n_cta, nullptr, 0, mg.d_counts_body, up.stream));
+            mg.ok = true;
+        }
         BLK_CUDA(cudaStreamSynchronize(up.stream));
         if ((int)m->vocab.size() != m->n_vocab) m->vocab.clear();
     });
@@ -419,6 +576,30 @@ void prefetch_after_current(blk_ctx* c, std::initializer_list<const QMat*> mats,
 void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
     blk_model* m = c->m;
     const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+    if (c->mega_on) {
+        // the whole step is one persistent cooperative kernel (mega_decode.cuh) + the top-k selection
+        MegaParams P = c->mega_params;
+        P.with_head = with_head ? 1 : 0; P.advance_pos = 1;
+        if (!with_head) P.chunk_counts = m->mega.d_counts_body;
+        BLK_CUDA(mega_launch(P, c->mega_smem, c->stream));
+        c->launches++;
+        prof_mark(c, "mega_decode");
+        if (with_head) {
+            TopkArgs tk{};
+            tk.logits = c->logits; tk.n = m->n_vocab; tk.chunk_max = c->chunk_max; tk.n_chunks = c->n_chunks;
+            tk.cand_l = c->cand_l; tk.cand_i = c->cand_i; tk.cap = c->cand_cap; tk.count = c->counters + 1; tk.done = c->counters + 2;
+            tk.out_ids = c->top_ids; tk.out_logits = c->top_logits; tk.feed_tok = feedback ? c->d_tok : nullptr;
+            topk_select_kernel<<<16, 1024, 0, c->stream>>>(tk);
+            BLK_CUDA(cudaGetLastError());
+            c->launches++;
+            prof_mark(c, "topk_select");
+            if (!feedback) {
+                BLK_CUDA(cudaMemcpyAsync(c->h_top_ids, c->top_ids, TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+                BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        return;
+    }
     BLK_CUDA(launch_pdl(embed_kernel, dim3(1), dim3(256), 0, c->stream, m->tok_embd, c->d_tok, c->d_pos, c->x, c->rope_cs, dh / 2, m->theta_scale, m->rope_freqs));
     c->launches++;
     prof_mark(c, "embed");
@@ -686,8 +867,11 @@ void step(blk_ctx* c, int32_t tok, bool with_head) {
     c->tok_slot = (c->tok_slot + 1) % blk_ctx::TOK_RING;
     *slot = tok;
     BLK_CUDA(cudaMemcpyAsync(c->d_tok, slot, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    BLK_CUDA(cudaGraphLaunch(with_head ? c->g_full : c->g_body, c->stream));
-    c->launches += with_head ? c->launches_full : c->launches_body;
+    if (c->mega_on) enqueue_step(c, with_head, false);
+    else {
+        BLK_CUDA(cudaGraphLaunch(with_head ? c->g_full : c->g_body, c->stream));
+        c->launches += with_head ? c->launches_full : c->launches_body;
+    }
     c->n_past++;
     c->have_logits = with_head;
 }
@@ -765,14 +949,48 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         c->ids_cap = 4096;
         c->d_ids = dalloc<int32_t>(c.get(), c->ids_cap); c->d_gath = dalloc<float>(c.get(), c->ids_cap);
         if (m->n_vocab % 2) throw BlkError(BLK_ERR_FORMAT, "vocabulary size must be even");
+        if (m->mega.ok) {   // persistent decode kernel: per-context parameters
+            const blk_mega_model& mg = m->mega;
+            MegaParams& P = c->mega_params;
+            P.phases = mg.d_phases; P.n_phases = (int)mg.phases.size(); P.n_layer = m->n_layer;
+            P.chunk_list = mg.d_list; P.chunk_counts = mg.d_counts; P.list_stride = mg.list_stride;
+            P.n_cta = mg.n_cta; P.slot_bytes = mg.slot_bytes; P.max_items = mg.max_items; P.act_bytes = mg.act_bytes;
+            P.tok_embd = m->tok_embd;
+            P.n_embd = d; P.n_head = m->n_head; P.n_head_kv = m->n_head_kv; P.d_head = dh; P.n_ff = ff; P.n_vocab = m->n_vocab; P.neox = m->neox ? 1 : 0;
+            P.eps = m->rms_eps; P.theta_scale = m->theta_scale; P.attn_scale = 1.0f / sqrtf((float)dh); P.rope_freqs = m->rope_freqs;
+            P.tok = c->d_tok; P.pos = c->d_pos;
+            P.x = c->x; P.qbuf = c->qbuf; P.hbuf = c->hbuf; P.attn_out = c->act_q.f32;
+            P.scores = c->scores; P.score_stride = c->n_pages * KV_PAGE;
+            P.max_split = std::max(1, std::min(32, mg.n_cta / m->n_head_kv));
+            P.part_o = dalloc<float>(c.get(), (size_t)m->n_head * dh * P.max_split);
+            __half** kp = dalloc<__half*>(c.get(), m->n_layer); __half** vp = dalloc<__half*>(c.get(), m->n_layer);
+            BLK_CUDA(cudaMemcpy(kp, c->k_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
+            BLK_CUDA(cudaMemcpy(vp, c->v_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
+            P.k_pools = kp; P.v_pools = vp; P.page_table = c->page_table; P.kv_dim = dkv;
+            P.logits = c->logits; P.chunk_max = c->chunk_max; P.chunk_shift = c->chunk_shift;
+            P.sync = dalloc<unsigned int>(c.get(), 4 + m->n_head_kv);
+            BLK_CUDA(cudaMemset(P.sync, 0, (4 + m->n_head_kv) * sizeof(unsigned int)));
+            { const char* tr = getenv("BLK_MEGA_TRACE"); if (tr && tr[0] == '1') { P.trace_cap = 1024; P.trace = dalloc<long long>(c.get(), (size_t)P.n_cta * P.trace_cap); } }
+            c->mega_smem = mega_smem_bytes(P);
+            int limit = 0;
+            c->mega_on = mega_setup(c->mega_smem, &limit) == cudaSuccess;
+            (void)cudaGetLastError();
+        }
         {   // one eager step: loads modules and sets per-function attributes outside of stream capture
             BLK_CUDA(cudaMemsetAsync(c->d_tok, 0, sizeof(int32_t), c->stream));
-            enqueue_step(c.get(), true, false);
-            BLK_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->mega_on) {
+                try { enqueue_step(c.get(), true, false); BLK_CUDA(cudaStreamSynchronize(c->stream)); }
+                catch (const BlkError& err) {
+                    (void)cudaGetLastError();
+                    log_msg(2, std::string("persistent decode kernel unavailable (") + err.what() + "); using the per-op graph");
+                    c->mega_on = false;
+                }
+            }
+            if (!c->mega_on) { enqueue_step(c.get(), true, false); BLK_CUDA(cudaStreamSynchronize(c->stream)); }
             BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, sizeof(int32_t), c->stream));
             c->launches = 0;
         }
-        build_graphs(c.get());
+        if (!c->mega_on) build_graphs(c.get());
         BLK_CUDA(cudaStreamSynchronize(c->stream));
     });
     if (st != BLK_OK) { fail(st == BLK_ERR_OOM ? BLK_ERR_OOM : st, std::string("Failed to create context: ") + g_last_error); return nullptr; }
@@ -783,6 +1001,7 @@ extern "C" int32_t blk_ctx_n_ctx(const blk_ctx* c) { return c->n_ctx; }
 extern "C" int32_t blk_ctx_n_batch(const blk_ctx* c) { return c->n_batch; }
 extern "C" int32_t blk_ctx_n_past(const blk_ctx* c) { return c->n_past; }
 extern "C" int64_t blk_ctx_kernel_launches(const blk_ctx* c) { return c->launches; }
+extern "C" int32_t blk_ctx_persistent_decode(const blk_ctx* c) { return c->mega_on ? 1 : 0; }
 
 extern "C" blk_status blk_ctx_set_verify_mode(blk_ctx* c, int32_t mode) {
     if (!c || mode < 0 || mode > 1) return fail(BLK_ERR_ARG, "blk_ctx_set_verify_mode: bad arguments");
@@ -824,8 +1043,11 @@ extern "C" blk_status blk_decode_loop(blk_ctx* c, int32_t first_token, int32_t n
         BLK_CUDA(cudaStreamSynchronize(c->stream));
         c->h_tok[0] = first_token; c->tok_slot = 1;
         BLK_CUDA(cudaMemcpyAsync(c->d_tok, c->h_tok, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        for (int i = 0; i < n_steps; i++) BLK_CUDA(cudaGraphLaunch(c->g_loop, c->stream));
-        c->launches += c->launches_loop * n_steps;
+        if (c->mega_on) { for (int i = 0; i < n_steps; i++) enqueue_step(c, true, true); }
+        else {
+            for (int i = 0; i < n_steps; i++) BLK_CUDA(cudaGraphLaunch(c->g_loop, c->stream));
+            c->launches += c->launches_loop * n_steps;
+        }
         c->n_past += n_steps;
         BLK_CUDA(cudaMemcpyAsync(c->h_top_ids, c->top_ids, TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1032,6 +1254,19 @@ extern "C" blk_status blk_profile_verify(blk_ctx* c, const int32_t* tokens, int3
         prefill_chunk(c, tokens, n, &io, 0);
         c->profiling = false;
         prof_report(c, report, cap);
+    });
+}
+
+extern "C" blk_status blk_debug_trace(blk_ctx* c, int64_t* out, int32_t cap, int32_t* n_cta, int32_t* per_cta) {
+    if (!c || !out || !n_cta || !per_cta) return fail(BLK_ERR_ARG, "blk_debug_trace: bad arguments");
+    return guarded([&] {
+        if (!c->mega_on || !c->mega_params.trace) throw BlkError(BLK_ERR_ARG, "no trace: set BLK_MEGA_TRACE=1 before creating the context");
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        const size_t n = (size_t)c->mega_params.n_cta * c->mega_params.trace_cap;
+        if ((size_t)cap < n) throw BlkError(BLK_ERR_ARG, "blk_debug_trace: buffer too small");
+        BLK_CUDA(cudaMemcpy(out, c->mega_params.trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        *n_cta = c->mega_params.n_cta; *per_cta = c->mega_params.trace_cap;
     });
 }
 

@@ -12,6 +12,7 @@
 #include "../../include/blama_b200.h"
 #include <cuda_bf16.h>
 #include "decode_kernels.cuh"
+#include "mega_decode.hpp"
 
 namespace blk {
 
@@ -41,8 +42,19 @@ struct LayerWeights {
 
 } // namespace blk
 
+// persistent decode kernel: stream copy of the weights + phase table (mega_decode.cuh)
+struct blk_mega_model {
+    bool ok = false;
+    std::vector<blk::MegaPhase> phases;      // host copy (device pointers inside)
+    blk::MegaPhase* d_phases = nullptr;
+    uint4* d_list = nullptr; int* d_counts = nullptr; int* d_counts_body = nullptr; int list_stride = 0;
+    uint8_t* arena = nullptr; size_t arena_bytes = 0;
+    int n_cta = 0, slot_bytes = 0, max_items = 0, act_bytes = 0;
+};
+
 struct blk_model {
     int device = 0;
+    blk_mega_model mega;
     std::string arch;
     int n_vocab = 0, n_embd = 0, n_layer = 0, n_head = 0, n_head_kv = 0, d_head = 0, n_ff = 0, n_ctx_train = 0, n_rot = 0;
     float rms_eps = 1e-5f, rope_theta = 10000.0f, theta_scale = 1.0f;
@@ -115,5 +127,9 @@ struct blk_ctx {
     // scratch for gather / verify
     int32_t* d_ids = nullptr; float* d_gath = nullptr; int ids_cap = 0;
     void* flush_buf = nullptr; size_t flush_bytes = 0;
+    // persistent decode kernel (one cooperative launch per token instead of the per-op graph)
+    bool mega_on = false;
+    blk::MegaParams mega_params{};
+    size_t mega_smem = 0;
     ~blk_ctx();
 };

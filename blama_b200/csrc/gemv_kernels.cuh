@@ -36,6 +36,19 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// rope table: cs[i] = {cos(theta_i), sin(theta_i)}, theta_i = pos * theta_scale^i / freq_factor_i, theta built by
+// repeated multiplication exactly as ggml_rope_cache_init does
+__device__ inline void rope_table_fill(float2* cs, int half_rot, int pos, float theta_scale, const float* freq_factors) {
+    for (int i = threadIdx.x; i < half_rot; i += blockDim.x) {
+        float theta = (float)pos;
+        for (int k = 0; k < i; k++) theta *= theta_scale;
+        const float ff = freq_factors ? freq_factors[i] : 1.0f;
+        const float th = theta / ff;
+        float s, c; sincosf(th, &s, &c);
+        cs[i] = make_float2(c, s);
+    }
+}
+
 // Programmatic dependent launch (PDL): every kernel of the decode step lets its successor start early
 // (launch_dependents) and only blocks (wait) right before it touches data its predecessor produced.  The mat-vecs
 // issue all their weight loads BEFORE waiting, so HBM keeps streaming across kernel boundaries.

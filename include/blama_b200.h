@@ -131,6 +131,12 @@ BLK_API blk_status blk_timer_start(blk_ctx*);
 BLK_API blk_status blk_timer_stop(blk_ctx*, float* ms);     /* synchronises the stream */
 /* number of kernels this context has launched since creation (graph replays count their kernel nodes) */
 BLK_API int64_t    blk_ctx_kernel_launches(const blk_ctx*);
+/* 1 when batch-1 decode steps of this context run as the single persistent cooperative kernel (mega_decode.cuh), 0 when
+ * they run as the per-operation CUDA graph (weight types or shapes the persistent kernel does not take, or BLK_MEGA=0) */
+BLK_API int32_t    blk_ctx_persistent_decode(const blk_ctx*);
+/* Debug: per-CTA stage-boundary clocks of the last persistent decode step (context created with BLK_MEGA_TRACE=1);
+ * out receives n_cta x per_cta SM-clock samples. */
+BLK_API blk_status blk_debug_trace(blk_ctx*, int64_t* out, int32_t cap, int32_t* n_cta, int32_t* per_cta);
 /* Times ONE kernel of the decode path in isolation, for the roofline line of bench.py: launches it `iters` times back to
  * back, cycling through the layers so consecutive launches stream different weights (working set >> L2), bracketed by
  * CUDA events on the context's stream.  which: 0 = gate/up + SwiGLU mat-vec, 1 = down-proj mat-vec, 2 = QKV mat-vec,

@@ -7,6 +7,7 @@ from blama_b200 import capi, gguf_synth
 shape = sys.argv[1] if len(sys.argv) > 1 else "llama-3.1-8b-q4km"
 path = ensure_model(shape, 0, lambda: None)
 m = capi.Model(path); c = capi.Ctx(m, 1024)
+print("persistent decode kernel:", c.persistent_decode)
 names = ["gate_up", "down", "qkv", "wo", "lm_head"]
 for w, n in enumerate(names):
     ms, b = c.bench_kernel(w, 64 if w < 4 else 16)
