@@ -243,7 +243,7 @@ class Ctx:
         return bool(lib().blk_ctx_persistent_decode(self.h))
 
     def debug_trace(self) -> np.ndarray:
-        buf = np.zeros(256 * 1024, dtype=np.int64)
+        buf = np.zeros(512 * 1024, dtype=np.int64)
         n_cta, per = C.c_int32(0), C.c_int32(0)
         _check(lib().blk_debug_trace(self.h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n_cta), C.byref(per)))
         return buf[: n_cta.value * per.value].reshape(n_cta.value, per.value)

@@ -192,6 +192,7 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
                 sg.type = type; sg.n_pairs = std::get<1>(sgd); sg.kind = kind;
                 sg.slice_bytes = mg_slice_bytes(type, ph.L / 2);
                 sg.rot = (int)(rot_acc % NGtot); rot_acc += sg.n_pairs;
+                sg.slot0 = items;
                 sg.bias = nullptr; sg.base = nullptr;
                 pl.seg_off[si].resize(pi + 1, 0);
                 pl.seg_off[si][pi] = pl.arena_bytes;
@@ -205,6 +206,11 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
         }
         ph.act_fmt = act_format_for(ph.seg[0].type);
         for (int s = 1; s < ph.nseg; s++) if (act_format_for(ph.seg[s].type) != ph.act_fmt) bad = true;
+        ph.items = items;
+        ph.NG = MG_WARPS / ph.W;
+        auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) s++; return (1 << s) == v ? s : -1; };
+        ph.wsh = ilog2(ph.W); ph.ngsh = ilog2(ph.NG);
+        if (src == MSRC_X && K > 2 * MG_WARPS * 256) bad = true;   // RMS-normed source rows: at most 2 blocks of 256 per warp
         max_items = std::max(max_items, items);
         kmax = std::max(kmax, K);
         mg.phases.push_back(ph);
@@ -221,13 +227,20 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
     if (bad) { mg.phases.clear(); return pl; }
     const int gq = m->n_head / m->n_head_kv;
     const int act_q = kmax + kmax / 4;
-    const int act_attn = std::max(gq * dh * 2, gq * MG_PCAP * 4 + MG_THREADS * gq * 4);
     mg.slot_bytes = (slot + 127) / 128 * 128;
     mg.max_items = max_items;
-    mg.act_bytes = (std::max(act_q, act_attn) + 127) / 128 * 128;
-    MegaParams probe{}; probe.slot_bytes = mg.slot_bytes; probe.max_items = mg.max_items; probe.act_bytes = mg.act_bytes; probe.d_head = dh;
+    MegaParams probe{}; probe.slot_bytes = mg.slot_bytes; probe.max_items = mg.max_items; probe.d_head = dh; probe.n_layer = m->n_layer;
     int limit = 0;
-    if (mega_setup(mega_smem_bytes(probe), &limit) != cudaSuccess) {
+    (void)mega_setup(0, &limit); (void)cudaGetLastError();
+    // attention tile: the largest power of two (<= 64 tokens) whose K + V rows fit beside the ring
+    mg.ts_cap = 0;
+    mg.attn_off = (d + d / 4 + 127) / 128 * 128;       // the tiles sit behind the (small) activations of the QKV phase
+    for (int ts = 64; ts >= 8; ts >>= 1) {
+        const int act_attn = mg.attn_off + gq * dh * 2 + gq * ts * 4 + std::max(2 * ts * dh * 2, MG_THREADS * gq * 4);
+        probe.act_bytes = (std::max(act_q, act_attn) + 127) / 128 * 128;
+        if (mega_smem_bytes(probe) <= (size_t)limit) { mg.ts_cap = ts; mg.act_bytes = probe.act_bytes; break; }
+    }
+    if (!mg.ts_cap || mega_setup(mega_smem_bytes(probe), &limit) != cudaSuccess) {
         (void)cudaGetLastError();
         log_msg(1, "persistent decode kernel disabled: needs " + std::to_string(mega_smem_bytes(probe)) + " B of shared memory");
         mg.phases.clear(); return pl;
@@ -954,7 +967,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             MegaParams& P = c->mega_params;
             P.phases = mg.d_phases; P.n_phases = (int)mg.phases.size(); P.n_layer = m->n_layer;
             P.chunk_list = mg.d_list; P.chunk_counts = mg.d_counts; P.list_stride = mg.list_stride;
-            P.n_cta = mg.n_cta; P.slot_bytes = mg.slot_bytes; P.max_items = mg.max_items; P.act_bytes = mg.act_bytes;
+            P.n_cta = mg.n_cta; P.slot_bytes = mg.slot_bytes; P.max_items = mg.max_items; P.act_bytes = mg.act_bytes; P.ts_cap = mg.ts_cap; P.attn_off = mg.attn_off;
             P.tok_embd = m->tok_embd;
             P.n_embd = d; P.n_head = m->n_head; P.n_head_kv = m->n_head_kv; P.d_head = dh; P.n_ff = ff; P.n_vocab = m->n_vocab; P.neox = m->neox ? 1 : 0;
             P.eps = m->rms_eps; P.theta_scale = m->theta_scale; P.attn_scale = 1.0f / sqrtf((float)dh); P.rope_freqs = m->rope_freqs;
@@ -970,7 +983,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             P.logits = c->logits; P.chunk_max = c->chunk_max; P.chunk_shift = c->chunk_shift;
             P.sync = dalloc<unsigned int>(c.get(), 4 + m->n_head_kv);
             BLK_CUDA(cudaMemset(P.sync, 0, (4 + m->n_head_kv) * sizeof(unsigned int)));
-            { const char* tr = getenv("BLK_MEGA_TRACE"); if (tr && tr[0] == '1') { P.trace_cap = 1024; P.trace = dalloc<long long>(c.get(), (size_t)P.n_cta * P.trace_cap); } }
+            { const char* tr = getenv("BLK_MEGA_TRACE"); if (tr && tr[0] == '1') { P.trace_cap = 2048; P.trace = dalloc<long long>(c.get(), (size_t)P.n_cta * P.trace_cap); } }
             c->mega_smem = mega_smem_bytes(P);
             int limit = 0;
             c->mega_on = mega_setup(c->mega_smem, &limit) == cudaSuccess;

@@ -49,7 +49,7 @@ struct blk_mega_model {
     blk::MegaPhase* d_phases = nullptr;
     uint4* d_list = nullptr; int* d_counts = nullptr; int* d_counts_body = nullptr; int list_stride = 0;
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
-    int n_cta = 0, slot_bytes = 0, max_items = 0, act_bytes = 0;
+    int n_cta = 0, slot_bytes = 0, max_items = 0, act_bytes = 0, ts_cap = 0, attn_off = 0;
 };
 
 struct blk_model {

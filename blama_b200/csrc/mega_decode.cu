@@ -6,11 +6,14 @@ namespace blk {
 size_t mega_smem_bytes(const MegaParams& P) {
     size_t b = (size_t)MG_WARPS * MG_SLOTS * P.slot_bytes;
     b += MG_WARPS * MG_SLOTS * 8;
+    b += 2 * sizeof(MegaPhase);
+    b += 2 * (size_t)P.n_layer * sizeof(void*);
     b += (size_t)P.max_items * MG_WARPS * sizeof(float2);
     b += (size_t)(P.d_head / 2) * sizeof(float2);
     b += 8 * MG_WARPS * sizeof(double);
     b += 8 * MG_WARPS * sizeof(float);
     b += 32 * sizeof(float);
+    b += 32 * sizeof(int);
     b += (size_t)P.act_bytes;
     return b;
 }
@@ -23,7 +26,9 @@ cudaError_t mega_setup(size_t smem, int* limit) {
     if (e != cudaSuccess) return e;
     if (limit) *limit = lim;
     if (smem > (size_t)lim) return cudaErrorInvalidValue;
-    return cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(mega_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mega_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 cudaError_t mega_launch(const MegaParams& P, size_t smem, cudaStream_t st) {
@@ -33,7 +38,9 @@ cudaError_t mega_launch(const MegaParams& P, size_t smem, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mega_decode_kernel, P);
+    // GQ = compile-time bound on the query heads per KV head (attention register arrays)
+    if (P.n_head / P.n_head_kv <= 4) return cudaLaunchKernelEx(&cfg, mega_decode_kernel<4>, P);
+    return cudaLaunchKernelEx(&cfg, mega_decode_kernel<8>, P);
 }
 
 cudaError_t mega_chunk_lists(const MegaPhase* d_phases, int n_phases, int n_cta, uint4* list, int list_stride, int* counts, cudaStream_t st) {

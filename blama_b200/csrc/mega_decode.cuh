@@ -39,6 +39,18 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 __device__ __forceinline__ int sext8(uint32_t w, int k) { return (int)(w << (24 - 8 * k)) >> 24; }
 
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+    unsigned int v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // activations of one lane: the 128 int8 values of its half super-block plus their scales / partial sums
 struct LaneAct {
     int q[32];
@@ -143,25 +155,13 @@ __device__ __forceinline__ float mg_dot_q80(const uint4* wb, const LaneAct& A) {
     return v;
 }
 
-// ---- activation quantisation of one 256-element block by one warp, into the swizzled shared-memory layout ---------------
-// Same arithmetic as quantize_256_warp (gemv_kernels.cuh).  The int8 values of half super-block hs live at
-// sq + hs*128, 16-byte chunk c stored at chunk position c ^ (hs & 7): the per-lane register loads (stride 128 B between
-// lanes) are then bank-conflict free.
-template <bool NORM>
-__device__ __forceinline__ void mg_quantize_block(const float* __restrict__ y /*global, block start*/, int fmt, int b,
-                                                  int8_t* sq, float* sd, int16_t* sbs, float scale, const float* __restrict__ w) {
+// ---- activation quantisation of one 256-element block by one warp (8 values per lane, in registers), into the swizzled
+// shared-memory layout.  Same arithmetic as quantize_256_warp (gemv_kernels.cuh).  The int8 values of half super-block hs
+// live at sq + hs*128, 16-byte chunk c stored at chunk position c ^ (hs & 7): the per-lane register loads (stride 128 B
+// between lanes) are then bank-conflict free.
+__device__ __noinline__ void mg_quantize_regs(float4 va, float4 vb, int fmt, int b, int8_t* sq, float* sd, int16_t* sbs) {
     const int lane = threadIdx.x & 31;
-    float v[8];
-    {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(y) + lane * 2), c = __ldcg(reinterpret_cast<const float4*>(y) + lane * 2 + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-        if (NORM) {
-            const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + lane * 2), wc = __ldg(reinterpret_cast<const float4*>(w) + lane * 2 + 1);
-            const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wc.x, wc.y, wc.z, wc.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), ww[i]);
-        }
-    }
+    const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
     int qi[8];
     if (fmt == ACT_Q8_K) {
         float amax = 0.0f; int idx = 0x7fffffff;
@@ -209,6 +209,10 @@ __device__ __forceinline__ void mg_quantize_block(const float* __restrict__ y /*
     pk.y = (uint32_t)(qi[4] & 0xff) | ((uint32_t)(qi[5] & 0xff) << 8) | ((uint32_t)(qi[6] & 0xff) << 16) | ((uint32_t)(qi[7] & 0xff) << 24);
     const int hs = 2 * b + (lane >> 4), c = (lane >> 1) & 7;
     *reinterpret_cast<uint2*>(sq + hs * 128 + ((c ^ (hs & 7)) << 4) + (lane & 1) * 8) = pk;
+}
+struct MgV8 { float4 a, b; };
+__device__ __forceinline__ MgV8 mg_load8(const float* p) {
+    MgV8 r; r.a = __ldcg(reinterpret_cast<const float4*>(p)); r.b = __ldcg(reinterpret_cast<const float4*>(p) + 1); return r;
 }
 
 // ---- stream cursor: the chunk sequence of one warp over the whole token ---------------------------------------------
@@ -287,14 +291,49 @@ __global__ void mg_chunk_list_kernel(const MegaPhase* phases, int n_phases, int 
     counts[id] = n;
 }
 
-// ---- grid barrier ---------------------------------------------------------------------------------------------------
+// ---- grid barrier (arrive / wait split so that work that does not depend on other CTAs sits in between) -----------------
 __device__ __forceinline__ void mg_grid_arrive(unsigned int* bar) {
     __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); atomicAdd(bar, 1u); }
+    if (threadIdx.x == 0) red_release_add(bar, 1u);
 }
 __device__ __forceinline__ void mg_grid_wait(const unsigned int* bar, unsigned int target) {
-    if (threadIdx.x == 0) { while (ld_acquire_u32(bar) < target) { } __threadfence(); }
+    if (threadIdx.x == 0) {
+        while (ld_relaxed_u32(bar) < target) { }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
     __syncthreads();
+}
+
+// ---- shared memory carve-up ------------------------------------------------------------------------------------------
+struct MgSmem {
+    uint64_t* bars; MegaPhase* ph; __half** kp; __half** vp; float2* part; float2* rope; double* redd; float* redf; float* stat; int* misc;
+    unsigned char* act;        // quantised activations of the running phase
+    unsigned char* attn;       // attention tiles (behind the activations of an n_embd-long row, so they can be filled early)
+};
+__device__ __forceinline__ MgSmem mg_carve(const MegaParams& P, unsigned char* smem) {
+    MgSmem s;
+    unsigned char* sp = smem + (size_t)MG_WARPS * MG_SLOTS * P.slot_bytes;
+    s.bars = reinterpret_cast<uint64_t*>(sp); sp += MG_WARPS * MG_SLOTS * 8;
+    s.ph = reinterpret_cast<MegaPhase*>(sp); sp += 2 * sizeof(MegaPhase);
+    s.kp = reinterpret_cast<__half**>(sp); sp += (size_t)P.n_layer * sizeof(__half*);
+    s.vp = reinterpret_cast<__half**>(sp); sp += (size_t)P.n_layer * sizeof(__half*);
+    s.part = reinterpret_cast<float2*>(sp); sp += (size_t)P.max_items * MG_WARPS * sizeof(float2);
+    s.rope = reinterpret_cast<float2*>(sp); sp += (size_t)(P.d_head / 2) * sizeof(float2);
+    s.redd = reinterpret_cast<double*>(sp); sp += 8 * MG_WARPS * sizeof(double);
+    s.redf = reinterpret_cast<float*>(sp); sp += 8 * MG_WARPS * sizeof(float);
+    s.stat = reinterpret_cast<float*>(sp); sp += 32 * sizeof(float);
+    s.misc = reinterpret_cast<int*>(sp); sp += 32 * sizeof(int);
+    s.act = sp;
+    s.attn = sp + P.attn_off;
+    return s;
+}
+
+// ---- optional event trace: thread 0 of every CTA appends (SM clock << 8 | tag); see tools/mega_trace.py --------------------
+__device__ __forceinline__ void mg_tr(const MegaParams& P, const MgSmem& S, int tag) {
+    if (P.trace && threadIdx.x == 0) {
+        const int i = S.misc[16]++;
+        if (i < P.trace_cap) P.trace[(size_t)blockIdx.x * P.trace_cap + i] = (clock64() << 8) | (long long)tag;
+    }
 }
 
 // ---- step 0: embedding row -> x (rows spread over the CTAs) -------------------------------------------------------------
@@ -323,11 +362,14 @@ __device__ __noinline__ void mg_embed(const MegaParams& P) {
 }
 
 // ---- attention of one layer, two grid-synchronised stages ------------------------------------------------------------------
-// CTA c serves KV head c % n_head_kv, context split c / n_head_kv.
+// CTA c serves KV head c % n_head_kv, context split c / n_head_kv.  The K and V rows of the CTA's token slice are copied
+// into shared memory with cp.async BEFORE the grid barrier that opens the layer's QKV phase (only the row of the token being
+// decoded has to wait for that phase), so both stages work out of shared memory.  Every global read on the critical path
+// is issued as one batch of independent loads: a dependent L2 round trip costs ~0.7 us under the weight stream.
 struct MgAttn { int hk, split, n_split, t0, nt; bool on; };
 __device__ __forceinline__ MgAttn mg_attn_setup(const MegaParams& P, int n_kv) {
     MgAttn a;
-    a.n_split = max(1, min(P.max_split, (n_kv + 63) / 64));
+    a.n_split = max(1, min(P.max_split, (n_kv + P.ts_cap - 1) / P.ts_cap));
     a.hk = (int)blockIdx.x % P.n_head_kv; a.split = (int)blockIdx.x / P.n_head_kv;
     a.on = a.split < a.n_split;
     const int per = (n_kv + a.n_split - 1) / a.n_split;
@@ -338,186 +380,272 @@ __device__ __forceinline__ MgAttn mg_attn_setup(const MegaParams& P, int n_kv) {
 __device__ __forceinline__ size_t mg_kv_row(const MegaParams& P, int hk, int t) {
     return ((size_t)P.page_table[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * P.kv_dim + (size_t)hk * P.d_head;
 }
+struct MgAttnSmem { __half* q; float* sc; __half* k; __half* v; float* red; };
+__device__ __forceinline__ MgAttnSmem mg_attn_carve(const MegaParams& P, unsigned char* base) {
+    const int gq = P.n_head / P.n_head_kv;
+    MgAttnSmem s;
+    s.q = reinterpret_cast<__half*>(base);
+    s.sc = reinterpret_cast<float*>(base + (size_t)gq * P.d_head * 2);
+    s.k = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(s.sc) + (size_t)gq * P.ts_cap * 4);
+    s.v = s.k + (size_t)P.ts_cap * P.d_head;
+    s.red = reinterpret_cast<float*>(s.k);          // [token group][gq][dh] partial outputs, once the tiles are dead
+    return s;
+}
+// rows [tile0, tile0 + cn) of the slice, restricted to tokens [t_begin, t_limit) -> shared memory
+template <bool ASYNC>
+__device__ __forceinline__ void mg_attn_load_rows(const MegaParams& P, const MgAttn& a, const __half* pool, __half* dst, int tile0, int cn, int t_begin, int t_limit) {
+    const int dh = P.d_head, csh = dh == 128 ? 4 : 3;               // 16-byte chunks per row: dh / 8
+    for (int idx = threadIdx.x; idx < (cn << csh); idx += MG_THREADS) {
+        const int tl = idx >> csh, c = idx & ((1 << csh) - 1);
+        const int t = a.t0 + tile0 + tl;
+        if (t < t_begin || t >= t_limit) continue;
+        const __half* src = pool + mg_kv_row(P, a.hk, t) + c * 8;
+        if (ASYNC) cp_async16(dst + (size_t)tl * dh + c * 8, src);
+        else *reinterpret_cast<uint4*>(dst + (size_t)tl * dh + c * 8) = __ldcg(reinterpret_cast<const uint4*>(src));
+    }
+}
 
-// stage 1: scaled scores of this CTA's token slice for the gq query heads of its KV head -> global
-__device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int n_kv, unsigned char* s_act) {
+// first tile of K and V of this CTA's slice, except the token being decoded (issued before the QKV phase's barrier)
+__device__ __noinline__ void mg_attn_prefetch(const MegaParams& P, int layer, int n_kv, const MgSmem& S) {
     const MgAttn a = mg_attn_setup(P, n_kv);
     if (!a.on || a.nt == 0) return;
+    const MgAttnSmem s = mg_attn_carve(P, S.attn);
+    const int cn = min(a.nt, P.ts_cap);
+    mg_attn_load_rows<true>(P, a, S.kp[layer], s.k, 0, cn, 0, n_kv - 1);
+    mg_attn_load_rows<true>(P, a, S.vp[layer], s.v, 0, cn, 0, n_kv - 1);
+    cp_async_commit();
+}
+
+// stage 1: scaled scores of this CTA's token slice for the gq query heads of its KV head -> global (+ shared for tile 0)
+template <int GQ>
+__device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int n_kv, const MgSmem& S) {
+    const MgAttn a = mg_attn_setup(P, n_kv);
+    if (!a.on || a.nt == 0) return;
+    const MgAttnSmem s = mg_attn_carve(P, S.attn);
     const int tid = threadIdx.x, dh = P.d_head, gq = P.n_head / P.n_head_kv;
-    __half* sqh = reinterpret_cast<__half*>(s_act);                 // [gq][dh]
-    for (int i = tid; i < gq * dh; i += MG_THREADS) sqh[i] = __float2half_rn(__ldcg(P.qbuf + (size_t)(a.hk * gq) * dh + i));
-    __syncthreads();
-    const __half* kp = P.k_pools[layer];
-    const int qd = tid & 3, QD = dh >> 2;                           // 4 lanes per token, a quarter of the head dim each
-    for (int tl0 = 0; tl0 < a.nt; tl0 += MG_THREADS / 4) {
-        const int tl = tl0 + (tid >> 2);
-        float s[MAX_GQ];
+    // one batch of global reads: the query heads, and (slice holding the new token only) the K / V rows written by this layer's QKV
+    float qv[2] = {0.0f, 0.0f};
 #pragma unroll
-        for (int gI = 0; gI < MAX_GQ; gI++) s[gI] = 0.0f;
-        if (tl < a.nt) {
-            const uint4* kr = reinterpret_cast<const uint4*>(kp + mg_kv_row(P, a.hk, a.t0 + tl) + qd * QD);
-            for (int c = 0; c < QD / 8; c++) {
-                const uint4 kv = __ldcg(kr + c);
+    for (int r = 0; r < 2; r++) { const int i = tid + r * MG_THREADS; if (i < gq * dh) qv[r] = __ldcg(P.qbuf + (size_t)(a.hk * gq) * dh + i); }
+    const int cn0 = min(P.ts_cap, a.nt);
+    const int tl_new = n_kv - 1 - a.t0;                             // local index of the token being decoded
+    uint4 newrow = make_uint4(0, 0, 0, 0);
+    const int cpr = dh >> 3;
+    const bool has_new = tl_new >= 0 && tl_new < cn0 && tid < 2 * cpr;
+    if (has_new) {
+        const __half* pool = tid < cpr ? S.kp[layer] : S.vp[layer];
+        newrow = __ldcg(reinterpret_cast<const uint4*>(pool + mg_kv_row(P, a.hk, n_kv - 1)) + (tid < cpr ? tid : tid - cpr));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) { const int i = tid + r * MG_THREADS; if (i < gq * dh) s.q[i] = __float2half_rn(qv[r]); }
+    if (has_new) *reinterpret_cast<uint4*>((tid < cpr ? s.k : s.v) + (size_t)tl_new * dh + (tid < cpr ? tid : tid - cpr) * 8) = newrow;
+    cp_async_wait_all();
+    const int ld = tid & 7, tl = tid >> 3;                          // 8 lanes per token, dh / 8 dims each
+    const int DL = dh >> 3;
+    for (int c0 = 0; c0 < a.nt; c0 += P.ts_cap) {
+        const int cn = min(P.ts_cap, a.nt - c0);
+        if (c0 > 0) { __syncthreads(); mg_attn_load_rows<false>(P, a, S.kp[layer], s.k, c0, cn, 0, n_kv); }
+        __syncthreads();
+        float sc[GQ];
+#pragma unroll
+        for (int gI = 0; gI < GQ; gI++) sc[gI] = 0.0f;
+        if (tl < cn) {
+            for (int c = 0; c < DL; c += 8) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(s.k + (size_t)tl * dh + ld * DL + c);
                 const __half2* kh = reinterpret_cast<const __half2*>(&kv);
                 float kf[8];
 #pragma unroll
                 for (int i = 0; i < 4; i++) { const float2 f = __half22float2(kh[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
 #pragma unroll
-                for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) {
-                    const __half2* qh = reinterpret_cast<const __half2*>(sqh + gI * dh + qd * QD + c * 8);
+                for (int gI = 0; gI < GQ; gI++) if (gI < gq) {
+                    const uint4 qq = *reinterpret_cast<const uint4*>(s.q + gI * dh + ld * DL + c);
+                    const __half2* qh = reinterpret_cast<const __half2*>(&qq);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(qh[i]); s[gI] += kf[2 * i] * f.x; s[gI] += kf[2 * i + 1] * f.y; }
+                    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(qh[i]); sc[gI] += kf[2 * i] * f.x; sc[gI] += kf[2 * i + 1] * f.y; }
                 }
             }
         }
 #pragma unroll
-        for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) {
-            float v = s[gI];
+        for (int gI = 0; gI < GQ; gI++) if (gI < gq) {
+            float v = sc[gI];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (tl < a.nt && qd == 0) P.scores[(size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + tl] = __fmul_rn(v, P.attn_scale);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v = __fmul_rn(v, P.attn_scale);
+            if (tl < cn && ld == 0) {
+                P.scores[(size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl] = v;
+                if (c0 == 0) s.sc[gI * P.ts_cap + tl] = v;
+            }
         }
     }
 }
 
 // stage 2: soft-max statistics over the whole context (redundantly per CTA), probabilities of the own slice rounded to f16,
 // partial V.p; the last CTA of the KV head to finish sums the split partials in split order.
-__device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv, unsigned char* s_act, float* s_redf, double* s_redd, float* s_stat) {
+template <int GQ>
+__device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv, const MgSmem& S) {
     const MgAttn a = mg_attn_setup(P, n_kv);
     if (!a.on) return;
+    const MgAttnSmem s = mg_attn_carve(P, S.attn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, dh = P.d_head, gq = P.n_head / P.n_head_kv;
-    float* sp_p = reinterpret_cast<float*>(s_act);                           // [gq][MG_PCAP] probabilities (f16-rounded)
-    float* s_red = sp_p + gq * MG_PCAP;                                      // [TG][gq][dh] partial outputs
     const int TG = MG_THREADS / dh;                                          // token groups
-    const int d = tid % dh, tg = tid / dh;
-    float acc[MAX_GQ];
+    const int d = tid & (dh - 1), tg = dh == 128 ? tid >> 7 : tid >> 6;
+    float acc[GQ];
 #pragma unroll
-    for (int gI = 0; gI < MAX_GQ; gI++) acc[gI] = 0.0f;
+    for (int gI = 0; gI < GQ; gI++) acc[gI] = 0.0f;
     if (a.nt > 0) {
-        float M[MAX_GQ], inv[MAX_GQ];
+        // -- row max, then row sum of expf(s - max) in double, over the WHOLE context: warps (g*ng .. g*ng+ng-1) serve head g.
+        //    Up to 8 scores per lane are loaded as ONE batch and kept in registers for both passes. --
+        const int ng = MG_WARPS / gq;
+        const int g_w = min(warp / ng, gq - 1), part = warp - (warp / ng) * ng;
+        const bool w_on = warp / ng < gq;
+        const float* sr = P.scores + (size_t)(a.hk * gq + g_w) * P.score_stride;
+        const int stride = ng * 32;
+        float M = -INFINITY;
+        float sv[8];
+        for (int b0 = 0; b0 < n_kv; b0 += 8 * stride) {
 #pragma unroll
-        for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) {
-            const float* sr = P.scores + (size_t)(a.hk * gq + gI) * P.score_stride;
-            float mx = -INFINITY;
-            for (int t = tid; t < n_kv; t += MG_THREADS) mx = fmaxf(mx, __ldcg(sr + t));
-            mx = warp_max(mx);
-            if (lane == 0) s_redf[gI * MG_WARPS + warp] = mx;
+            for (int i = 0; i < 8; i++) { const int t = b0 + i * stride + part * 32 + lane; sv[i] = (w_on && t < n_kv) ? __ldcg(sr + t) : -INFINITY; }
+#pragma unroll
+            for (int i = 0; i < 8; i++) M = fmaxf(M, sv[i]);
         }
+        M = warp_max(M);
+        if (lane == 0) S.redf[warp] = M;
+        mg_tr(P, S, 17);
         __syncthreads();
+        M = -INFINITY;
+        for (int w = 0; w < ng; w++) M = fmaxf(M, S.redf[g_w * ng + w]);
+        double sum = 0.0;
+        for (int b0 = 0; b0 < n_kv; b0 += 8 * stride) {
+            if (n_kv > 8 * stride) {          // long context: the first pass could not keep the row in registers
 #pragma unroll
-        for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) {
-            float mx = s_redf[gI * MG_WARPS];
-            for (int w = 1; w < MG_WARPS; w++) mx = fmaxf(mx, s_redf[gI * MG_WARPS + w]);
-            M[gI] = mx;
+                for (int i = 0; i < 8; i++) { const int t = b0 + i * stride + part * 32 + lane; sv[i] = (w_on && t < n_kv) ? __ldcg(sr + t) : -INFINITY; }
+            }
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) e[i] = expf(sv[i] - M);             // expf(-inf) = 0 for the padding
+            // ggml sums the row in double; any order gives the same double to ~1e-16, i.e. the same float reciprocal
+            sum += ((double)e[0] + (double)e[1]) + ((double)e[2] + (double)e[3]) + (((double)e[4] + (double)e[5]) + ((double)e[6] + (double)e[7]));
         }
 #pragma unroll
-        for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) {
-            const float* sr = P.scores + (size_t)(a.hk * gq + gI) * P.score_stride;
-            double sum = 0.0;
-            for (int t = tid; t < n_kv; t += MG_THREADS) sum += (double)expf(__ldcg(sr + t) - M[gI]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) s_redd[gI * MG_WARPS + warp] = sum;
-        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) S.redd[warp] = sum;
         __syncthreads();
-#pragma unroll
-        for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) {
-            double sum = 0.0;
-            for (int w = 0; w < MG_WARPS; w++) sum += s_redd[gI * MG_WARPS + w];
-            inv[gI] = (float)(1.0 / sum);
-        }
-        const __half* vp = P.v_pools[layer];
-        for (int c0 = 0; c0 < a.nt; c0 += MG_PCAP) {
-            const int cn = min(MG_PCAP, a.nt - c0);
-            __syncthreads();
-            for (int i = tid; i < gq * cn; i += MG_THREADS) {
-                const int gI = i / cn, tl = i - gI * cn;
-                const float sc = __ldcg(P.scores + (size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl);
-                float m = M[0], iv = inv[0];
-#pragma unroll
-                for (int g2 = 1; g2 < MAX_GQ; g2++) if (g2 == gI) { m = M[g2]; iv = inv[g2]; }
-                sp_p[gI * MG_PCAP + tl] = __half2float(__float2half_rn(__fmul_rn(expf(sc - m), iv)));
+        double tot = 0.0;
+        for (int w = 0; w < ng; w++) tot += S.redd[g_w * ng + w];
+        const float inv = (float)(1.0 / tot);
+        mg_tr(P, S, 13);
+        for (int c0 = 0; c0 < a.nt; c0 += P.ts_cap) {
+            const int cn = min(P.ts_cap, a.nt - c0);
+            if (c0 > 0) { __syncthreads(); mg_attn_load_rows<false>(P, a, S.vp[layer], s.v, c0, cn, 0, n_kv); }
+            // probabilities of this tile: the warps of head g handle head g (they hold its max and 1/sum)
+            if (w_on) for (int tl = part * 32 + lane; tl < cn; tl += stride) {
+                const float scv = (c0 == 0) ? s.sc[g_w * P.ts_cap + tl] : __ldcg(sr + a.t0 + c0 + tl);
+                s.sc[g_w * P.ts_cap + tl] = __half2float(__float2half_rn(__fmul_rn(expf(scv - M), inv)));
             }
             __syncthreads();
             for (int tl = tg; tl < cn; tl += TG) {
-                const float v = __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(vp + mg_kv_row(P, a.hk, a.t0 + c0 + tl) + d))));
+                const float v = __half2float(s.v[(size_t)tl * dh + d]);
 #pragma unroll
-                for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) acc[gI] += sp_p[gI * MG_PCAP + tl] * v;
+                for (int gI = 0; gI < GQ; gI++) if (gI < gq) acc[gI] += s.sc[gI * P.ts_cap + tl] * v;
             }
         }
     }
-    // token groups meet in shared memory, summed in fixed order
+    // token groups meet in shared memory (the tiles are dead), summed in fixed order
     __syncthreads();
+    mg_tr(P, S, 14);
 #pragma unroll
-    for (int gI = 0; gI < MAX_GQ; gI++) if (gI < gq) s_red[(tg * gq + gI) * dh + d] = acc[gI];
+    for (int gI = 0; gI < GQ; gI++) if (gI < gq) s.red[(tg * gq + gI) * dh + d] = acc[gI];
     __syncthreads();
-    for (int e = tid; e < gq * dh; e += MG_THREADS) {
+    const int E = gq * dh, NO = P.n_head * dh;
+    for (int e = tid; e < E; e += MG_THREADS) {
         float o = 0.0f;
-        for (int k = 0; k < TG; k++) o += s_red[k * gq * dh + e];
-        P.part_o[((size_t)(a.hk * gq * dh + e)) * P.max_split + a.split] = o;
+        for (int k = 0; k < TG; k++) o += s.red[k * E + e];
+        P.part_o[(size_t)a.split * NO + a.hk * E + e] = o;
     }
     // the last CTA of this KV head sums the split partials in split order
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         const unsigned int old = atomicAdd(P.sync + 4 + a.hk, 1u);
         const bool last = old == (unsigned int)(a.n_split - 1);
-        s_stat[0] = last ? 1.0f : 0.0f;
-        if (last) P.sync[4 + a.hk] = 0u;
+        if (last) { P.sync[4 + a.hk] = 0u; __threadfence(); }
+        S.misc[8] = last ? 1 : 0;
     }
     __syncthreads();
-    if (s_stat[0] != 0.0f) {
-        __threadfence();
-        for (int e = tid; e < gq * dh; e += MG_THREADS) {
-            const float* pp = P.part_o + ((size_t)(a.hk * gq * dh + e)) * P.max_split;
+    mg_tr(P, S, 15);
+    if (S.misc[8]) {
+        for (int e = tid; e < E; e += MG_THREADS) {
+            const float* pp = P.part_o + a.hk * E + e;
             float o = 0.0f;
-            for (int s = 0; s < a.n_split; s++) o += __ldcg(pp + s);
-            P.attn_out[(size_t)a.hk * gq * dh + e] = o;
+            for (int s0 = 0; s0 < a.n_split; s0 += 8) {        // batches of 8 independent loads, added in split order
+                float pv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) pv[i] = (s0 + i < a.n_split) ? __ldcg(pp + (size_t)(s0 + i) * NO) : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) o += pv[i];
+            }
+            P.attn_out[(size_t)a.hk * E + e] = o;
         }
     }
 }
 
+// ---- warp group bookkeeping without integer divisions ---------------------------------------------------------------------------
+__device__ __forceinline__ void mg_warp_group(const MegaPhase* ph, int warp, int& g_local, int& ws, bool& active) {
+    if (ph->wsh >= 0) { g_local = warp >> ph->wsh; ws = warp & (ph->W - 1); }
+    else { g_local = warp / ph->W; ws = warp - g_local * ph->W; }
+    active = g_local < ph->NG;
+}
+// first pair of group gg in a segment (pairs gg', gg' + NGtot, ... with gg' = (gg + rot) mod NGtot)
+__device__ __forceinline__ int mg_first_pair(const MegaSeg& sg, int gg, int NGtot) { const int v = gg + sg.rot; return v >= NGtot ? v - NGtot : v; }
+
+// row pair e of this CTA in a phase: e -> (warp group, partial-sum slot) -> (segment, pair index)
+__device__ __forceinline__ bool mg_item_of(const MegaPhase* ph, int n_cta, int e, int& gl, int& ks, int& seg, int& p) {
+    const int NG = ph->NG, NGtot = n_cta * NG;
+    if (ph->ngsh >= 0) { gl = e & (NG - 1); ks = e >> ph->ngsh; } else { ks = e / NG; gl = e - ks * NG; }
+    const int gg = (int)blockIdx.x * NG + gl;
+    seg = 0;
+    if (ph->nseg > 1 && ks >= ph->seg[1].slot0) seg = 1;
+    if (ph->nseg > 2 && ks >= ph->seg[2].slot0) seg = 2;
+    const MegaSeg& sg = ph->seg[seg];
+    p = mg_first_pair(sg, gg, NGtot) + (ks - sg.slot0) * NGtot;
+    return p < sg.n_pairs;
+}
+
 // ---- epilogue of a stream phase: combine the K-slice partials of every row pair of this CTA and finish the rows ---------
-__device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* ph, int pos, const float2* s_part, const float2* s_rope) {
+// res: x[r0], x[r1] of the pair of thread tid (residual phases: fetched before the mat-vec, see the kernel)
+__device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* ph, int pos, const MgSmem& S, float2 res, bool have_res) {
     const int tid = threadIdx.x, dh = P.d_head;
-    const MgGroup g = mg_group(ph, P.n_cta, (int)blockIdx.x, 0);
-    for (int e = tid; e < g.NG * P.max_items; e += MG_THREADS) {
-        const int gl = e % g.NG, ks = e / g.NG;
-        const int gg = (int)blockIdx.x * g.NG + gl;
-        int rem = ks, s = 0, vg = 0, n = 0;
-        const MegaSeg* sg = nullptr;
-        for (; s < ph->nseg; s++) {
-            sg = ph->seg + s;
-            vg = (gg + sg->rot) % g.NGtot;
-            n = vg < sg->n_pairs ? (sg->n_pairs - 1 - vg) / g.NGtot + 1 : 0;
-            if (rem < n) break;
-            rem -= n;
-        }
-        if (s >= ph->nseg) continue;
-        const int p = vg + rem * g.NGtot;
+    const int NG = ph->NG, W = ph->W;
+    for (int e = tid; e < NG * ph->items; e += MG_THREADS) {
+        int gl, ks, s, p;
+        if (!mg_item_of(ph, P.n_cta, e, gl, ks, s, p)) continue;
+        const MegaSeg& sg = ph->seg[s];
         float v0 = 0.0f, v1 = 0.0f;
-        for (int w = 0; w < g.W; w++) { const float2 t = s_part[ks * MG_WARPS + gl * g.W + w]; v0 += t.x; v1 += t.y; }
-        const int kind = sg->kind;
+        for (int w = 0; w < W; w++) { const float2 t = S.part[ks * MG_WARPS + gl * W + w]; v0 += t.x; v1 += t.y; }
+        const int kind = sg.kind;
         if (kind == MK_SWIGLU) { P.hbuf[p] = (v0 / (1.0f + expf(-v0))) * v1; continue; }     // ggml_silu_f32 then ggml_mul
         int r0 = 2 * p, r1 = 2 * p + 1;
-        if ((kind == MK_Q || kind == MK_K) && P.neox) { const int hd = dh >> 1; r0 = (p / hd) * dh + (p % hd); r1 = r0 + hd; }
-        if (sg->bias) { v0 += sg->bias[r0]; v1 += sg->bias[r1]; }
-        if (kind == MK_RESID) { P.x[r0] = __ldcg(P.x + r0) + v0; P.x[r1] = __ldcg(P.x + r1) + v1; }
-        else if (kind == MK_LOGITS) {
-            P.logits[r0] = v0; P.logits[r1] = v1;
+        if ((kind == MK_Q || kind == MK_K) && P.neox) { const int hd = dh >> 1; const int hh = dh == 128 ? p >> 6 : p >> 5; r0 = hh * dh + (p & (hd - 1)); r1 = r0 + hd; }
+        if (sg.bias) { v0 += sg.bias[r0]; v1 += sg.bias[r1]; }
+        if (kind == MK_RESID) {
+            if (!(have_res && e == tid)) { res.x = __ldcg(P.x + r0); res.y = __ldcg(P.x + r1); }
+            *reinterpret_cast<float2*>(P.x + r0) = make_float2(res.x + v0, res.y + v1);
+        } else if (kind == MK_LOGITS) {
+            *reinterpret_cast<float2*>(P.logits + r0) = make_float2(v0, v1);
             atomicMax(P.chunk_max + (r0 >> P.chunk_shift), float_order_key(fmaxf(v0, v1)));
         } else {
             if (kind != MK_V) {                                   // rotary embedding on the pair: ggml rope NORM / NEOX
-                const int i = P.neox ? (r0 % dh) : ((r0 % dh) >> 1);
-                const float2 cs = s_rope[i];
+                const int i = P.neox ? (r0 & (dh - 1)) : ((r0 & (dh - 1)) >> 1);
+                const float2 cs = S.rope[i];
                 const float x0 = v0, x1 = v1;
                 v0 = x0 * cs.x - x1 * cs.y;
                 v1 = x0 * cs.y + x1 * cs.x;
             }
             if (kind == MK_Q) { P.qbuf[r0] = v0; P.qbuf[r1] = v1; }
             else {
-                const size_t base = ((size_t)P.page_table[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * P.kv_dim;
-                __half* dst = (kind == MK_K ? P.k_pools : P.v_pools)[ph->layer];
+                const size_t base = ((size_t)S.misc[0] * KV_PAGE + (pos % KV_PAGE)) * P.kv_dim;
+                __half* dst = (kind == MK_K ? S.kp : S.vp)[ph->layer];
                 dst[base + r0] = __float2half_rn(v0);           // ggml_cpy f32 -> f16 into the cache
                 dst[base + r1] = __float2half_rn(v1);
             }
@@ -526,54 +654,73 @@ __device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* p
 }
 
 // ---- prologue of a stream phase: (RMSNorm *) quantise the source vector into shared memory, redundantly per CTA -------------
-__device__ __noinline__ void mg_prologue(const MegaParams& P, const MegaPhase* ph, unsigned char* s_act, double* s_redd) {
+// One warp per 256-element block.  With a norm the row has at most 2 blocks per warp (K <= 8192), loaded ONCE into registers
+// for both the sum of squares and the quantisation; nw: this lane's norm weights, fetched before the grid barrier.
+// Code size matters here (the whole decode loop has to stay resident in the instruction cache): ONE quantiser instance.
+__device__ __forceinline__ float4 mg_norm4(float4 v, float scale, float4 w) {
+    return make_float4(__fmul_rn(__fmul_rn(v.x, scale), w.x), __fmul_rn(__fmul_rn(v.y, scale), w.y), __fmul_rn(__fmul_rn(v.z, scale), w.z), __fmul_rn(__fmul_rn(v.w, scale), w.w));
+}
+__device__ __forceinline__ double mg_sq4(float4 v) {
+    return ((double)__fmul_rn(v.x, v.x) + (double)__fmul_rn(v.y, v.y)) + ((double)__fmul_rn(v.z, v.z) + (double)__fmul_rn(v.w, v.w));
+}
+__device__ __noinline__ void mg_prologue(const MegaParams& P, const MegaPhase* ph, const MgSmem& S, float4 nw0, float4 nw1, float4 nw2, float4 nw3) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = ph->K, fmt = ph->act_fmt;
-    int8_t* sq = reinterpret_cast<int8_t*>(s_act);
-    float* sd = reinterpret_cast<float*>(s_act + K);
-    int16_t* sbs = reinterpret_cast<int16_t*>(s_act + K + (K >> 5) * 4);
-    const float* src = ph->src == MSRC_X ? P.x : (ph->src == MSRC_ATTN ? P.attn_out : P.hbuf);
-    float scale = 1.0f;
+    const int K = ph->K, fmt = ph->act_fmt, nblk = K >> 8;
+    int8_t* sq = reinterpret_cast<int8_t*>(S.act);
+    float* sd = reinterpret_cast<float*>(S.act + K);
+    int16_t* sbs = reinterpret_cast<int16_t*>(S.act + K + (K >> 5) * 4);
+    const float* src = (ph->src == MSRC_X ? P.x : (ph->src == MSRC_ATTN ? P.attn_out : P.hbuf)) + lane * 8;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ph->norm_w) {
-        double sum = 0.0;
-        for (int i = tid; i < (K >> 2); i += MG_THREADS) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + i);
-            sum += (double)__fmul_rn(v.x, v.x); sum += (double)__fmul_rn(v.y, v.y); sum += (double)__fmul_rn(v.z, v.z); sum += (double)__fmul_rn(v.w, v.w);
-        }
+        MgV8 v0, v1; v0.a = v0.b = v1.a = v1.b = z4;
+        const int b0 = warp, b1 = warp + MG_WARPS;
+        if (b0 < nblk) v0 = mg_load8(src + b0 * 256);
+        if (b1 < nblk) v1 = mg_load8(src + b1 * 256);
+        double sum = (mg_sq4(v0.a) + mg_sq4(v0.b)) + (mg_sq4(v1.a) + mg_sq4(v1.b));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) s_redd[warp] = sum;
+        if (lane == 0) S.redd[warp] = sum;
+        mg_tr(P, S, 30);
         __syncthreads();
-        double tot = 0.0;
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int i = 0; i < MG_WARPS; i++) tot += s_redd[i];
+        for (int i = 0; i < MG_WARPS; i++) t4[i & 3] += S.redd[i];
+        const double tot = (t4[0] + t4[1]) + (t4[2] + t4[3]);
         const float mean = (float)(tot / (double)K);
-        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+        mg_tr(P, S, 31);
+#pragma unroll 1
+        for (int r = 0; r < 2; r++) {
+            const int b = r ? b1 : b0;
+            if (b < nblk) mg_quantize_regs(mg_norm4(r ? v1.a : v0.a, scale, r ? nw2 : nw0), mg_norm4(r ? v1.b : v0.b, scale, r ? nw3 : nw1), fmt, b, sq, sd, sbs);
+        }
+    } else {
+        // software pipeline: the loads of the warp's next block are in flight while the current one is quantised
+        MgV8 cur; cur.a = cur.b = z4;
+        if (warp < nblk) cur = mg_load8(src + warp * 256);
+        mg_tr(P, S, 32);
+#pragma unroll 1
+        for (int b = warp; b < nblk; b += MG_WARPS) {
+            MgV8 nxt; nxt.a = nxt.b = z4;
+            if (b + MG_WARPS < nblk) nxt = mg_load8(src + (b + MG_WARPS) * 256);
+            mg_quantize_regs(cur.a, cur.b, fmt, b, sq, sd, sbs);
+            cur = nxt;
+        }
     }
-    for (int b = warp; b < (K >> 8); b += MG_WARPS) {
-        if (ph->norm_w) mg_quantize_block<true>(src + b * 256, fmt, b, sq, sd, sbs, scale, ph->norm_w + b * 256);
-        else mg_quantize_block<false>(src + b * 256, fmt, b, sq, sd, sbs, 1.0f, nullptr);
-    }
+    mg_tr(P, S, 34);
     __syncthreads();
 }
 
 // =================================================================================================================
 // the kernel
 // =================================================================================================================
+template <int GQ>
 __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid_constant__ MegaParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // ---- shared memory carve-up ----
+    const MgSmem S = mg_carve(P, smem);
     unsigned char* ring = smem + (size_t)warp * MG_SLOTS * P.slot_bytes;
-    unsigned char* sp = smem + (size_t)MG_WARPS * MG_SLOTS * P.slot_bytes;
-    uint64_t* my_bar = reinterpret_cast<uint64_t*>(sp) + warp * MG_SLOTS; sp += MG_WARPS * MG_SLOTS * 8;
-    float2* s_part = reinterpret_cast<float2*>(sp); sp += (size_t)P.max_items * MG_WARPS * sizeof(float2);
-    float2* s_rope = reinterpret_cast<float2*>(sp); sp += (size_t)(P.d_head / 2) * sizeof(float2);
-    double* s_redd = reinterpret_cast<double*>(sp); sp += 8 * MG_WARPS * sizeof(double);
-    float* s_redf = reinterpret_cast<float*>(sp); sp += 8 * MG_WARPS * sizeof(float);
-    float* s_stat = reinterpret_cast<float*>(sp); sp += 32 * sizeof(float);
-    unsigned char* s_act = sp;                                      // P.act_bytes: activations | attention scratch
+    uint64_t* my_bar = S.bars + warp * MG_SLOTS;
 
     if (lane == 0) { for (int s = 0; s < MG_SLOTS; s++) mbar_init(my_bar + s, 1); mbar_fence_init(); }
     __syncwarp();
@@ -594,39 +741,77 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             if (p_issued < p_total) p_desc = __ldg(plist + p_issued);
         }
     };
+#pragma unroll 1
     for (int s = 0; s < MG_SLOTS; s++) issue_next();
 
+    // ---- per-token constants into shared memory: phase descriptors 0 / 1, KV pool pointers, the page of this position ----
     const int pos = P.pos[0];
     const int n_kv = pos + 1;
+    auto fetch_phase = [&](int phi) {     // one warp copies descriptor phi into its shared-memory slot (visible after a CTA sync)
+        if (phi < P.n_phases && lane < (int)(sizeof(MegaPhase) / 16))
+            reinterpret_cast<uint4*>(S.ph + (phi & 1))[lane] = __ldg(reinterpret_cast<const uint4*>(P.phases + phi) + lane);
+    };
+    if (warp == 0) fetch_phase(0);
+    if (warp == 1) fetch_phase(1);
+    for (int l = tid; l < P.n_layer; l += MG_THREADS) { S.kp[l] = P.k_pools[l]; S.vp[l] = P.v_pools[l]; }
+    if (tid == 0) { S.misc[0] = P.page_table[pos / KV_PAGE]; S.misc[16] = 0; }
+    __syncthreads();
+
     unsigned int bar_target = 0;
-    // optional per-CTA event trace (SM clock of thread 0 at every stage boundary), see tools/mega_trace.py
-    int tr_i = 0;
-    auto TR = [&]() { if (P.trace && tid == 0) { if (tr_i < P.trace_cap) P.trace[(size_t)blockIdx.x * P.trace_cap + tr_i] = clock64(); tr_i++; } };
-    auto grid_sync = [&]() { mg_grid_arrive(P.sync); bar_target += (unsigned int)P.n_cta; mg_grid_wait(P.sync, bar_target); };
-
-    TR();
+    mg_tr(P, S, 1);
     mg_embed(P);
-    rope_table_fill(s_rope, P.d_head / 2, pos, P.theta_scale, P.rope_freqs);
-    grid_sync();
-    TR();
+    rope_table_fill(S.rope, P.d_head / 2, pos, P.theta_scale, P.rope_freqs);
+    mg_grid_arrive(P.sync);
+    auto grid_sync = [&]() { bar_target += (unsigned int)P.n_cta; mg_grid_wait(P.sync, bar_target); };
 
-    // ================================= one stream phase (mat-vec group) =================================
-    auto run_phase = [&](int phi) {
-        const MegaPhase* ph = P.phases + phi;
-        mg_prologue(P, ph, s_act, s_redd);
-        TR();
-        const MgGroup g = mg_group(ph, P.n_cta, (int)blockIdx.x, warp);
+    // ================================= the token: one stream phase per iteration =================================
+    // pre-barrier part | grid wait | prologue | mat-vec | epilogue | grid arrive (| the two attention stages after a QKV phase)
+    // ONE instance of this body (the kernel must stay small enough for the instruction cache): the phase table drives it.
+    const int n_run = P.with_head ? P.n_phases : P.n_phases - 1;
+#pragma unroll 1
+    for (int phi = 0; phi < n_run; phi++) {
+        const MegaPhase* ph = S.ph + (phi & 1);
+        const bool is_qkv = ph->seg[0].kind == MK_Q;
+        const int layer = ph->layer;
+        const int trk = (is_qkv ? 0 : ph->seg[0].kind == MK_SWIGLU ? 2 : ph->seg[0].kind == MK_LOGITS ? 4 : (ph->src == MSRC_ATTN ? 1 : 3)) << 5;
+        // -- before the barrier: everything that does not depend on the other CTAs --
+        float4 nw[4];
+        nw[0] = nw[1] = nw[2] = nw[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ph->norm_w) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int b = warp + r * MG_WARPS;
+                if (b < (ph->K >> 8)) { const float4* wp = reinterpret_cast<const float4*>(ph->norm_w + b * 256 + lane * 8); nw[2 * r] = __ldg(wp); nw[2 * r + 1] = __ldg(wp + 1); }
+            }
+        }
+        if (is_qkv) mg_attn_prefetch(P, layer, n_kv, S);      // this layer's K / V tiles start streaming into shared memory
+        int g_local, ws; bool g_active;
+        mg_warp_group(ph, warp, g_local, ws, g_active);
+        const int L = ph->L, rpc = ph->rpc, NGtot = P.n_cta * ph->NG, gg = (int)blockIdx.x * ph->NG + g_local;
         const int K = ph->K, fmt = ph->act_fmt;
+        const int sub = lane >= L ? (lane >= 2 * L ? 2 : 1) : 0;     // row of the chunk this lane works on
+        const int hsl = lane - sub * L;                   // half super-block inside the slice
+        const int hs = ws * L + hsl;                      // ... inside the row
+        const bool lane_on = g_active && sub < rpc && hs < (K >> 7);
+        // residual rows of the pair this thread will finish in the epilogue (x is not written by anyone in between)
+        float2 res = make_float2(0.f, 0.f);
+        const bool have_res = ph->seg[0].kind == MK_RESID && ph->NG * ph->items <= MG_THREADS;
+        if (have_res && tid < ph->NG * ph->items) {
+            int gl, ks, s, p;
+            if (mg_item_of(ph, P.n_cta, tid, gl, ks, s, p)) { const float2 t = __ldcg(reinterpret_cast<const float2*>(P.x + 2 * p)); res = t; }
+        }
+        bar_target += (unsigned int)P.n_cta;
+        mg_grid_wait(P.sync, bar_target);
+        mg_tr(P, S, trk | 2);
+        if (warp == 2) fetch_phase(phi + 1);              // next phase's descriptor (its slot's last reader was phase phi - 1)
+        mg_prologue(P, ph, S, nw[0], nw[1], nw[2], nw[3]);
+        mg_tr(P, S, trk | 3);
         // -- this lane's activations --
-        const int sub = lane / g.L;                       // row of the chunk this lane works on
-        const int hsl = lane - sub * g.L;                 // half super-block inside the slice
-        const int hs = g.ws * g.L + hsl;                  // ... inside the row
-        const bool lane_on = g.active && sub < g.rpc && hs < (K >> 7);
         LaneAct A;
         if (lane_on) {
-            const int8_t* sq = reinterpret_cast<const int8_t*>(s_act);
-            const float* sd = reinterpret_cast<const float*>(s_act + K);
-            const int16_t* sbs = reinterpret_cast<const int16_t*>(s_act + K + (K >> 5) * 4);
+            const int8_t* sq = reinterpret_cast<const int8_t*>(S.act);
+            const float* sd = reinterpret_cast<const float*>(S.act + K);
+            const int16_t* sbs = reinterpret_cast<const int16_t*>(S.act + K + (K >> 5) * 4);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const uint4 t = lds128(sq + hs * 128 + ((c ^ (hs & 7)) << 4));
@@ -652,19 +837,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 6; i++) A.aux[i] = 0u;
         }
+        mg_tr(P, S, trk | 4);
         // -- main loop: every chunk of this warp in this phase --
         const int sb = hsl >> 1, hf = hsl & 1;
-        const int cpp = 2 / g.rpc;
-        int slot_i = 0;                                   // running item index of this group inside the phase
         for (int s = 0; s < ph->nseg; s++) {
             const MegaSeg* sg = ph->seg + s;
-            int vg, n; mg_seg_items(g, sg, vg, n);
-            const int type = sg->type;
+            const int type = sg->type, n_pairs = g_active ? sg->n_pairs : 0;
             const int sub_off = sub * sg->slice_bytes;
-            const int tail_off = (g.L >> 1) * 208 + sb * 2;     // Q6_K: this super-block's d in the slice tail
-            for (int k = 0; k < n; k++, slot_i++) {
-                float v0 = 0.0f, v1 = 0.0f;
-                for (int c = 0; c < cpp; c++) {
+            const int tail_off = (L >> 1) * 208 + sb * 2;     // Q6_K: this super-block's d in the slice tail
+            int slot_i = sg->slot0;
+            for (int p = mg_first_pair(*sg, gg, NGtot); p < n_pairs; p += NGtot, slot_i++) {
+                float va = 0.0f, vb = 0.0f;
+#pragma unroll 1
+                for (int c = 0; c < 2 / rpc; c++) {           // one code instance for both rows of the pair
                     const int slot = c_done % MG_SLOTS;
                     mbar_wait(my_bar + slot, (uint32_t)((c_done / MG_SLOTS) & 1));
                     const unsigned char* sl = ring + (size_t)slot * P.slot_bytes + sub_off;
@@ -702,38 +887,38 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                             v = mg_dot_q5k(wb, hf, A);
                         }
                     }
-                    __syncwarp();                         // every lane has read the slot: refill it
+                    __syncwarp();                             // every lane has read the slot: refill it
                     c_done++;
                     issue_next();
-                    if (g.rpc == 2) { v0 = warp_sum(sub == 0 ? v : 0.0f); v1 = warp_sum(sub == 1 ? v : 0.0f); }
-                    else if (c == 0) v0 = warp_sum(v); else v1 = warp_sum(v);
+                    if (c == 0) va = v; else vb = v;
                 }
-                if (lane == 0) s_part[slot_i * MG_WARPS + warp] = make_float2(v0, v1);
+                float v0, v1;
+                if (rpc == 2) {     // both rows in one chunk: lanes [0, L) row a, [L, 2L) row b
+                    v0 = warp_sum(sub == 0 ? va : 0.0f); v1 = warp_sum(sub == 1 ? va : 0.0f);
+                } else {            // ONE butterfly for both rows: lanes 0-15 carry row a, lanes 16-31 row b
+                    const float oa = __shfl_xor_sync(0xffffffffu, va, 16), ob = __shfl_xor_sync(0xffffffffu, vb, 16);
+                    float y = lane < 16 ? va + oa : vb + ob;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+                    v0 = y; v1 = __shfl_sync(0xffffffffu, y, 16);
+                }
+                if (lane == 0) S.part[slot_i * MG_WARPS + warp] = make_float2(v0, v1);
             }
         }
         __syncthreads();
-        TR();
-        mg_epilogue(P, ph, pos, s_part, s_rope);
-        TR();
-    };
-
-    // ================================= the token =================================
-    int phase = 0;
-    for (int l = 0; l < P.n_layer; l++) {
-        run_phase(phase++);            // QKV (+bias, RoPE, KV write)
-        grid_sync(); TR();
-        mg_attn_scores(P, l, n_kv, s_act);
-        TR(); grid_sync(); TR();
-        mg_attn_pv(P, l, n_kv, s_act, s_redf, s_redd, s_stat);
-        TR(); grid_sync(); TR();
-        run_phase(phase++);            // Wo + residual
-        grid_sync(); TR();
-        run_phase(phase++);            // gate / up + SwiGLU
-        grid_sync(); TR();
-        run_phase(phase++);            // down + residual
-        grid_sync(); TR();
+        mg_tr(P, S, trk | 5);
+        mg_epilogue(P, ph, pos, S, res, have_res);
+        mg_tr(P, S, trk | 6);
+        mg_grid_arrive(P.sync);
+        if (is_qkv) {
+            grid_sync(); mg_tr(P, S, 10);
+            mg_attn_scores<GQ>(P, layer, n_kv, S);
+            mg_tr(P, S, 11); mg_grid_arrive(P.sync); grid_sync(); mg_tr(P, S, 12);
+            mg_attn_pv<GQ>(P, layer, n_kv, S);
+            mg_tr(P, S, 16); mg_grid_arrive(P.sync);
+        }
     }
-    if (P.with_head) { run_phase(phase++); grid_sync(); TR(); }
+    grid_sync(); mg_tr(P, S, 20);
 
     // ---- exit: the last CTA out resets the barrier state for the next launch ----
     if (tid == 0) {

@@ -10,7 +10,10 @@ namespace blk {
 
 constexpr int MG_WARPS = 16;
 constexpr int MG_THREADS = MG_WARPS * 32;
-constexpr int MG_SLOTS = 3;
+#ifndef MG_SLOTS_N
+#define MG_SLOTS_N 3
+#endif
+constexpr int MG_SLOTS = MG_SLOTS_N;
 constexpr int MG_PCAP = 512;          // tokens of one softmax / V.p sub-slice held in shared memory
 
 enum : int { MK_Q = 0, MK_K = 1, MK_V = 2, MK_RESID = 3, MK_SWIGLU = 4, MK_LOGITS = 5 };
@@ -41,7 +44,7 @@ struct MegaSeg {
     int slice_bytes;
     int rot;                 // rotation of the pair -> warp-group assignment (balances the remainder across phases)
     int kind;                // MK_*
-    int pad;
+    int slot0;               // first partial-sum slot of this segment: items of the earlier segments (ceil(n_pairs / groups))
 };
 struct MegaPhase {
     MegaSeg seg[3];
@@ -54,12 +57,19 @@ struct MegaPhase {
     int act_fmt;             // ACT_Q8_K / ACT_Q8_0
     int src;                 // MSRC_*
     int layer;
+    int items;               // upper bound of row pairs per warp group in this phase (all segments)
+    int NG;                  // warp groups per CTA = MG_WARPS / W
+    int wsh;                 // log2(W) when W is a power of two, else -1
+    int ngsh;                // log2(NG) when NG is a power of two, else -1
 };
+static_assert(sizeof(MegaPhase) % 16 == 0, "MegaPhase must be a whole number of 16-byte words");
 
 struct MegaParams {
     const MegaPhase* phases; int n_phases; int n_layer;
     const uint4* chunk_list; const int* chunk_counts; int list_stride;     // per (cta, warp): chunk descriptors {addr.lo, addr.hi, bytes, 0}
     int n_cta; int slot_bytes; int max_items; int act_bytes;
+    int attn_off;            // offset of the attention tiles inside the activation scratch (behind an n_embd-long row's activations)
+    int ts_cap;              // tokens of one attention tile (K and V rows of a CTA's context slice held in shared memory)
     // model
     QMat tok_embd;
     int n_embd, n_head, n_head_kv, d_head, n_ff, n_vocab, neox;

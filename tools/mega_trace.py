@@ -1,4 +1,5 @@
-"""Stage-level timeline of the persistent decode kernel (BLK_MEGA_TRACE=1): where a token's time goes."""
+"""Stage-level timeline of the persistent decode kernel (BLK_MEGA_TRACE=1): where a token's time goes.
+Every CTA's thread 0 records (SM clock, tag) at stage boundaries; intervals are attributed to the tag that ENDS them."""
 import os, sys
 os.environ["BLK_MEGA_TRACE"] = "1"
 sys.path.insert(0, '.')
@@ -12,23 +13,27 @@ m = capi.Model(path); c = capi.Ctx(m, 2048)
 c.decode(gguf_synth.synth_prompt(shape, ctx_len, 1))
 first = int(c.topk(1)["token"][0])
 c.decode_loop(first, 4)
-tr = c.debug_trace().astype(np.float64)
-names = ["embed+sync"]
-per_layer = ["qkv.prologue", "qkv.mac", "qkv.epilogue", "qkv.sync", "attn.scores", "attn.sync1", "attn.pv", "attn.sync2",
-             "wo.prologue", "wo.mac", "wo.epilogue", "wo.sync", "gu.prologue", "gu.mac", "gu.epilogue", "gu.sync",
-             "down.prologue", "down.mac", "down.epilogue", "down.sync"]
-n_layer = m.n_layer
-names += per_layer * n_layer + ["head.prologue", "head.mac", "head.epilogue", "head.sync"]
-d = np.diff(tr[:, : len(names) + 1], axis=1)          # [cta][event]
+raw = c.debug_trace()
+KIND = ["qkv", "wo", "gu", "down", "head"]
+TAG = {2: "wait(barrier)", 3: "prologue.tail", 4: "act regs", 5: "mac", 6: "epilogue"}
+PRO = {30: "pro.load+sumsq", 31: "pro.sync+scale", 32: "pro.issue loads", 33: "pro.quant blk0 (+load wait)", 34: "pro.quant rest"}
+ATT = {17: "attn.pv.load+max", 10: "attn.wait1", 11: "attn.scores", 12: "attn.wait2", 13: "attn.pv.stats", 14: "attn.pv.pv", 15: "attn.pv.partials", 16: "attn.pv.combine", 20: "final wait"}
+clk = 1.965e3
 agg = {}
-for i, nme in enumerate(names):
-    agg.setdefault(nme, []).append(d[:, i])
-clk = 1.965e3   # cycles per us at the max SM clock
+for cta in range(raw.shape[0]):
+    row = raw[cta]; row = row[row != 0]
+    t = (row >> 8).astype(np.float64); tag = (row & 0xff).astype(int)
+    kind = 0
+    for i in range(1, len(t)):
+        tg = int(tag[i])
+        if tg in ATT: name = ATT[tg]
+        elif tg in PRO: name = PRO[tg]
+        else: name = KIND[tg >> 5] + "." + TAG.get(tg & 31, str(tg & 31))
+        agg.setdefault(name, {}).setdefault(cta, []).append((t[i] - t[i - 1]) / clk)
 tot = 0.0
-print(f"{'stage':16s} {'n':>4s} {'mean us':>9s} {'max-cta us':>10s} {'sum us':>9s}")
-for nme, lst in agg.items():
-    a = np.stack(lst, 1)                              # [cta][occurrence]
-    mean = a.mean() / clk; mx = a.max(0).mean() / clk; s = a.mean(0).sum() / clk
-    tot += s
-    print(f"{nme:16s} {a.shape[1]:4d} {mean:9.2f} {mx:10.2f} {s:9.1f}")
+print(f"{'stage':28s} {'n':>4s} {'mean us':>9s} {'max-cta us':>10s} {'sum us':>9s}")
+for name, per in agg.items():
+    a = np.array([per[k] for k in sorted(per) if len(per[k]) == len(per[0])])
+    mean = a.mean(); mx = a.max(0).mean(); s = a.mean(0).sum(); tot += s
+    print(f"{name:28s} {a.shape[1]:4d} {mean:9.2f} {mx:10.2f} {s:9.1f}")
 print(f"total {tot:.1f} us")
