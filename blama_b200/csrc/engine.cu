@@ -593,6 +593,7 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
         // the whole step is one persistent cooperative kernel (mega_decode.cuh) + the top-k selection
         MegaParams P = c->mega_params;
         P.with_head = with_head ? 1 : 0; P.advance_pos = 1;
+        P.seq = ++c->mega_seq;
         if (!with_head) P.chunk_counts = m->mega.d_counts_body;
         BLK_CUDA(mega_launch(P, c->mega_smem, c->stream));
         c->launches++;
@@ -870,6 +871,14 @@ void build_graphs(blk_ctx* c) {
     }
 }
 
+// after a stream synchronisation: did a poll of the persistent decode kernel give up?
+void check_mega(blk_ctx* c) {
+    if (c->mega_err && *c->mega_err) {
+        const int w = *c->mega_err; *c->mega_err = 0;
+        throw BlkError(BLK_ERR_CUDA, "persistent decode kernel: a phase never arrived (poll " + std::to_string(w) + " timed out)");
+    }
+}
+
 void step(blk_ctx* c, int32_t tok, bool with_head) {
     blk_model* m = c->m;
     if (tok < 0 || tok >= m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
@@ -972,17 +981,22 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             P.n_embd = d; P.n_head = m->n_head; P.n_head_kv = m->n_head_kv; P.d_head = dh; P.n_ff = ff; P.n_vocab = m->n_vocab; P.neox = m->neox ? 1 : 0;
             P.eps = m->rms_eps; P.theta_scale = m->theta_scale; P.attn_scale = 1.0f / sqrtf((float)dh); P.rope_freqs = m->rope_freqs;
             P.tok = c->d_tok; P.pos = c->d_pos;
-            P.x = c->x; P.qbuf = c->qbuf; P.hbuf = c->hbuf; P.attn_out = c->act_q.f32;
-            P.scores = c->scores; P.score_stride = c->n_pages * KV_PAGE;
+            P.score_stride = c->n_pages * KV_PAGE;
             P.max_split = std::max(1, std::min(32, mg.n_cta / m->n_head_kv));
-            P.part_o = dalloc<float>(c.get(), (size_t)m->n_head * dh * P.max_split);
+            auto ll = [&](size_t n) { uint2* p = dalloc<uint2>(c.get(), n); BLK_CUDA(cudaMemset(p, 0, n * sizeof(uint2))); return p; };
+            P.x2 = ll(d); P.q2 = ll(dq); P.h2 = ll(ff); P.ao2 = ll(dq);
+            P.sc2 = ll((size_t)m->n_head * P.score_stride); P.po2 = ll((size_t)P.max_split * dq); P.kvn2 = ll(2 * (size_t)dkv);
             __half** kp = dalloc<__half*>(c.get(), m->n_layer); __half** vp = dalloc<__half*>(c.get(), m->n_layer);
             BLK_CUDA(cudaMemcpy(kp, c->k_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
             BLK_CUDA(cudaMemcpy(vp, c->v_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
             P.k_pools = kp; P.v_pools = vp; P.page_table = c->page_table; P.kv_dim = dkv;
             P.logits = c->logits; P.chunk_max = c->chunk_max; P.chunk_shift = c->chunk_shift;
-            P.sync = dalloc<unsigned int>(c.get(), 4 + m->n_head_kv);
-            BLK_CUDA(cudaMemset(P.sync, 0, (4 + m->n_head_kv) * sizeof(unsigned int)));
+            {   // a poll that times out reports here instead of hanging the GPU (mapped pinned host word)
+                void* hp = nullptr;
+                BLK_CUDA(cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped)); c->host_allocs.push_back(hp);
+                c->mega_err = reinterpret_cast<int*>(hp); *c->mega_err = 0;
+                void* dp = nullptr; BLK_CUDA(cudaHostGetDevicePointer(&dp, hp, 0)); P.err = reinterpret_cast<int*>(dp);
+            }
             { const char* tr = getenv("BLK_MEGA_TRACE"); if (tr && tr[0] == '1') { P.trace_cap = 2048; P.trace = dalloc<long long>(c.get(), (size_t)P.n_cta * P.trace_cap); } }
             c->mega_smem = mega_smem_bytes(P);
             int limit = 0;
@@ -992,7 +1006,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         {   // one eager step: loads modules and sets per-function attributes outside of stream capture
             BLK_CUDA(cudaMemsetAsync(c->d_tok, 0, sizeof(int32_t), c->stream));
             if (c->mega_on) {
-                try { enqueue_step(c.get(), true, false); BLK_CUDA(cudaStreamSynchronize(c->stream)); }
+                try { enqueue_step(c.get(), true, false); BLK_CUDA(cudaStreamSynchronize(c->stream)); check_mega(c.get()); }
                 catch (const BlkError& err) {
                     (void)cudaGetLastError();
                     log_msg(2, std::string("persistent decode kernel unavailable (") + err.what() + "); using the per-op graph");
@@ -1029,7 +1043,7 @@ extern "C" blk_status blk_kv_clear(blk_ctx* c) {
     });
 }
 extern "C" blk_status blk_sync(blk_ctx* c) {
-    return guarded([&] { BLK_CUDA(cudaSetDevice(c->m->device)); BLK_CUDA(cudaStreamSynchronize(c->stream)); });
+    return guarded([&] { BLK_CUDA(cudaSetDevice(c->m->device)); BLK_CUDA(cudaStreamSynchronize(c->stream)); check_mega(c); });
 }
 
 extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
@@ -1075,6 +1089,7 @@ extern "C" blk_status blk_topk_last(blk_ctx* c, int32_t k, blk_token_data* out) 
         if (!c->have_logits) throw BlkError(BLK_ERR_ARG, "no logits available: decode first");
         BLK_CUDA(cudaSetDevice(c->m->device));
         BLK_CUDA(cudaStreamSynchronize(c->stream));
+        check_mega(c);
         for (int i = 0; i < k; i++) { out[i].token = c->h_top_ids[i]; out[i].logit = c->h_top_logits[i]; }
     });
 }
@@ -1085,6 +1100,7 @@ extern "C" blk_status blk_decode_topk(blk_ctx* c, int32_t token, int32_t k, blk_
         BLK_CUDA(cudaSetDevice(c->m->device));
         step(c, token, true);
         BLK_CUDA(cudaStreamSynchronize(c->stream));
+        check_mega(c);
         for (int i = 0; i < k; i++) { out[i].token = c->h_top_ids[i]; out[i].logit = c->h_top_logits[i]; }
     });
 }

@@ -131,5 +131,7 @@ struct blk_ctx {
     bool mega_on = false;
     blk::MegaParams mega_params{};
     size_t mega_smem = 0;
+    uint32_t mega_seq = 0;
+    int* mega_err = nullptr;               // mapped host word the kernel sets when a poll times out
     ~blk_ctx();
 };

@@ -26,9 +26,13 @@ cudaError_t mega_setup(size_t smem, int* limit) {
     if (e != cudaSuccess) return e;
     if (limit) *limit = lim;
     if (smem > (size_t)lim) return cudaErrorInvalidValue;
-    e = cudaFuncSetAttribute(mega_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(mega_decode_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mega_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(mega_decode_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mega_decode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mega_decode_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 cudaError_t mega_launch(const MegaParams& P, size_t smem, cudaStream_t st) {
@@ -39,8 +43,9 @@ cudaError_t mega_launch(const MegaParams& P, size_t smem, cudaStream_t st) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     // GQ = compile-time bound on the query heads per KV head (attention register arrays)
-    if (P.n_head / P.n_head_kv <= 4) return cudaLaunchKernelEx(&cfg, mega_decode_kernel<4>, P);
-    return cudaLaunchKernelEx(&cfg, mega_decode_kernel<8>, P);
+    const bool g4 = P.n_head / P.n_head_kv <= 4;
+    if (P.trace) return g4 ? cudaLaunchKernelEx(&cfg, mega_decode_kernel<4, true>, P) : cudaLaunchKernelEx(&cfg, mega_decode_kernel<8, true>, P);
+    return g4 ? cudaLaunchKernelEx(&cfg, mega_decode_kernel<4, false>, P) : cudaLaunchKernelEx(&cfg, mega_decode_kernel<8, false>, P);
 }
 
 cudaError_t mega_chunk_lists(const MegaPhase* d_phases, int n_phases, int n_cta, uint4* list, int list_stride, int* counts, cudaStream_t st) {

@@ -51,6 +51,29 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- LL exchange: every value that crosses CTAs travels with an epoch tag in ONE 8-byte store; readers poll the data itself.
+// Measured on B200 (tools/micro/lat.cu): store -> visible -> read = ~900 cycles, against ~3500 for grid barrier + read.
+// No fences: an 8-byte store is single-copy atomic, so a reader sees {value, tag} of the same store or an older one.
+__device__ __forceinline__ uint32_t mg_tag(uint32_t seq, int phi, int sub) { return seq * 4096u + (uint32_t)(phi + 1) * 4u + (uint32_t)sub; }
+__device__ __forceinline__ uint2 ll_ld(const uint2* p) {
+    uint2 v; asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ uint4 ll_ld2(const uint2* p) {      // two consecutive {value, tag} words
+    uint4 v; asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void ll_st(uint2* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ll_st2(uint2* p, float v0, float v1, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(tag), "r"(__float_as_uint(v1)), "r"(tag) : "memory");
+}
+constexpr int MG_SPIN_LIMIT = 1 << 20;       // a few 100 ms of polling: a phase that never arrives sets *P.err instead of hanging the GPU
+struct MgV8F { uint4 a, b, c, d; };          // 8 x {value, tag}
+__device__ __forceinline__ MgV8F ll_ld8(const uint2* p) { MgV8F r; r.a = ll_ld2(p); r.b = ll_ld2(p + 2); r.c = ll_ld2(p + 4); r.d = ll_ld2(p + 6); return r; }
+__device__ __forceinline__ bool ll_ok8(const MgV8F& r, uint32_t tag) {
+    return r.a.y == tag && r.a.w == tag && r.b.y == tag && r.b.w == tag && r.c.y == tag && r.c.w == tag && r.d.y == tag && r.d.w == tag;
+}
+
 // activations of one lane: the 128 int8 values of its half super-block plus their scales / partial sums
 struct LaneAct {
     int q[32];
@@ -164,19 +187,16 @@ __device__ __noinline__ void mg_quantize_regs(float4 va, float4 vb, int fmt, int
     const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
     int qi[8];
     if (fmt == ACT_Q8_K) {
-        float amax = 0.0f; int idx = 0x7fffffff;
+        // max |x| of the block, then the FIRST element attaining it decides the sign of the scale (quantize_row_q8_K_ref)
+        float amax = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) { const float ax = fabsf(v[i]); if (ax > amax) { amax = ax; idx = lane * 8 + i; } }
+        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+        amax = warp_max(amax);
+        float mine = 0.0f; bool has = false;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (oa > amax || (oa == amax && oi < idx)) { amax = oa; idx = oi; }
-        }
-        float mx = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) if (lane * 8 + i == idx) mx = v[i];
-        mx = __shfl_sync(0xffffffffu, mx, (idx == 0x7fffffff ? 0 : idx) >> 3);
+        for (int i = 7; i >= 0; i--) if (fabsf(v[i]) == amax) { mine = v[i]; has = true; }      // lowest i wins
+        const unsigned int who = __ballot_sync(0xffffffffu, has);
+        const float mx = __shfl_sync(0xffffffffu, mine, who ? __ffs(who) - 1 : 0);
         if (amax == 0.0f) {
 #pragma unroll
             for (int i = 0; i < 8; i++) qi[i] = 0;
@@ -291,19 +311,6 @@ __global__ void mg_chunk_list_kernel(const MegaPhase* phases, int n_phases, int 
     counts[id] = n;
 }
 
-// ---- grid barrier (arrive / wait split so that work that does not depend on other CTAs sits in between) -----------------
-__device__ __forceinline__ void mg_grid_arrive(unsigned int* bar) {
-    __syncthreads();
-    if (threadIdx.x == 0) red_release_add(bar, 1u);
-}
-__device__ __forceinline__ void mg_grid_wait(const unsigned int* bar, unsigned int target) {
-    if (threadIdx.x == 0) {
-        while (ld_relaxed_u32(bar) < target) { }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    }
-    __syncthreads();
-}
-
 // ---- shared memory carve-up ------------------------------------------------------------------------------------------
 struct MgSmem {
     uint64_t* bars; MegaPhase* ph; __half** kp; __half** vp; float2* part; float2* rope; double* redd; float* redf; float* stat; int* misc;
@@ -329,8 +336,9 @@ __device__ __forceinline__ MgSmem mg_carve(const MegaParams& P, unsigned char* s
 }
 
 // ---- optional event trace: thread 0 of every CTA appends (SM clock << 8 | tag); see tools/mega_trace.py --------------------
+template <bool TR>
 __device__ __forceinline__ void mg_tr(const MegaParams& P, const MgSmem& S, int tag) {
-    if (P.trace && threadIdx.x == 0) {
+    if (TR && threadIdx.x == 0) {
         const int i = S.misc[16]++;
         if (i < P.trace_cap) P.trace[(size_t)blockIdx.x * P.trace_cap + i] = (clock64() << 8) | (long long)tag;
     }
@@ -340,6 +348,7 @@ __device__ __forceinline__ void mg_tr(const MegaParams& P, const MgSmem& S, int 
 __device__ __noinline__ void mg_embed(const MegaParams& P) {
     const int tid = threadIdx.x;
     const int tok = P.tok[0];
+    const uint32_t tag = P.seq * 4096u;               // epoch of the embedding row
     const int per = (P.n_embd / 64 + P.n_cta - 1) / P.n_cta;      // 64-element units per CTA
     const int u0 = (int)blockIdx.x * per, u1 = min(P.n_embd / 64, u0 + per);
     const QMat& E = P.tok_embd;
@@ -347,35 +356,41 @@ __device__ __noinline__ void mg_embed(const MegaParams& P) {
         for (int u = u0 + tid; u < u1; u += MG_THREADS) {
             float v[64];
             if (E.type == QT_Q4_K) dequant_unit_q4k(E, tok, u, v); else if (E.type == QT_Q5_K) dequant_unit_q5k(E, tok, u, v); else dequant_unit_q6k(E, tok, u, v);
-            if (E.type == QT_Q6_K) { for (int l = 0; l < 64; l++) P.x[q6k_unit_elem(u, l)] = v[l]; }
-            else { for (int l = 0; l < 64; l++) P.x[u * 64 + l] = v[l]; }
+            if (E.type == QT_Q6_K) { for (int l = 0; l < 64; l++) ll_st(P.x2 + q6k_unit_elem(u, l), v[l], tag); }
+            else { for (int l = 0; l < 64; l++) ll_st(P.x2 + u * 64 + l, v[l], tag); }
         }
     } else if (E.type == QT_Q8_0) {
-        for (int u = 2 * u0 + tid; u < 2 * u1; u += MG_THREADS) { float v[32]; dequant_unit_q80(E, tok, u, v); for (int l = 0; l < 32; l++) P.x[u * 32 + l] = v[l]; }
+        for (int u = 2 * u0 + tid; u < 2 * u1; u += MG_THREADS) { float v[32]; dequant_unit_q80(E, tok, u, v); for (int l = 0; l < 32; l++) ll_st(P.x2 + u * 32 + l, v[l], tag); }
     } else if (E.type == QT_F32) {
         const float* src = reinterpret_cast<const float*>(E.p0) + (size_t)tok * E.K;
-        for (int i = u0 * 64 + tid; i < u1 * 64; i += MG_THREADS) P.x[i] = src[i];
+        for (int i = u0 * 64 + tid; i < u1 * 64; i += MG_THREADS) ll_st(P.x2 + i, src[i], tag);
     } else {
         const __half* src = reinterpret_cast<const __half*>(E.p0) + (size_t)tok * E.K;
-        for (int i = u0 * 64 + tid; i < u1 * 64; i += MG_THREADS) P.x[i] = __half2float(src[i]);
+        for (int i = u0 * 64 + tid; i < u1 * 64; i += MG_THREADS) ll_st(P.x2 + i, __half2float(src[i]), tag);
     }
 }
 
-// ---- attention of one layer, two grid-synchronised stages ------------------------------------------------------------------
+// a poll that never completes: record it (mapped host word) and carry on with whatever is there -- never hang the GPU
+__device__ __noinline__ void mg_poll_timeout(const MegaParams& P, const MgSmem& S, int where) {
+    if (P.err && !S.misc[20]) *reinterpret_cast<volatile int*>(P.err) = where;
+    S.misc[20] = 1;                                   // every later poll of this CTA gives up at once: the launch drains quickly
+}
+__device__ __forceinline__ bool mg_spin_out(const MgSmem& S, int& spins) { return ++spins > (S.misc[20] ? 0 : MG_SPIN_LIMIT); }
+
+// ---- attention of one layer, two stages chained through LL words ------------------------------------------------------------
 // CTA c serves KV head c % n_head_kv, context split c / n_head_kv.  The K and V rows of the CTA's token slice are copied
-// into shared memory with cp.async BEFORE the grid barrier that opens the layer's QKV phase (only the row of the token being
-// decoded has to wait for that phase), so both stages work out of shared memory.  Every global read on the critical path
-// is issued as one batch of independent loads: a dependent L2 round trip costs ~0.7 us under the weight stream.
+// into shared memory with cp.async at the START of the layer's QKV phase (only the row of the token being decoded has to wait
+// for that phase: it arrives as f32 LL words), so both stages work out of shared memory.
 struct MgAttn { int hk, split, n_split, t0, nt; bool on; };
-__device__ __forceinline__ MgAttn mg_attn_setup(const MegaParams& P, int n_kv) {
-    MgAttn a;
-    a.n_split = max(1, min(P.max_split, (n_kv + P.ts_cap - 1) / P.ts_cap));
-    a.hk = (int)blockIdx.x % P.n_head_kv; a.split = (int)blockIdx.x / P.n_head_kv;
-    a.on = a.split < a.n_split;
-    const int per = (n_kv + a.n_split - 1) / a.n_split;
-    a.t0 = a.split * per;
-    a.nt = max(0, min(n_kv, a.t0 + per) - a.t0);
-    return a;
+__device__ __forceinline__ MgAttn mg_attn_get(const MgSmem& S) {   // computed once per token (mg_attn_setup), kept in shared memory
+    MgAttn a; a.hk = S.misc[1]; a.split = S.misc[2]; a.n_split = S.misc[3]; a.t0 = S.misc[4]; a.nt = S.misc[5]; a.on = S.misc[6] != 0; return a;
+}
+__device__ __forceinline__ void mg_attn_setup(const MegaParams& P, int n_kv, const MgSmem& S) {
+    const int n_split = max(1, min(P.max_split, (n_kv + P.ts_cap - 1) / P.ts_cap));
+    const int hk = (int)blockIdx.x % P.n_head_kv, split = (int)blockIdx.x / P.n_head_kv;
+    const int per = (n_kv + n_split - 1) / n_split;
+    const int t0 = split * per;
+    S.misc[1] = hk; S.misc[2] = split; S.misc[3] = n_split; S.misc[4] = t0; S.misc[5] = max(0, min(n_kv, t0 + per) - t0); S.misc[6] = split < n_split ? 1 : 0;
 }
 __device__ __forceinline__ size_t mg_kv_row(const MegaParams& P, int hk, int t) {
     return ((size_t)P.page_table[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * P.kv_dim + (size_t)hk * P.d_head;
@@ -391,60 +406,77 @@ __device__ __forceinline__ MgAttnSmem mg_attn_carve(const MegaParams& P, unsigne
     s.red = reinterpret_cast<float*>(s.k);          // [token group][gq][dh] partial outputs, once the tiles are dead
     return s;
 }
-// rows [tile0, tile0 + cn) of the slice, restricted to tokens [t_begin, t_limit) -> shared memory
+// rows [tile0, tile0 + cn) of the slice, restricted to tokens < t_limit -> shared memory
 template <bool ASYNC>
-__device__ __forceinline__ void mg_attn_load_rows(const MegaParams& P, const MgAttn& a, const __half* pool, __half* dst, int tile0, int cn, int t_begin, int t_limit) {
+__device__ __forceinline__ void mg_attn_load_rows(const MegaParams& P, const MgAttn& a, const __half* pool, __half* dst, int tile0, int cn, int t_limit) {
     const int dh = P.d_head, csh = dh == 128 ? 4 : 3;               // 16-byte chunks per row: dh / 8
     for (int idx = threadIdx.x; idx < (cn << csh); idx += MG_THREADS) {
         const int tl = idx >> csh, c = idx & ((1 << csh) - 1);
         const int t = a.t0 + tile0 + tl;
-        if (t < t_begin || t >= t_limit) continue;
+        if (t >= t_limit) continue;
         const __half* src = pool + mg_kv_row(P, a.hk, t) + c * 8;
         if (ASYNC) cp_async16(dst + (size_t)tl * dh + c * 8, src);
         else *reinterpret_cast<uint4*>(dst + (size_t)tl * dh + c * 8) = __ldcg(reinterpret_cast<const uint4*>(src));
     }
 }
 
-// first tile of K and V of this CTA's slice, except the token being decoded (issued before the QKV phase's barrier)
+// first tile of K and V of this CTA's slice, except the token being decoded
 __device__ __noinline__ void mg_attn_prefetch(const MegaParams& P, int layer, int n_kv, const MgSmem& S) {
-    const MgAttn a = mg_attn_setup(P, n_kv);
+    const MgAttn a = mg_attn_get(S);
     if (!a.on || a.nt == 0) return;
     const MgAttnSmem s = mg_attn_carve(P, S.attn);
     const int cn = min(a.nt, P.ts_cap);
-    mg_attn_load_rows<true>(P, a, S.kp[layer], s.k, 0, cn, 0, n_kv - 1);
-    mg_attn_load_rows<true>(P, a, S.vp[layer], s.v, 0, cn, 0, n_kv - 1);
+    mg_attn_load_rows<true>(P, a, S.kp[layer], s.k, 0, cn, n_kv - 1);
+    mg_attn_load_rows<true>(P, a, S.vp[layer], s.v, 0, cn, n_kv - 1);
     cp_async_commit();
 }
 
-// stage 1: scaled scores of this CTA's token slice for the gq query heads of its KV head -> global (+ shared for tile 0)
+// stage 1: scaled scores of this CTA's token slice for the gq query heads of its KV head -> LL words (+ shared for tile 0)
 template <int GQ>
-__device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int n_kv, const MgSmem& S) {
-    const MgAttn a = mg_attn_setup(P, n_kv);
+__device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int phi, int n_kv, const MgSmem& S) {
+    const MgAttn a = mg_attn_get(S);
     if (!a.on || a.nt == 0) return;
     const MgAttnSmem s = mg_attn_carve(P, S.attn);
     const int tid = threadIdx.x, dh = P.d_head, gq = P.n_head / P.n_head_kv;
-    // one batch of global reads: the query heads, and (slice holding the new token only) the K / V rows written by this layer's QKV
-    float qv[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int r = 0; r < 2; r++) { const int i = tid + r * MG_THREADS; if (i < gq * dh) qv[r] = __ldcg(P.qbuf + (size_t)(a.hk * gq) * dh + i); }
+    const uint32_t tag_in = mg_tag(P.seq, phi, 0), tag_out = mg_tag(P.seq, phi, 1);
+    // poll: the query heads, and (slice holding the new token only) the K / V rows this layer's QKV phase produced
     const int cn0 = min(P.ts_cap, a.nt);
     const int tl_new = n_kv - 1 - a.t0;                             // local index of the token being decoded
-    uint4 newrow = make_uint4(0, 0, 0, 0);
-    const int cpr = dh >> 3;
-    const bool has_new = tl_new >= 0 && tl_new < cn0 && tid < 2 * cpr;
-    if (has_new) {
-        const __half* pool = tid < cpr ? S.kp[layer] : S.vp[layer];
-        newrow = __ldcg(reinterpret_cast<const uint4*>(pool + mg_kv_row(P, a.hk, n_kv - 1)) + (tid < cpr ? tid : tid - cpr));
-    }
+    const bool has_new = tl_new >= 0 && tl_new < cn0;
+    const int nq = gq * dh, nnew = has_new ? 2 * dh : 0;            // words this CTA needs: thread i takes i, i + 512, ...
+    {
+        uint2 w[3];
+        int spins = 0;
+        bool ok;
+        do {
+            ok = true;
 #pragma unroll
-    for (int r = 0; r < 2; r++) { const int i = tid + r * MG_THREADS; if (i < gq * dh) s.q[i] = __float2half_rn(qv[r]); }
-    if (has_new) *reinterpret_cast<uint4*>((tid < cpr ? s.k : s.v) + (size_t)tl_new * dh + (tid < cpr ? tid : tid - cpr) * 8) = newrow;
+            for (int r = 0; r < 3; r++) {
+                const int i = tid + r * MG_THREADS;
+                if (i < nq) w[r] = ll_ld(P.q2 + (size_t)(a.hk * gq) * dh + i);
+                else if (i < nq + nnew) { const int j = i - nq; w[r] = ll_ld(P.kvn2 + (size_t)(j < dh ? 0 : P.kv_dim) + a.hk * dh + (j < dh ? j : j - dh)); }
+                else w[r] = make_uint2(0u, tag_in);
+                ok = ok && w[r].y == tag_in;
+            }
+            if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 1); break; }
+        } while (!__syncthreads_and(ok));
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int i = tid + r * MG_THREADS;
+            if (i < nq) s.q[i] = __float2half_rn(__uint_as_float(w[r].x));
+            else if (i < nq + nnew) { const int j = i - nq; (j < dh ? s.k : s.v)[(size_t)tl_new * dh + (j < dh ? j : j - dh)] = __float2half_rn(__uint_as_float(w[r].x)); }
+        }
+    }
     cp_async_wait_all();
     const int ld = tid & 7, tl = tid >> 3;                          // 8 lanes per token, dh / 8 dims each
     const int DL = dh >> 3;
     for (int c0 = 0; c0 < a.nt; c0 += P.ts_cap) {
         const int cn = min(P.ts_cap, a.nt - c0);
-        if (c0 > 0) { __syncthreads(); mg_attn_load_rows<false>(P, a, S.kp[layer], s.k, c0, cn, 0, n_kv); }
+        if (c0 > 0) {       // long context: further tiles are fetched synchronously
+            __syncthreads();
+            mg_attn_load_rows<false>(P, a, S.kp[layer], s.k, c0, cn, n_kv - 1);
+            if (tl_new >= c0 && tl_new < c0 + cn) for (int j = tid; j < dh; j += MG_THREADS) s.k[(size_t)(tl_new - c0) * dh + j] = __float2half_rn(__uint_as_float(ll_ld(P.kvn2 + a.hk * dh + j).x));
+        }
         __syncthreads();
         float sc[GQ];
 #pragma unroll
@@ -473,7 +505,7 @@ __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int 
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v = __fmul_rn(v, P.attn_scale);
             if (tl < cn && ld == 0) {
-                P.scores[(size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl] = v;
+                ll_st(P.sc2 + (size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl, v, tag_out);
                 if (c0 == 0) s.sc[gI * P.ts_cap + tl] = v;
             }
         }
@@ -481,13 +513,14 @@ __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int 
 }
 
 // stage 2: soft-max statistics over the whole context (redundantly per CTA), probabilities of the own slice rounded to f16,
-// partial V.p; the last CTA of the KV head to finish sums the split partials in split order.
-template <int GQ>
-__device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv, const MgSmem& S) {
-    const MgAttn a = mg_attn_setup(P, n_kv);
+// partial V.p -> LL words; the CTA of split 0 sums the split partials in split order.
+template <int GQ, bool TR>
+__device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int phi, int n_kv, const MgSmem& S) {
+    const MgAttn a = mg_attn_get(S);
     if (!a.on) return;
     const MgAttnSmem s = mg_attn_carve(P, S.attn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, dh = P.d_head, gq = P.n_head / P.n_head_kv;
+    const uint32_t tag_sc = mg_tag(P.seq, phi, 1), tag_po = mg_tag(P.seq, phi, 2), tag_ao = mg_tag(P.seq, phi, 3);
     const int TG = MG_THREADS / dh;                                          // token groups
     const int d = tid & (dh - 1), tg = dh == 128 ? tid >> 7 : tid >> 6;
     float acc[GQ];
@@ -495,31 +528,40 @@ __device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv
     for (int gI = 0; gI < GQ; gI++) acc[gI] = 0.0f;
     if (a.nt > 0) {
         // -- row max, then row sum of expf(s - max) in double, over the WHOLE context: warps (g*ng .. g*ng+ng-1) serve head g.
-        //    Up to 8 scores per lane are loaded as ONE batch and kept in registers for both passes. --
-        const int ng = MG_WARPS / gq;
-        const int g_w = min(warp / ng, gq - 1), part = warp - (warp / ng) * ng;
-        const bool w_on = warp / ng < gq;
-        const float* sr = P.scores + (size_t)(a.hk * gq + g_w) * P.score_stride;
+        //    Up to 8 scores per lane are polled as ONE batch and kept in registers for both passes. --
+        const int ng = S.misc[7];                                            // MG_WARPS / gq
+        const int wq = S.misc[9 + 0] ? warp >> S.misc[9 + 1] : warp / ng;    // power-of-two ng: shift
+        const int g_w = min(wq, gq - 1), part = warp - wq * ng;
+        const bool w_on = wq < gq;
+        const uint2* sr = P.sc2 + (size_t)(a.hk * gq + g_w) * P.score_stride;
         const int stride = ng * 32;
         float M = -INFINITY;
         float sv[8];
         for (int b0 = 0; b0 < n_kv; b0 += 8 * stride) {
+            int spins = 0;
+            bool ok;
+            do {
+                ok = true;
 #pragma unroll
-            for (int i = 0; i < 8; i++) { const int t = b0 + i * stride + part * 32 + lane; sv[i] = (w_on && t < n_kv) ? __ldcg(sr + t) : -INFINITY; }
+                for (int i = 0; i < 8; i++) {
+                    const int t = b0 + i * stride + part * 32 + lane;
+                    if (w_on && t < n_kv) { const uint2 w = ll_ld(sr + t); sv[i] = __uint_as_float(w.x); ok = ok && w.y == tag_sc; } else sv[i] = -INFINITY;
+                }
+                if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 2); break; }
+            } while (!__all_sync(0xffffffffu, ok));
 #pragma unroll
             for (int i = 0; i < 8; i++) M = fmaxf(M, sv[i]);
         }
         M = warp_max(M);
         if (lane == 0) S.redf[warp] = M;
-        mg_tr(P, S, 17);
         __syncthreads();
         M = -INFINITY;
         for (int w = 0; w < ng; w++) M = fmaxf(M, S.redf[g_w * ng + w]);
         double sum = 0.0;
         for (int b0 = 0; b0 < n_kv; b0 += 8 * stride) {
-            if (n_kv > 8 * stride) {          // long context: the first pass could not keep the row in registers
+            if (n_kv > 8 * stride) {          // long context: the first pass could not keep the row in registers (all tags seen valid)
 #pragma unroll
-                for (int i = 0; i < 8; i++) { const int t = b0 + i * stride + part * 32 + lane; sv[i] = (w_on && t < n_kv) ? __ldcg(sr + t) : -INFINITY; }
+                for (int i = 0; i < 8; i++) { const int t = b0 + i * stride + part * 32 + lane; sv[i] = (w_on && t < n_kv) ? __uint_as_float(ll_ld(sr + t).x) : -INFINITY; }
             }
             float e[8];
 #pragma unroll
@@ -534,13 +576,18 @@ __device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv
         double tot = 0.0;
         for (int w = 0; w < ng; w++) tot += S.redd[g_w * ng + w];
         const float inv = (float)(1.0 / tot);
-        mg_tr(P, S, 13);
+        mg_tr<TR>(P, S, 13);
         for (int c0 = 0; c0 < a.nt; c0 += P.ts_cap) {
             const int cn = min(P.ts_cap, a.nt - c0);
-            if (c0 > 0) { __syncthreads(); mg_attn_load_rows<false>(P, a, S.vp[layer], s.v, c0, cn, 0, n_kv); }
+            if (c0 > 0) {
+                __syncthreads();
+                mg_attn_load_rows<false>(P, a, S.vp[layer], s.v, c0, cn, n_kv - 1);
+                const int tn = n_kv - 1 - a.t0;
+                if (tn >= c0 && tn < c0 + cn) for (int j = tid; j < dh; j += MG_THREADS) s.v[(size_t)(tn - c0) * dh + j] = __float2half_rn(__uint_as_float(ll_ld(P.kvn2 + P.kv_dim + a.hk * dh + j).x));
+            }
             // probabilities of this tile: the warps of head g handle head g (they hold its max and 1/sum)
             if (w_on) for (int tl = part * 32 + lane; tl < cn; tl += stride) {
-                const float scv = (c0 == 0) ? s.sc[g_w * P.ts_cap + tl] : __ldcg(sr + a.t0 + c0 + tl);
+                const float scv = (c0 == 0) ? s.sc[g_w * P.ts_cap + tl] : __uint_as_float(ll_ld(sr + a.t0 + c0 + tl).x);
                 s.sc[g_w * P.ts_cap + tl] = __half2float(__float2half_rn(__fmul_rn(expf(scv - M), inv)));
             }
             __syncthreads();
@@ -553,7 +600,7 @@ __device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv
     }
     // token groups meet in shared memory (the tiles are dead), summed in fixed order
     __syncthreads();
-    mg_tr(P, S, 14);
+    mg_tr<TR>(P, S, 14);
 #pragma unroll
     for (int gI = 0; gI < GQ; gI++) if (gI < gq) s.red[(tg * gq + gI) * dh + d] = acc[gI];
     __syncthreads();
@@ -561,31 +608,30 @@ __device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int n_kv
     for (int e = tid; e < E; e += MG_THREADS) {
         float o = 0.0f;
         for (int k = 0; k < TG; k++) o += s.red[k * E + e];
-        P.part_o[(size_t)a.split * NO + a.hk * E + e] = o;
+        ll_st(P.po2 + (size_t)a.split * NO + a.hk * E + e, o, tag_po);
     }
-    // the last CTA of this KV head sums the split partials in split order
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int old = atomicAdd(P.sync + 4 + a.hk, 1u);
-        const bool last = old == (unsigned int)(a.n_split - 1);
-        if (last) { P.sync[4 + a.hk] = 0u; __threadfence(); }
-        S.misc[8] = last ? 1 : 0;
-    }
-    __syncthreads();
-    mg_tr(P, S, 15);
-    if (S.misc[8]) {
+    mg_tr<TR>(P, S, 15);
+    // the CTA of split 0 sums the split partials of its KV head in split order
+    if (a.split == 0) {
         for (int e = tid; e < E; e += MG_THREADS) {
-            const float* pp = P.part_o + a.hk * E + e;
+            const uint2* pp = P.po2 + a.hk * E + e;
             float o = 0.0f;
-            for (int s0 = 0; s0 < a.n_split; s0 += 8) {        // batches of 8 independent loads, added in split order
+            for (int s0 = 0; s0 < a.n_split; s0 += 8) {        // batches of 8 polled together, added in split order
                 float pv[8];
+                int spins = 0;
+                bool ok;
+                do {
+                    ok = true;
 #pragma unroll
-                for (int i = 0; i < 8; i++) pv[i] = (s0 + i < a.n_split) ? __ldcg(pp + (size_t)(s0 + i) * NO) : 0.0f;
+                    for (int i = 0; i < 8; i++) {
+                        if (s0 + i < a.n_split) { const uint2 w = ll_ld(pp + (size_t)(s0 + i) * NO); pv[i] = __uint_as_float(w.x); ok = ok && w.y == tag_po; } else pv[i] = 0.0f;
+                    }
+                    if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 3); break; }
+                } while (!ok);
 #pragma unroll
                 for (int i = 0; i < 8; i++) o += pv[i];
             }
-            P.attn_out[(size_t)a.hk * E + e] = o;
+            ll_st(P.ao2 + (size_t)a.hk * E + e, o, tag_ao);
         }
     }
 }
@@ -612,11 +658,12 @@ __device__ __forceinline__ bool mg_item_of(const MegaPhase* ph, int n_cta, int e
     return p < sg.n_pairs;
 }
 
-// ---- epilogue of a stream phase: combine the K-slice partials of every row pair of this CTA and finish the rows ---------
+// ---- epilogue of a stream phase: combine the K-slice partials of every row pair of this CTA and publish the rows ---------
 // res: x[r0], x[r1] of the pair of thread tid (residual phases: fetched before the mat-vec, see the kernel)
-__device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* ph, int pos, const MgSmem& S, float2 res, bool have_res) {
+__device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* ph, int phi, int pos, const MgSmem& S, float2 res, bool have_res) {
     const int tid = threadIdx.x, dh = P.d_head;
     const int NG = ph->NG, W = ph->W;
+    const uint32_t tag = mg_tag(P.seq, phi, 0);
     for (int e = tid; e < NG * ph->items; e += MG_THREADS) {
         int gl, ks, s, p;
         if (!mg_item_of(ph, P.n_cta, e, gl, ks, s, p)) continue;
@@ -624,13 +671,13 @@ __device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* p
         float v0 = 0.0f, v1 = 0.0f;
         for (int w = 0; w < W; w++) { const float2 t = S.part[ks * MG_WARPS + gl * W + w]; v0 += t.x; v1 += t.y; }
         const int kind = sg.kind;
-        if (kind == MK_SWIGLU) { P.hbuf[p] = (v0 / (1.0f + expf(-v0))) * v1; continue; }     // ggml_silu_f32 then ggml_mul
+        if (kind == MK_SWIGLU) { ll_st(P.h2 + p, (v0 / (1.0f + expf(-v0))) * v1, tag); continue; }     // ggml_silu_f32 then ggml_mul
         int r0 = 2 * p, r1 = 2 * p + 1;
         if ((kind == MK_Q || kind == MK_K) && P.neox) { const int hd = dh >> 1; const int hh = dh == 128 ? p >> 6 : p >> 5; r0 = hh * dh + (p & (hd - 1)); r1 = r0 + hd; }
         if (sg.bias) { v0 += sg.bias[r0]; v1 += sg.bias[r1]; }
         if (kind == MK_RESID) {
-            if (!(have_res && e == tid)) { res.x = __ldcg(P.x + r0); res.y = __ldcg(P.x + r1); }
-            *reinterpret_cast<float2*>(P.x + r0) = make_float2(res.x + v0, res.y + v1);
+            if (!(have_res && e == tid)) { res.x = __uint_as_float(ll_ld(P.x2 + r0).x); res.y = __uint_as_float(ll_ld(P.x2 + r1).x); }
+            ll_st2(P.x2 + r0, res.x + v0, res.y + v1, tag);
         } else if (kind == MK_LOGITS) {
             *reinterpret_cast<float2*>(P.logits + r0) = make_float2(v0, v1);
             atomicMax(P.chunk_max + (r0 >> P.chunk_shift), float_order_key(fmaxf(v0, v1)));
@@ -642,20 +689,22 @@ __device__ __noinline__ void mg_epilogue(const MegaParams& P, const MegaPhase* p
                 v0 = x0 * cs.x - x1 * cs.y;
                 v1 = x0 * cs.y + x1 * cs.x;
             }
-            if (kind == MK_Q) { P.qbuf[r0] = v0; P.qbuf[r1] = v1; }
+            if (kind == MK_Q) { ll_st(P.q2 + r0, v0, tag); ll_st(P.q2 + r1, v1, tag); }
             else {
                 const size_t base = ((size_t)S.misc[0] * KV_PAGE + (pos % KV_PAGE)) * P.kv_dim;
                 __half* dst = (kind == MK_K ? S.kp : S.vp)[ph->layer];
-                dst[base + r0] = __float2half_rn(v0);           // ggml_cpy f32 -> f16 into the cache
+                dst[base + r0] = __float2half_rn(v0);           // ggml_cpy f32 -> f16 into the cache (read by later tokens)
                 dst[base + r1] = __float2half_rn(v1);
+                uint2* kn = P.kvn2 + (kind == MK_K ? 0 : P.kv_dim);     // ... and as LL words for this token's attention
+                ll_st(kn + r0, v0, tag); ll_st(kn + r1, v1, tag);
             }
         }
     }
 }
 
-// ---- prologue of a stream phase: (RMSNorm *) quantise the source vector into shared memory, redundantly per CTA -------------
-// One warp per 256-element block.  With a norm the row has at most 2 blocks per warp (K <= 8192), loaded ONCE into registers
-// for both the sum of squares and the quantisation; nw: this lane's norm weights, fetched before the grid barrier.
+// ---- prologue of a stream phase: wait for the source vector (LL words), (RMSNorm *) quantise it into shared memory ---------
+// One warp per 256-element block, redundantly per CTA.  With a norm the row has at most 2 blocks per warp (K <= 8192), held in
+// registers for both the sum of squares and the quantisation; nw: this lane's norm weights, fetched before the wait.
 // Code size matters here (the whole decode loop has to stay resident in the instruction cache): ONE quantiser instance.
 __device__ __forceinline__ float4 mg_norm4(float4 v, float scale, float4 w) {
     return make_float4(__fmul_rn(__fmul_rn(v.x, scale), w.x), __fmul_rn(__fmul_rn(v.y, scale), w.y), __fmul_rn(__fmul_rn(v.z, scale), w.z), __fmul_rn(__fmul_rn(v.w, scale), w.w));
@@ -663,24 +712,42 @@ __device__ __forceinline__ float4 mg_norm4(float4 v, float scale, float4 w) {
 __device__ __forceinline__ double mg_sq4(float4 v) {
     return ((double)__fmul_rn(v.x, v.x) + (double)__fmul_rn(v.y, v.y)) + ((double)__fmul_rn(v.z, v.z) + (double)__fmul_rn(v.w, v.w));
 }
-__device__ __noinline__ void mg_prologue(const MegaParams& P, const MegaPhase* ph, const MgSmem& S, float4 nw0, float4 nw1, float4 nw2, float4 nw3) {
+__device__ __forceinline__ MgV8 mg_ll_vals(const MgV8F& r) {
+    MgV8 v;
+    v.a = make_float4(__uint_as_float(r.a.x), __uint_as_float(r.a.z), __uint_as_float(r.b.x), __uint_as_float(r.b.z));
+    v.b = make_float4(__uint_as_float(r.c.x), __uint_as_float(r.c.z), __uint_as_float(r.d.x), __uint_as_float(r.d.z));
+    return v;
+}
+// 8 consecutive values of a block (this lane's share), polled until every word carries the tag (warp-uniform exit)
+__device__ __forceinline__ MgV8 mg_ll_wait8(const MegaParams& P, const MgSmem& S, const uint2* p, uint32_t tag, bool active) {
+    MgV8F r = ll_ld8(p);
+    int spins = 0;
+    while (!__all_sync(0xffffffffu, !active || ll_ok8(r, tag))) {
+        if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 4); break; }
+        r = ll_ld8(p);
+    }
+    return mg_ll_vals(r);
+}
+template <bool TR>
+__device__ __noinline__ void mg_prologue(const MegaParams& P, const MegaPhase* ph, int phi, const MgSmem& S, float4 nw0, float4 nw1, float4 nw2, float4 nw3) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = ph->K, fmt = ph->act_fmt, nblk = K >> 8;
     int8_t* sq = reinterpret_cast<int8_t*>(S.act);
     float* sd = reinterpret_cast<float*>(S.act + K);
     int16_t* sbs = reinterpret_cast<int16_t*>(S.act + K + (K >> 5) * 4);
-    const float* src = (ph->src == MSRC_X ? P.x : (ph->src == MSRC_ATTN ? P.attn_out : P.hbuf)) + lane * 8;
+    const uint2* src = (ph->src == MSRC_X ? P.x2 : (ph->src == MSRC_ATTN ? P.ao2 : P.h2)) + lane * 8;
+    const uint32_t tag = phi == 0 ? P.seq * 4096u : mg_tag(P.seq, phi - 1, ph->src == MSRC_ATTN ? 3 : 0);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ph->norm_w) {
-        MgV8 v0, v1; v0.a = v0.b = v1.a = v1.b = z4;
         const int b0 = warp, b1 = warp + MG_WARPS;
-        if (b0 < nblk) v0 = mg_load8(src + b0 * 256);
-        if (b1 < nblk) v1 = mg_load8(src + b1 * 256);
+        MgV8 v0, v1; v0.a = v0.b = v1.a = v1.b = z4;
+        if (b0 < nblk) v0 = mg_ll_wait8(P, S, src + b0 * 256, tag, true);
+        if (b1 < nblk) v1 = mg_ll_wait8(P, S, src + b1 * 256, tag, true);
         double sum = (mg_sq4(v0.a) + mg_sq4(v0.b)) + (mg_sq4(v1.a) + mg_sq4(v1.b));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) S.redd[warp] = sum;
-        mg_tr(P, S, 30);
+        mg_tr<TR>(P, S, 30);
         __syncthreads();
         double t4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -688,33 +755,28 @@ __device__ __noinline__ void mg_prologue(const MegaParams& P, const MegaPhase* p
         const double tot = (t4[0] + t4[1]) + (t4[2] + t4[3]);
         const float mean = (float)(tot / (double)K);
         const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-        mg_tr(P, S, 31);
+        mg_tr<TR>(P, S, 31);
 #pragma unroll 1
         for (int r = 0; r < 2; r++) {
             const int b = r ? b1 : b0;
             if (b < nblk) mg_quantize_regs(mg_norm4(r ? v1.a : v0.a, scale, r ? nw2 : nw0), mg_norm4(r ? v1.b : v0.b, scale, r ? nw3 : nw1), fmt, b, sq, sd, sbs);
         }
     } else {
-        // software pipeline: the loads of the warp's next block are in flight while the current one is quantised
-        MgV8 cur; cur.a = cur.b = z4;
-        if (warp < nblk) cur = mg_load8(src + warp * 256);
-        mg_tr(P, S, 32);
 #pragma unroll 1
         for (int b = warp; b < nblk; b += MG_WARPS) {
-            MgV8 nxt; nxt.a = nxt.b = z4;
-            if (b + MG_WARPS < nblk) nxt = mg_load8(src + (b + MG_WARPS) * 256);
+            const MgV8 cur = mg_ll_wait8(P, S, src + b * 256, tag, true);
+            if (b == warp) mg_tr<TR>(P, S, 32);
             mg_quantize_regs(cur.a, cur.b, fmt, b, sq, sd, sbs);
-            cur = nxt;
         }
     }
-    mg_tr(P, S, 34);
+    mg_tr<TR>(P, S, 34);
     __syncthreads();
 }
 
 // =================================================================================================================
 // the kernel
 // =================================================================================================================
-template <int GQ>
+template <int GQ, bool TR>
 __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid_constant__ MegaParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -744,7 +806,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll 1
     for (int s = 0; s < MG_SLOTS; s++) issue_next();
 
-    // ---- per-token constants into shared memory: phase descriptors 0 / 1, KV pool pointers, the page of this position ----
+    // ---- per-token constants into shared memory: phase descriptors 0 / 1, KV pool pointers, the page of this position,
+    //      this CTA's attention assignment ----
     const int pos = P.pos[0];
     const int n_kv = pos + 1;
     auto fetch_phase = [&](int phi) {     // one warp copies descriptor phi into its shared-memory slot (visible after a CTA sync)
@@ -754,18 +817,23 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
     if (warp == 0) fetch_phase(0);
     if (warp == 1) fetch_phase(1);
     for (int l = tid; l < P.n_layer; l += MG_THREADS) { S.kp[l] = P.k_pools[l]; S.vp[l] = P.v_pools[l]; }
-    if (tid == 0) { S.misc[0] = P.page_table[pos / KV_PAGE]; S.misc[16] = 0; }
+    if (tid == 0) {
+        S.misc[0] = P.page_table[pos / KV_PAGE]; S.misc[16] = 0; S.misc[20] = 0;
+        mg_attn_setup(P, n_kv, S);
+        const int gq = P.n_head / P.n_head_kv, ng = MG_WARPS / gq;
+        int sh = 0; while ((1 << sh) < ng) sh++;
+        S.misc[7] = ng; S.misc[9] = (1 << sh) == ng ? 1 : 0; S.misc[10] = sh;
+    }
     __syncthreads();
 
-    unsigned int bar_target = 0;
-    mg_tr(P, S, 1);
+    mg_tr<TR>(P, S, 1);
     mg_embed(P);
     rope_table_fill(S.rope, P.d_head / 2, pos, P.theta_scale, P.rope_freqs);
-    mg_grid_arrive(P.sync);
-    auto grid_sync = [&]() { bar_target += (unsigned int)P.n_cta; mg_grid_wait(P.sync, bar_target); };
+    __syncthreads();
 
     // ================================= the token: one stream phase per iteration =================================
-    // pre-barrier part | grid wait | prologue | mat-vec | epilogue | grid arrive (| the two attention stages after a QKV phase)
+    // pre-wait part | prologue (waits for the source vector's LL words) | mat-vec | epilogue (publishes LL words)
+    //   (| the two attention stages after a QKV phase).  There is no grid barrier: the data carries its own epoch.
     // ONE instance of this body (the kernel must stay small enough for the instruction cache): the phase table drives it.
     const int n_run = P.with_head ? P.n_phases : P.n_phases - 1;
 #pragma unroll 1
@@ -774,7 +842,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         const bool is_qkv = ph->seg[0].kind == MK_Q;
         const int layer = ph->layer;
         const int trk = (is_qkv ? 0 : ph->seg[0].kind == MK_SWIGLU ? 2 : ph->seg[0].kind == MK_LOGITS ? 4 : (ph->src == MSRC_ATTN ? 1 : 3)) << 5;
-        // -- before the barrier: everything that does not depend on the other CTAs --
+        mg_tr<TR>(P, S, trk | 2);
+        // -- before the wait: everything that does not depend on the other CTAs --
         float4 nw[4];
         nw[0] = nw[1] = nw[2] = nw[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ph->norm_w) {
@@ -793,19 +862,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         const int hsl = lane - sub * L;                   // half super-block inside the slice
         const int hs = ws * L + hsl;                      // ... inside the row
         const bool lane_on = g_active && sub < rpc && hs < (K >> 7);
-        // residual rows of the pair this thread will finish in the epilogue (x is not written by anyone in between)
+        // residual rows of the pair this thread will finish in the epilogue (x is stable: its last writer phase was waited for
+        // by this CTA's previous normed prologue, the next writer is this phase)
         float2 res = make_float2(0.f, 0.f);
         const bool have_res = ph->seg[0].kind == MK_RESID && ph->NG * ph->items <= MG_THREADS;
         if (have_res && tid < ph->NG * ph->items) {
             int gl, ks, s, p;
-            if (mg_item_of(ph, P.n_cta, tid, gl, ks, s, p)) { const float2 t = __ldcg(reinterpret_cast<const float2*>(P.x + 2 * p)); res = t; }
+            if (mg_item_of(ph, P.n_cta, tid, gl, ks, s, p)) { const uint4 t = ll_ld2(P.x2 + 2 * p); res = make_float2(__uint_as_float(t.x), __uint_as_float(t.z)); }
         }
-        bar_target += (unsigned int)P.n_cta;
-        mg_grid_wait(P.sync, bar_target);
-        mg_tr(P, S, trk | 2);
         if (warp == 2) fetch_phase(phi + 1);              // next phase's descriptor (its slot's last reader was phase phi - 1)
-        mg_prologue(P, ph, S, nw[0], nw[1], nw[2], nw[3]);
-        mg_tr(P, S, trk | 3);
+        mg_prologue<TR>(P, ph, phi, S, nw[0], nw[1], nw[2], nw[3]);
+        mg_tr<TR>(P, S, trk | 3);
         // -- this lane's activations --
         LaneAct A;
         if (lane_on) {
@@ -837,7 +904,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 6; i++) A.aux[i] = 0u;
         }
-        mg_tr(P, S, trk | 4);
+        mg_tr<TR>(P, S, trk | 4);
         // -- main loop: every chunk of this warp in this phase --
         const int sb = hsl >> 1, hf = hsl & 1;
         for (int s = 0; s < ph->nseg; s++) {
@@ -906,26 +973,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
         }
         __syncthreads();
-        mg_tr(P, S, trk | 5);
-        mg_epilogue(P, ph, pos, S, res, have_res);
-        mg_tr(P, S, trk | 6);
-        mg_grid_arrive(P.sync);
+        mg_tr<TR>(P, S, trk | 5);
+        mg_epilogue(P, ph, phi, pos, S, res, have_res);
+        mg_tr<TR>(P, S, trk | 6);
         if (is_qkv) {
-            grid_sync(); mg_tr(P, S, 10);
-            mg_attn_scores<GQ>(P, layer, n_kv, S);
-            mg_tr(P, S, 11); mg_grid_arrive(P.sync); grid_sync(); mg_tr(P, S, 12);
-            mg_attn_pv<GQ>(P, layer, n_kv, S);
-            mg_tr(P, S, 16); mg_grid_arrive(P.sync);
+            mg_attn_scores<GQ>(P, layer, phi, n_kv, S);
+            mg_tr<TR>(P, S, 11);
+            mg_attn_pv<GQ, TR>(P, layer, phi, n_kv, S);
+            mg_tr<TR>(P, S, 16);
         }
+        __syncthreads();                                  // S.part, S.act and the phase descriptor slot are reused by the next phase
     }
-    grid_sync(); mg_tr(P, S, 20);
-
-    // ---- exit: the last CTA out resets the barrier state for the next launch ----
-    if (tid == 0) {
-        if (blockIdx.x == 0 && P.advance_pos) P.pos[0] = pos + 1;
-        const unsigned int old = atomicAdd(P.sync + 1, 1u);
-        if (old == (unsigned int)(P.n_cta - 1)) { P.sync[0] = 0u; P.sync[1] = 0u; __threadfence(); }
-    }
+    mg_tr<TR>(P, S, 20);
+    if (tid == 0 && blockIdx.x == 0 && P.advance_pos) P.pos[0] = pos + 1;
 }
 
 } // namespace blk

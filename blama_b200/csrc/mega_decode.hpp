@@ -77,11 +77,14 @@ struct MegaParams {
     const float* rope_freqs;
     // context
     const int32_t* tok; int32_t* pos;
-    float* x; float* qbuf; float* hbuf; float* attn_out;
-    float* scores; int score_stride; float* part_o; int max_split;
+    // cross-CTA vectors as LL words {value bits, epoch tag} (mega_decode.cuh): residual stream, q, SwiGLU output, attention output,
+    // scores [n_head][score_stride], split partials [max_split][n_head * d_head], the new token's K | V rows [2][kv_dim]
+    uint2* x2; uint2* q2; uint2* h2; uint2* ao2; uint2* sc2; uint2* po2; uint2* kvn2;
+    int score_stride; int max_split;
+    uint32_t seq;            // launch counter of the context (epoch base of every tag)
+    int* err;                // mapped host word: set when a poll timed out
     __half* const* k_pools; __half* const* v_pools; const int32_t* page_table; int kv_dim;
     float* logits; int* chunk_max; int chunk_shift;
-    unsigned int* sync;      // [0] grid barrier, [1] exit count, [4 + hk] per-KV-head arrival counters
     int with_head; int advance_pos;
     long long* trace; int trace_cap;      // optional event trace [n_cta][trace_cap] (debug / profiling)
 };

@@ -15,9 +15,9 @@ first = int(c.topk(1)["token"][0])
 c.decode_loop(first, 4)
 raw = c.debug_trace()
 KIND = ["qkv", "wo", "gu", "down", "head"]
-TAG = {2: "wait(barrier)", 3: "prologue.tail", 4: "act regs", 5: "mac", 6: "epilogue"}
-PRO = {30: "pro.load+sumsq", 31: "pro.sync+scale", 32: "pro.issue loads", 33: "pro.quant blk0 (+load wait)", 34: "pro.quant rest"}
-ATT = {17: "attn.pv.load+max", 10: "attn.wait1", 11: "attn.scores", 12: "attn.wait2", 13: "attn.pv.stats", 14: "attn.pv.pv", 15: "attn.pv.partials", 16: "attn.pv.combine", 20: "final wait"}
+TAG = {2: "(loop top)", 3: "prologue.tail", 4: "act regs", 5: "mac", 6: "epilogue"}
+PRO = {30: "pro.wait x+sumsq", 31: "pro.sync+scale", 32: "pro.wait src blk0", 34: "pro.quantise"}
+ATT = {17: "attn.pv.wait+max", 11: "attn.scores(+wait q)", 13: "attn.pv.stats", 14: "attn.pv.pv", 15: "attn.pv.partials", 16: "attn.pv.combine", 20: "final wait"}
 clk = 1.965e3
 agg = {}
 for cta in range(raw.shape[0]):
