@@ -1172,10 +1172,38 @@ extern "C" blk_status blk_timer_stop(blk_ctx* c, float* ms) {
     });
 }
 extern "C" blk_status blk_bench_kernel(blk_ctx* c, int32_t which, int32_t iters, float* avg_ms, int64_t* bytes_per_launch) {
-    if (!c || iters <= 0 || !avg_ms || !bytes_per_launch || which < 0 || which > 4) return fail(BLK_ERR_ARG, "blk_bench_kernel: bad arguments");
+    if (!c || iters <= 0 || !avg_ms || !bytes_per_launch || which < 0 || which > 5) return fail(BLK_ERR_ARG, "blk_bench_kernel: bad arguments");
     return guarded([&] {
         blk_model* m = c->m;
         BLK_CUDA(cudaSetDevice(m->device));
+        if (which == 5) {
+            // the persistent decode kernel alone (no top-k, position held): one launch = one token's whole forward
+            if (!c->mega_on) throw BlkError(BLK_ERR_ARG, "blk_bench_kernel(5): this context does not run the persistent decode kernel");
+            if (c->n_past + 1 > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+            auto one = [&] {
+                MegaParams P = c->mega_params;
+                P.with_head = 1; P.advance_pos = 0; P.seq = ++c->mega_seq;
+                BLK_CUDA(mega_launch(P, c->mega_smem, c->stream));
+                c->launches++;
+            };
+            BLK_CUDA(cudaMemsetAsync(c->d_tok, 0, sizeof(int32_t), c->stream));
+            for (int i = 0; i < std::min(iters, 4); i++) one();
+            BLK_CUDA(cudaEventRecord(c->ev0, c->stream));
+            for (int i = 0; i < iters; i++) one();
+            BLK_CUDA(cudaEventRecord(c->ev1, c->stream));
+            BLK_CUDA(cudaEventSynchronize(c->ev1));
+            check_mega(c);
+            float ms = 0.0f;
+            BLK_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            *avg_ms = ms / (float)iters;
+            *bytes_per_launch = m->weight_bytes_per_token + (int64_t)(c->n_past + 1) * blk_model_kv_bytes_per_token(m);
+            // the launches left chunk maxima behind (no top-k ran): clear them, and forget the logits
+            std::vector<int> init(256, (int)0x80000000);
+            BLK_CUDA(cudaMemcpyAsync(c->chunk_max, init.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            BLK_CUDA(cudaStreamSynchronize(c->stream));
+            c->have_logits = false;
+            return;
+        }
         const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
         // make the activation buffers hold something sane
         BLK_CUDA(cudaMemsetAsync(c->x, 0, d * sizeof(float), c->stream));

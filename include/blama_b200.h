@@ -140,8 +140,9 @@ BLK_API blk_status blk_debug_trace(blk_ctx*, int64_t* out, int32_t cap, int32_t*
 /* Times ONE kernel of the decode path in isolation, for the roofline line of bench.py: launches it `iters` times back to
  * back, cycling through the layers so consecutive launches stream different weights (working set >> L2), bracketed by
  * CUDA events on the context's stream.  which: 0 = gate/up + SwiGLU mat-vec, 1 = down-proj mat-vec, 2 = QKV mat-vec,
- * 3 = attention-output mat-vec, 4 = lm_head mat-vec.  Returns the average launch duration and the algorithmic bytes one
- * launch must move (quantised weight planes + activations + outputs). */
+ * 3 = attention-output mat-vec, 4 = lm_head mat-vec, 5 = the persistent decode kernel (one launch = the whole forward of
+ * one token at the context's current position, top-k not included; needs blk_ctx_persistent_decode() == 1).  Returns the
+ * average launch duration and the algorithmic bytes one launch must move (quantised weights + KV rows read / activations). */
 BLK_API blk_status blk_bench_kernel(blk_ctx*, int32_t which, int32_t iters, float* avg_ms, int64_t* bytes_per_launch);
 /* Decodes `token` with the step's kernels launched eagerly and a CUDA event between every pair of launches (so without
  * the cross-kernel overlap of the graph), and writes a CSV breakdown (kernel, launches, total_us, avg_us, share). */
