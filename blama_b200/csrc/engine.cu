@@ -740,6 +740,21 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
     c->pf_h = dalloc<__nv_bfloat16>(c, t * ff);
     c->pf_logit_rows = 256;
     c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
+    {   // bf16 weight panel of the two-pass GEMM form (largest single launch: QKV | Wo | gate+up | down | lm_head)
+        auto rows = [](int n) { return (size_t)((n + 255) / 256) * 256; };
+        size_t elems = (rows(dq) + 2 * rows(dkv)) * (size_t)d;
+        elems = std::max(elems, rows(d) * (size_t)dq);
+        elems = std::max(elems, 2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d);
+        elems = std::max(elems, rows(d) * (size_t)ff);
+        elems = std::max(elems, rows(m->n_vocab) * (size_t)d);
+        const char* pm = getenv("BLK_PANEL_MIN");
+        c->panel_min = pm ? atoi(pm) : 1024;
+        if (c->panel_min > 0 && cap >= c->panel_min) {
+            void* p = nullptr;
+            if (cudaMalloc(&p, elems * sizeof(__nv_bfloat16)) == cudaSuccess) { c->allocs.push_back(p); c->pf_panel = reinterpret_cast<__nv_bfloat16*>(p); }
+            else (void)cudaGetLastError();
+        }
+    }
     c->pf_claimed = dalloc<int32_t>(c, t * 10); c->pf_nclaimed = dalloc<int32_t>(c, t);
     c->pf_gath = dalloc<float>(c, t * 10); c->pf_topi = dalloc<int32_t>(c, t * 10); c->pf_topl = dalloc<float>(c, t * 10);
     c->pf_cap = cap;
@@ -772,6 +787,9 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff, V = m->n_vocab;
     ensure_prefill_bufs(c, n);
     cudaStream_t st = c->stream;
+    // many tokens: dequantise every matrix ONCE into the bf16 panel and run the GEMMs TMA-fed on both operands; few tokens: the
+    // fused form (weights dequantised inside the GEMM, once per 256 tokens) moves fewer bytes
+    __nv_bfloat16* panel = (c->pf_panel && c->panel_min > 0 && n >= c->panel_min) ? c->pf_panel : nullptr;
     BLK_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     embed_kernel<<<n, 256, 0, st>>>(m->tok_embd, c->pf_tokens, c->d_pos, c->pf_x, c->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
     BLK_CUDA(cudaGetLastError()); c->launches++;
@@ -783,7 +801,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
-        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st));
+        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st, panel));
         prof_mark(c, "gemm_qkv");
         QkvPostArgs qa{};
         qa.qkv = c->pf_qkv; qa.ld = ldq; qa.rope_cs = c->pf_rope; qa.pos0 = c->d_pos; qa.q_out = c->pf_q;
@@ -800,14 +818,14 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         else prefill_attn_kernel<64><<<agrid, 128, 3 * 64 * (64 + 8) * 2, st>>>(pa);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "flash_attn");
-        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st));
+        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, panel));
         prof_mark(c, "gemm_wo");
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
-        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st));
+        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, panel));
         prof_mark(c, "gemm_gate_up_swiglu");
-        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st));
+        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, panel));
         prof_mark(c, "gemm_down");
         c->launches += 12;
     }
@@ -820,7 +838,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         BLK_CUDA(cudaGetLastError()); c->launches++;
         for (int r0 = 0; r0 < n; r0 += c->pf_logit_rows) {
             const int rows = std::min(c->pf_logit_rows, n - r0);
-            BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st));
+            BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st, panel, r0 == 0));
             prof_mark(c, "gemm_lm_head");
             RowTopkArgs ta{};
             ta.logits = c->pf_logits; ta.ld = V; ta.n_vocab = V; ta.row0 = r0;
@@ -1406,7 +1424,9 @@ extern "C" blk_status blk_test_gemm(int32_t device, int32_t type, const void* bl
         float* d_y = dalloc<float>(&c, (size_t)n_tok * rows);
         BLK_CUDA(cudaMemcpyAsync(d_x, x, (size_t)n_tok * k * 4, cudaMemcpyHostToDevice, c.stream));
         BLK_CUDA(convert_f32_to_bf16(d_x, d_xb, (size_t)n_tok * k, c.stream));
-        BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream));
+        __nv_bfloat16* panel = nullptr;        // BLK_TEST_PANEL=1: the two-pass form (dequantise to a bf16 panel, TMA-fed GEMM)
+        { const char* tp = getenv("BLK_TEST_PANEL"); if (tp && tp[0] == '1' && type != GT_F32 && type != GT_F16) panel = dalloc<__nv_bfloat16>(&c, prefill_panel_rows((int)rows) * (size_t)k); }
+        BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream, panel));
         BLK_CUDA(cudaMemcpyAsync(y, d_y, (size_t)n_tok * rows * 4, cudaMemcpyDeviceToHost, c.stream));
         BLK_CUDA(cudaStreamSynchronize(c.stream));
     });
@@ -1422,9 +1442,11 @@ extern "C" blk_status blk_bench_gemm(int32_t device, int32_t type, const void* b
         __nv_bfloat16* d_xb = dalloc<__nv_bfloat16>(&c, (size_t)n_tok * k);
         float* d_y = dalloc<float>(&c, (size_t)n_tok * rows);
         BLK_CUDA(cudaMemsetAsync(d_xb, 0x3c, (size_t)n_tok * k * 2, c.stream));
-        for (int i = 0; i < 3; i++) BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream));
+        __nv_bfloat16* panel = nullptr;        // BLK_TEST_PANEL=1: time the two-pass form (dequantisation pass included)
+        { const char* tp = getenv("BLK_TEST_PANEL"); if (tp && tp[0] == '1') panel = dalloc<__nv_bfloat16>(&c, prefill_panel_rows((int)rows) * (size_t)k); }
+        for (int i = 0; i < 3; i++) BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream, panel));
         BLK_CUDA(cudaEventRecord(c.ev0, c.stream));
-        for (int i = 0; i < iters; i++) BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream));
+        for (int i = 0; i < iters; i++) BLK_CUDA(prefill_gemm(tm.W, d_xb, (int)n_tok, d_y, rows, nullptr, 0, c.stream, panel));
         BLK_CUDA(cudaEventRecord(c.ev1, c.stream));
         BLK_CUDA(cudaEventSynchronize(c.ev1));
         float ms = 0.0f;

@@ -45,31 +45,40 @@ cudaError_t convert_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cuda
 }
 
 namespace {
-using GemmKernel = void (*)(const CUtensorMap, const PrefillGemmArgs);
+using GemmKernel = void (*)(const CUtensorMap, const CUtensorMap, const PrefillGemmArgs);
 
 GemmKernel pick_kernel(int ta, int tb) {
 #define BLK_K(A, B) if (ta == A && tb == B) return prefill_gemm_kernel<A, B>;
     BLK_K(QT_Q4_K, QT_Q4_K) BLK_K(QT_Q6_K, QT_Q6_K) BLK_K(QT_Q8_0, QT_Q8_0) BLK_K(QT_Q5_K, QT_Q5_K) BLK_K(QT_F32, QT_F32) BLK_K(QT_F16, QT_F16)
-    BLK_K(QT_Q4_K, QT_Q6_K) BLK_K(QT_Q4_K, QT_Q5_K)
+    BLK_K(QT_Q4_K, QT_Q6_K) BLK_K(QT_Q4_K, QT_Q5_K) BLK_K(QT_PANEL, QT_PANEL)
 #undef BLK_K
     return nullptr;
 }
 
-cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16* X, cudaStream_t st) {
+// panel: nullptr for the fused (in-kernel dequantisation) form, else the bf16 panel [panel_rows][K] the B tiles are read from
+cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16* X, cudaStream_t st, const __nv_bfloat16* panel = nullptr, long long panel_rows = 0) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
     if (a.K % PG_BK || a.T <= 0 || a.n_tiles <= 0) return cudaErrorInvalidValue;
-    GemmKernel kernel = pick_kernel(ta, tb);
+    GemmKernel kernel = panel ? pick_kernel(QT_PANEL, QT_PANEL) : pick_kernel(ta, tb);
     if (!kernel) return cudaErrorInvalidValue;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_w;
     const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.T};
     const cuuint64_t gstride[1] = {(cuuint64_t)a.K * sizeof(__nv_bfloat16)};
     const cuuint32_t box[2] = {(cuuint32_t)PG_BK, 128u};
     const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(X), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(X), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    tmap_w = tmap;
+    if (panel) {
+        const cuuint64_t wdim[2] = {(cuuint64_t)a.K, (cuuint64_t)panel_rows};
+        r = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(panel), wdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -78,26 +87,64 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = ((a.T + PG_BM - 1) / PG_BM) * a.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
-    kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, a);
+    kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, tmap_w, a);
     return cudaGetLastError();
 }
+
+// first pass of the two-pass form: W -> panel rows [row0, row0 + W.N)
+cudaError_t panel_dequant(const QMat& W, __nv_bfloat16* panel, long long row0, cudaStream_t st) {
+    const long long total = (long long)W.N * (W.K >> 6);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    __nv_bfloat16* dst = panel + (size_t)row0 * W.K;
+    switch (W.type) {
+        case QT_Q4_K: panel_dequant_kernel<QT_Q4_K><<<grid, 256, 0, st>>>(W, dst); break;
+        case QT_Q5_K: panel_dequant_kernel<QT_Q5_K><<<grid, 256, 0, st>>>(W, dst); break;
+        case QT_Q6_K: panel_dequant_kernel<QT_Q6_K><<<grid, 256, 0, st>>>(W, dst); break;
+        case QT_Q8_0: panel_dequant_kernel<QT_Q8_0><<<grid, 256, 0, st>>>(W, dst); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+bool panel_type_ok(int t) { return t == QT_Q4_K || t == QT_Q5_K || t == QT_Q6_K || t == QT_Q8_0; }
 } // namespace
 
-cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st) {
+cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st,
+                         __nv_bfloat16* panel, bool panel_fill) {
     PrefillGemmArgs a{};
     a.nseg = 1; a.seg[0] = {W, bias, 0, 0};
     a.C = C; a.ldc = ldc; a.T = T; a.K = W.K; a.mode = mode;
     a.n_tiles = (W.N + PG_BN - 1) / PG_BN;
+    if (panel && panel_type_ok(W.type) && W.K % 64 == 0) {
+        if (panel_fill) { cudaError_t e = panel_dequant(W, panel, 0, st); if (e != cudaSuccess) return e; }
+        return launch_gemm(a, W.type, W.type, X, st, panel, (long long)a.n_tiles * PG_BN);
+    }
     return launch_gemm(a, W.type, W.type, X, st);
 }
+size_t prefill_panel_rows(int N) { return (size_t)((N + PG_BN - 1) / PG_BN) * PG_BN; }
 
-cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st) {
+cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st,
+                               __nv_bfloat16* panel) {
+    bool all_panel = panel != nullptr && n_parts >= 1 && n_parts <= 3;
+    for (int i = 0; i < n_parts && all_panel; i++) all_panel = panel_type_ok(parts[i].W->type) && parts[i].W->K == parts[0].W->K && parts[i].col0 % 4 == 0;
     bool fuse = n_parts >= 2 && n_parts <= 3 && parts[0].W->type == parts[1].W->type;
     for (int i = 0; i < n_parts && fuse; i++) fuse = (parts[i].col0 % 4 == 0) && parts[i].W->K == parts[0].W->K;
     if (fuse && n_parts == 3 && !pick_kernel(parts[0].W->type, parts[2].W->type)) fuse = false;
+    if (all_panel) {      // any mix of weight types: every segment is dequantised to its tile-aligned rows of the panel
+        PrefillGemmArgs a{};
+        a.nseg = n_parts; a.C = C; a.ldc = ldc; a.T = T; a.K = parts[0].W->K; a.mode = PG_STORE;
+        int tile0 = 0;
+        for (int i = 0; i < n_parts; i++) {
+            a.seg[i] = {*parts[i].W, parts[i].bias, parts[i].col0, tile0};
+            cudaError_t e = panel_dequant(*parts[i].W, panel, (long long)tile0 * PG_BN, st);
+            if (e != cudaSuccess) return e;
+            tile0 += (parts[i].W->N + PG_BN - 1) / PG_BN;
+        }
+        a.n_tiles = tile0;
+        return launch_gemm(a, QT_PANEL, QT_PANEL, X, st, panel, (long long)tile0 * PG_BN);
+    }
     if (!fuse) {
         for (int i = 0; i < n_parts; i++) {
-            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st);
+            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st, nullptr, false);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
@@ -113,12 +160,21 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
     return launch_gemm(a, parts[0].W->type, n_parts == 3 ? parts[2].W->type : parts[0].W->type, X, st);
 }
 
-cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st) {
+cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,
+                                __nv_bfloat16* panel) {
     if (gate.type != up.type || gate.N != up.N || gate.K != up.K || ldh % 8) return cudaErrorInvalidValue;
     PrefillGemmArgs a{};
     a.nseg = 2; a.seg[0] = {gate, nullptr, 0, 0}; a.seg[1] = {up, nullptr, 0, 0};
     a.H = H; a.ldh = ldh; a.T = T; a.K = gate.K; a.mode = PG_SWIGLU;
     a.n_tiles = (gate.N + 127) / 128;
+    if (panel && panel_type_ok(gate.type) && gate.K % 64 == 0) {
+        a.panel_up_row0 = a.n_tiles * 128;                         // gate rows, then (tile-aligned) the up rows
+        cudaError_t e = panel_dequant(gate, panel, 0, st);
+        if (e != cudaSuccess) return e;
+        e = panel_dequant(up, panel, a.panel_up_row0, st);
+        if (e != cudaSuccess) return e;
+        return launch_gemm(a, gate.type, gate.type, X, st, panel, 2LL * a.panel_up_row0);
+    }
     return launch_gemm(a, gate.type, gate.type, X, st);
 }
 

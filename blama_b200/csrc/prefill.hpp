@@ -9,15 +9,22 @@ namespace blk {
 
 // C[T][N] (f32, row stride ldc) = or += X[T][K] (bf16, row-major, device) . W^T  through the tcgen05 GEMM
 // mode: 0 store (+bias), 1 accumulate into C.  Returns a CUDA error (cudaErrorNotSupported if the driver lacks TMA).
-cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st);
+// panel != nullptr selects the two-pass form: W is dequantised once into the bf16 panel (panel_fill) and the GEMM reads its B
+// tiles from there by TMA -- for many-token batches, where the fused form would dequantise every weight tile T / 256 times.
+cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st,
+                         __nv_bfloat16* panel = nullptr, bool panel_fill = true);
+// rows a matrix of N rows occupies in a panel (tile aligned)
+size_t prefill_panel_rows(int N);
 
 // several matrices with the same K in one launch: C[:, col0_s : col0_s + N_s] = X . W_s^T (+bias_s).  Matrices 0 and 1 must share
 // a weight type.  Falls back to one launch per matrix when a column offset is not 4-element aligned.
 struct GemmPart { const QMat* W; const float* bias; int col0; };
-cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st);
+cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st,
+                               __nv_bfloat16* panel = nullptr);
 
 // H[T][ff] (bf16) = silu(X . Wgate^T) * (X . Wup^T), one launch, SwiGLU in the GEMM epilogue
-cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st);
+cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,
+                                __nv_bfloat16* panel = nullptr);
 
 // y[i] = bf16(x[i])
 cudaError_t convert_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t st);

@@ -31,6 +31,9 @@ constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
 constexpr int PG_SMEM_BYTES = PG_STAGES * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum : int { PG_STORE = 0, PG_ACCUM = 1, PG_SWIGLU = 2 };
+// pseudo weight type of the two-pass form: the weights were dequantised once into a bf16 "panel" [rows][K] in global memory
+// (panel_dequant_kernel) and the B tile is fetched by TMA like the activations; no dequantisation inside the GEMM
+constexpr int QT_PANEL = 100;
 
 // Up to three weight matrices share one launch (q | k | v, or gate | up): more tiles per launch = less wave-quantisation
 // loss on 148 SMs.  Segment s covers output columns [col0, col0 + W.N); its tiles are 256 rows of W (the last may be
@@ -45,6 +48,7 @@ struct PrefillGemmArgs {
     int T, K;
     int n_tiles;                // total column tiles over all segments
     int mode;
+    int panel_up_row0;          // QT_PANEL + PG_SWIGLU: panel row of ffn_up row 0 (ffn_gate starts at panel row 0)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -304,7 +308,8 @@ template <int TYPE> struct RawK64 {
 };
 
 template <int TA, int TB>
-__global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const PrefillGemmArgs a) {
+__global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const PrefillGemmArgs a) {
+    constexpr bool PANEL = (TA == QT_PANEL);
     extern __shared__ unsigned char pg_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PG_STAGES * PG_STAGE_BYTES);
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PG_STAGES; s++) { mbar_init(full + s, 1 + PG_PRODUCER_THREADS / 32); mbar_init(empty + s, 1); }
+        for (int s = 0; s < PG_STAGES; s++) { mbar_init(full + s, PANEL ? 1 : 1 + PG_PRODUCER_THREADS / 32); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 8);
         mbar_fence_init();
@@ -339,14 +344,21 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile % m_tiles) * PG_BM;
+                const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
+                // panel rows of the two 128-row halves of the B tile
+                const int w0 = a.mode == PG_SWIGLU ? nt * 128 : nt * PG_BN;
+                const int w1 = a.mode == PG_SWIGLU ? a.panel_up_row0 + nt * 128 : nt * PG_BN + 128;
                 for (int kb = 0; kb < k_blocks; kb++, it++) {
                     const int s = it % PG_STAGES;
                     mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
                     unsigned char* sa = smem + s * PG_STAGE_BYTES;
-                    mbar_expect_tx(full + s, PG_A_BYTES);
+                    mbar_expect_tx(full + s, PANEL ? PG_A_BYTES + PG_B_BYTES : PG_A_BYTES);
                     tma_load_2d(sa, &tmap_x, kb * PG_BK, m0, full + s);
                     tma_load_2d(sa + PG_A_BYTES / 2, &tmap_x, kb * PG_BK, m0 + 128, full + s);
+                    if (PANEL) {
+                        tma_load_2d(sa + PG_A_BYTES, &tmap_w, kb * PG_BK, w0, full + s);
+                        tma_load_2d(sa + PG_A_BYTES + PG_B_BYTES / 2, &tmap_w, kb * PG_BK, w1, full + s);
+                    }
                 }
             }
         }
@@ -418,7 +430,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                     if (DEEP) nxt = nx2;
                 }
             };
-            if (TA != TB && si == 2) produce(RawK64<TB>{}); else produce(RawK64<TA>{});
+            if constexpr (!PANEL) { if (TA != TB && si == 2) produce(RawK64<TB>{}); else produce(RawK64<TA>{}); }
+            else { (void)produce; (void)row_ok; }
             {
                 // ---- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31; warps 0-3 drain the first accumulator
                 //      (token rows 0-127), warps 4-7 the second (rows 128-255) ----
@@ -507,6 +520,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     if (warp == 9) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+}
+
+// ---- first pass of the two-pass form: one weight matrix -> bf16 panel rows [N][K] (row stride K), same values the fused
+// producers write into shared memory (bf16 of ggml's dequantised f32) ----------------------------------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(256) panel_dequant_kernel(const QMat W, __nv_bfloat16* __restrict__ dst) {
+    const int kbs = W.K >> 6;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)W.N * kbs) return;
+    const int64_t row = idx / kbs; const int kb = (int)(idx - row * kbs);
+    RawK64<TYPE> raw;
+    raw.load(W, row, kb);
+    raw.expand(reinterpret_cast<unsigned char*>(dst + (size_t)row * W.K + (size_t)kb * 64), 0, kb);      // r = 0: no swizzle, 8 x 16 B in order
 }
 
 } // namespace blk

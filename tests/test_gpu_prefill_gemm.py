@@ -20,8 +20,15 @@ CASES = [(256, 256, 256), (300, 384, 1024), (1, 256, 512), (77, 1000, 256), (512
 
 @pytest.mark.parametrize("gtype,name", [(gs.Q4_K, "Q4_K"), (gs.Q6_K, "Q6_K"), (gs.Q8_0, "Q8_0"), (gs.Q5_K, "Q5_K"), (gs.F32, "F32")])
 @pytest.mark.parametrize("T,N,K", CASES)
-def test_prefill_gemm(gtype, name, T, N, K, oracle):
+@pytest.mark.parametrize("form", ["fused", "panel"])
+def test_prefill_gemm(gtype, name, T, N, K, form, oracle, monkeypatch):
+    """form = fused: weights dequantised inside the GEMM; panel: dequantised once to a bf16 panel, both operands TMA-fed."""
     from blama_b200 import capi
+
+    if form == "panel":
+        if gtype == gs.F32:
+            pytest.skip("the panel form covers the quantised types")
+        monkeypatch.setenv("BLK_TEST_PANEL", "1")
 
     if gtype == gs.F32 and K > 4096:
         pytest.skip("F32 weights are a test-only format")
