@@ -451,6 +451,7 @@ blk_ctx::~blk_ctx() {
     for (void* p : host_allocs) cudaFreeHost(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (int i = 0; i < 4; i++) { if (pn_filled[i]) cudaEventDestroy(pn_filled[i]); if (pn_start[i]) cudaEventDestroy(pn_start[i]); }
     if (pf_fork) cudaEventDestroy(pf_fork);
     if (pf_join) cudaEventDestroy(pf_join);
     if (pf_stream) cudaStreamDestroy(pf_stream);
@@ -741,18 +742,25 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
     c->pf_logit_rows = 256;
     c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
     {   // bf16 weight panel of the two-pass GEMM form (largest single launch: QKV | Wo | gate+up | down | lm_head)
+        // one panel per GEMM kind, so the dequantisation of the NEXT matrix (second stream) runs while the current GEMM does:
+        //   [0] QKV   [1] Wo   [2] gate+up | lm_head   [3] down
         auto rows = [](int n) { return (size_t)((n + 255) / 256) * 256; };
-        size_t elems = (rows(dq) + 2 * rows(dkv)) * (size_t)d;
-        elems = std::max(elems, rows(d) * (size_t)dq);
-        elems = std::max(elems, 2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d);
-        elems = std::max(elems, rows(d) * (size_t)ff);
-        elems = std::max(elems, rows(m->n_vocab) * (size_t)d);
+        const size_t pe[4] = {(rows(dq) + 2 * rows(dkv)) * (size_t)d, rows(d) * (size_t)dq,
+                              std::max(2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d, rows(m->n_vocab) * (size_t)d), rows(d) * (size_t)ff};
         const char* pm = getenv("BLK_PANEL_MIN");
         c->panel_min = pm ? atoi(pm) : 1024;
         if (c->panel_min > 0 && cap >= c->panel_min) {
-            void* p = nullptr;
-            if (cudaMalloc(&p, elems * sizeof(__nv_bfloat16)) == cudaSuccess) { c->allocs.push_back(p); c->pf_panel = reinterpret_cast<__nv_bfloat16*>(p); }
-            else (void)cudaGetLastError();
+            bool ok = true;
+            for (int i = 0; i < 4 && ok; i++) {
+                void* p = nullptr;
+                ok = cudaMalloc(&p, pe[i] * sizeof(__nv_bfloat16)) == cudaSuccess;
+                if (ok) { c->allocs.push_back(p); c->pf_panel[i] = reinterpret_cast<__nv_bfloat16*>(p); }
+            }
+            if (!ok) { (void)cudaGetLastError(); for (int i = 0; i < 4; i++) c->pf_panel[i] = nullptr; }
+            else for (int i = 0; i < 4; i++) {
+                BLK_CUDA(cudaEventCreateWithFlags(&c->pn_filled[i], cudaEventDisableTiming));
+                BLK_CUDA(cudaEventCreateWithFlags(&c->pn_start[i], cudaEventDisableTiming));
+            }
         }
     }
     c->pf_claimed = dalloc<int32_t>(c, t * 10); c->pf_nclaimed = dalloc<int32_t>(c, t);
@@ -789,19 +797,57 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     cudaStream_t st = c->stream;
     // many tokens: dequantise every matrix ONCE into the bf16 panel and run the GEMMs TMA-fed on both operands; few tokens: the
     // fused form (weights dequantised inside the GEMM, once per 256 tokens) moves fewer bytes
-    __nv_bfloat16* panel = (c->pf_panel && c->panel_min > 0 && n >= c->panel_min) ? c->pf_panel : nullptr;
+    const bool panel = c->pf_panel[0] && c->panel_min > 0 && n >= c->panel_min;
     BLK_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     embed_kernel<<<n, 256, 0, st>>>(m->tok_embd, c->pf_tokens, c->d_pos, c->pf_x, c->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
     BLK_CUDA(cudaGetLastError()); c->launches++;
     prof_mark(c, "embed");
     const long long ldq = dq + 2 * dkv;
+    // ---- two-pass form: the dequantisation passes run on the side stream, one GEMM ahead of the main stream ----
+    //   op 4l + {0: QKV, 1: Wo, 2: gate+up, 3: down}, op 4 n_layer: lm_head (panel 2).  The fill of op i+1 starts when GEMM i
+    //   starts (its panel's previous user, GEMM i-3, is then done), so fills overlap GEMMs, not the small bandwidth-bound kernels.
+    const int n_ops = 4 * m->n_layer + (verify ? 1 : 0);
+    std::vector<char> op_panel(n_ops + 1, 0);
+    auto panel_of = [&](int i) { return i >= 4 * m->n_layer ? 2 : (i & 3); };
+    auto fill_op = [&](int i) {      // enqueue the fill of op i on the side stream
+        if (!panel || i >= n_ops) return;
+        const int b = panel_of(i), l = i >> 2, k = i & 3;
+        cudaStream_t ss = c->pf_stream;
+        cudaError_t err = cudaSuccess; bool ok = false;
+        if (l >= m->n_layer) { const GemmPart o[1] = {{&m->output, nullptr, 0}}; ok = prefill_panel_fill(o, 1, c->pf_panel[b], ss, &err); }
+        else {
+            const LayerWeights& L = m->layers[l];
+            if (k == 0) { const GemmPart q[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}}; ok = prefill_panel_fill(q, 3, c->pf_panel[b], ss, &err); }
+            else if (k == 1) { const GemmPart o[1] = {{&L.wo, nullptr, 0}}; ok = prefill_panel_fill(o, 1, c->pf_panel[b], ss, &err); }
+            else if (k == 2) ok = prefill_panel_fill_swiglu(L.gate, L.up, c->pf_panel[b], ss, &err);
+            else { const GemmPart o[1] = {{&L.down, nullptr, 0}}; ok = prefill_panel_fill(o, 1, c->pf_panel[b], ss, &err); }
+        }
+        BLK_CUDA(err);
+        op_panel[i] = ok ? 1 : 0;
+        BLK_CUDA(cudaEventRecord(c->pn_filled[b], ss));
+        c->launches += ok ? 2 : 0;
+    };
+    auto before_gemm = [&](int i) -> __nv_bfloat16* {      // main stream, right before GEMM i; returns its panel (nullptr: fused form)
+        if (!panel) return nullptr;
+        const int b = panel_of(i);
+        BLK_CUDA(cudaEventRecord(c->pn_start[b], st));                      // GEMM i is about to start ...
+        BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[b], 0));     // ... so is the fill of op i + 1 (other panel)
+        BLK_CUDA(cudaStreamWaitEvent(st, c->pn_filled[b], 0));
+        __nv_bfloat16* mine = op_panel[i] ? c->pf_panel[b] : nullptr;
+        fill_op(i + 1);
+        return mine;
+    };
+    auto after_gemm = [&](int) {};
+    if (panel) { BLK_CUDA(cudaEventRecord(c->pn_start[0], st)); BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[0], 0)); }   // after whatever ran before
+    fill_op(0);
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
-        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st, panel));
+        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st, before_gemm(4 * l), false));
+        after_gemm(4 * l);
         prof_mark(c, "gemm_qkv");
         QkvPostArgs qa{};
         qa.qkv = c->pf_qkv; qa.ld = ldq; qa.rope_cs = c->pf_rope; qa.pos0 = c->d_pos; qa.q_out = c->pf_q;
@@ -818,14 +864,17 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         else prefill_attn_kernel<64><<<agrid, 128, 3 * 64 * (64 + 8) * 2, st>>>(pa);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "flash_attn");
-        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, panel));
+        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 1), false));
+        after_gemm(4 * l + 1);
         prof_mark(c, "gemm_wo");
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
-        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, panel));
+        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, before_gemm(4 * l + 2), false));
+        after_gemm(4 * l + 2);
         prof_mark(c, "gemm_gate_up_swiglu");
-        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, panel));
+        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 3), false));
+        after_gemm(4 * l + 3);
         prof_mark(c, "gemm_down");
         c->launches += 12;
     }
@@ -836,9 +885,10 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         BLK_CUDA(cudaMemcpyAsync(c->pf_nclaimed, verify->n_claimed + verify_row0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError()); c->launches++;
+        __nv_bfloat16* head_panel = nullptr;
         for (int r0 = 0; r0 < n; r0 += c->pf_logit_rows) {
             const int rows = std::min(c->pf_logit_rows, n - r0);
-            BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st, panel, r0 == 0));
+            BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st, r0 == 0 ? (head_panel = before_gemm(4 * m->n_layer)) : head_panel, false));
             prof_mark(c, "gemm_lm_head");
             RowTopkArgs ta{};
             ta.logits = c->pf_logits; ta.ld = V; ta.n_vocab = V; ta.row0 = r0;

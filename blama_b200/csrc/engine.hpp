@@ -122,7 +122,9 @@ struct blk_ctx {
     float* pf_x = nullptr; __nv_bfloat16* pf_xn = nullptr; float* pf_qkv = nullptr; __half* pf_q = nullptr;
     __nv_bfloat16* pf_ao = nullptr; float* pf_g = nullptr; float* pf_u = nullptr; __nv_bfloat16* pf_h = nullptr;
     float* pf_logits = nullptr;
-    __nv_bfloat16* pf_panel = nullptr; int panel_min = 1024;   // two-pass GEMM form from this many tokens per chunk on (0 = never)
+    __nv_bfloat16* pf_panel[4] = {nullptr, nullptr, nullptr, nullptr};     // bf16 weight panels of the two-pass GEMM form, one per GEMM kind
+    cudaEvent_t pn_filled[4] = {nullptr, nullptr, nullptr, nullptr}, pn_start[4] = {nullptr, nullptr, nullptr, nullptr};
+    int panel_min = 1024;   // two-pass GEMM form from this many tokens per chunk on (0 = never)
     int32_t* pf_claimed = nullptr; int32_t* pf_nclaimed = nullptr; float* pf_gath = nullptr; int32_t* pf_topi = nullptr; float* pf_topl = nullptr;
     int prefill_min = 32;                  // blk_decode / blk_verify_prefill use the tcgen05 path from this many tokens on
     // scratch for gather / verify

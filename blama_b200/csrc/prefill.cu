@@ -120,10 +120,32 @@ cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C,
     }
     return launch_gemm(a, W.type, W.type, X, st);
 }
+// the dequantisation passes alone (same panel layout as the GEMM entry points above use), so that a caller can run them on a
+// second stream one GEMM ahead; false = this combination takes the fused form (the GEMM call must then get panel = nullptr)
+bool prefill_panel_fill(const GemmPart* parts, int n_parts, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err) {
+    *err = cudaSuccess;
+    if (!panel || n_parts < 1 || n_parts > 3) return false;
+    for (int i = 0; i < n_parts; i++) if (!panel_type_ok(parts[i].W->type) || parts[i].W->K != parts[0].W->K || parts[i].col0 % 4 || parts[i].W->K % 64) return false;
+    int tile0 = 0;
+    for (int i = 0; i < n_parts; i++) {
+        *err = panel_dequant(*parts[i].W, panel, (long long)tile0 * PG_BN, st);
+        if (*err != cudaSuccess) return true;
+        tile0 += (parts[i].W->N + PG_BN - 1) / PG_BN;
+    }
+    return true;
+}
+bool prefill_panel_fill_swiglu(const QMat& gate, const QMat& up, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err) {
+    *err = cudaSuccess;
+    if (!panel || gate.type != up.type || !panel_type_ok(gate.type) || gate.K % 64) return false;
+    const long long up0 = (long long)((gate.N + 127) / 128) * 128;
+    *err = panel_dequant(gate, panel, 0, st);
+    if (*err == cudaSuccess) *err = panel_dequant(up, panel, up0, st);
+    return true;
+}
 size_t prefill_panel_rows(int N) { return (size_t)((N + PG_BN - 1) / PG_BN) * PG_BN; }
 
 cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st,
-                               __nv_bfloat16* panel) {
+                               __nv_bfloat16* panel, bool panel_fill) {
     bool all_panel = panel != nullptr && n_parts >= 1 && n_parts <= 3;
     for (int i = 0; i < n_parts && all_panel; i++) all_panel = panel_type_ok(parts[i].W->type) && parts[i].W->K == parts[0].W->K && parts[i].col0 % 4 == 0;
     bool fuse = n_parts >= 2 && n_parts <= 3 && parts[0].W->type == parts[1].W->type;
@@ -135,8 +157,7 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
         int tile0 = 0;
         for (int i = 0; i < n_parts; i++) {
             a.seg[i] = {*parts[i].W, parts[i].bias, parts[i].col0, tile0};
-            cudaError_t e = panel_dequant(*parts[i].W, panel, (long long)tile0 * PG_BN, st);
-            if (e != cudaSuccess) return e;
+            if (panel_fill) { cudaError_t e = panel_dequant(*parts[i].W, panel, (long long)tile0 * PG_BN, st); if (e != cudaSuccess) return e; }
             tile0 += (parts[i].W->N + PG_BN - 1) / PG_BN;
         }
         a.n_tiles = tile0;
@@ -161,7 +182,7 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
 }
 
 cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,
-                                __nv_bfloat16* panel) {
+                                __nv_bfloat16* panel, bool panel_fill) {
     if (gate.type != up.type || gate.N != up.N || gate.K != up.K || ldh % 8) return cudaErrorInvalidValue;
     PrefillGemmArgs a{};
     a.nseg = 2; a.seg[0] = {gate, nullptr, 0, 0}; a.seg[1] = {up, nullptr, 0, 0};
@@ -169,10 +190,12 @@ cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfl
     a.n_tiles = (gate.N + 127) / 128;
     if (panel && panel_type_ok(gate.type) && gate.K % 64 == 0) {
         a.panel_up_row0 = a.n_tiles * 128;                         // gate rows, then (tile-aligned) the up rows
-        cudaError_t e = panel_dequant(gate, panel, 0, st);
-        if (e != cudaSuccess) return e;
-        e = panel_dequant(up, panel, a.panel_up_row0, st);
-        if (e != cudaSuccess) return e;
+        if (panel_fill) {
+            cudaError_t e = panel_dequant(gate, panel, 0, st);
+            if (e != cudaSuccess) return e;
+            e = panel_dequant(up, panel, a.panel_up_row0, st);
+            if (e != cudaSuccess) return e;
+        }
         return launch_gemm(a, gate.type, gate.type, X, st, panel, 2LL * a.panel_up_row0);
     }
     return launch_gemm(a, gate.type, gate.type, X, st);

@@ -20,11 +20,15 @@ size_t prefill_panel_rows(int N);
 // a weight type.  Falls back to one launch per matrix when a column offset is not 4-element aligned.
 struct GemmPart { const QMat* W; const float* bias; int col0; };
 cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st,
-                               __nv_bfloat16* panel = nullptr);
+                               __nv_bfloat16* panel = nullptr, bool panel_fill = true);
 
 // H[T][ff] (bf16) = silu(X . Wgate^T) * (X . Wup^T), one launch, SwiGLU in the GEMM epilogue
 cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,
-                                __nv_bfloat16* panel = nullptr);
+                                __nv_bfloat16* panel = nullptr, bool panel_fill = true);
+// The dequantisation passes alone (same panel layout), so that a caller can run them on a second stream one GEMM ahead.
+// Return false when the combination takes the fused form (the GEMM call must then get panel = nullptr).
+bool prefill_panel_fill(const GemmPart* parts, int n_parts, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);
+bool prefill_panel_fill_swiglu(const QMat& gate, const QMat& up, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);
 
 // y[i] = bf16(x[i])
 cudaError_t convert_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t st);
