@@ -785,6 +785,33 @@ void topk_of_logits(blk_ctx* c) {
     BLK_CUDA(cudaMemcpyAsync(c->h_top_logits, c->top_logits, TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 }
 
+// causal flash attention of a prefill chunk: the query heads of a KV head share a CTA when the GQA ratio is a power of two
+template <int DH, int GQ>
+void launch_attn_gqa(const PrefillAttnArgs& pa, int n, int n_head_kv, cudaStream_t st) {
+    static bool attr_done = false;     // per process is enough: the attribute is per function, set before the first launch
+    constexpr int smem = prefill_attn_gqa_smem<DH, GQ>();
+    if (!attr_done) { BLK_CUDA(cudaFuncSetAttribute(prefill_attn_gqa_kernel<DH, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done = true; }
+    constexpr int BQ = 128 / GQ;
+    prefill_attn_gqa_kernel<DH, GQ><<<dim3((n + BQ - 1) / BQ, n_head_kv), 256, smem, st>>>(pa);
+}
+void launch_prefill_attn(blk_ctx* c, const PrefillAttnArgs& pa, int n, cudaStream_t st) {
+    const blk_model* m = c->m;
+    const int dh = m->d_head, gq = m->n_head / m->n_head_kv;
+    static const bool per_head = [] { const char* e = getenv("BLK_ATTN_PER_HEAD"); return e && e[0] == '1'; }();
+    if (!per_head && dh == 128 && gq == 4) launch_attn_gqa<128, 4>(pa, n, m->n_head_kv, st);
+    else if (!per_head && dh == 128 && gq == 8) launch_attn_gqa<128, 8>(pa, n, m->n_head_kv, st);
+    else if (!per_head && dh == 128 && gq == 2) launch_attn_gqa<128, 2>(pa, n, m->n_head_kv, st);
+    else if (!per_head && dh == 64 && gq == 4) launch_attn_gqa<64, 4>(pa, n, m->n_head_kv, st);
+    else if (!per_head && dh == 64 && gq == 8) launch_attn_gqa<64, 8>(pa, n, m->n_head_kv, st);
+    else if (!per_head && dh == 64 && gq == 2) launch_attn_gqa<64, 2>(pa, n, m->n_head_kv, st);
+    else {
+        const dim3 agrid((n + 63) / 64, m->n_head);
+        if (dh == 128) prefill_attn_kernel<128><<<agrid, 128, 3 * 64 * (128 + 8) * 2, st>>>(pa);
+        else prefill_attn_kernel<64><<<agrid, 128, 3 * 64 * (64 + 8) * 2, st>>>(pa);
+    }
+    BLK_CUDA(cudaGetLastError());
+}
+
 // One causal prefill of n tokens at positions n_past.. .  verify != nullptr: logits of EVERY position go through the
 // per-row top-10 + claimed-id gather (never stored beyond a 256-row chunk); otherwise only the last position's logits are
 // produced (decode mat-vec on the last row).
@@ -859,10 +886,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         PrefillAttnArgs pa{};
         pa.q = c->pf_q; pa.k_pool = c->k_pool[l]; pa.v_pool = c->v_pool[l]; pa.page_table = c->page_table; pa.pos0 = c->d_pos;
         pa.out = c->pf_ao; pa.T = n; pa.n_head = m->n_head; pa.n_head_kv = m->n_head_kv; pa.kv_dim = dkv; pa.scale = 1.0f / sqrtf((float)dh);
-        const dim3 agrid((n + 63) / 64, m->n_head);
-        if (dh == 128) prefill_attn_kernel<128><<<agrid, 128, 3 * 64 * (128 + 8) * 2, st>>>(pa);
-        else prefill_attn_kernel<64><<<agrid, 128, 3 * 64 * (64 + 8) * 2, st>>>(pa);
-        BLK_CUDA(cudaGetLastError());
+        launch_prefill_attn(c, pa, n, st);
         prof_mark(c, "flash_attn");
         BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 1), false));
         after_gemm(4 * l + 1);

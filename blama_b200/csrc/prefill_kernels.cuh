@@ -230,6 +230,144 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnArgs
     }
 }
 
+// ---- the same attention with the query heads of one KV head sharing a CTA -----------------------------------------------------
+// grid = (ceil(T / BQ), n_head_kv), block = 256 (8 warps).  BQ = 128 / GQ tokens x GQ query heads = 128 rows per CTA: a K / V tile
+// is fetched ONCE for all GQ heads (the per-head kernel above fetches it GQ times), by cp.async into a double buffer so the next
+// tile streams in while this one is multiplied.  Heavy (late, causal) query tiles are scheduled first.
+__device__ __forceinline__ void pa_cp16(void* smem_dst, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
+}
+template <int DH, int GQ>
+__global__ void __launch_bounds__(256, 2) prefill_attn_gqa_kernel(const PrefillAttnArgs a) {
+    constexpr int BQ = 128 / GQ, BKV = 64, LD = DH + 8, MT = BQ / 16;      // MT m16 tiles per head
+    extern __shared__ __align__(16) unsigned char pa_smem[];
+    __half* sQ = reinterpret_cast<__half*>(pa_smem);                        // [GQ][BQ][LD]
+    __half* sKV = sQ + GQ * BQ * LD;                                        // [2 buffers][K | V][BKV][LD]
+    const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, hk = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g_h = warp / MT, mt = warp % MT, h = hk * GQ + g_h;
+    const int pos0 = a.pos0[0];
+    const int q0 = qt * BQ;
+    const int dq = a.n_head * DH;
+    const int kv_end = min(pos0 + a.T, pos0 + q0 + BQ);                     // causal: keys up to the last query of the tile
+    const int n_tiles = (kv_end + BKV - 1) / BKV;
+    auto load_tile = [&](int ti, int buf) {
+        __half* dK = sKV + (size_t)buf * 2 * BKV * LD; __half* dV = dK + BKV * LD;
+        for (int i = tid; i < BKV * (DH / 8); i += 256) {
+            const int r = i / (DH / 8), c = i % (DH / 8);
+            const int key = min(ti * BKV + r, kv_end - 1);                  // rows past the end repeat the last key (masked below)
+            const size_t off = ((size_t)a.page_table[key / KV_PAGE] * KV_PAGE + (key % KV_PAGE)) * a.kv_dim + (size_t)hk * DH + c * 8;
+            pa_cp16(dK + r * LD + c * 8, a.k_pool + off);
+            pa_cp16(dV + r * LD + c * 8, a.v_pool + off);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_tile(0, 0);
+    // Q tiles of the GQ heads -> smem
+    for (int i = tid; i < GQ * BQ * (DH / 8); i += 256) {
+        const int c = i % (DH / 8), r = (i / (DH / 8)) % BQ, gg = i / (BQ * (DH / 8));
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + r < a.T) v = *reinterpret_cast<const uint4*>(a.q + (size_t)(q0 + r) * dq + (size_t)(hk * GQ + gg) * DH + c * 8);
+        *reinterpret_cast<uint4*>(sQ + (gg * BQ + r) * LD + c * 8) = v;
+    }
+    float o[DH / 8][4];
+#pragma unroll
+    for (int i = 0; i < DH / 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
+    const int g = lane >> 2, t4 = lane & 3;
+    const int qrow0 = q0 + mt * 16 + g;                   // this thread's two query tokens: qrow0, qrow0 + 8
+    const __half* myQ = sQ + (g_h * BQ + mt * 16) * LD;
+    const float sl2 = a.scale * 1.4426950408889634f;
+    for (int ti = 0; ti < n_tiles; ti++) {
+        const int k0 = ti * BKV, buf = ti & 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // tile ti landed for everyone; everyone is done with buffer buf ^ 1
+        if (ti + 1 < n_tiles) load_tile(ti + 1, buf ^ 1);
+        const __half* sK = sKV + (size_t)buf * 2 * BKV * LD; const __half* sV = sK + BKV * LD;
+        if (k0 > pos0 + q0 + mt * 16 + 15) continue;      // every key of this tile is in the future of this warp's rows
+        float s[BKV / 8][4];
+#pragma unroll
+        for (int i = 0; i < BKV / 8; i++) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f; }
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; kk++) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(a0, a1, a2, a3, myQ + ((lane & 7) + 8 * ((lane >> 3) & 1)) * LD + kk * 16 + 8 * (lane >> 4));
+#pragma unroll
+            for (int nb = 0; nb < BKV / 16; nb++) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(b0, b1, b2, b3, sK + (nb * 16 + (lane & 7) + 8 * (lane >> 4)) * LD + kk * 16 + 8 * ((lane >> 3) & 1));
+                mma_f16(s[2 * nb], a0, a1, a2, a3, b0, b1);
+                mma_f16(s[2 * nb + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < BKV / 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int key = k0 + i * 8 + 2 * t4 + (j & 1);
+                const int qr = qrow0 + 8 * (j >> 1);
+                const bool ok = (key <= pos0 + qr) && (qr < a.T);
+                s[i][j] = ok ? s[i][j] * sl2 : -INFINITY;
+                mx[j >> 1] = fmaxf(mx[j >> 1], s[i][j]);
+            }
+        }
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float mn = fmaxf(m_run[r], mx[r]);
+            corr[r] = (m_run[r] == -INFINITY) ? 0.0f : exp2f(m_run[r] - mn);
+            m_run[r] = mn;
+        }
+        float ls[2] = {0.0f, 0.0f};
+        uint32_t pfrag[BKV / 8][2];
+#pragma unroll
+        for (int i = 0; i < BKV / 8; i++) {
+            float pp[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                pp[j] = (m_run[j >> 1] == -INFINITY) ? 0.0f : exp2f(s[i][j] - m_run[j >> 1]);
+                ls[j >> 1] += pp[j];
+            }
+            pfrag[i][0] = pack_f16x2(pp[0], pp[1]);
+            pfrag[i][1] = pack_f16x2(pp[2], pp[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            ls[r] += __shfl_xor_sync(0xffffffffu, ls[r], 1);
+            ls[r] += __shfl_xor_sync(0xffffffffu, ls[r], 2);
+            l_run[r] = l_run[r] * corr[r] + ls[r];
+        }
+#pragma unroll
+        for (int i = 0; i < DH / 8; i++) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; kk++) {
+            const uint32_t a0 = pfrag[2 * kk][0], a1 = pfrag[2 * kk][1], a2 = pfrag[2 * kk + 1][0], a3 = pfrag[2 * kk + 1][1];
+#pragma unroll
+            for (int nb = 0; nb < DH / 16; nb++) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(b0, b1, b2, b3, sV + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + nb * 16 + 8 * (lane >> 4));
+                mma_f16(o[2 * nb], a0, a1, a2, a3, b0, b1);
+                mma_f16(o[2 * nb + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int qr = qrow0 + 8 * r;
+        if (qr >= a.T) continue;
+        const float inv = l_run[r] > 0.0f ? 1.0f / l_run[r] : 0.0f;
+        __nv_bfloat16* dst = a.out + (size_t)qr * dq + (size_t)h * DH;
+#pragma unroll
+        for (int i = 0; i < DH / 8; i++) {
+            __nv_bfloat162 pr = __floats2bfloat162_rn(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+            *reinterpret_cast<__nv_bfloat162*>(dst + i * 8 + 2 * t4) = pr;
+        }
+    }
+}
+template <int DH, int GQ> constexpr int prefill_attn_gqa_smem() { return (128 * (DH + 8) + 2 * 2 * 64 * (DH + 8)) * 2; }
+
 // ---- per-row top-10 + gather at claimed ids over a chunk of vocabulary logits (one CTA per row) --------------------------------
 // Session::getLogitsFromCtx(10) / getLogitsFromCtx(TokenDataVector) for every position of the verification fill.
 struct RowTopkArgs {
