@@ -1,0 +1,89 @@
+"""The persistent cooperative decode kernel (mega_decode.cuh) against the per-op CUDA-graph path (BLK_MEGA=0) and the oracle:
+same arithmetic contract, different kernels.  Covers what the short model tests do not reach: contexts long enough for several
+attention tiles per CTA, the path selection, a body-only step (no lm_head) followed by a full one, many tokens in one loop."""
+import numpy as np
+import pytest
+
+from blama_b200 import gguf_synth as gs
+
+pytestmark = pytest.mark.gpu
+
+FLIP_TOL = 0.45        # see tests/test_gpu_model.py: bound of a flipped Q8_K / f16 rounding
+CLEAN_TOL = 1e-4
+
+
+def _two_paths(path, n_ctx, monkeypatch):
+    """(persistent-kernel context, per-op context) on the same GGUF; BLK_MEGA is read when the model is loaded"""
+    from blama_b200 import capi
+
+    monkeypatch.delenv("BLK_MEGA", raising=False)
+    m1 = capi.Model(path); c1 = capi.Ctx(m1, n_ctx)
+    monkeypatch.setenv("BLK_MEGA", "0")
+    m0 = capi.Model(path); c0 = capi.Ctx(m0, n_ctx)
+    monkeypatch.delenv("BLK_MEGA", raising=False)
+    return (m1, c1), (m0, c0)
+
+
+@pytest.mark.parametrize("name", ["small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "tiny-llama-q8"])
+def test_path_selection_and_agreement(name, gguf_path, monkeypatch):
+    (m1, c1), (m0, c0) = _two_paths(gguf_path(name), 256, monkeypatch)
+    assert c1.persistent_decode and not c0.persistent_decode
+    toks = gs.synth_prompt(name, 20, 3)
+    clean = 0
+    for t in toks:
+        c1.decode([int(t)]); c0.decode([int(t)])
+        a, b = c1.logits(), c0.logits()
+        err = float(np.abs(a - b).max())
+        assert err <= FLIP_TOL, err
+        clean += err <= CLEAN_TOL
+    assert clean >= 4            # the two implementations are the same arithmetic up to fp32 summation order
+    for c, m in ((c1, m1), (c0, m0)):
+        c.close(); m.close()
+
+
+def test_f32_weights_take_the_per_op_path(gguf_path):
+    from blama_b200 import capi
+
+    m = capi.Model(gguf_path("tiny-llama-f32")); c = capi.Ctx(m, 64)
+    assert not c.persistent_decode
+    c.decode([1, 2, 3]); assert c.n_past == 3
+    c.close(); m.close()
+
+
+def test_long_context_several_attention_tiles(gguf_path, oracle, monkeypatch):
+    """n_head_kv = 2 -> 32 context splits of 64-token tiles: past 2048 tokens a CTA loops over several tiles (the first one is
+    prefetched with cp.async, the others are fetched synchronously); also crosses KV page boundaries."""
+    name = "small-llama-q4km"
+    (m1, c1), (m0, c0) = _two_paths(gguf_path(name), 2400, monkeypatch)
+    fill = gs.synth_prompt(name, 2200, 11)
+    c1.decode(fill); c0.decode(fill)                      # tcgen05 prefill on both (identical kernels)
+    assert np.array_equal(c1.logits(), c0.logits())
+    toks = gs.synth_prompt(name, 12, 12)
+    worst = 0.0
+    for t in toks:
+        c1.decode([int(t)]); c0.decode([int(t)])
+        worst = max(worst, float(np.abs(c1.logits() - c0.logits()).max()))
+        assert np.array_equal(c1.topk(10)["logit"], np.sort(c1.logits())[::-1][:10])
+    assert worst <= FLIP_TOL, worst
+    for c, m in ((c1, m1), (c0, m0)):
+        c.close(); m.close()
+
+
+def test_body_steps_then_head_and_device_loop(gguf_path, monkeypatch):
+    """blk_decode(n < prefill_min) = n-1 steps without the lm_head + one with; blk_decode_loop = greedy feedback on the device"""
+    from blama_b200 import capi
+
+    name = "small-llama-q4km"
+    m = capi.Model(gguf_path(name)); a = capi.Ctx(m, 512); b = capi.Ctx(m, 512)
+    toks = gs.synth_prompt(name, 9, 21)
+    a.decode(toks)                                        # 8 body-only launches + 1 full
+    for t in toks:
+        b.decode([int(t)])                                # 9 full launches
+    assert np.array_equal(a.logits(), b.logits())
+    first = int(a.topk(1)["token"][0])
+    last = a.decode_loop(first, 40)                       # 40 launches back to back, arg-max fed back on the device
+    tok = first
+    for _ in range(40):
+        tok = int(b.decode_topk(tok, 1)["token"][0])      # the same through the host
+    assert last == tok and a.n_past == b.n_past
+    a.close(); b.close(); m.close()

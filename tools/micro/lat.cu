@@ -5,6 +5,19 @@
 #include "mega_decode.cuh"
 using namespace blk;
 
+// the grid barrier the first version of the persistent kernel used (kept here for the measurement)
+__device__ __forceinline__ void mg_grid_arrive(unsigned int* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_add(bar, 1u);
+}
+__device__ __forceinline__ void mg_grid_wait(const unsigned int* bar, unsigned int target) {
+    if (threadIdx.x == 0) {
+        while (ld_relaxed_u32(bar) < target) { }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 __global__ void k_quant(float* src, int8_t* out, long long* t, int iters) {
     __shared__ __align__(16) int8_t sq[4096]; __shared__ float sd[64]; __shared__ int16_t sbs[512];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
