@@ -28,15 +28,15 @@ def _two_paths(path, n_ctx, monkeypatch):
 def test_path_selection_and_agreement(name, gguf_path, monkeypatch):
     (m1, c1), (m0, c0) = _two_paths(gguf_path(name), 256, monkeypatch)
     assert c1.persistent_decode and not c0.persistent_decode
-    toks = gs.synth_prompt(name, 20, 3)
-    clean = 0
-    for t in toks:
-        c1.decode([int(t)]); c0.decode([int(t)])
-        a, b = c1.logits(), c0.logits()
-        err = float(np.abs(a - b).max())
-        assert err <= FLIP_TOL, err
-        clean += err <= CLEAN_TOL
-    assert clean >= 4            # the two implementations are the same arithmetic up to fp32 summation order
+    clean = total = 0
+    for seq in range(6):                      # independent short sequences: a flipped rounding only taints its own sequence
+        c1.clear(); c0.clear()
+        for t in gs.synth_prompt(name, 6, 40 + seq):
+            c1.decode([int(t)]); c0.decode([int(t)])
+            err = float(np.abs(c1.logits() - c0.logits()).max())
+            assert err <= FLIP_TOL, (seq, err)
+            clean += err <= CLEAN_TOL; total += 1
+    assert clean >= 0.3 * total, (clean, total)      # the same arithmetic up to fp32 summation order
     for c, m in ((c1, m1), (c0, m0)):
         c.close(); m.close()
 
