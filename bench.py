@@ -161,7 +161,7 @@ def run_reference(args, rank: int, world: int):
         "gpu_launches": 0,
         "note": "CPU restatement of the reference's llama.cpp CPU path (the upstream binary cannot be built offline)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -327,9 +327,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     kv_per_tok = sh.n_layer * sh.n_head_kv * sh.d_head * 2 * 2
     mean_ctx = args.prompt + args.new / 2
     bytes_per_token = wbytes + kv_per_tok * mean_ctx
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the same kernel and shape
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_mega_decode_summary.json")) as fh:
+            ns = json.load(fh)
+        if ctx.persistent_decode and ns.get("shape") == args.shape:
+            traffic = ns["dram__bytes_read"] + ns["dram__bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom_name,
-        "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": None,
+        "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic,
+        "traffic_source": "profiles/r1_ncu_mega_decode_summary.json (ncu --set full, one launch at a 512-token context)" if traffic else None,
         "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
         "kernels": {k: {"gbs": round(v["gbs"], 1), "ms": round(v["ms"], 5), "bytes": v["bytes"]} for k, v in kernels.items()},
         "step": {"bytes_per_token": int(bytes_per_token), "achieved_gbs": bytes_per_token * (value / world) / 1e9,
@@ -361,9 +371,31 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "verify": verify,
         "model_load_s": load_s,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     inst.close(); hm.close()
     dist.close()
+
+
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner on the first communicator,
+    with NCCL_DEBUG=VERSION set by some launchers), so everything else is sent to stderr and the line goes to the saved fd."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -380,6 +412,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not (args.gpus > 1 and world == 1):
+        quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
