@@ -285,6 +285,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         inst.set_initial_prompt(prompt[:32])
         vt_l, vtop_l = inst.complete(args.verify)
         inst.stop_session()
+        vt_l = np.ascontiguousarray(vt_l, dtype=np.int32); vtop_l = np.ascontiguousarray(vtop_l)      # the request, unmarshalled
         inst.start_session(seed=1, sequential_verify=args.sequential_verify)
         inst.set_initial_prompt(prompt[:32])
         t0 = time.perf_counter()

@@ -126,13 +126,14 @@ BLK_API int blh_session_verify(void* i, const int32_t* toks, int n, const blk_to
         std::vector<TokenPrediction> orig(static_cast<size_t>(n));
         for (int t = 0; t < n; ++t) { orig[size_t(t)].token = toks[t]; orig[size_t(t)].logits = toVec(claimed + size_t(t) * 10, n_claimed[t]); }
         auto mine = static_cast<InstanceBox*>(i)->session->fillCtx(orig);
+        // The reference pushes the metrics one by one and re-sums its whole history on every push (Server.cpp:153-156, O(n^2));
+        // only the value of the LAST push is returned, and that is the in-order double sum over all metrics: one push of the
+        // whole span computes exactly that float.
+        std::vector<TokenPredictionView> pairs(orig.size());
+        for (size_t t = 0; t < orig.size(); ++t) pairs[t] = {&orig[t].logits, &mine[t].logits};
+        const std::vector<ComparisonMetrics> ms = compareAll(pairs);
         MetricsAggregator agg;
-        float s = 0;
-        for (size_t t = 0; t < orig.size(); ++t) {
-            auto m = LogitComparer::compare(orig[t].logits, mine[t].logits);
-            s = agg.pushAndVerify({&m, 1});
-        }
-        *score = s;
+        *score = ms.empty() ? 0.0f : agg.pushAndVerify(ms);
     });
 }
 BLK_API int blh_session_get_state(void* i) { return guard([&] { (void)static_cast<InstanceBox*>(i)->session->getState(); }); }

@@ -8,6 +8,9 @@
 #include "LogitComparer.hpp"
 
 #include <algorithm>
+#include <thread>
+
+#include <algorithm>
 #include <cmath>
 #include <unordered_map>
 
@@ -82,6 +85,21 @@ float LogitComparer::logitSimilarity(const TokenDataVector& data1, const TokenDa
         weights += w;
     }
     return weights > 0.0f ? weighted / weights : 0.0f;
+}
+
+std::vector<ComparisonMetrics> compareAll(std::span<const TokenPredictionView> pairs) {
+    std::vector<ComparisonMetrics> out(pairs.size());
+    const size_t n = pairs.size();
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_thr = n >= 256 ? std::min<size_t>({size_t(hw), size_t(8), n / 128}) : 1;
+    auto work = [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) out[i] = LogitComparer::compare(*pairs[i].a, *pairs[i].b); };
+    if (n_thr <= 1) { work(0, n); return out; }
+    std::vector<std::thread> thr;
+    const size_t per = (n + n_thr - 1) / n_thr;
+    for (size_t t = 1; t < n_thr; ++t) thr.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+    work(0, std::min(n, per));
+    for (auto& t : thr) t.join();
+    return out;
 }
 
 float MetricsAggregator::pushAndVerify(std::span<const ComparisonMetrics> m) {

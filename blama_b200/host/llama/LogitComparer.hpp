@@ -19,6 +19,11 @@ public:
     static float logitSimilarity(const TokenDataVector& data1, const TokenDataVector& data2);
 };
 
+// LogitComparer::compare for every position of a verified response (prover's list vs verifier's list).  The positions are
+// independent, so long responses are compared on several host threads; each metric is the same float either way.
+struct TokenPredictionView { const TokenDataVector* a; const TokenDataVector* b; };
+std::vector<ComparisonMetrics> compareAll(std::span<const TokenPredictionView> pairs);
+
 struct MetricsAggregator {
     // appends m and returns the mean of 0.5(1-distance) + 0.5(1-jsd) over everything pushed so far
     float pushAndVerify(std::span<const ComparisonMetrics> m);

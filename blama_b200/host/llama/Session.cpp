@@ -169,9 +169,9 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
         std::copy(uniq.begin(), uniq.end(), claimed.begin() + long(i * 10));
     }
     std::vector<float> gathered(n * 10, 0.0f);
-    std::vector<blk_token_data> top(n * 10);
     throwIfFailed(blk_ctx_set_verify_mode(m_ctx, m_params.sequentialVerify ? 1 : 0), "verify mode");
-    const int st = blk_verify_prefill(m_ctx, ids.data(), int32_t(n), claimed.data(), nClaimed.data(), gathered.data(), top.data());
+    // the per-position top-10 of the verifier is not needed here (only the claimed ids are compared): nullptr skips that pass
+    const int st = blk_verify_prefill(m_ctx, ids.data(), int32_t(n), claimed.data(), nClaimed.data(), gathered.data(), nullptr);
     if (st != BLK_OK) Raise{} << "Failed to decode tokens";
     m_numPast += uint32_t(n);
 
@@ -181,9 +181,7 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
         std::sort(v.begin(), v.end(), [](const TokenData& a, const TokenData& b) { return a.logit > b.logit; });
         result.push_back({ids[i], std::move(v)});
     }
-    // the verifier's own candidates for whoever continues generating after the fill
-    m_candidates.resize(10);
-    for (size_t j = 0; j < 10; ++j) m_candidates[j] = {top[(n - 1) * 10 + j].token, top[(n - 1) * 10 + j].logit};
+    // the verifier's own candidates (last position) for whoever continues generating after the fill
     refreshCandidates();
     return result;
 }

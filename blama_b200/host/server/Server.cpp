@@ -114,13 +114,13 @@ struct Server::Impl {
             session.setInitialPrompt(prompt);
             auto orig = unmarshal(resp);
             auto mine = session.fillCtx(orig);
+            // the reference pushes one metric at a time and re-sums the history on every push (Server.cpp:153-156); only the last
+            // push's value is reported, which is the in-order double sum over all metrics: one push of the whole span
+            std::vector<TokenPredictionView> pairs(orig.size());
+            for (size_t i = 0; i < orig.size(); i++) pairs[i] = {&orig[i].logits, &mine[i].logits};
+            const std::vector<ComparisonMetrics> ms = compareAll(pairs);
             MetricsAggregator agg;
-            float score = 0;
-            for (size_t i = 0; i < orig.size(); i++) {
-                auto m = LogitComparer::compare(orig[i].logits, mine[i].logits);
-                score = agg.pushAndVerify({&m, 1});
-            }
-            cb(score);
+            cb(ms.empty() ? 0.0f : agg.pushAndVerify(ms));
             w.instance->stopSession();
         });
     }

@@ -87,3 +87,26 @@ def test_body_steps_then_head_and_device_loop(gguf_path, monkeypatch):
         tok = int(b.decode_topk(tok, 1)["token"][0])      # the same through the host
     assert last == tok and a.n_past == b.n_past
     a.close(); b.close(); m.close()
+
+
+def test_run_to_run_determinism(gguf_path):
+    """the same request twice gives the same bits: decode (LL hand-offs, fixed summation orders) and batched verify"""
+    from blama_b200 import host_api
+
+    name = "small-llama-q4km"
+    hm = host_api.Model(gguf_path(name)); inst = host_api.Instance(hm, 1400)
+    prompt = gs.synth_prompt(name, 12, 5)
+    runs = []
+    for _ in range(2):
+        inst.start_session(seed=3); inst.set_initial_prompt(prompt)
+        toks, top = inst.complete(1100)                   # long enough for the two-pass GEMM form in the verify below
+        inst.stop_session()
+        runs.append((np.asarray(toks), np.ascontiguousarray(top)))
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1].tobytes() == runs[1][1].tobytes()
+    scores = []
+    for _ in range(2):
+        inst.start_session(seed=3); inst.set_initial_prompt(prompt)
+        scores.append(inst.verify(runs[0][0], runs[0][1]))
+        inst.stop_session()
+    assert scores[0] == scores[1] and scores[0] >= 0.98, scores
+    inst.close(); hm.close()
