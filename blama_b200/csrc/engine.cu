@@ -739,7 +739,7 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
     c->pf_ao = dalloc<__nv_bfloat16>(c, t * dq);
     c->pf_g = dalloc<float>(c, t * ff); c->pf_u = dalloc<float>(c, t * ff);
     c->pf_h = dalloc<__nv_bfloat16>(c, t * ff);
-    c->pf_logit_rows = 256;
+    c->pf_logit_rows = 512;     // rows of one lm_head chunk: two M tiles share every weight tile through L2
     c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
     {   // bf16 weight panel of the two-pass GEMM form (largest single launch: QKV | Wo | gate+up | down | lm_head)
         // one panel per GEMM kind, so the dequantisation of the NEXT matrix (second stream) runs while the current GEMM does:

@@ -526,13 +526,30 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 // producers write into shared memory (bf16 of ggml's dequantised f32) ----------------------------------------------------
 template <int TYPE>
 __global__ void __launch_bounds__(256) panel_dequant_kernel(const QMat W, __nv_bfloat16* __restrict__ dst) {
+    // one thread expands one 64-element slice (128 B of bf16) into its warp's staging rows in shared memory; the warp then writes
+    // its 32 slices (4 KB, contiguous in the panel: consecutive threads = consecutive slices of a row, rows back to back) with
+    // fully coalesced 512-byte stores -- storing straight from the expander would issue 16-byte pieces at a 128-byte stride
+    __shared__ __align__(16) unsigned char stage[8][32 * 144];     // 144 B row pitch: 4-way instead of 32-way bank conflicts
     const int kbs = W.K >> 6;
+    const int64_t total = (int64_t)W.N * kbs;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)W.N * kbs) return;
-    const int64_t row = idx / kbs; const int kb = (int)(idx - row * kbs);
-    RawK64<TYPE> raw;
-    raw.load(W, row, kb);
-    raw.expand(reinterpret_cast<unsigned char*>(dst + (size_t)row * W.K + (size_t)kb * 64), 0, kb);      // r = 0: no swizzle, 8 x 16 B in order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = stage[warp] + lane * 144;
+    if (idx < total) {
+        const int64_t row = idx / kbs; const int kb = (int)(idx - row * kbs);
+        RawK64<TYPE> raw;
+        raw.load(W, row, kb);
+        raw.expand(mine, 0, kb);                                    // r = 0: no swizzle, 8 x 16 B in order
+    }
+    __syncwarp();
+    const int64_t idx0 = idx - lane;                                // first slice of this warp
+    unsigned char* out = reinterpret_cast<unsigned char*>(dst) + idx0 * 128;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int j = i * 32 + lane;                                // 16-byte chunk j of the warp's 4 KB
+        if (idx0 + (j >> 3) < total)
+            *reinterpret_cast<uint4*>(out + (size_t)j * 16) = *reinterpret_cast<const uint4*>(stage[warp] + (j >> 3) * 144 + (j & 7) * 16);
+    }
 }
 
 } // namespace blk
