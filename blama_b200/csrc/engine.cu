@@ -763,6 +763,10 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
             }
         }
     }
+    if (prefill_attn_tc_supported(dh, m->n_head, m->n_head_kv)) {      // transposed-V scratch of the tcgen05 attention (one layer at a time)
+        c->pf_vt_pad = (c->n_pages * KV_PAGE + 127) / 128 * 128;
+        c->pf_vt = dalloc<__half>(c, (size_t)m->n_head_kv * 128 * c->pf_vt_pad);
+    }
     c->pf_claimed = dalloc<int32_t>(c, t * 10); c->pf_nclaimed = dalloc<int32_t>(c, t);
     c->pf_gath = dalloc<float>(c, t * 10); c->pf_topi = dalloc<int32_t>(c, t * 10); c->pf_topl = dalloc<float>(c, t * 10);
     c->pf_cap = cap;
@@ -798,6 +802,13 @@ void launch_prefill_attn(blk_ctx* c, const PrefillAttnArgs& pa, int n, cudaStrea
     const blk_model* m = c->m;
     const int dh = m->d_head, gq = m->n_head / m->n_head_kv;
     static const bool per_head = [] { const char* e = getenv("BLK_ATTN_PER_HEAD"); return e && e[0] == '1'; }();
+    static const bool no_tc = [] { const char* e = getenv("BLK_ATTN_TC"); return e && e[0] == '0'; }();
+    if (!no_tc && !per_head && c->pf_vt && prefill_attn_tc_supported(dh, m->n_head, m->n_head_kv)) {
+        // tcgen05 attention: the layer's pools are recovered from the arguments
+        BLK_CUDA(prefill_attn_tc(pa.q, pa.k_pool, pa.v_pool, pa.page_table, c->n_pages, pa.pos0, c->n_past, pa.out, c->pf_vt, c->pf_vt_pad, n,
+                                 m->n_head, m->n_head_kv, pa.kv_dim, pa.scale, st));
+        return;
+    }
     if (!per_head && dh == 128 && gq == 4) launch_attn_gqa<128, 4>(pa, n, m->n_head_kv, st);
     else if (!per_head && dh == 128 && gq == 8) launch_attn_gqa<128, 8>(pa, n, m->n_head_kv, st);
     else if (!per_head && dh == 128 && gq == 2) launch_attn_gqa<128, 2>(pa, n, m->n_head_kv, st);

@@ -1,6 +1,7 @@
 // prefill.cu -- launchers of the multi-token prefill path (tcgen05 GEMM + helpers).
 #include "prefill.hpp"
 #include "prefill_gemm.cuh"
+#include "prefill_attn_tc.cuh"
 
 #include <mutex>
 
@@ -199,6 +200,59 @@ cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfl
         return launch_gemm(a, gate.type, gate.type, X, st, panel, 2LL * a.panel_up_row0);
     }
     return launch_gemm(a, gate.type, gate.type, X, st);
+}
+
+namespace {
+bool encode_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_stride_elems * sizeof(__half)};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <int GQ>
+cudaError_t launch_attn_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnTcArgs& a, int n_head_kv, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(prefill_attn_tc_kernel<GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    constexpr int BQ = 128 / GQ;
+    prefill_attn_tc_kernel<GQ><<<dim3((a.T + BQ - 1) / BQ, n_head_kv), AT_THREADS, AT_SMEM_BYTES, st>>>(mq, mk, mv, a);
+    return cudaGetLastError();
+}
+} // namespace
+
+bool prefill_attn_tc_supported(int d_head, int n_head, int n_head_kv) {
+    const int gq = n_head_kv > 0 ? n_head / n_head_kv : 0;
+    return d_head == 128 && (gq == 1 || gq == 2 || gq == 4 || gq == 8) && encode_tiled() != nullptr;
+}
+
+cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half* v_pool, const int32_t* page_table, int n_pages, const int32_t* pos0_dev,
+                            int pos0, __nv_bfloat16* out, __half* vt, int ctx_pad, int T, int n_head, int n_head_kv, int kv_dim, float scale, cudaStream_t st) {
+    const int gq = n_head / n_head_kv, dq = n_head * 128, n_keys = pos0 + T;
+    if (n_keys > ctx_pad || ctx_pad % 128) return cudaErrorInvalidValue;
+    // V^T of every key this chunk can see (zero padded to the key tile)
+    vt_transpose_kernel<<<dim3((n_keys + 127) / 128 * 2, n_head_kv), 256, 0, st>>>(v_pool, page_table, kv_dim, n_keys, ctx_pad, vt);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    CUtensorMap mq, mk, mv;
+    if (!encode_2d_f16(&mq, q, (uint64_t)dq, (uint64_t)T, (uint64_t)dq, 64, (uint32_t)(128 / gq))) return cudaErrorInvalidValue;
+    if (!encode_2d_f16(&mk, k_pool, (uint64_t)kv_dim, (uint64_t)n_pages * KV_PAGE, (uint64_t)kv_dim, 64, 64)) return cudaErrorInvalidValue;
+    if (!encode_2d_f16(&mv, vt, (uint64_t)ctx_pad, (uint64_t)n_head_kv * 128, (uint64_t)ctx_pad, 64, 128)) return cudaErrorInvalidValue;
+    AttnTcArgs a{};
+    a.page_table = page_table; a.pos0 = pos0_dev; a.out = out; a.T = T; a.n_head = n_head; a.n_pages = n_pages; a.scale = scale;
+    switch (gq) {
+        case 1: return launch_attn_tc<1>(mq, mk, mv, a, n_head_kv, st);
+        case 2: return launch_attn_tc<2>(mq, mk, mv, a, n_head_kv, st);
+        case 4: return launch_attn_tc<4>(mq, mk, mv, a, n_head_kv, st);
+        case 8: return launch_attn_tc<8>(mq, mk, mv, a, n_head_kv, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 } // namespace blk

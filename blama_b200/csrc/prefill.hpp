@@ -1,6 +1,7 @@
 // prefill.hpp -- host-side entry points of the multi-token prefill path (implemented in prefill.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "qweights.cuh"
@@ -29,6 +30,13 @@ cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfl
 // Return false when the combination takes the fused form (the GEMM call must then get panel = nullptr).
 bool prefill_panel_fill(const GemmPart* parts, int n_parts, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);
 bool prefill_panel_fill_swiglu(const QMat& gate, const QMat& up, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);
+
+// Causal attention of a prefill chunk on tcgen05 (prefill_attn_tc.cuh): d_head = 128, GQA ratio 1 / 2 / 4 / 8.
+//   q [T][n_head*128] f16 (post-RoPE), paged f16 K / V pools of the layer, out [T][n_head*128] bf16;
+//   vt: scratch [n_head_kv*128][ctx_pad] f16 for the transposed V of this layer (ctx_pad: multiple of 128 >= pos0 + T).
+bool prefill_attn_tc_supported(int d_head, int n_head, int n_head_kv);
+cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half* v_pool, const int32_t* page_table, int n_pages, const int32_t* pos0_dev,
+                            int pos0, __nv_bfloat16* out, __half* vt, int ctx_pad, int T, int n_head, int n_head_kv, int kv_dim, float scale, cudaStream_t st);
 
 // y[i] = bf16(x[i])
 cudaError_t convert_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t st);

@@ -1,0 +1,278 @@
+// prefill_attn_tc.cuh -- causal attention of a prefill chunk on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// CTA = (tile of BQ = 128 / GQ tokens, KV head): the GQ query heads of the KV head stacked head-major give the 128 rows of one
+// UMMA M = 128 tile.  Keys are walked in tiles of 128.  All four operands are K-major SWIZZLE_128B tiles fetched by TMA:
+//   Q  [128 rows][dh = 128]   from the f16 query buffer (GQ boxes of BQ rows per 64-wide K block)
+//   K  [128 keys][128]        from the paged f16 cache (one 64-row box per page and K block)
+//   V^T [128 dims][128 keys]  from a per-layer transposed scratch (vt_transpose_kernel): P.V needs V with the KEYS contiguous
+//   P  [128 rows][128 keys]   written by the soft-max warps (f16, the same swizzle the GEMM producers write)
+// Two passes over the keys instead of an online rescale of O in TMEM:
+//   pass 1: S = Q.K^T -> row max m and row sum l = sum exp2(s - m) (scalar rescale only, in registers)
+//   pass 2: S again, P = exp2(s - m) -> f16, O += P.V^T in TMEM (never rescaled); O / l at the end.
+// Q.K^T is done twice (1.5x the MMA work of one pass), which is cheap next to keeping O out of the register file.
+// Warp roles: warp 0 = TMA, warp 1 = MMA issue (one elected thread), warps 2-5 = soft-max / epilogue (thread = row = TMEM lane).
+// Arithmetic as the mma.sync kernel (prefill_kernels.cuh): f16 operands, f32 accumulation, P rounded to f16 before P.V.
+#pragma once
+#include "prefill_gemm.cuh"
+
+namespace blk {
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_TILE_BYTES = 128 * 64 * 2;                 // one [128][64] f16 K block = 16 KB
+constexpr int AT_SMEM_BYTES = (2 + 2 * 2 + 2 * 2 + 2) * AT_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;      // Q, K x2, V x2, P
+
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {      // f16 x f16 -> f32, both K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct AttnTcArgs {
+    const int32_t* page_table; const int32_t* pos0;
+    __nv_bfloat16* out;          // [T][n_head * 128]
+    int T, n_head, n_pages;
+    float scale;
+};
+
+// V rows [key][128] of one KV head -> V^T [128][ctx_pad] (keys contiguous), zero beyond n_keys (P is 0 there, V must be finite)
+__global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restrict__ v_pool, const int32_t* __restrict__ page_table,
+                                                           int kv_dim, int n_keys, int ctx_pad, __half* __restrict__ vt) {
+    __shared__ __half tile[64][128 + 2];
+    const int k0 = blockIdx.x * 64, hk = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < 64 * 16; i += 256) {
+        const int r = i >> 4, c = i & 15, key = k0 + r;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (key < n_keys) v = *reinterpret_cast<const uint4*>(v_pool + ((size_t)page_table[key / KV_PAGE] * KV_PAGE + (key % KV_PAGE)) * kv_dim + (size_t)hk * 128 + c * 8);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) tile[r][c * 8 + j] = h[j];
+    }
+    __syncthreads();
+    for (int i = tid; i < 128 * 8; i += 256) {          // 8 keys (16 B) per store
+        const int d = i >> 3, kc = i & 7;
+        __align__(16) __half o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = tile[kc * 8 + j][d];
+        *reinterpret_cast<uint4*>(vt + ((size_t)hk * 128 + d) * ctx_pad + k0 + kc * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+template <int GQ>
+__global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                                                                        const __grid_constant__ CUtensorMap tmap_vt, const AttnTcArgs a) {
+    constexpr int BQ = 128 / GQ;
+    extern __shared__ unsigned char at_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sQ = smem;                                   // 2 K blocks
+    unsigned char* sK = sQ + 2 * AT_TILE_BYTES;                 // 2 stages x 2 K blocks
+    unsigned char* sV = sK + 4 * AT_TILE_BYTES;                 // 2 stages x 2 key blocks
+    unsigned char* sP = sV + 4 * AT_TILE_BYTES;                 // 2 key blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_TILE_BYTES);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // [2]
+    uint64_t* kv_empty = bars + 3;      // [2]
+    uint64_t* s_full = bars + 5;        // [2]
+    uint64_t* s_empty = bars + 7;       // [2]  128 soft-max threads
+    uint64_t* p_full = bars + 9;        // 128 soft-max threads
+    uint64_t* p_empty = bars + 10;      // tcgen05.commit
+    uint64_t* o_full = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, hk = blockIdx.y;      // late (long) query tiles first
+    const int pos0 = a.pos0[0];
+    const int q0 = qt * BQ;
+    const int kv_end = min(pos0 + a.T, pos0 + q0 + BQ);         // keys this tile can see
+    const int n_tiles = (kv_end + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); mbar_init(s_full + s, 1); mbar_init(s_empty + s, 128); }
+        mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS[2] = {tmem, tmem + 128}, tO = tmem + 256;
+
+    if (warp == 0) {
+        // ===================== TMA =====================
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * AT_TILE_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < 2; kb++)
+                for (int g = 0; g < GQ; g++)
+                    tma_load_2d(sQ + kb * AT_TILE_BYTES + g * BQ * 128, &tmap_q, (hk * GQ + g) * 128 + kb * 64, q0, q_full);
+            int it = 0;
+            for (int pass = 0; pass < 2; pass++) {
+                for (int t = 0; t < n_tiles; t++, it++) {
+                    const int s = it & 1;
+                    mbar_wait(kv_empty + s, ((it >> 1) & 1) ^ 1);
+                    mbar_expect_tx(kv_full + s, pass ? 4 * AT_TILE_BYTES : 2 * AT_TILE_BYTES);
+                    const int pg0 = min(2 * t, a.n_pages - 1), pg1 = min(2 * t + 1, a.n_pages - 1);     // a tile = two 64-token pages
+                    const int r0 = a.page_table[pg0] * KV_PAGE, r1 = a.page_table[pg1] * KV_PAGE;
+#pragma unroll
+                    for (int kb = 0; kb < 2; kb++) {
+                        unsigned char* dk = sK + (s * 2 + kb) * AT_TILE_BYTES;
+                        tma_load_2d(dk, &tmap_k, hk * 128 + kb * 64, r0, kv_full + s);
+                        tma_load_2d(dk + 64 * 128, &tmap_k, hk * 128 + kb * 64, r1, kv_full + s);
+                    }
+                    if (pass) {
+#pragma unroll
+                        for (int kb = 0; kb < 2; kb++)      // key block kb of the tile: [128 dims][64 keys]
+                            tma_load_2d(sV + (s * 2 + kb) * AT_TILE_BYTES, &tmap_vt, t * 128 + kb * 64, hk * 128, kv_full + s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issue =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            auto qk = [&](int s, int b) {       // S[b] = Q . K[s]^T over dh = 2 K blocks x 4 steps of 16
+#pragma unroll
+                for (int kb = 0; kb < 2; kb++) {
+                    const uint64_t dq = umma_desc_sw128(sQ + kb * AT_TILE_BYTES), dk = umma_desc_sw128(sK + (s * 2 + kb) * AT_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) tc_mma_f16(tS[b], dq + (uint64_t)((k * 32) >> 4), dk + (uint64_t)((k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
+                }
+            };
+            int it = 0, si = 0;                 // it: K/V stage counter, si: S buffer counter
+            // ---- pass 1: scores only ----
+            for (int t = 0; t < n_tiles; t++, it++, si++) {
+                const int s = it & 1, b = si & 1;
+                mbar_wait(kv_full + s, (it >> 1) & 1);
+                mbar_wait(s_empty + b, ((si >> 1) & 1) ^ 1);
+                tc_fence_after();
+                qk(s, b);
+                tc_commit(kv_empty + s);
+                tc_commit(s_full + b);
+            }
+            // ---- pass 2: scores, then O += P . V ----
+            for (int t = 0; t < n_tiles; t++, it++, si++) {
+                const int s = it & 1, b = si & 1;
+                mbar_wait(kv_full + s, (it >> 1) & 1);
+                mbar_wait(s_empty + b, ((si >> 1) & 1) ^ 1);
+                tc_fence_after();
+                qk(s, b);
+                tc_commit(s_full + b);
+                mbar_wait(p_full, t & 1);                                   // P of this tile is in shared memory
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < 2; kb++) {
+                    const uint64_t dp = umma_desc_sw128(sP + kb * AT_TILE_BYTES), dv = umma_desc_sw128(sV + (s * 2 + kb) * AT_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) tc_mma_f16(tO, dp + (uint64_t)((k * 32) >> 4), dv + (uint64_t)((k * 32) >> 4), idesc, (t | kb | k) ? 1u : 0u);
+                }
+                tc_commit(kv_empty + s);
+                tc_commit(p_empty);
+            }
+            tc_commit(o_full);
+        }
+    } else {
+        // ===================== soft-max / epilogue: thread = row = TMEM lane =====================
+        const int row = 32 * (warp & 3) + lane;             // warp w may touch TMEM lanes 32 (w % 4) .. +31
+        const int g = row / BQ, tok = q0 + (row % BQ);
+        const bool row_ok = tok < a.T;
+        const int last_key = pos0 + tok;                    // causal: keys <= last_key
+        const float sl2 = a.scale * 1.4426950408889634f;
+        const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+        float m = -INFINITY, l = 0.0f;
+        int si = 0;
+        // ---- pass 1 ----
+        for (int t = 0; t < n_tiles; t++, si++) {
+            const int b = si & 1;
+            mbar_wait(s_full + b, (si >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + c * 32) + lane_off, v);
+                tc_wait_ld();
+                float cm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int key = t * 128 + c * 32 + j;
+                    const float sv = (row_ok && key <= last_key) ? __uint_as_float(v[j]) * sl2 : -INFINITY;
+                    v[j] = __float_as_uint(sv);
+                    cm = fmaxf(cm, sv);
+                }
+                if (cm > -INFINITY) {
+                    const float mn = fmaxf(m, cm);
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) acc += exp2f(__uint_as_float(v[j]) - mn);
+                    l = l * exp2f(m - mn) + acc;
+                    m = mn;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(s_empty + b);
+        }
+        // ---- pass 2 ----
+        for (int t = 0; t < n_tiles; t++, si++) {
+            const int b = si & 1;
+            mbar_wait(s_full + b, (si >> 1) & 1);
+            mbar_wait(p_empty, (t & 1) ^ 1);                // the P.V of the previous tile has read the P buffer
+            tc_fence_after();
+            unsigned char* prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + c * 32) + lane_off, v);
+                tc_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int key = t * 128 + c * 32 + j;
+                    const float p0 = (row_ok && key <= last_key) ? exp2f(__uint_as_float(v[j]) * sl2 - m) : 0.0f;
+                    const float p1 = (row_ok && key + 1 <= last_key) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - m) : 0.0f;
+                    __half2 h = __floats2half2_rn(p0, p1);
+                    pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                // 32 keys = four 16-byte chunks of key block (c >> 1); chunk index inside the 128-byte row: (c & 1) * 4 + q
+                unsigned char* pb = prow + (c >> 1) * AT_TILE_BYTES;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<uint4*>(pb + ((((c & 1) * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(s_empty + b);
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> bf16 ----
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+        __nv_bfloat16* dst = a.out + (size_t)tok * ((size_t)a.n_head * 128) + (size_t)(hk * GQ + g) * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            uint32_t v[32];
+            tc_ld_32x32b_x32(tO + (uint32_t)(c * 32) + lane_off, v);
+            tc_wait_ld();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+                    o.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+                    o.z = pack_bf16x2(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+                    o.w = pack_bf16x2(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c * 32 + j) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+} // namespace blk

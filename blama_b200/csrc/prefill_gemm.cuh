@@ -72,6 +72,10 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 covers f16 and bf16 inputs; the instruction descriptor says which
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    tc_mma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
