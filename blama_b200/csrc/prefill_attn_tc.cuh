@@ -7,20 +7,23 @@
 //   V^T [128 dims][128 keys]  from a per-layer transposed scratch (vt_transpose_kernel): P.V needs V with the KEYS contiguous
 //   P  [128 rows][128 keys]   written by the soft-max warps (f16, the same swizzle the GEMM producers write)
 // Two passes over the keys instead of an online rescale of O in TMEM:
-//   pass 1: S = Q.K^T -> row max m and row sum l = sum exp2(s - m) (scalar rescale only, in registers)
-//   pass 2: S again, P = exp2(s - m) -> f16, O += P.V^T in TMEM (never rescaled); O / l at the end.
+//   pass 1: S = Q.K^T -> row max m
+//   pass 2: S again, P = exp2(s - m) -> f16 (row sum l alongside), O += P.V^T in TMEM (never rescaled); O / l at the end.
 // Q.K^T is done twice (1.5x the MMA work of one pass), which is cheap next to keeping O out of the register file.
-// Warp roles: warp 0 = TMA, warp 1 = MMA issue (one elected thread), warps 2-5 = soft-max / epilogue (thread = row = TMEM lane).
+// Warp roles: warp 0 = TMA, warp 1 = MMA issue (one elected thread), warps 2-9 = soft-max / epilogue: two threads per row
+// (= TMEM lane), 64 key columns each.  The exponentials (MUFU, 16 / clk / SM) are the floor of this kernel, so they are
+// evaluated once: pass 1 only takes the row maximum, pass 2 computes P and the row sum together.
 // Arithmetic as the mma.sync kernel (prefill_kernels.cuh): f16 operands, f32 accumulation, P rounded to f16 before P.V.
 #pragma once
 #include "prefill_gemm.cuh"
 
 namespace blk {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;                            // warp 0 TMA, warp 1 MMA, warps 2-9 soft-max (two threads per row)
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;                 // one [128][64] f16 K block = 16 KB
-constexpr int AT_SMEM_BYTES = (2 + 2 * 2 + 2 * 2 + 2) * AT_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;      // Q, K x2, V x2, P
+constexpr int AT_SMEM_BYTES = (2 + 2 * 2 + 2 * 2 + 2) * AT_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row statistics*/;      // Q, K x2, V x2, P
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {      // f16 x f16 -> f32, both K-major
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -70,8 +73,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     uint64_t* kv_full = bars + 1;       // [2]
     uint64_t* kv_empty = bars + 3;      // [2]
     uint64_t* s_full = bars + 5;        // [2]
-    uint64_t* s_empty = bars + 7;       // [2]  128 soft-max threads
-    uint64_t* p_full = bars + 9;        // 128 soft-max threads
+    uint64_t* s_empty = bars + 7;       // [2]  256 soft-max threads
+    uint64_t* p_full = bars + 9;        // 256 soft-max threads
     uint64_t* p_empty = bars + 10;      // tcgen05.commit
     uint64_t* o_full = bars + 11;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
@@ -85,8 +88,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); mbar_init(s_full + s, 1); mbar_init(s_empty + s, 128); }
-        mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); mbar_init(s_full + s, 1); mbar_init(s_empty + s, 256); }
+        mbar_init(p_full, 256); mbar_init(p_empty, 1); mbar_init(o_full, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -154,14 +157,20 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
                 tc_commit(kv_empty + s);
                 tc_commit(s_full + b);
             }
-            // ---- pass 2: scores, then O += P . V ----
-            for (int t = 0; t < n_tiles; t++, it++, si++) {
-                const int s = it & 1, b = si & 1;
-                mbar_wait(kv_full + s, (it >> 1) & 1);
-                mbar_wait(s_empty + b, ((si >> 1) & 1) ^ 1);
+            // ---- pass 2: scores of tile t+1 are issued BEFORE P.V of tile t, so its soft-max overlaps that product ----
+            const int it0 = it, si0 = si;
+            auto issue_qk = [&](int t) {
+                const int i2 = it0 + t, s2 = si0 + t, s = i2 & 1, bb = s2 & 1;
+                mbar_wait(kv_full + s, (i2 >> 1) & 1);
+                mbar_wait(s_empty + bb, ((s2 >> 1) & 1) ^ 1);
                 tc_fence_after();
-                qk(s, b);
-                tc_commit(s_full + b);
+                qk(s, bb);
+                tc_commit(s_full + bb);
+            };
+            if (n_tiles > 0) issue_qk(0);
+            for (int t = 0; t < n_tiles; t++) {
+                if (t + 1 < n_tiles) issue_qk(t + 1);
+                const int s = (it0 + t) & 1;
                 mbar_wait(p_full, t & 1);                                   // P of this tile is in shared memory
                 tc_fence_after();
 #pragma unroll
@@ -176,8 +185,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
             tc_commit(o_full);
         }
     } else {
-        // ===================== soft-max / epilogue: thread = row = TMEM lane =====================
+        // ===================== soft-max / epilogue: two threads per row (= TMEM lane), 64 key columns each =====================
+        float* s_x = reinterpret_cast<float*>(tmem_slot + 4);   // [2 halves][128 rows] exchange of row maxima, then row sums
         const int row = 32 * (warp & 3) + lane;             // warp w may touch TMEM lanes 32 (w % 4) .. +31
+        const int half = warp >= 6 ? 1 : 0;                 // key columns [64 half, 64 half + 64) of every tile
         const int g = row / BQ, tok = q0 + (row % BQ);
         const bool row_ok = tok < a.T;
         const int last_key = pos0 + tok;                    // causal: keys <= last_key
@@ -185,77 +196,87 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
         const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
         float m = -INFINITY, l = 0.0f;
         int si = 0;
-        // ---- pass 1 ----
+        // ---- pass 1: row maximum ----
         for (int t = 0; t < n_tiles; t++, si++) {
             const int b = si & 1;
             mbar_wait(s_full + b, (si >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 2; c++) {
                 uint32_t v[32];
-                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + c * 32) + lane_off, v);
+                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + half * 64 + c * 32) + lane_off, v);
                 tc_wait_ld();
-                float cm = -INFINITY;
+                const int key0 = t * 128 + half * 64 + c * 32;
+                if (row_ok && key0 + 31 <= last_key) {      // no key of this chunk is masked (every tile but the diagonal one)
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int key = t * 128 + c * 32 + j;
-                    const float sv = (row_ok && key <= last_key) ? __uint_as_float(v[j]) * sl2 : -INFINITY;
-                    v[j] = __float_as_uint(sv);
-                    cm = fmaxf(cm, sv);
-                }
-                if (cm > -INFINITY) {
-                    const float mn = fmaxf(m, cm);
-                    float acc = 0.0f;
+                    for (int j = 0; j < 32; j++) m = fmaxf(m, __uint_as_float(v[j]));
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) acc += exp2f(__uint_as_float(v[j]) - mn);
-                    l = l * exp2f(m - mn) + acc;
-                    m = mn;
+                    for (int j = 0; j < 32; j++) if (row_ok && key0 + j <= last_key) m = fmaxf(m, __uint_as_float(v[j]));
                 }
             }
             tc_fence_before();
             mbar_arrive(s_empty + b);
         }
-        // ---- pass 2 ----
+        s_x[half * 128 + row] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(s_x[row], s_x[128 + row]) * sl2;          // scale > 0: max commutes with the scaling
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ---- pass 2: P = exp2(s - m), row sum alongside ----
+        unsigned char* prow = sP + half * AT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
         for (int t = 0; t < n_tiles; t++, si++) {
             const int b = si & 1;
             mbar_wait(s_full + b, (si >> 1) & 1);
-            mbar_wait(p_empty, (t & 1) ^ 1);                // the P.V of the previous tile has read the P buffer
             tc_fence_after();
-            unsigned char* prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
                 uint32_t v[32];
-                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + c * 32) + lane_off, v);
+                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + half * 64 + c * 32) + lane_off, v);
                 tc_wait_ld();
-                uint32_t pk[16];
+                const int key0 = t * 128 + half * 64 + c * 32;
+                if (row_ok && key0 + 31 <= last_key) {      // unmasked chunk
+                    float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const int key = t * 128 + c * 32 + j;
-                    const float p0 = (row_ok && key <= last_key) ? exp2f(__uint_as_float(v[j]) * sl2 - m) : 0.0f;
-                    const float p1 = (row_ok && key + 1 <= last_key) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - m) : 0.0f;
-                    __half2 h = __floats2half2_rn(p0, p1);
-                    pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -m)), p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -m));
+                        l0 += p0; l1 += p1;
+                        __half2 h = __floats2half2_rn(p0, p1);
+                        pk[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    l += l0 + l1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = (row_ok && key0 + j <= last_key) ? ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -m)) : 0.0f;
+                        const float p1 = (row_ok && key0 + j + 1 <= last_key) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -m)) : 0.0f;
+                        l += p0 + p1;
+                        __half2 h = __floats2half2_rn(p0, p1);
+                        pk[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+                    }
                 }
-                // 32 keys = four 16-byte chunks of key block (c >> 1); chunk index inside the 128-byte row: (c & 1) * 4 + q
-                unsigned char* pb = prow + (c >> 1) * AT_TILE_BYTES;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    *reinterpret_cast<uint4*>(pb + ((((c & 1) * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
-            fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(s_empty + b);
+            mbar_arrive(s_empty + b);                       // S[b] is free for the scores of tile t + 2
+            mbar_wait(p_empty, (t & 1) ^ 1);                // the P.V of the previous tile has read the P buffer
+#pragma unroll
+            for (int q = 0; q < 8; q++)                     // this thread's 64 keys = the eight 16-byte chunks of its row in key block `half`
+                *reinterpret_cast<uint4*>(prow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            fence_proxy_async();
             mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l -> bf16 ----
+        s_x[half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l = s_x[row] + s_x[128 + row];
+        // ---- epilogue: O / l -> bf16, this thread's 64 of the 128 head dims ----
         mbar_wait(o_full, 0);
         tc_fence_after();
         const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-        __nv_bfloat16* dst = a.out + (size_t)tok * ((size_t)a.n_head * 128) + (size_t)(hk * GQ + g) * 128;
+        __nv_bfloat16* dst = a.out + (size_t)tok * ((size_t)a.n_head * 128) + (size_t)(hk * GQ + g) * 128 + half * 64;
 #pragma unroll 1
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < 2; c++) {
             uint32_t v[32];
-            tc_ld_32x32b_x32(tO + (uint32_t)(c * 32) + lane_off, v);
+            tc_ld_32x32b_x32(tO + (uint32_t)(half * 64 + c * 32) + lane_off, v);
             tc_wait_ld();
             if (row_ok) {
 #pragma unroll
