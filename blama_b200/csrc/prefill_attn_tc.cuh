@@ -21,7 +21,7 @@ namespace blk {
 
 constexpr int AT_THREADS = 320;                            // warp 0 TMA, warp 1 MMA, warps 2-9 soft-max (two threads per row)
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;                 // one [128][64] f16 K block = 16 KB
-constexpr int AT_SMEM_BYTES = (2 + 2 * 2 + 2 * 2 + 2) * AT_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row statistics*/;      // Q, K x2, V x2, P
+constexpr int AT_SMEM_BYTES = (2 + 2 * 2 + 2 * 2 + 2 * 2) * AT_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row statistics*/;      // Q, K x2, V x2, P x2
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {      // f16 x f16 -> f32, both K-major
@@ -67,17 +67,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     unsigned char* sQ = smem;                                   // 2 K blocks
     unsigned char* sK = sQ + 2 * AT_TILE_BYTES;                 // 2 stages x 2 K blocks
     unsigned char* sV = sK + 4 * AT_TILE_BYTES;                 // 2 stages x 2 key blocks
-    unsigned char* sP = sV + 4 * AT_TILE_BYTES;                 // 2 key blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_TILE_BYTES);
+    unsigned char* sP = sV + 4 * AT_TILE_BYTES;                 // 2 buffers x 2 key blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * AT_TILE_BYTES);
     uint64_t* q_full = bars;            // 1
     uint64_t* kv_full = bars + 1;       // [2]
     uint64_t* kv_empty = bars + 3;      // [2]
     uint64_t* s_full = bars + 5;        // [2]
     uint64_t* s_empty = bars + 7;       // [2]  256 soft-max threads
-    uint64_t* p_full = bars + 9;        // 256 soft-max threads
-    uint64_t* p_empty = bars + 10;      // tcgen05.commit
-    uint64_t* o_full = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* p_full = bars + 9;        // [2]  256 soft-max threads
+    uint64_t* p_empty = bars + 11;      // [2]  tcgen05.commit
+    uint64_t* o_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, hk = blockIdx.y;      // late (long) query tiles first
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); mbar_init(s_full + s, 1); mbar_init(s_empty + s, 256); }
-        mbar_init(p_full, 256); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(p_full + s, 256); mbar_init(p_empty + s, 1); }
+        mbar_init(o_full, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -171,16 +172,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
             for (int t = 0; t < n_tiles; t++) {
                 if (t + 1 < n_tiles) issue_qk(t + 1);
                 const int s = (it0 + t) & 1;
-                mbar_wait(p_full, t & 1);                                   // P of this tile is in shared memory
+                mbar_wait(p_full + (t & 1), (t >> 1) & 1);                  // P of this tile is in shared memory
                 tc_fence_after();
 #pragma unroll
                 for (int kb = 0; kb < 2; kb++) {
-                    const uint64_t dp = umma_desc_sw128(sP + kb * AT_TILE_BYTES), dv = umma_desc_sw128(sV + (s * 2 + kb) * AT_TILE_BYTES);
+                    const uint64_t dp = umma_desc_sw128(sP + ((t & 1) * 2 + kb) * AT_TILE_BYTES), dv = umma_desc_sw128(sV + (s * 2 + kb) * AT_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; k++) tc_mma_f16(tO, dp + (uint64_t)((k * 32) >> 4), dv + (uint64_t)((k * 32) >> 4), idesc, (t | kb | k) ? 1u : 0u);
                 }
                 tc_commit(kv_empty + s);
-                tc_commit(p_empty);
+                tc_commit(p_empty + (t & 1));
             }
             tc_commit(o_full);
         }
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
         m = fmaxf(s_x[row], s_x[128 + row]) * sl2;          // scale > 0: max commutes with the scaling
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // ---- pass 2: P = exp2(s - m), row sum alongside ----
-        unsigned char* prow = sP + half * AT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        unsigned char* prow0 = sP + half * AT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
         for (int t = 0; t < n_tiles; t++, si++) {
             const int b = si & 1;
             mbar_wait(s_full + b, (si >> 1) & 1);
@@ -258,12 +259,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
             }
             tc_fence_before();
             mbar_arrive(s_empty + b);                       // S[b] is free for the scores of tile t + 2
-            mbar_wait(p_empty, (t & 1) ^ 1);                // the P.V of the previous tile has read the P buffer
+            mbar_wait(p_empty + (t & 1), ((t >> 1) & 1) ^ 1);   // the P.V of tile t - 2 has read this P buffer
+            unsigned char* prow = prow0 + (t & 1) * 2 * AT_TILE_BYTES;
 #pragma unroll
             for (int q = 0; q < 8; q++)                     // this thread's 64 keys = the eight 16-byte chunks of its row in key block `half`
                 *reinterpret_cast<uint4*>(prow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             fence_proxy_async();
-            mbar_arrive(p_full);
+            mbar_arrive(p_full + (t & 1));
         }
         s_x[half * 128 + row] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
