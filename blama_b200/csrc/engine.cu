@@ -844,7 +844,11 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     // ---- two-pass form: the dequantisation passes run on the side stream, one GEMM ahead of the main stream ----
     //   op 4l + {0: QKV, 1: Wo, 2: gate+up, 3: down}, op 4 n_layer: lm_head (panel 2).  The fill of op i+1 starts when GEMM i
     //   starts (its panel's previous user, GEMM i-3, is then done), so fills overlap GEMMs, not the small bandwidth-bound kernels.
-    const int n_ops = 4 * m->n_layer + (verify ? 1 : 0);
+    // verify without the verifier's own per-position top-10: only the logits at the claimed ids are needed (what the reference's
+    // fillCtx reads, Session.cpp:263-282) -> sparse rows of the vocabulary projection instead of the T x V GEMM
+    static const bool full_head_env = [] { const char* e = getenv("BLK_VERIFY_FULL_HEAD"); return e && e[0] == '1'; }();
+    const bool sparse_head = verify && !verify->top && !full_head_env && m->output.type != QT_F32 && m->output.type != QT_F16 && (d % 64) == 0;
+    const int n_ops = 4 * m->n_layer + (verify && !sparse_head ? 1 : 0);
     std::vector<char> op_panel(n_ops + 1, 0);
     auto panel_of = [&](int i) { return i >= 4 * m->n_layer ? 2 : (i & 3); };
     auto fill_op = [&](int i) {      // enqueue the fill of op i on the side stream
@@ -921,7 +925,16 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn);
         BLK_CUDA(cudaGetLastError()); c->launches++;
         __nv_bfloat16* head_panel = nullptr;
-        for (int r0 = 0; r0 < n; r0 += c->pf_logit_rows) {
+        if (sparse_head) {
+            BLK_CUDA(prefill_claimed_logits(m->output, c->pf_xn, c->pf_claimed, c->pf_nclaimed, n, c->pf_gath, st));
+            c->launches++;
+            prof_mark(c, "claimed_logits");
+            // the last position's full row (sampling may continue after the fill): decode mat-vec on the last row
+            GemvArgs a{};
+            a.nseg = 1; a.seg[0] = {m->output, nullptr, 0, 0}; a.total_pairs = V / 2; a.out = c->logits;
+            matvec<EPI_STORE>(c, a, c->pf_x + (size_t)(n - 1) * d, m->out_norm, c->act_d, "gemv_lm_head");
+        }
+        for (int r0 = 0; r0 < n && !sparse_head; r0 += c->pf_logit_rows) {
             const int rows = std::min(c->pf_logit_rows, n - r0);
             BLK_CUDA(prefill_gemm(m->output, c->pf_xn + (size_t)r0 * d, rows, c->pf_logits, V, nullptr, 0, st, r0 == 0 ? (head_panel = before_gemm(4 * m->n_layer)) : head_panel, false));
             prof_mark(c, "gemm_lm_head");

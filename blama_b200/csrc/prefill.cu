@@ -227,6 +227,50 @@ cudaError_t launch_attn_tc(const CUtensorMap& mq, const CUtensorMap& mk, const C
 }
 } // namespace
 
+// ---- verifier logits at the claimed ids only (Session.cpp:263-282 reads nothing else of the row) -------------------------
+// One warp per (position, claimed id): dot(bf16(dequant(W[id])), xn[t]) in f32 -- the arithmetic of the GEMM form (bf16
+// operands, f32 accumulation) without the 2 T V d flops of the full vocabulary projection.
+__global__ void __launch_bounds__(256) claimed_logits_kernel(const QMat W, const __nv_bfloat16* __restrict__ xn, const int32_t* __restrict__ claimed,
+                                                             const int32_t* __restrict__ n_claimed, int n, float* __restrict__ gathered) {
+    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int t = gw / 10, j = gw - t * 10;
+    if (t >= n) return;
+    float out = 0.0f;
+    if (j < n_claimed[t]) {
+        const int id = claimed[(size_t)t * 10 + j];
+        if (id < 0 || id >= W.N) out = -INFINITY;
+        else {
+            float acc = 0.0f;
+            const __nv_bfloat16* x = xn + (size_t)t * W.K;
+            for (int kb = lane; kb < (W.K >> 6); kb += 32) {
+                float w[64];
+                dequant_k64(W, id, kb, w);
+                const uint4* xv = reinterpret_cast<const uint4*>(x + (size_t)kb * 64);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const uint4 xx = xv[c];
+                    const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xx);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float2 xf = __bfloat1622float2(xb[i]);
+                        acc += __bfloat162float(__float2bfloat16_rn(w[c * 8 + 2 * i])) * xf.x;
+                        acc += __bfloat162float(__float2bfloat16_rn(w[c * 8 + 2 * i + 1])) * xf.y;
+                    }
+                }
+            }
+            out = warp_sum(acc);
+        }
+    }
+    if (lane == 0) gathered[(size_t)t * 10 + j] = out;
+}
+
+cudaError_t prefill_claimed_logits(const QMat& W, const __nv_bfloat16* xn, const int32_t* claimed, const int32_t* n_claimed, int n, float* gathered, cudaStream_t st) {
+    if (W.K % 64 || n <= 0) return cudaErrorInvalidValue;
+    const long long warps = (long long)n * 10;
+    claimed_logits_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(W, xn, claimed, n_claimed, n, gathered);
+    return cudaGetLastError();
+}
+
 bool prefill_attn_tc_supported(int d_head, int n_head, int n_head_kv) {
     const int gq = n_head_kv > 0 ? n_head / n_head_kv : 0;
     return d_head == 128 && (gq == 1 || gq == 2 || gq == 4 || gq == 8) && encode_tiled() != nullptr;

@@ -38,6 +38,10 @@ bool prefill_attn_tc_supported(int d_head, int n_head, int n_head_kv);
 cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half* v_pool, const int32_t* page_table, int n_pages, const int32_t* pos0_dev,
                             int pos0, __nv_bfloat16* out, __half* vt, int ctx_pad, int T, int n_head, int n_head_kv, int kv_dim, float scale, cudaStream_t st);
 
+// gathered[t][j] = logit of vocabulary row claimed[t][j] at position t (j < n_claimed[t]; 0 past that, -inf for an id outside the
+// vocabulary): sparse rows of the vocabulary projection, bf16 operands / f32 accumulation like the GEMM form
+cudaError_t prefill_claimed_logits(const QMat& W, const __nv_bfloat16* xn, const int32_t* claimed, const int32_t* n_claimed, int n, float* gathered, cudaStream_t st);
+
 // y[i] = bf16(x[i])
 cudaError_t convert_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t st);
 

@@ -95,3 +95,35 @@ def test_chunked_prefill_equals_single_chunk(gguf_path):
     assert np.abs(a.logits() - b.logits()).max() <= 0.3
     assert a.n_past == b.n_past == 200
     a.close(); b.close(); m.close()
+
+
+@pytest.mark.parametrize("name", ["small-llama-q4km", "small-qwen2-q8"])
+def test_sparse_claimed_logits_equal_the_full_head(name, gguf_path):
+    """without the verifier's own top-10 (what fillCtx needs) the vocabulary projection is evaluated only at the claimed ids:
+    same bf16 x bf16 -> f32 arithmetic as the GEMM form, so the gathered logits agree to fp32 summation order; ragged
+    n_claimed, ids outside the vocabulary and the state left behind (n_past, last-position top-k) behave the same"""
+    from blama_b200 import capi
+
+    m = capi.Model(gguf_path(name))
+    a, b = capi.Ctx(m, 512), capi.Ctx(m, 512)
+    rng = np.random.default_rng(5)
+    prompt = gs.synth_prompt(name, 40, 1)
+    toks = gs.synth_prompt(name, 300, 2)
+    claimed = rng.integers(0, m.n_vocab, size=(len(toks), 10)).astype(np.int32)
+    claimed[7, 3] = m.n_vocab + 5; claimed[9, 0] = -1                  # outside the vocabulary -> -inf
+    n_claimed = rng.integers(0, 11, size=len(toks)).astype(np.int32)
+    n_claimed[7] = n_claimed[9] = 10
+    a.decode(prompt); b.decode(prompt)
+    g_full, top = a.verify_prefill(toks, claimed, n_claimed, want_top=True)
+    g_sparse, none = b.verify_prefill(toks, claimed, n_claimed, want_top=False)
+    assert none is None and a.n_past == b.n_past == len(prompt) + len(toks)
+    finite = np.isfinite(g_full)
+    assert np.array_equal(finite, np.isfinite(g_sparse))
+    assert np.isneginf(g_sparse[7, 3]) and np.isneginf(g_sparse[9, 0])
+    assert np.abs(g_full[finite] - g_sparse[finite]).max() <= 2e-3 * max(1.0, np.abs(g_full[finite]).max())
+    for i in range(len(toks)):
+        assert np.all(g_sparse[i, n_claimed[i]:] == 0.0)
+    # the last position's row: bf16 GEMM (full head) vs the decode mat-vec (sparse path): same top-1 unless it is a near tie
+    ta, tb = a.topk(10), b.topk(10)
+    assert ta["token"][0] == tb["token"][0] or abs(ta["logit"][0] - ta["logit"][1]) < 0.2
+    a.close(); b.close(); m.close()
