@@ -213,18 +213,19 @@ bool encode_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t 
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-template <int GQ>
+template <int GQ, int GQS = GQ>
 cudaError_t launch_attn_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnTcArgs& a, int n_head_kv, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(prefill_attn_tc_kernel<GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(prefill_attn_tc_kernel<GQ, GQS>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    constexpr int BQ = 128 / GQ;
-    prefill_attn_tc_kernel<GQ><<<dim3((a.T + BQ - 1) / BQ, n_head_kv), AT_THREADS, AT_SMEM_BYTES, st>>>(mq, mk, mv, a);
+    constexpr int BQ = 128 / GQS;
+    prefill_attn_tc_kernel<GQ, GQS><<<dim3((a.T + BQ - 1) / BQ, n_head_kv), AT_THREADS, AT_SMEM_BYTES, st>>>(mq, mk, mv, a);
     return cudaGetLastError();
 }
+int attn_tc_slots(int gq) { return gq <= 1 ? 1 : gq <= 2 ? 2 : gq <= 4 ? 4 : 8; }
 } // namespace
 
 // ---- verifier logits at the claimed ids only (Session.cpp:263-282 reads nothing else of the row) -------------------------
@@ -273,7 +274,7 @@ cudaError_t prefill_claimed_logits(const QMat& W, const __nv_bfloat16* xn, const
 
 bool prefill_attn_tc_supported(int d_head, int n_head, int n_head_kv) {
     const int gq = n_head_kv > 0 ? n_head / n_head_kv : 0;
-    return d_head == 128 && (gq == 1 || gq == 2 || gq == 4 || gq == 8) && encode_tiled() != nullptr;
+    return d_head == 128 && gq >= 1 && gq <= 8 && encode_tiled() != nullptr;
 }
 
 cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half* v_pool, const int32_t* page_table, int n_pages, const int32_t* pos0_dev,
@@ -285,7 +286,7 @@ cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half*
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap mq, mk, mv;
-    if (!encode_2d_f16(&mq, q, (uint64_t)dq, (uint64_t)T, (uint64_t)dq, 64, (uint32_t)(128 / gq))) return cudaErrorInvalidValue;
+    if (!encode_2d_f16(&mq, q, (uint64_t)dq, (uint64_t)T, (uint64_t)dq, 64, (uint32_t)(128 / attn_tc_slots(gq)))) return cudaErrorInvalidValue;
     if (!encode_2d_f16(&mk, k_pool, (uint64_t)kv_dim, (uint64_t)n_pages * KV_PAGE, (uint64_t)kv_dim, 64, 64)) return cudaErrorInvalidValue;
     if (!encode_2d_f16(&mv, vt, (uint64_t)ctx_pad, (uint64_t)n_head_kv * 128, (uint64_t)ctx_pad, 64, 128)) return cudaErrorInvalidValue;
     AttnTcArgs a{};
@@ -293,7 +294,11 @@ cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half*
     switch (gq) {
         case 1: return launch_attn_tc<1>(mq, mk, mv, a, n_head_kv, st);
         case 2: return launch_attn_tc<2>(mq, mk, mv, a, n_head_kv, st);
+        case 3: return launch_attn_tc<3, 4>(mq, mk, mv, a, n_head_kv, st);
         case 4: return launch_attn_tc<4>(mq, mk, mv, a, n_head_kv, st);
+        case 5: return launch_attn_tc<5, 8>(mq, mk, mv, a, n_head_kv, st);
+        case 6: return launch_attn_tc<6, 8>(mq, mk, mv, a, n_head_kv, st);
+        case 7: return launch_attn_tc<7, 8>(mq, mk, mv, a, n_head_kv, st);
         case 8: return launch_attn_tc<8>(mq, mk, mv, a, n_head_kv, st);
         default: return cudaErrorInvalidValue;
     }

@@ -31,7 +31,7 @@ cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfl
 bool prefill_panel_fill(const GemmPart* parts, int n_parts, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);
 bool prefill_panel_fill_swiglu(const QMat& gate, const QMat& up, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);
 
-// Causal attention of a prefill chunk on tcgen05 (prefill_attn_tc.cuh): d_head = 128, GQA ratio 1 / 2 / 4 / 8.
+// Causal attention of a prefill chunk on tcgen05 (prefill_attn_tc.cuh): d_head = 128, GQA ratio 1 .. 8.
 //   q [T][n_head*128] f16 (post-RoPE), paged f16 K / V pools of the layer, out [T][n_head*128] bf16;
 //   vt: scratch [n_head_kv*128][ctx_pad] f16 for the transposed V of this layer (ctx_pad: multiple of 128 >= pos0 + T).
 bool prefill_attn_tc_supported(int d_head, int n_head, int n_head_kv);

@@ -58,10 +58,11 @@ __global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restr
     }
 }
 
-template <int GQ>
+// GQ = query heads per KV head; GQS = head slots of the 128-row tile (power of two >= GQ; rows of the unused slots are dead)
+template <int GQ, int GQS = GQ>
 __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                                                                         const __grid_constant__ CUtensorMap tmap_vt, const AttnTcArgs a) {
-    constexpr int BQ = 128 / GQ;
+    constexpr int BQ = 128 / GQS;
     extern __shared__ unsigned char at_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;                                   // 2 K blocks
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     if (warp == 0) {
         // ===================== TMA =====================
         if (lane == 0) {
-            mbar_expect_tx(q_full, 2 * AT_TILE_BYTES);
+            mbar_expect_tx(q_full, 2 * GQ * BQ * 128);
 #pragma unroll
             for (int kb = 0; kb < 2; kb++)
                 for (int g = 0; g < GQ; g++)
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
         const int row = 32 * (warp & 3) + lane;             // warp w may touch TMEM lanes 32 (w % 4) .. +31
         const int half = warp >= 6 ? 1 : 0;                 // key columns [64 half, 64 half + 64) of every tile
         const int g = row / BQ, tok = q0 + (row % BQ);
-        const bool row_ok = tok < a.T;
+        const bool row_ok = tok < a.T && g < GQ;
         const int last_key = pos0 + tok;                    // causal: keys <= last_key
         const float sl2 = a.scale * 1.4426950408889634f;
         const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;

@@ -12,7 +12,7 @@ from blama_b200 import gguf_synth as gs
 pytestmark = pytest.mark.gpu
 
 PREFILL_TOL = 0.08          # absolute, logits have std ~2: bf16 operand rounding + f16 flash-attention ordering
-MODELS = ["tiny-llama-q4km", "tiny-qwen2-q8", "small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "tiny-llama-f32"]
+MODELS = ["tiny-llama-q4km", "tiny-qwen2-q8", "small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "tiny-llama-f32", "small-llama-gq3", "small-qwen2-gq7"]
 
 
 @pytest.mark.parametrize("name", MODELS)
