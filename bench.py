@@ -53,6 +53,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return 2250.0, "fallback (B200_PROFILING.md nominal dense bf16)"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
 
@@ -295,6 +306,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         t_v = max_over_ranks(dt)
         verify = {"tokens": int(len(vt_l)), "tok_s": sum_over_ranks(float(len(vt_l))) / t_v, "ms": t_v * 1e3,
                   "score": score, "mode": "batched prefill" if not args.sequential_verify else "sequential decode"}
+        # tensor roofline of the verify prefill: 2 T (P_layers + V d) + attention 4 n_head d_head L sum_t ctx_t, per replica,
+        # against the measured dense bf16 peak; the wall time includes fillCtx's host side and the LogitComparer pass
+        sh_v = gguf_synth.SHAPES[args.shape]
+        T, p0 = int(len(vt_l)), 32
+        dq, dkv = sh_v.n_head * sh_v.d_head, sh_v.n_head_kv * sh_v.d_head
+        p_layers = sh_v.n_layer * (sh_v.d_model * (dq + 2 * dkv) + dq * sh_v.d_model + 3 * sh_v.d_model * sh_v.d_ffn)
+        flops = 2.0 * T * (p_layers + sh_v.vocab * sh_v.d_model) + 4.0 * dq * sh_v.n_layer * (T * p0 + T * (T + 1) / 2)
+        tf_peak, tf_src = measured_tensor_peak()
+        verify["roofline"] = {"bound": "tensor", "achieved": flops / t_v / 1e12, "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / t_v / 1e12 / tf_peak,
+                              "flops": flops, "peak_source": tf_src,
+                              "note": "full-vocabulary head counted (SURVEY 8d figure); only the claimed-id rows of it are computed when the verifier's own top-10 is not requested"}
 
     if rank != 0:
         dist.close()
@@ -361,7 +383,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"{args.shape}: {args.prompt}-token prompt + {args.new} new tokens per request (BASELINE configs[1]), "
                                "one replica per GPU, independent requests", "shape": args.shape, "prompt_tokens": args.prompt,
-                   "new_tokens": args.new, "l2": "flushed (256 MiB memset) before every timed region; per-token weight stream 4.6 GB >> 126 MB L2",
+                   "new_tokens": args.new, "l2": f"flushed (256 MiB memset) before every timed region; per-token weight stream {wbytes / 1e9:.1f} GB >> 126 MB L2",
                    "parallelism": f"replicas x{world} (no collective on the data path)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 4 * (args.prompt + args.new), "d2h_bytes_per_step": 512 * (args.new + 1),

@@ -179,6 +179,15 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
         ph.K = K; ph.src = src; ph.layer = layer; ph.nseg = 0;
         const int NGtot = n_sms * (MG_WARPS / ph.W);
         int items = 0;
+        // The segments of a phase occupy consecutive warp groups, starting so that the chain ENDS at the last group: the groups that
+        // carry one pair more than the others are the highest CTAs.  CTAs 0 .. n_head_kv * n_split - 1 run the attention stages (and
+        // CTAs 0 .. n_head_kv - 1 the split combine), so the extra QKV pairs and the idle groups of Wo keep off the attention's path.
+        {
+            int64_t total = 0;
+            for (auto& sgd : segs) if (!(std::get<2>(sgd) == MK_SWIGLU && std::get<4>(sgd) == 1)) total += std::get<1>(sgd);
+            static const bool top = [] { const char* e = getenv("BLK_ROT_TOP"); return !(e && e[0] == '0'); }();
+            if (top) rot_acc = (NGtot - total % NGtot) % NGtot;          // first group of the chain
+        }
         const int pi = (int)mg.phases.size();
         for (auto& sgd : segs) {
             const std::string& name = std::get<0>(sgd);
@@ -191,7 +200,7 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
                 MegaSeg& sg = ph.seg[si];
                 sg.type = type; sg.n_pairs = std::get<1>(sgd); sg.kind = kind;
                 sg.slice_bytes = mg_slice_bytes(type, ph.L / 2);
-                sg.rot = (int)(rot_acc % NGtot); rot_acc += sg.n_pairs;
+                sg.rot = (int)((NGtot - rot_acc % NGtot) % NGtot); rot_acc += sg.n_pairs;     // group gg starts at pair (gg + rot) mod NGtot
                 sg.slot0 = items;
                 sg.bias = nullptr; sg.base = nullptr;
                 pl.seg_off[si].resize(pi + 1, 0);
@@ -1092,7 +1101,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             MegaParams& P = c->mega_params;
             P.phases = mg.d_phases; P.n_phases = (int)mg.phases.size(); P.n_layer = m->n_layer;
             P.chunk_list = mg.d_list; P.chunk_counts = mg.d_counts; P.list_stride = mg.list_stride;
-            P.n_cta = mg.n_cta; P.slot_bytes = mg.slot_bytes; P.max_items = mg.max_items; P.act_bytes = mg.act_bytes; P.ts_cap = mg.ts_cap; P.attn_off = mg.attn_off;
+            P.n_cta = mg.n_cta; P.slot_bytes = mg.slot_bytes; P.max_items = mg.max_items; P.act_bytes = mg.act_bytes; P.ts_cap = mg.ts_cap; P.ts_target = mg.ts_cap; { const char* e = getenv("BLK_ATTN_TS"); if (e && atoi(e) >= 8) P.ts_target = std::min(mg.ts_cap, atoi(e)); } P.attn_off = mg.attn_off;
             P.tok_embd = m->tok_embd;
             P.n_embd = d; P.n_head = m->n_head; P.n_head_kv = m->n_head_kv; P.d_head = dh; P.n_ff = ff; P.n_vocab = m->n_vocab; P.neox = m->neox ? 1 : 0;
             P.eps = m->rms_eps; P.theta_scale = m->theta_scale; P.attn_scale = 1.0f / sqrtf((float)dh); P.rope_freqs = m->rope_freqs;
@@ -1113,7 +1122,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
                 c->mega_err = reinterpret_cast<int*>(hp); *c->mega_err = 0;
                 void* dp = nullptr; BLK_CUDA(cudaHostGetDevicePointer(&dp, hp, 0)); P.err = reinterpret_cast<int*>(dp);
             }
-            { const char* tr = getenv("BLK_MEGA_TRACE"); if (tr && tr[0] == '1') { P.trace_cap = 2048; P.trace = dalloc<long long>(c.get(), (size_t)P.n_cta * P.trace_cap); } }
+            { const char* tr = getenv("BLK_MEGA_TRACE"); if (tr && (tr[0] == '1' || tr[0] == '2')) { P.trace_cap = 2048; P.trace_global = tr[0] == '2'; P.trace = dalloc<long long>(c.get(), (size_t)P.n_cta * P.trace_cap); } }
             c->mega_smem = mega_smem_bytes(P);
             int limit = 0;
             c->mega_on = mega_setup(c->mega_smem, &limit) == cudaSuccess;

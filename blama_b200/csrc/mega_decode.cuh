@@ -340,7 +340,9 @@ template <bool TR>
 __device__ __forceinline__ void mg_tr(const MegaParams& P, const MgSmem& S, int tag) {
     if (TR && threadIdx.x == 0) {
         const int i = S.misc[16]++;
-        if (i < P.trace_cap) P.trace[(size_t)blockIdx.x * P.trace_cap + i] = (clock64() << 8) | (long long)tag;
+        long long t;
+        if (P.trace_global) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); else t = clock64();     // ns, common to all SMs | SM clock
+        if (i < P.trace_cap) P.trace[(size_t)blockIdx.x * P.trace_cap + i] = (t << 8) | (long long)tag;
     }
 }
 
@@ -386,7 +388,7 @@ __device__ __forceinline__ MgAttn mg_attn_get(const MgSmem& S) {   // computed o
     MgAttn a; a.hk = S.misc[1]; a.split = S.misc[2]; a.n_split = S.misc[3]; a.t0 = S.misc[4]; a.nt = S.misc[5]; a.on = S.misc[6] != 0; return a;
 }
 __device__ __forceinline__ void mg_attn_setup(const MegaParams& P, int n_kv, const MgSmem& S) {
-    const int n_split = max(1, min(P.max_split, (n_kv + P.ts_cap - 1) / P.ts_cap));
+    const int n_split = max(1, min(P.max_split, (n_kv + P.ts_target - 1) / P.ts_target));
     const int hk = (int)blockIdx.x % P.n_head_kv, split = (int)blockIdx.x / P.n_head_kv;
     const int per = (n_kv + n_split - 1) / n_split;
     const int t0 = split * per;

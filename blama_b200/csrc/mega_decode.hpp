@@ -69,6 +69,7 @@ struct MegaParams {
     const uint4* chunk_list; const int* chunk_counts; int list_stride;     // per (cta, warp): chunk descriptors {addr.lo, addr.hi, bytes, 0}
     int n_cta; int slot_bytes; int max_items; int act_bytes;
     int attn_off;            // offset of the attention tiles inside the activation scratch (behind an n_embd-long row's activations)
+    int ts_target;           // tokens per context split the attention aims for (<= ts_cap: more, shorter splits)
     int ts_cap;              // tokens of one attention tile (K and V rows of a CTA's context slice held in shared memory)
     // model
     QMat tok_embd;
@@ -86,7 +87,7 @@ struct MegaParams {
     __half* const* k_pools; __half* const* v_pools; const int32_t* page_table; int kv_dim;
     float* logits; int* chunk_max; int chunk_shift;
     int with_head; int advance_pos;
-    long long* trace; int trace_cap;      // optional event trace [n_cta][trace_cap] (debug / profiling)
+    long long* trace; int trace_cap; int trace_global;      // optional event trace [n_cta][trace_cap] (debug / profiling)
 };
 
 // ---- host entry points (mega_decode.cu) ----

@@ -17,7 +17,7 @@ raw = c.debug_trace()
 KIND = ["qkv", "wo", "gu", "down", "head"]
 TAG = {2: "(loop top)", 3: "prologue.tail", 4: "act regs", 5: "mac", 6: "epilogue"}
 PRO = {30: "pro.wait x+sumsq", 31: "pro.sync+scale", 32: "pro.wait src blk0", 34: "pro.quantise"}
-ATT = {17: "attn.pv.wait+max", 11: "attn.scores(+wait q)", 13: "attn.pv.stats", 14: "attn.pv.pv", 15: "attn.pv.partials", 16: "attn.pv.combine", 20: "final wait"}
+ATT = {40: "wo.mac.wait", 41: "wo.mac.dot", 42: "wo.mac.issue", 43: "wo.mac.butterfly", 44: "wo.mac.end", 17: "attn.pv.wait+max", 11: "attn.scores(+wait q)", 13: "attn.pv.stats", 14: "attn.pv.pv", 15: "attn.pv.partials", 16: "attn.pv.combine", 20: "final wait"}
 clk = 1.965e3
 agg = {}
 for cta in range(raw.shape[0]):
