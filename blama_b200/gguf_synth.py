@@ -66,6 +66,9 @@ SHAPES: Dict[str, ModelShape] = {
     # GQA ratios that are not powers of two (Qwen2.5-7B has 7): 3 query heads per KV head, and 7 with NEOX rotary + biases
     "small-llama-gq3": ModelShape("llama", "small-llama-gq3", 768, 2, 6, 2, 128, 1536, 2048, 4096, 5e5, 1e-5, "Q4_K_M", rope_freqs=True),
     "small-qwen2-gq7": ModelShape("qwen2", "small-qwen2-gq7", 1792, 2, 14, 2, 128, 2304, 3000, 4096, 1e6, 1e-6, "Q8_0", qkv_bias=True),
+    # FFN rows longer than 16 blocks of 256: the persistent decode kernel quantises the SwiGLU output once and shares it (K-quant and Q8_0 forms)
+    "small-llama-wideffn-q4km": ModelShape("llama", "small-llama-wideffn", 512, 2, 4, 2, 128, 4608, 2048, 4096, 5e5, 1e-5, "Q4_K_M", rope_freqs=True),
+    "small-qwen2-wideffn-q8": ModelShape("qwen2", "small-qwen2-wideffn", 512, 2, 4, 2, 128, 4608, 2048, 4096, 1e6, 1e-6, "Q8_0", qkv_bias=True),
     # BASELINE.json configs
     "llama-3.2-1b-q8": ModelShape("llama", "Llama-3.2-1B-arch", 2048, 16, 32, 8, 64, 8192, 128256, 131072, 5e5, 1e-5, "Q8_0", tied=True, rope_freqs=True),
     "llama-3.1-8b-q4km": ModelShape("llama", "Llama-3.1-8B-arch", 4096, 32, 32, 8, 128, 14336, 128256, 131072, 5e5, 1e-5, "Q4_K_M", rope_freqs=True),

@@ -6,7 +6,8 @@ from blama_b200 import gguf_synth as gs
 
 pytestmark = pytest.mark.gpu
 
-MODELS = ["tiny-llama-q4km", "tiny-llama-q8", "tiny-qwen2-q8", "tiny-llama-f32", "small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "small-llama-gq3", "small-qwen2-gq7"]
+MODELS = ["tiny-llama-q4km", "tiny-llama-q8", "tiny-qwen2-q8", "tiny-llama-f32", "small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "small-llama-gq3", "small-qwen2-gq7",
+          "small-llama-wideffn-q4km", "small-qwen2-wideffn-q8"]
 # Two implementations of ggml's arithmetic agree on every integer partial sum but not on the ORDER of the fp32
 # additions.  A 1e-7 difference occasionally flips one Q8_K / f16 rounding, and the requantise-matmul chain amplifies a
 # flip into ~0.1 logit differences that then persist through the KV cache (measured: the oracle against itself with a

@@ -24,7 +24,8 @@ def _two_paths(path, n_ctx, monkeypatch):
     return (m1, c1), (m0, c0)
 
 
-@pytest.mark.parametrize("name", ["small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "tiny-llama-q8"])
+@pytest.mark.parametrize("name", ["small-llama-q4km", "small-qwen2-q8", "small-llama70-q4km", "tiny-llama-q8",
+                                  "small-llama-wideffn-q4km", "small-qwen2-wideffn-q8"])
 def test_path_selection_and_agreement(name, gguf_path, monkeypatch):
     (m1, c1), (m0, c0) = _two_paths(gguf_path(name), 256, monkeypatch)
     assert c1.persistent_decode and not c0.persistent_decode
