@@ -893,7 +893,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     fill_op(0);
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
-        rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn);
+        rmsnorm_bf16_launch(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn, n, st);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
@@ -915,7 +915,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 1), false));
         after_gemm(4 * l + 1);
         prof_mark(c, "gemm_wo");
-        rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn);
+        rmsnorm_bf16_launch(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn, n, st);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, before_gemm(4 * l + 2), false));
@@ -931,7 +931,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     if (verify) {
         BLK_CUDA(cudaMemcpyAsync(c->pf_claimed, verify->claimed + (size_t)verify_row0 * 10, (size_t)n * 10 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         BLK_CUDA(cudaMemcpyAsync(c->pf_nclaimed, verify->n_claimed + verify_row0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        rmsnorm_bf16_kernel<<<n, 256, 0, st>>>(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn);
+        rmsnorm_bf16_launch(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn, n, st);
         BLK_CUDA(cudaGetLastError()); c->launches++;
         __nv_bfloat16* head_panel = nullptr;
         if (sparse_head) {

@@ -11,14 +11,36 @@
 namespace blk {
 
 // ---- RMSNorm * weight -> bf16 (one CTA per token row) -------------------------------------------------------------------
+// The row is read ONCE with 16-byte loads and stays in registers between the two passes (K <= 8192; longer rows re-read it).
+__host__ inline void rmsnorm_bf16_launch(const float* x, const float* w, int K, float eps, __nv_bfloat16* y, int rows, cudaStream_t st);
+__device__ __forceinline__ double rms_sq4(float4 v) {
+    return ((double)__fmul_rn(v.x, v.x) + (double)__fmul_rn(v.y, v.y)) + ((double)__fmul_rn(v.z, v.z) + (double)__fmul_rn(v.w, v.w));
+}
+__device__ __forceinline__ uint2 rms_out4(float4 v, float scale, float4 w) {
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(__fmul_rn(__fmul_rn(v.x, scale), w.x), __fmul_rn(__fmul_rn(v.y, scale), w.y));
+    const __nv_bfloat162 p1 = __floats2bfloat162_rn(__fmul_rn(__fmul_rn(v.z, scale), w.z), __fmul_rn(__fmul_rn(v.w, scale), w.w));
+    uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
+    return o;
+}
+template <int NV>     // 16-byte words of the row a thread keeps in registers: rows up to NV * 1024 elements are read once
 __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, int K, float eps,
                                                           __nv_bfloat16* __restrict__ y) {
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    x += (size_t)row * K; y += (size_t)row * K;
+    const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * K);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    uint2* y2 = reinterpret_cast<uint2*>(y + (size_t)row * K);
+    const int n4 = K >> 2;                               // K % 4 == 0 (checked at load: every row length is a multiple of 32)
+    const bool in_regs = n4 <= NV * 256;
     __shared__ double red[8];
     __shared__ float s_scale;
+    float4 v[NV];
     double sum = 0.0;
-    for (int i = tid; i < K; i += 256) { const float v = x[i]; sum += (double)__fmul_rn(v, v); }
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) { const int i = tid + j * 256; if (i < n4) { v[j] = x4[i]; sum += rms_sq4(v[j]); } }
+    } else {
+        for (int i = tid; i < n4; i += 256) sum += rms_sq4(x4[i]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) red[wid] = sum;
@@ -30,10 +52,20 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restri
     }
     __syncthreads();
     const float scale = s_scale;
-    for (int i = tid; i < K; i += 256) y[i] = __float2bfloat16_rn(__fmul_rn(__fmul_rn(x[i], scale), w[i]));
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) { const int i = tid + j * 256; if (i < n4) y2[i] = rms_out4(v[j], scale, __ldg(w4 + i)); }
+    } else {
+        for (int i = tid; i < n4; i += 256) y2[i] = rms_out4(x4[i], scale, __ldg(w4 + i));
+    }
 }
 
-// ---- RoPE on q,k; q -> f16 [T][dq]; k,v -> f16 KV pages (one CTA per token) ---------------------------------------------------
+__host__ inline void rmsnorm_bf16_launch(const float* x, const float* w, int K, float eps, __nv_bfloat16* y, int rows, cudaStream_t st) {
+    if (K <= 4096) rmsnorm_bf16_kernel<4><<<rows, 256, 0, st>>>(x, w, K, eps, y);
+    else rmsnorm_bf16_kernel<8><<<rows, 256, 0, st>>>(x, w, K, eps, y);
+}
+
+// ---- RoPE on q,k; q -> f16 [T][dq]; k,v -> f16 KV pages (one CTA per token, four elements per thread and step) --------------------
 struct QkvPostArgs {
     const float* qkv; long long ld;            // [T][dq + 2*dkv] f32 (bias already added by the GEMM)
     const float2* rope_cs;                     // [T][d_head/2]
@@ -42,28 +74,49 @@ struct QkvPostArgs {
     __half* k_pool; __half* v_pool; const int32_t* page_table;
     int dq, dkv, d_head, neox;
 };
+__device__ __forceinline__ uint2 pack_h4(float a, float b, float c, float d) {
+    const __half2 p0 = __floats2half2_rn(a, b), p1 = __floats2half2_rn(c, d);
+    uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
+    return o;
+}
 __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
     const int t = blockIdx.x, tid = threadIdx.x;
     const float* row = a.qkv + (size_t)t * a.ld;
     const float2* cs = a.rope_cs + (size_t)t * (a.d_head / 2);
     const int pos = a.pos0[0] + t;
     const size_t base = ((size_t)a.page_table[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * a.dkv;
-    const int hd = a.d_head / 2;
-    // rotary pairs of q and k
-    for (int p = tid; p < (a.dq + a.dkv) / 2; p += 256) {
-        const bool is_k = p >= a.dq / 2;
-        const int pp = is_k ? p - a.dq / 2 : p;
-        const int h = pp / hd, i = pp % hd;
-        const int r0 = a.neox ? h * a.d_head + i : h * a.d_head + 2 * i;
-        const int r1 = a.neox ? r0 + hd : r0 + 1;
-        const float* src = row + (is_k ? a.dq : 0);
-        const float x0 = src[r0], x1 = src[r1];
-        const float2 c = cs[i];
-        const float y0 = x0 * c.x - x1 * c.y, y1 = x0 * c.y + x1 * c.x;
-        if (is_k) { a.k_pool[base + r0] = __float2half_rn(y0); a.k_pool[base + r1] = __float2half_rn(y1); }
-        else { a.q_out[(size_t)t * a.dq + r0] = __float2half_rn(y0); a.q_out[(size_t)t * a.dq + r1] = __float2half_rn(y1); }
+    const int dh = a.d_head, hd = dh >> 1;               // d_head is 64 or 128 (checked at load)
+    const int nqk = a.dq + a.dkv;                        // q then k: contiguous in the row, both whole heads
+    __half* qdst = a.q_out + (size_t)t * a.dq;
+    __half* kdst = a.k_pool + base;
+    if (!a.neox) {
+        // NORM pairs (2i, 2i+1): four consecutive elements are two pairs
+        for (int e = tid * 4; e < nqk; e += 1024) {
+            const float4 x = *reinterpret_cast<const float4*>(row + e);
+            const float4 c = *reinterpret_cast<const float4*>(cs + ((e & (dh - 1)) >> 1));      // {cos, sin} of the two pairs
+            const float y0 = x.x * c.x - x.y * c.y, y1 = x.x * c.y + x.y * c.x;
+            const float y2 = x.z * c.z - x.w * c.w, y3 = x.z * c.w + x.w * c.z;
+            *reinterpret_cast<uint2*>(e < a.dq ? qdst + e : kdst + (e - a.dq)) = pack_h4(y0, y1, y2, y3);
+        }
+    } else {
+        // NEOX pairs (i, i + d_head/2) inside a head: four consecutive i
+        const int hsh = dh == 128 ? 6 : 5;
+        for (int idx = tid * 4; idx < (nqk >> 1); idx += 1024) {
+            const int h = idx >> hsh, i = idx & (hd - 1);
+            const int r0 = h * dh + i;
+            const float4 x0 = *reinterpret_cast<const float4*>(row + r0), x1 = *reinterpret_cast<const float4*>(row + r0 + hd);
+            const float4 c01 = *reinterpret_cast<const float4*>(cs + i), c23 = *reinterpret_cast<const float4*>(cs + i + 2);
+            const uint2 lo = pack_h4(x0.x * c01.x - x1.x * c01.y, x0.y * c01.z - x1.y * c01.w, x0.z * c23.x - x1.z * c23.y, x0.w * c23.z - x1.w * c23.w);
+            const uint2 hi = pack_h4(x0.x * c01.y + x1.x * c01.x, x0.y * c01.w + x1.y * c01.z, x0.z * c23.y + x1.z * c23.x, x0.w * c23.w + x1.w * c23.z);
+            __half* dst = r0 < a.dq ? qdst + r0 : kdst + (r0 - a.dq);
+            *reinterpret_cast<uint2*>(dst) = lo;
+            *reinterpret_cast<uint2*>(dst + hd) = hi;
+        }
     }
-    for (int i = tid; i < a.dkv; i += 256) a.v_pool[base + i] = __float2half_rn(row[a.dq + a.dkv + i]);
+    for (int e = tid * 4; e < a.dkv; e += 1024) {
+        const float4 x = *reinterpret_cast<const float4*>(row + nqk + e);
+        *reinterpret_cast<uint2*>(a.v_pool + base + e) = pack_h4(x.x, x.y, x.z, x.w);
+    }
 }
 
 // ---- SwiGLU: h = silu(g) * u -> bf16 ------------------------------------------------------------------------------------------
