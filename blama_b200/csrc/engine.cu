@@ -748,6 +748,12 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
     c->pf_ao = dalloc<__nv_bfloat16>(c, t * dq);
     c->pf_g = dalloc<float>(c, t * ff); c->pf_u = dalloc<float>(c, t * ff);
     c->pf_h = dalloc<__nv_bfloat16>(c, t * ff);
+    {   // split-K workspace of the prefill GEMMs (few-token batches): splits * tiles <= SMs, a tile is 256 x 256 f32
+        const char* e = getenv("BLK_SPLITK");
+        int sms = 0; BLK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+        c->pf_splitk_elems = (e && e[0] == '0') ? 0 : (size_t)sms * 65536;
+        c->pf_splitk = c->pf_splitk_elems ? dalloc<float>(c, c->pf_splitk_elems) : nullptr;
+    }
     c->pf_logit_rows = 512;     // rows of one lm_head chunk: two M tiles share every weight tile through L2
     c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
     {   // bf16 weight panel of the two-pass GEMM form (largest single launch: QKV | Wo | gate+up | down | lm_head)
@@ -891,13 +897,14 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     auto after_gemm = [&](int) {};
     if (panel) { BLK_CUDA(cudaEventRecord(c->pn_start[0], st)); BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[0], 0)); }   // after whatever ran before
     fill_op(0);
+    const SplitKWs sk{c->pf_splitk, c->pf_splitk_elems};
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
         rmsnorm_bf16_launch(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn, n, st);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
-        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st, before_gemm(4 * l), false));
+        BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, c->pf_xn, n, c->pf_qkv, ldq, st, before_gemm(4 * l), false, &sk));
         after_gemm(4 * l);
         prof_mark(c, "gemm_qkv");
         QkvPostArgs qa{};
@@ -912,7 +919,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         pa.out = c->pf_ao; pa.T = n; pa.n_head = m->n_head; pa.n_head_kv = m->n_head_kv; pa.kv_dim = dkv; pa.scale = 1.0f / sqrtf((float)dh);
         launch_prefill_attn(c, pa, n, st);
         prof_mark(c, "flash_attn");
-        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 1), false));
+        BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 1), false, &sk));
         after_gemm(4 * l + 1);
         prof_mark(c, "gemm_wo");
         rmsnorm_bf16_launch(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn, n, st);
@@ -921,7 +928,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, before_gemm(4 * l + 2), false));
         after_gemm(4 * l + 2);
         prof_mark(c, "gemm_gate_up_swiglu");
-        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 3), false));
+        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 3), false, &sk));
         after_gemm(4 * l + 3);
         prof_mark(c, "gemm_down");
         c->launches += 12;

@@ -123,6 +123,7 @@ struct blk_ctx {
     __nv_bfloat16* pf_ao = nullptr; float* pf_g = nullptr; float* pf_u = nullptr; __nv_bfloat16* pf_h = nullptr;
     float* pf_logits = nullptr;
     __half* pf_vt = nullptr; int pf_vt_pad = 0;           // transposed V of one layer for the tcgen05 prefill attention
+    float* pf_splitk = nullptr; size_t pf_splitk_elems = 0;               // partial sums of the split-K prefill GEMMs (few-token batches)
     __nv_bfloat16* pf_panel[4] = {nullptr, nullptr, nullptr, nullptr};     // bf16 weight panels of the two-pass GEMM form, one per GEMM kind
     cudaEvent_t pn_filled[4] = {nullptr, nullptr, nullptr, nullptr}, pn_start[4] = {nullptr, nullptr, nullptr, nullptr};
     int panel_min = 32;   // two-pass GEMM form from this many tokens per chunk on (0 = never)

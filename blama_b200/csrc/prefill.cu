@@ -57,7 +57,8 @@ GemmKernel pick_kernel(int ta, int tb) {
 }
 
 // panel: nullptr for the fused (in-kernel dequantisation) form, else the bf16 panel [panel_rows][K] the B tiles are read from
-cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16* X, cudaStream_t st, const __nv_bfloat16* panel = nullptr, long long panel_rows = 0) {
+cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16* X, cudaStream_t st, const __nv_bfloat16* panel = nullptr, long long panel_rows = 0,
+                        const SplitKWs* sk = nullptr) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
     if (a.K % PG_BK || a.T <= 0 || a.n_tiles <= 0) return cudaErrorInvalidValue;
@@ -87,8 +88,24 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = ((a.T + PG_BM - 1) / PG_BM) * a.n_tiles;
-    const int grid = tiles < sms ? tiles : sms;
+    // few-token batches: split K so that (tile, split) work items fill the SMs; partial sums go to the workspace and are added in
+    // split order by a second kernel (deterministic).  Every split gets at least 8 K blocks (hence never an empty one).
+    a.k_splits = 1; a.ws = nullptr; a.ws_stride = 0;
+    if (panel && sk && sk->ws && a.mode != PG_SWIGLU && 2 * tiles <= sms) {
+        int S = std::min(8, std::min(sms / tiles, (a.K / PG_BK) / 8));
+        while (S > 1 && (size_t)S * (size_t)a.T * (size_t)a.ldc > sk->elems) S--;
+        if (S > 1) { a.k_splits = S; a.ws = sk->ws; a.ws_stride = (long long)a.T * a.ldc; }
+    }
+    const int items = tiles * a.k_splits;
+    const int grid = items < sms ? items : sms;
     kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, tmap_w, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || a.k_splits == 1) return e;
+    SplitKReduceArgs ra{};
+    ra.C = a.C; ra.ws = a.ws; ra.ldc = a.ldc; ra.ws_stride = a.ws_stride; ra.T = a.T; ra.n_split = a.k_splits; ra.accumulate = a.mode == PG_ACCUM ? 1 : 0; ra.nseg = a.nseg;
+    int nmax = 0;
+    for (int i = 0; i < a.nseg; i++) { ra.col0[i] = a.seg[i].col0; ra.n[i] = a.seg[i].W.N; ra.bias[i] = a.seg[i].bias; nmax = std::max(nmax, a.seg[i].W.N); if (a.seg[i].W.N % 4) return cudaErrorInvalidValue; }
+    splitk_reduce_kernel<<<dim3((unsigned)((nmax + 1023) / 1024), (unsigned)a.T), 256, 0, st>>>(ra);
     return cudaGetLastError();
 }
 
@@ -110,14 +127,14 @@ bool panel_type_ok(int t) { return t == QT_Q4_K || t == QT_Q5_K || t == QT_Q6_K 
 } // namespace
 
 cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st,
-                         __nv_bfloat16* panel, bool panel_fill) {
+                         __nv_bfloat16* panel, bool panel_fill, const SplitKWs* sk) {
     PrefillGemmArgs a{};
     a.nseg = 1; a.seg[0] = {W, bias, 0, 0};
     a.C = C; a.ldc = ldc; a.T = T; a.K = W.K; a.mode = mode;
     a.n_tiles = (W.N + PG_BN - 1) / PG_BN;
     if (panel && panel_type_ok(W.type) && W.K % 64 == 0) {
         if (panel_fill) { cudaError_t e = panel_dequant(W, panel, 0, st); if (e != cudaSuccess) return e; }
-        return launch_gemm(a, W.type, W.type, X, st, panel, (long long)a.n_tiles * PG_BN);
+        return launch_gemm(a, W.type, W.type, X, st, panel, (long long)a.n_tiles * PG_BN, (W.N % 4 == 0 && ldc % 4 == 0) ? sk : nullptr);
     }
     return launch_gemm(a, W.type, W.type, X, st);
 }
@@ -146,7 +163,7 @@ bool prefill_panel_fill_swiglu(const QMat& gate, const QMat& up, __nv_bfloat16* 
 size_t prefill_panel_rows(int N) { return (size_t)((N + PG_BN - 1) / PG_BN) * PG_BN; }
 
 cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st,
-                               __nv_bfloat16* panel, bool panel_fill) {
+                               __nv_bfloat16* panel, bool panel_fill, const SplitKWs* sk) {
     bool all_panel = panel != nullptr && n_parts >= 1 && n_parts <= 3;
     for (int i = 0; i < n_parts && all_panel; i++) all_panel = panel_type_ok(parts[i].W->type) && parts[i].W->K == parts[0].W->K && parts[i].col0 % 4 == 0;
     bool fuse = n_parts >= 2 && n_parts <= 3 && parts[0].W->type == parts[1].W->type;
@@ -162,11 +179,13 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
             tile0 += (parts[i].W->N + PG_BN - 1) / PG_BN;
         }
         a.n_tiles = tile0;
-        return launch_gemm(a, QT_PANEL, QT_PANEL, X, st, panel, (long long)tile0 * PG_BN);
+        bool sk_ok = ldc % 4 == 0;
+        for (int i = 0; i < n_parts; i++) sk_ok = sk_ok && parts[i].W->N % 4 == 0;
+        return launch_gemm(a, QT_PANEL, QT_PANEL, X, st, panel, (long long)tile0 * PG_BN, sk_ok ? sk : nullptr);
     }
     if (!fuse) {
         for (int i = 0; i < n_parts; i++) {
-            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st, nullptr, false);
+            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st, nullptr, false, nullptr);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;

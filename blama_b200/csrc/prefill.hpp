@@ -12,8 +12,11 @@ namespace blk {
 // mode: 0 store (+bias), 1 accumulate into C.  Returns a CUDA error (cudaErrorNotSupported if the driver lacks TMA).
 // panel != nullptr selects the two-pass form: W is dequantised once into the bf16 panel (panel_fill) and the GEMM reads its B
 // tiles from there by TMA -- for many-token batches, where the fused form would dequantise every weight tile T / 256 times.
+// sk != nullptr (two-pass form only): workspace for a deterministic split-K when the batch has too few tiles to fill the SMs
+// (n_sm * 65536 floats always suffice: splits * tiles never exceeds the SM count)
+struct SplitKWs { float* ws; size_t elems; };
 cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st,
-                         __nv_bfloat16* panel = nullptr, bool panel_fill = true);
+                         __nv_bfloat16* panel = nullptr, bool panel_fill = true, const SplitKWs* sk = nullptr);
 // rows a matrix of N rows occupies in a panel (tile aligned)
 size_t prefill_panel_rows(int N);
 
@@ -21,7 +24,7 @@ size_t prefill_panel_rows(int N);
 // a weight type.  Falls back to one launch per matrix when a column offset is not 4-element aligned.
 struct GemmPart { const QMat* W; const float* bias; int col0; };
 cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bfloat16* X, int T, float* C, long long ldc, cudaStream_t st,
-                               __nv_bfloat16* panel = nullptr, bool panel_fill = true);
+                               __nv_bfloat16* panel = nullptr, bool panel_fill = true, const SplitKWs* sk = nullptr);
 
 // H[T][ff] (bf16) = silu(X . Wgate^T) * (X . Wup^T), one launch, SwiGLU in the GEMM epilogue
 cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,

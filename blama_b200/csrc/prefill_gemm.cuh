@@ -49,6 +49,11 @@ struct PrefillGemmArgs {
     int n_tiles;                // total column tiles over all segments
     int mode;
     int panel_up_row0;          // QT_PANEL + PG_SWIGLU: panel row of ffn_up row 0 (ffn_gate starts at panel row 0)
+    // deterministic split-K (QT_PANEL, PG_STORE / PG_ACCUM; few-token batches whose tiles do not fill the SMs): a work item is
+    // (tile, K split); split s stores its partial sums to ws + s * ws_stride (same row stride and column offsets as C) and
+    // splitk_reduce_kernel adds the partials in split order (+ bias, or onto C)
+    int k_splits;               // 1 = off
+    float* ws; long long ws_stride;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -340,19 +345,23 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     const uint32_t tmem_base = *tmem_base_slot;
 
     const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = a.n_tiles;
-    const int k_blocks = a.K / PG_BK;
-    const int total_tiles = m_tiles * n_tiles;
+    const int k_blocks_all = a.K / PG_BK;
+    const int n_split = PANEL ? a.k_splits : 1;
+    const int k_per = (k_blocks_all + n_split - 1) / n_split;      // K blocks per split (the last split may be shorter)
+    const int total_tiles = m_tiles * n_tiles * n_split;          // work items: item = tile * n_split + split
 
     if (warp == 8) {
         // ===================== TMA producer (activations) =====================
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int tile = item / n_split, split = item - tile * n_split;
+                const int kb0 = split * k_per, kb1 = min(k_blocks_all, kb0 + k_per);
                 const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
                 // panel rows of the two 128-row halves of the B tile
                 const int w0 = a.mode == PG_SWIGLU ? nt * 128 : nt * PG_BN;
                 const int w1 = a.mode == PG_SWIGLU ? a.panel_up_row0 + nt * 128 : nt * PG_BN + 128;
-                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % PG_STAGES;
                     mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
                     unsigned char* sa = smem + s * PG_STAGE_BYTES;
@@ -371,10 +380,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, PG_BN);
             int it = 0, tile_i = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_i++) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
+                const int split = item % n_split;
+                const int kb0 = split * k_per, kb1 = min(k_blocks_all, kb0 + k_per);
                 mbar_wait(tmem_empty, (tile_i & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
-                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % PG_STAGES;
                     mbar_wait(full + s, (it / PG_STAGES) & 1);
                     tc_fence_after();
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 #pragma unroll
                     for (int k = 0; k < PG_BK / 16; k++) {
                         const uint64_t koff = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 B along K inside the swizzle atom
-                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
                         tc_mma_bf16(tmem_base, da0 + koff, db + koff, idesc, acc);
                         tc_mma_bf16(tmem_base + PG_BN, da1 + koff, db + koff, idesc, acc);
                     }
@@ -397,7 +408,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         // ===================== dequant producers (warps 0-7); warps 4-7 also run the epilogue =====================
         const int r = threadIdx.x;                                // B-tile row handled by this thread
         int it = 0, tile_i = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_i++) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
+            const int tile = item / n_split, split = item - tile * n_split;
+            const int k_blocks = PANEL ? 0 : k_blocks_all;        // (the fused form has no K split: n_split == 1)
             const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
             // which matrix / row this thread dequantises, and where the tile's columns land in the output
             int si = 0;
@@ -492,19 +505,21 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                         tc_ld_32x32b_x32(tbase + cc * 32, v);
                         tc_wait_ld();
                         if (trow < a.T && cc * 32 < n_valid) {
-                            float* dst = a.C + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
-                            const float* bias = Ts.bias ? Ts.bias + tn0 + cc * 32 : nullptr;
+                            const bool part = PANEL && n_split > 1;                 // a K split stores its partial sums, nothing else
+                            float* dst = (part ? a.ws + (size_t)split * a.ws_stride : a.C) + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
+                            const float* bias = (Ts.bias && !part) ? Ts.bias + tn0 + cc * 32 : nullptr;
+                            const int mode = part ? PG_STORE : a.mode;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (cc * 32 + j + 3 < n_valid) {
                                     float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                                    if (a.mode == PG_ACCUM) { const float4 c0 = *reinterpret_cast<const float4*>(dst + j); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
+                                    if (mode == PG_ACCUM) { const float4 c0 = *reinterpret_cast<const float4*>(dst + j); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
                                     else if (bias) { o.x += bias[j]; o.y += bias[j + 1]; o.z += bias[j + 2]; o.w += bias[j + 3]; }
                                     *reinterpret_cast<float4*>(dst + j) = o;
                                 } else {
                                     for (int jj = 0; jj < 4; jj++) if (cc * 32 + j + jj < n_valid) {
                                         float o = __uint_as_float(v[j + jj]);
-                                        if (a.mode == PG_ACCUM) o += dst[j + jj]; else if (bias) o += bias[j + jj];
+                                        if (mode == PG_ACCUM) o += dst[j + jj]; else if (bias) o += bias[j + jj];
                                         dst[j + jj] = o;
                                     }
                                 }
@@ -523,6 +538,25 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     __syncthreads();
     if (warp == 9) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- second step of a split-K GEMM: C[t][col0 + j] = (accumulate ? C : bias) + sum_s ws[s][t][col0 + j], splits added in order ------
+struct SplitKReduceArgs { float* C; const float* ws; long long ldc, ws_stride; int T, n_split, accumulate, nseg; int col0[3], n[3]; const float* bias[3]; };
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReduceArgs a) {
+    const int t = blockIdx.y;
+    for (int sg = 0; sg < a.nseg; sg++) {
+        const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
+        if (j >= a.n[sg]) continue;
+        const size_t off = (size_t)t * a.ldc + a.col0[sg] + j;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.accumulate) o = *reinterpret_cast<const float4*>(a.C + off);
+        else if (a.bias[sg]) o = *reinterpret_cast<const float4*>(a.bias[sg] + j);
+        for (int s = 0; s < a.n_split; s++) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(a.ws + (size_t)s * a.ws_stride + off));
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(a.C + off) = o;
     }
 }
 
