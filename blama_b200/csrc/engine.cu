@@ -763,7 +763,8 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
         const size_t pe[4] = {(rows(dq) + 2 * rows(dkv)) * (size_t)d, rows(d) * (size_t)dq,
                               std::max(2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d, rows(m->n_vocab) * (size_t)d), rows(d) * (size_t)ff};
         const char* pm = getenv("BLK_PANEL_MIN");
-        c->panel_min = pm ? atoi(pm) : 32;       // measured: the two-pass form wins from the smallest prefill on (tools/prefill_sweep.py)
+        c->panel_min = pm ? atoi(pm) : 257;      // measured (tools/prefill_sweep.py, both forms with split-K): up to one 256-token M tile the fused
+        //                                          form wins (no 14 GB bf16 panel to write and read back), beyond it the two-pass form
         if (c->panel_min > 0 && cap >= c->panel_min) {
             bool ok = true;
             for (int i = 0; i < 4 && ok; i++) {

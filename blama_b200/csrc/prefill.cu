@@ -91,7 +91,7 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     // few-token batches: split K so that (tile, split) work items fill the SMs; partial sums go to the workspace and are added in
     // split order by a second kernel (deterministic).  Every split gets at least 8 K blocks (hence never an empty one).
     a.k_splits = 1; a.ws = nullptr; a.ws_stride = 0;
-    if (panel && sk && sk->ws && a.mode != PG_SWIGLU && 2 * tiles <= sms) {
+    if (sk && sk->ws && a.mode != PG_SWIGLU && 2 * tiles <= sms) {
         int S = std::min(8, std::min(sms / tiles, (a.K / PG_BK) / 8));
         while (S > 1 && (size_t)S * (size_t)a.T * (size_t)a.ldc > sk->elems) S--;
         if (S > 1) { a.k_splits = S; a.ws = sk->ws; a.ws_stride = (long long)a.T * a.ldc; }
@@ -136,7 +136,7 @@ cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C,
         if (panel_fill) { cudaError_t e = panel_dequant(W, panel, 0, st); if (e != cudaSuccess) return e; }
         return launch_gemm(a, W.type, W.type, X, st, panel, (long long)a.n_tiles * PG_BN, (W.N % 4 == 0 && ldc % 4 == 0) ? sk : nullptr);
     }
-    return launch_gemm(a, W.type, W.type, X, st);
+    return launch_gemm(a, W.type, W.type, X, st, nullptr, 0, (W.N % 4 == 0 && ldc % 4 == 0) ? sk : nullptr);
 }
 // the dequantisation passes alone (same panel layout as the GEMM entry points above use), so that a caller can run them on a
 // second stream one GEMM ahead; false = this combination takes the fused form (the GEMM call must then get panel = nullptr)
@@ -185,7 +185,7 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
     }
     if (!fuse) {
         for (int i = 0; i < n_parts; i++) {
-            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st, nullptr, false, nullptr);
+            cudaError_t e = prefill_gemm(*parts[i].W, X, T, C + parts[i].col0, ldc, parts[i].bias, 0, st, nullptr, false, nullptr);     // (column-offset C: no split-K)
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
@@ -198,7 +198,9 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
         tile0 += (parts[i].W->N + PG_BN - 1) / PG_BN;
     }
     a.n_tiles = tile0;
-    return launch_gemm(a, parts[0].W->type, n_parts == 3 ? parts[2].W->type : parts[0].W->type, X, st);
+    bool sk_ok = ldc % 4 == 0;
+    for (int i = 0; i < n_parts; i++) sk_ok = sk_ok && parts[i].W->N % 4 == 0;
+    return launch_gemm(a, parts[0].W->type, n_parts == 3 ? parts[2].W->type : parts[0].W->type, X, st, nullptr, 0, sk_ok ? sk : nullptr);
 }
 
 cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,

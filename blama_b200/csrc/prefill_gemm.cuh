@@ -49,7 +49,7 @@ struct PrefillGemmArgs {
     int n_tiles;                // total column tiles over all segments
     int mode;
     int panel_up_row0;          // QT_PANEL + PG_SWIGLU: panel row of ffn_up row 0 (ffn_gate starts at panel row 0)
-    // deterministic split-K (QT_PANEL, PG_STORE / PG_ACCUM; few-token batches whose tiles do not fill the SMs): a work item is
+    // deterministic split-K (PG_STORE / PG_ACCUM; few-token batches whose tiles do not fill the SMs): a work item is
     // (tile, K split); split s stores its partial sums to ws + s * ws_stride (same row stride and column offsets as C) and
     // splitk_reduce_kernel adds the partials in split order (+ bias, or onto C)
     int k_splits;               // 1 = off
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 
     const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = a.n_tiles;
     const int k_blocks_all = a.K / PG_BK;
-    const int n_split = PANEL ? a.k_splits : 1;
+    const int n_split = a.k_splits;
     const int k_per = (k_blocks_all + n_split - 1) / n_split;      // K blocks per split (the last split may be shorter)
     const int total_tiles = m_tiles * n_tiles * n_split;          // work items: item = tile * n_split + split
 
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         int it = 0, tile_i = 0;
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
             const int tile = item / n_split, split = item - tile * n_split;
-            const int k_blocks = PANEL ? 0 : k_blocks_all;        // (the fused form has no K split: n_split == 1)
+            const int kb0 = split * k_per, kb1 = min(k_blocks_all, kb0 + k_per);
             const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
             // which matrix / row this thread dequantises, and where the tile's columns land in the output
             int si = 0;
@@ -428,11 +428,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                 using Raw = decltype(raw_tag);
                 constexpr bool DEEP = sizeof(Raw) <= 64;           // small raw slices (Q4_K): three in flight; large ones: two
                 Raw cur, nxt, nx2;
-                if (row_ok) { cur.load(Sg.W, row, 0); if (DEEP && k_blocks > 1) nxt.load(Sg.W, row, 1); }
-                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                if (row_ok) { cur.load(Sg.W, row, kb0); if (DEEP && kb0 + 1 < kb1) nxt.load(Sg.W, row, kb0 + 1); }
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % PG_STAGES;
-                    if (DEEP) { if (row_ok && kb + 2 < k_blocks) nx2.load(Sg.W, row, kb + 2); }      // loads fly while the current slice is expanded
-                    else { if (row_ok && kb + 1 < k_blocks) nxt.load(Sg.W, row, kb + 1); }
+                    if (DEEP) { if (row_ok && kb + 2 < kb1) nx2.load(Sg.W, row, kb + 2); }      // loads fly while the current slice is expanded
+                    else { if (row_ok && kb + 1 < kb1) nxt.load(Sg.W, row, kb + 1); }
                     mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
                     unsigned char* srow = smem + s * PG_STAGE_BYTES + PG_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
                     if (row_ok) cur.expand(srow, r, kb);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                         tc_ld_32x32b_x32(tbase + cc * 32, v);
                         tc_wait_ld();
                         if (trow < a.T && cc * 32 < n_valid) {
-                            const bool part = PANEL && n_split > 1;                 // a K split stores its partial sums, nothing else
+                            const bool part = n_split > 1;                          // a K split stores its partial sums, nothing else
                             float* dst = (part ? a.ws + (size_t)split * a.ws_stride : a.C) + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
                             const float* bias = (Ts.bias && !part) ? Ts.bias + tn0 + cc * 32 : nullptr;
                             const int mode = part ? PG_STORE : a.mode;

@@ -18,11 +18,12 @@ MODELS = ["tiny-llama-q4km", "tiny-qwen2-q8", "small-llama-q4km", "small-qwen2-q
 @pytest.mark.parametrize("name", MODELS)
 @pytest.mark.parametrize("form", ["two-pass", "fused"])
 def test_prompt_prefill_matches_bf16_oracle(name, form, gguf_path, oracle, monkeypatch):
-    """form: the GEMMs read a bf16 weight panel dequantised once per matrix (default) / dequantise inside the GEMM"""
+    """form: the GEMMs read a bf16 weight panel dequantised once per matrix (default above 256 tokens) / dequantise inside the GEMM;
+    both with the deterministic split-K that few-token batches get"""
     from blama_b200 import capi
 
-    if form == "fused":
-        monkeypatch.setenv("BLK_PANEL_MIN", "0")
+    # (the default switches form at 257 tokens: pick explicitly so that both are covered at this size)
+    monkeypatch.setenv("BLK_PANEL_MIN", "0" if form == "fused" else "32")
 
     path = gguf_path(name)
     toks = gs.synth_prompt(name, 75, 11)                     # 75 >= prefill_min and not a multiple of any tile size

@@ -6,7 +6,7 @@ from blama_b200 import capi, gguf_synth
 shape = sys.argv[1] if len(sys.argv) > 1 else "llama-3.1-8b-q4km"
 path = ensure_model(shape, 0, lambda: None)
 m = capi.Model(path)
-for name, pm, sk in (("fused form        ", 1 << 30, "0"), ("two-pass          ", 32, "0"), ("two-pass + split-K", 32, "1")):
+for name, pm, sk in (("fused form        ", 1 << 30, "0"), ("fused + split-K   ", 1 << 30, "1"), ("two-pass          ", 32, "0"), ("two-pass + split-K", 32, "1")):
     os.environ["BLK_PANEL_MIN"] = str(pm); os.environ["BLK_SPLITK"] = sk
     c = capi.Ctx(m, 2304)
     row = []
