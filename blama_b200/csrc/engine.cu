@@ -926,7 +926,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         rmsnorm_bf16_launch(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn, n, st);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
-        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, before_gemm(4 * l + 2), false));
+        BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, before_gemm(4 * l + 2), false, &sk));
         after_gemm(4 * l + 2);
         prof_mark(c, "gemm_gate_up_swiglu");
         BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 3), false, &sk));

@@ -88,24 +88,27 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = ((a.T + PG_BM - 1) / PG_BM) * a.n_tiles;
-    // few-token batches: split K so that (tile, split) work items fill the SMs; partial sums go to the workspace and are added in
-    // split order by a second kernel (deterministic).  Every split gets at least 8 K blocks (hence never an empty one).
-    a.k_splits = 1; a.ws = nullptr; a.ws_stride = 0;
-    if (sk && sk->ws && a.mode != PG_SWIGLU && 2 * tiles <= sms) {
-        int S = std::min(8, std::min(sms / tiles, (a.K / PG_BK) / 8));
-        while (S > 1 && (size_t)S * (size_t)a.T * (size_t)a.ldc > sk->elems) S--;
-        if (S > 1) { a.k_splits = S; a.ws = sk->ws; a.ws_stride = (long long)a.T * a.ldc; }
+    // The last, partial wave of tiles (all of them when there are fewer tiles than SMs) is split along K so that its work items fill
+    // the SMs; partial sums go to the workspace and are added in split order by a second kernel (deterministic).  Every split gets
+    // at least 8 K blocks (hence never an empty one); a wave that is at least half full is left alone.
+    a.k_splits = 1; a.n_whole = tiles; a.ws = nullptr;
+    if (sk && sk->ws && sms > 0) {
+        const int n_whole = (tiles / sms) * sms, rem = tiles - n_whole;
+        if (rem > 0 && 2 * rem <= sms) {
+            int S = std::min(8, std::min(sms / rem, (a.K / PG_BK) / 8));
+            while (S > 1 && (size_t)S * (size_t)rem * (size_t)(PG_BM * PG_BN) > sk->elems) S--;
+            bool ok = S > 1;
+            for (int i = 0; i < a.nseg && ok; i++) ok = a.seg[i].W.N % 4 == 0 && a.seg[i].col0 % 4 == 0;
+            if (a.mode == PG_SWIGLU) ok = ok && a.ldh % 4 == 0; else ok = ok && a.ldc % 4 == 0;
+            if (ok) { a.k_splits = S; a.n_whole = n_whole; a.ws = sk->ws; }
+        }
     }
-    const int items = tiles * a.k_splits;
+    const int items = a.n_whole + (tiles - a.n_whole) * a.k_splits;
     const int grid = items < sms ? items : sms;
     kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, tmap_w, a);
     e = cudaGetLastError();
     if (e != cudaSuccess || a.k_splits == 1) return e;
-    SplitKReduceArgs ra{};
-    ra.C = a.C; ra.ws = a.ws; ra.ldc = a.ldc; ra.ws_stride = a.ws_stride; ra.T = a.T; ra.n_split = a.k_splits; ra.accumulate = a.mode == PG_ACCUM ? 1 : 0; ra.nseg = a.nseg;
-    int nmax = 0;
-    for (int i = 0; i < a.nseg; i++) { ra.col0[i] = a.seg[i].col0; ra.n[i] = a.seg[i].W.N; ra.bias[i] = a.seg[i].bias; nmax = std::max(nmax, a.seg[i].W.N); if (a.seg[i].W.N % 4) return cudaErrorInvalidValue; }
-    splitk_reduce_kernel<<<dim3((unsigned)((nmax + 1023) / 1024), (unsigned)a.T), 256, 0, st>>>(ra);
+    splitk_reduce_kernel<<<dim3((unsigned)(tiles - a.n_whole), 8), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -204,7 +207,7 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
 }
 
 cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,
-                                __nv_bfloat16* panel, bool panel_fill) {
+                                __nv_bfloat16* panel, bool panel_fill, const SplitKWs* sk) {
     if (gate.type != up.type || gate.N != up.N || gate.K != up.K || ldh % 8) return cudaErrorInvalidValue;
     PrefillGemmArgs a{};
     a.nseg = 2; a.seg[0] = {gate, nullptr, 0, 0}; a.seg[1] = {up, nullptr, 0, 0};
@@ -218,9 +221,9 @@ cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfl
             e = panel_dequant(up, panel, a.panel_up_row0, st);
             if (e != cudaSuccess) return e;
         }
-        return launch_gemm(a, gate.type, gate.type, X, st, panel, 2LL * a.panel_up_row0);
+        return launch_gemm(a, gate.type, gate.type, X, st, panel, 2LL * a.panel_up_row0, sk);
     }
-    return launch_gemm(a, gate.type, gate.type, X, st);
+    return launch_gemm(a, gate.type, gate.type, X, st, nullptr, 0, sk);
 }
 
 namespace {

@@ -12,8 +12,8 @@ namespace blk {
 // mode: 0 store (+bias), 1 accumulate into C.  Returns a CUDA error (cudaErrorNotSupported if the driver lacks TMA).
 // panel != nullptr selects the two-pass form: W is dequantised once into the bf16 panel (panel_fill) and the GEMM reads its B
 // tiles from there by TMA -- for many-token batches, where the fused form would dequantise every weight tile T / 256 times.
-// sk != nullptr (two-pass form only): workspace for a deterministic split-K when the batch has too few tiles to fill the SMs
-// (n_sm * 65536 floats always suffice: splits * tiles never exceeds the SM count)
+// sk != nullptr: workspace for the deterministic split-K of the last, partial wave of tiles (all tiles when the batch has fewer
+// tiles than SMs); n_sm * 65536 floats always suffice (split tiles * splits never exceeds the SM count)
 struct SplitKWs { float* ws; size_t elems; };
 cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st,
                          __nv_bfloat16* panel = nullptr, bool panel_fill = true, const SplitKWs* sk = nullptr);
@@ -28,7 +28,7 @@ cudaError_t prefill_gemm_multi(const GemmPart* parts, int n_parts, const __nv_bf
 
 // H[T][ff] (bf16) = silu(X . Wgate^T) * (X . Wup^T), one launch, SwiGLU in the GEMM epilogue
 cudaError_t prefill_gemm_swiglu(const QMat& gate, const QMat& up, const __nv_bfloat16* X, int T, __nv_bfloat16* H, long long ldh, cudaStream_t st,
-                                __nv_bfloat16* panel = nullptr, bool panel_fill = true);
+                                __nv_bfloat16* panel = nullptr, bool panel_fill = true, const SplitKWs* sk = nullptr);
 // The dequantisation passes alone (same panel layout), so that a caller can run them on a second stream one GEMM ahead.
 // Return false when the combination takes the fused form (the GEMM call must then get panel = nullptr).
 bool prefill_panel_fill(const GemmPart* parts, int n_parts, __nv_bfloat16* panel, cudaStream_t st, cudaError_t* err);

@@ -49,11 +49,12 @@ struct PrefillGemmArgs {
     int n_tiles;                // total column tiles over all segments
     int mode;
     int panel_up_row0;          // QT_PANEL + PG_SWIGLU: panel row of ffn_up row 0 (ffn_gate starts at panel row 0)
-    // deterministic split-K (PG_STORE / PG_ACCUM; few-token batches whose tiles do not fill the SMs): a work item is
-    // (tile, K split); split s stores its partial sums to ws + s * ws_stride (same row stride and column offsets as C) and
-    // splitk_reduce_kernel adds the partials in split order (+ bias, or onto C)
-    int k_splits;               // 1 = off
-    float* ws; long long ws_stride;
+    // deterministic split-K of the LAST, partial wave of tiles (and of every tile when the batch has fewer tiles than SMs): tiles
+    // [0, n_whole) are computed whole; each tile t >= n_whole becomes k_splits work items, item (t, s) stores its partial sums as a
+    // 256 x 256 f32 tile at ws + ((t - n_whole) * k_splits + s) * 65536 and splitk_reduce_kernel adds the partials in split order and
+    // applies the epilogue (bias / accumulate / SwiGLU).  k_splits == 1: off.
+    int n_whole, k_splits;
+    float* ws;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -316,6 +317,19 @@ template <int TYPE> struct RawK64 {
     }
 };
 
+// work item -> (tile, K split, K-block range); `part`: the item stores partial sums to the workspace
+struct PgItem { int tile, split, kb0, kb1; bool part; };
+__device__ __forceinline__ PgItem pg_item(int item, int n_whole, int n_split, int k_per, int k_blocks_all) {
+    PgItem w;
+    if (item < n_whole || n_split <= 1) { w.tile = item; w.split = 0; w.kb0 = 0; w.kb1 = k_blocks_all; w.part = false; }
+    else {
+        const int r = item - n_whole;
+        w.tile = n_whole + r / n_split; w.split = r - (w.tile - n_whole) * n_split;
+        w.kb0 = w.split * k_per; w.kb1 = min(k_blocks_all, w.kb0 + k_per); w.part = true;
+    }
+    return w;
+}
+
 template <int TA, int TB>
 __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const PrefillGemmArgs a) {
     constexpr bool PANEL = (TA == QT_PANEL);
@@ -346,17 +360,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 
     const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = a.n_tiles;
     const int k_blocks_all = a.K / PG_BK;
-    const int n_split = a.k_splits;
+    const int n_split = a.k_splits, n_whole = a.k_splits > 1 ? a.n_whole : m_tiles * n_tiles;
     const int k_per = (k_blocks_all + n_split - 1) / n_split;      // K blocks per split (the last split may be shorter)
-    const int total_tiles = m_tiles * n_tiles * n_split;          // work items: item = tile * n_split + split
+    const int total_tiles = n_whole + (m_tiles * n_tiles - n_whole) * n_split;     // work items (pg_item)
 
     if (warp == 8) {
         // ===================== TMA producer (activations) =====================
         if (lane == 0) {
             int it = 0;
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-                const int tile = item / n_split, split = item - tile * n_split;
-                const int kb0 = split * k_per, kb1 = min(k_blocks_all, kb0 + k_per);
+                const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
+                const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
                 const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
                 // panel rows of the two 128-row halves of the B tile
                 const int w0 = a.mode == PG_SWIGLU ? nt * 128 : nt * PG_BN;
@@ -381,8 +395,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
             constexpr uint32_t idesc = umma_idesc_bf16(128, PG_BN);
             int it = 0, tile_i = 0;
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
-                const int split = item % n_split;
-                const int kb0 = split * k_per, kb1 = min(k_blocks_all, kb0 + k_per);
+                const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
+                const int kb0 = w.kb0, kb1 = w.kb1;
                 mbar_wait(tmem_empty, (tile_i & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
                 for (int kb = kb0; kb < kb1; kb++, it++) {
@@ -409,8 +423,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         const int r = threadIdx.x;                                // B-tile row handled by this thread
         int it = 0, tile_i = 0;
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
-            const int tile = item / n_split, split = item - tile * n_split;
-            const int kb0 = split * k_per, kb1 = min(k_blocks_all, kb0 + k_per);
+            const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
+            const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
             const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
             // which matrix / row this thread dequantises, and where the tile's columns land in the output
             int si = 0;
@@ -468,7 +482,21 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                     const int h = warp >> 2;
                     const int trow = m0 + h * 128 + q * 32 + lane;
                     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * PG_BN);
-                    if (a.mode == PG_SWIGLU) {
+                    if (w.part) {
+                        // a K split: the raw partial sums of the tile go to the workspace (row-major 256 x 256), nothing else
+                        float* wt = a.ws + ((size_t)(tile - n_whole) * n_split + w.split) * (size_t)(PG_BM * PG_BN) + (size_t)(h * 128 + q * 32 + lane) * PG_BN;
+#pragma unroll 1
+                        for (int cc = 0; cc < PG_BN / 32; cc++) {
+                            uint32_t v[32];
+                            tc_ld_32x32b_x32(tbase + cc * 32, v);
+                            tc_wait_ld();
+                            if (trow < a.T) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(wt + cc * 32 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            }
+                        }
+                    } else if (a.mode == PG_SWIGLU) {
 #pragma unroll 1
                         for (int cc = 0; cc < 4; cc++) {
                             uint32_t g[32], u[32];
@@ -505,10 +533,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                         tc_ld_32x32b_x32(tbase + cc * 32, v);
                         tc_wait_ld();
                         if (trow < a.T && cc * 32 < n_valid) {
-                            const bool part = n_split > 1;                          // a K split stores its partial sums, nothing else
-                            float* dst = (part ? a.ws + (size_t)split * a.ws_stride : a.C) + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
-                            const float* bias = (Ts.bias && !part) ? Ts.bias + tn0 + cc * 32 : nullptr;
-                            const int mode = part ? PG_STORE : a.mode;
+                            float* dst = a.C + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
+                            const float* bias = Ts.bias ? Ts.bias + tn0 + cc * 32 : nullptr;
+                            const int mode = a.mode;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (cc * 32 + j + 3 < n_valid) {
@@ -541,22 +568,47 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     }
 }
 
-// ---- second step of a split-K GEMM: C[t][col0 + j] = (accumulate ? C : bias) + sum_s ws[s][t][col0 + j], splits added in order ------
-struct SplitKReduceArgs { float* C; const float* ws; long long ldc, ws_stride; int T, n_split, accumulate, nseg; int col0[3], n[3]; const float* bias[3]; };
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReduceArgs a) {
-    const int t = blockIdx.y;
-    for (int sg = 0; sg < a.nseg; sg++) {
-        const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
-        if (j >= a.n[sg]) continue;
-        const size_t off = (size_t)t * a.ldc + a.col0[sg] + j;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.accumulate) o = *reinterpret_cast<const float4*>(a.C + off);
-        else if (a.bias[sg]) o = *reinterpret_cast<const float4*>(a.bias[sg] + j);
-        for (int s = 0; s < a.n_split; s++) {
-            const float4 p = __ldcg(reinterpret_cast<const float4*>(a.ws + (size_t)s * a.ws_stride + off));
-            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+// ---- second step of a split-K GEMM: the split tiles' partial sums are added in split order, then the tile's epilogue runs --------
+// grid = (split tiles, 8): block (i, y) finishes rows 32 y .. 32 y + 31 of tile n_whole + i
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const PrefillGemmArgs a) {
+    const int m_tiles = (a.T + PG_BM - 1) / PG_BM;
+    const int tile = a.n_whole + blockIdx.x, S = a.k_splits;
+    const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;
+    const float* wt = a.ws + (size_t)blockIdx.x * S * (size_t)(PG_BM * PG_BN);
+    int ts = 0;
+    if (a.mode != PG_SWIGLU) {
+        if (a.nseg > 1 && nt >= a.seg[1].tile0) ts = 1;
+        if (a.nseg > 2 && nt >= a.seg[2].tile0) ts = 2;
+    }
+    const PgSeg& Ts = a.seg[ts];
+    const int tn0 = (a.mode == PG_SWIGLU) ? nt * 128 : (nt - Ts.tile0) * PG_BN;
+    const int n_valid = Ts.W.N - tn0;
+    const int ncol4 = a.mode == PG_SWIGLU ? 32 : 64;          // float4 columns of the output per row
+    for (int idx = threadIdx.x; idx < 32 * ncol4; idx += 256) {
+        const int r = blockIdx.y * 32 + idx / ncol4, c = (idx % ncol4) * 4;
+        const int trow = m0 + r;
+        if (trow >= a.T || c >= n_valid) continue;
+        auto sum4 = [&](int col) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < S; s++) {
+                const float4 p = __ldcg(reinterpret_cast<const float4*>(wt + (size_t)s * (PG_BM * PG_BN) + (size_t)r * PG_BN + col));
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            return o;
+        };
+        if (a.mode == PG_SWIGLU) {
+            const float4 g = sum4(c), u = sum4(128 + c);
+            uint2 o;
+            o.x = pack_bf16x2(__fdividef(g.x, 1.0f + __expf(-g.x)) * u.x, __fdividef(g.y, 1.0f + __expf(-g.y)) * u.y);
+            o.y = pack_bf16x2(__fdividef(g.z, 1.0f + __expf(-g.z)) * u.z, __fdividef(g.w, 1.0f + __expf(-g.w)) * u.w);
+            *reinterpret_cast<uint2*>(a.H + (size_t)trow * a.ldh + tn0 + c) = o;
+        } else {
+            float4 o = sum4(c);
+            float* dst = a.C + (size_t)trow * a.ldc + Ts.col0 + tn0 + c;
+            if (a.mode == PG_ACCUM) { const float4 c0 = *reinterpret_cast<const float4*>(dst); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
+            else if (Ts.bias) { const float* b = Ts.bias + tn0 + c; o.x += b[0]; o.y += b[1]; o.z += b[2]; o.w += b[3]; }
+            *reinterpret_cast<float4*>(dst) = o;
         }
-        *reinterpret_cast<float4*>(a.C + off) = o;
     }
 }
 
