@@ -94,7 +94,7 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     a.k_splits = 1; a.n_whole = tiles; a.ws = nullptr;
     if (sk && sk->ws && sms > 0) {
         const int n_whole = (tiles / sms) * sms, rem = tiles - n_whole;
-        if (rem > 0 && 2 * rem <= sms) {
+        if (rem > 0 && 2 * rem <= sms && n_whole <= 2 * sms) {      // (after many whole waves the partial one is a small share: not worth a second kernel)
             int S = std::min(8, std::min(sms / rem, (a.K / PG_BK) / 8));
             while (S > 1 && (size_t)S * (size_t)rem * (size_t)(PG_BM * PG_BN) > sk->elems) S--;
             bool ok = S > 1;
@@ -108,7 +108,7 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, tmap_w, a);
     e = cudaGetLastError();
     if (e != cudaSuccess || a.k_splits == 1) return e;
-    splitk_reduce_kernel<<<dim3((unsigned)(tiles - a.n_whole), 8), 256, 0, st>>>(a);
+    splitk_reduce_kernel<<<dim3((unsigned)(tiles - a.n_whole), 32), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 }
 
 // ---- second step of a split-K GEMM: the split tiles' partial sums are added in split order, then the tile's epilogue runs --------
-// grid = (split tiles, 8): block (i, y) finishes rows 32 y .. 32 y + 31 of tile n_whole + i
+// grid = (split tiles, 32): block (i, y) finishes rows 8 y .. 8 y + 7 of tile n_whole + i
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const PrefillGemmArgs a) {
     const int m_tiles = (a.T + PG_BM - 1) / PG_BM;
     const int tile = a.n_whole + blockIdx.x, S = a.k_splits;
@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const PrefillGemmArg
     const int tn0 = (a.mode == PG_SWIGLU) ? nt * 128 : (nt - Ts.tile0) * PG_BN;
     const int n_valid = Ts.W.N - tn0;
     const int ncol4 = a.mode == PG_SWIGLU ? 32 : 64;          // float4 columns of the output per row
-    for (int idx = threadIdx.x; idx < 32 * ncol4; idx += 256) {
-        const int r = blockIdx.y * 32 + idx / ncol4, c = (idx % ncol4) * 4;
+    for (int idx = threadIdx.x; idx < 8 * ncol4; idx += 256) {
+        const int r = blockIdx.y * 8 + idx / ncol4, c = (idx % ncol4) * 4;
         const int trow = m0 + r;
         if (trow >= a.T || c >= n_valid) continue;
         auto sum4 = [&](int col) {
