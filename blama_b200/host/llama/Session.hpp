@@ -44,7 +44,12 @@ public:
     Session& operator=(const Session&) = delete;
     ~Session();
 
+    // Prompt prefill (Session.cpp:65-107): BOS is prepended when the model asks for it; >= BLK_PREFILL_MIN tokens take the tcgen05
+    // prefill path, the last position's logits come from the decode mat-vec.  Throws "Session already started" /
+    // "Initial prompt too long. Got N tokens, max: M" with the reference's texts.
     void setInitialPrompt(std::span<const Token> prompt);
+    // Context save / restore (Session.cpp:284-310) is outside the scope of this build: both throw after the reference's own
+    // state checks ("Session already started" / "Session hasn't started yet").
     bool setState(std::span<uint8_t> state);
 
     struct CompleteParams {
@@ -52,6 +57,8 @@ public:
         std::span<const Token> suffix;
         int32_t maxTokens = 0;
     };
+    // The /complete loop (Session.cpp:192-213): one persistent-kernel launch per token (blk_decode_topk), the sampler chain on
+    // the 64 device candidates, top-10 of the NEXT distribution attached to every token; stops at an end-of-generation token.
     std::vector<TokenPrediction> complete(CompleteParams params);
 
     class StreamGenerator {
@@ -68,10 +75,15 @@ public:
         int32_t m_genTokens;
         Status m_status;
     };
+    // Token-at-a-time form of complete() (Session.cpp:215-229, 407-432); only one generator may be active.
     StreamGenerator completeStream(CompleteParams params);
 
+    // The /verify_completion context fill (Session.cpp:231-244): decodes the claimed tokens and returns, per position, this
+    // model's logits at the claimed ids sorted by logit.  ONE causal prefill here (or N single-token decodes when
+    // InitParams::sequentialVerify is set: bit-identical to complete()).
     std::vector<TokenPrediction> fillCtx(std::span<TokenPrediction> tokens);
     std::vector<uint8_t> getState();
+    // New sampler chain for the rest of the session (Session.cpp:403-405); the KV cache is kept.
     void resetSampler(const Sampler::Params& params);
 
 private:

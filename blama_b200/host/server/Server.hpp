@@ -39,7 +39,11 @@ public:
     };
     using CompleteReponse = std::vector<TokenData>;
 
+    // POST /complete (Server.cpp:45-77): tokenize, fresh session on the worker's replica, Session::complete, token strings + top-10
+    // per token to the callback (called on the worker thread).
     void completeText(CompleteRequestParams params, std::function<void(CompleteReponse)> cb);
+    // POST /verify_completion (Server.cpp:127-161): re-fill the context with the response's tokens (one batched prefill), compare the
+    // claimed logits with this replica's through LogitComparer, aggregate with MetricsAggregator; the callback gets the score.
     void verify(CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb);
 
     // extension used by the benchmark harness: prompts given as token ids (no tokenizer on the path)
