@@ -527,10 +527,25 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                             }
                         }
                     } else {
+                    // PG_ACCUM: the residual values of column chunk cc + 1 are requested before chunk cc is drained (one exposed L2
+                    // round trip per tile instead of eight)
+                    float4 cres[8];
+                    auto fetch_res = [&](int cc) {
+                        if (a.mode == PG_ACCUM && trow < a.T) {
+                            const float* src = a.C + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) if (cc * 32 + j + 3 < n_valid) cres[j >> 2] = *reinterpret_cast<const float4*>(src + j);
+                        }
+                    };
+                    fetch_res(0);
 #pragma unroll 1
                     for (int cc = 0; cc < PG_BN / 32; cc++) {
                         uint32_t v[32];
                         tc_ld_32x32b_x32(tbase + cc * 32, v);
+                        float4 ccur[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) ccur[j] = cres[j];
+                        if (cc + 1 < PG_BN / 32) fetch_res(cc + 1);
                         tc_wait_ld();
                         if (trow < a.T && cc * 32 < n_valid) {
                             float* dst = a.C + (size_t)trow * a.ldc + Ts.col0 + tn0 + cc * 32;
@@ -540,7 +555,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                             for (int j = 0; j < 32; j += 4) {
                                 if (cc * 32 + j + 3 < n_valid) {
                                     float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                                    if (mode == PG_ACCUM) { const float4 c0 = *reinterpret_cast<const float4*>(dst + j); o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
+                                    if (mode == PG_ACCUM) { const float4 c0 = ccur[j >> 2]; o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w; }
                                     else if (bias) { o.x += bias[j]; o.y += bias[j + 1]; o.z += bias[j + 2]; o.w += bias[j + 3]; }
                                     *reinterpret_cast<float4*>(dst + j) = o;
                                 } else {
