@@ -9,9 +9,9 @@ OBJDIR    := build
 
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
-HOST_SRCS := $(wildcard $(HOST)/llama/*.cpp) $(wildcard $(HOST)/*.cpp)
+HOST_SRCS := $(wildcard $(HOST)/llama/*.cpp) $(wildcard $(HOST)/server/*.cpp) $(wildcard $(HOST)/*.cpp)
 HOST_OBJS := $(patsubst $(HOST)/%.cpp,$(OBJDIR)/host/%.o,$(HOST_SRCS))
-HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(HOST)/llama/*.hpp) $(wildcard $(HOST)/*.hpp) include/blama_b200.h
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(HOST)/llama/*.hpp) $(wildcard $(HOST)/server/*.hpp) $(wildcard $(HOST)/*.hpp) include/blama_b200.h
 
 all: $(LIBDIR)/libblama_b200.so oracle
 

@@ -2,19 +2,28 @@
 // the reference-shaped API: Model / Instance / Session / LogitComparer / MetricsAggregator / Sampler.
 // Every function returns 0 on success, 1 when the C++ layer threw; blh_last_error() then holds e.what() -- the same
 // strings the reference's tests pin (inference/test/t-integration.cpp:137-217).
+#include "llama/Errors.hpp"
 #include "llama/Init.hpp"
 #include "llama/Instance.hpp"
 #include "llama/LogitComparer.hpp"
 #include "llama/Model.hpp"
 #include "llama/Sampler.hpp"
 #include "llama/Session.hpp"
+#include "server/Http.hpp"
+#include "server/Json.hpp"
+#include "server/Server.hpp"
+#include "server/Wire.hpp"
 
 #include <blama_b200.h>
 
+#include <condition_variable>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 
 using namespace bl::llama;
+namespace json = bl::json;
 
 namespace {
 thread_local std::string g_err;
@@ -31,6 +40,57 @@ TokenDataVector toVec(const blk_token_data* p, int32_t n) {
     TokenDataVector v(static_cast<size_t>(n));
     for (int32_t i = 0; i < n; ++i) v[size_t(i)] = {p[i].token, p[i].logit};
     return v;
+}
+// claimed lists arrive as [n][10] blocks: the count of every position must lie in 0..10 (prover-controlled input)
+TokenDataVector claimedVec(const blk_token_data* block, int32_t n_claimed) {
+    if (n_claimed < 0 || n_claimed > 10) Raise{} << "n_claimed must be in 0..10, got " << n_claimed;
+    return toVec(block, n_claimed);
+}
+
+// ---- Server over the C boundary: asynchronous submit -> ticket -> wait ----------------------------------------------------
+struct Ticket {
+    bool done = false;
+    server::Server::CompleteReponse response;
+    float score = 0.0f;
+};
+struct ServerBox {
+    std::unique_ptr<server::Server> srv;
+    std::unique_ptr<server::HttpFrontEnd> http;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::map<int64_t, std::shared_ptr<Ticket>> tickets;
+    int64_t next = 1;
+    std::string lastWorkerError;
+
+    std::pair<int64_t, std::shared_ptr<Ticket>> open() {
+        std::lock_guard<std::mutex> lk(mu);
+        auto t = std::make_shared<Ticket>();
+        const int64_t id = next++;
+        tickets[id] = t;
+        return {id, t};
+    }
+    void finish(const std::shared_ptr<Ticket>& t) {
+        { std::lock_guard<std::mutex> lk(mu); t->done = true; }
+        cv.notify_all();
+    }
+    std::shared_ptr<Ticket> wait(int64_t id) {
+        std::unique_lock<std::mutex> lk(mu);
+        auto it = tickets.find(id);
+        if (it == tickets.end()) Raise{} << "unknown ticket " << id;
+        auto t = it->second;
+        cv.wait(lk, [&] { return t->done; });
+        tickets.erase(id);
+        return t;
+    }
+};
+server::Server::CompleteReponse responseOf(const int32_t* toks, int n, const blk_token_data* claimed, const int32_t* n_claimed) {
+    server::Server::CompleteReponse resp(static_cast<size_t>(n));
+    for (int t = 0; t < n; ++t) {
+        if (n_claimed[t] < 0 || n_claimed[t] > 10) Raise{} << "n_claimed must be in 0..10, got " << n_claimed[t];
+        resp[size_t(t)].tokenId = uint32_t(toks[t]);
+        for (int j = 0; j < n_claimed[t]; ++j) resp[size_t(t)].logits.push_back({uint32_t(claimed[size_t(t) * 10 + size_t(j)].token), claimed[size_t(t) * 10 + size_t(j)].logit});
+    }
+    return resp;
 }
 } // namespace
 
@@ -112,7 +172,7 @@ BLK_API int blh_session_fill_ctx(void* i, const int32_t* toks, int n, const blk_
                                  blk_token_data* out /*[n][10]*/, int32_t* out_n) {
     return guard([&] {
         std::vector<TokenPrediction> in(static_cast<size_t>(n));
-        for (int t = 0; t < n; ++t) { in[size_t(t)].token = toks[t]; in[size_t(t)].logits = toVec(claimed + size_t(t) * 10, n_claimed[t]); }
+        for (int t = 0; t < n; ++t) { in[size_t(t)].token = toks[t]; in[size_t(t)].logits = claimedVec(claimed + size_t(t) * 10, n_claimed[t]); }
         auto res = static_cast<InstanceBox*>(i)->session->fillCtx(in);
         for (size_t t = 0; t < res.size(); ++t) {
             out_n[t] = int32_t(res[t].logits.size());
@@ -124,7 +184,7 @@ BLK_API int blh_session_fill_ctx(void* i, const int32_t* toks, int n, const blk_
 BLK_API int blh_session_verify(void* i, const int32_t* toks, int n, const blk_token_data* claimed /*[n][10]*/, const int32_t* n_claimed, float* score) {
     return guard([&] {
         std::vector<TokenPrediction> orig(static_cast<size_t>(n));
-        for (int t = 0; t < n; ++t) { orig[size_t(t)].token = toks[t]; orig[size_t(t)].logits = toVec(claimed + size_t(t) * 10, n_claimed[t]); }
+        for (int t = 0; t < n; ++t) { orig[size_t(t)].token = toks[t]; orig[size_t(t)].logits = claimedVec(claimed + size_t(t) * 10, n_claimed[t]); }
         auto mine = static_cast<InstanceBox*>(i)->session->fillCtx(orig);
         // The reference pushes the metrics one by one and re-sums its whole history on every push (Server.cpp:153-156, O(n^2));
         // only the value of the LAST push is returned, and that is the in-order double sum over all metrics: one push of the
@@ -141,7 +201,7 @@ BLK_API int blh_session_set_state(void* i) { return guard([&] { (void)static_cas
 
 // ---- verdict -------------------------------------------------------------------------------------------------------
 BLK_API void blh_lc_compare(const blk_token_data* a, int32_t na, const blk_token_data* b, int32_t nb, float* out3) {
-    auto m = LogitComparer::compare(toVec(a, na), toVec(b, nb));
+    auto m = compareChecked(toVec(a, na < 0 ? 0 : na), toVec(b, nb < 0 ? 0 : nb));
     out3[0] = m.top1Match; out3[1] = m.distance; out3[2] = m.jsd;
 }
 BLK_API float blh_lc_similarity(const blk_token_data* a, int32_t na, const blk_token_data* b, int32_t nb) {
@@ -164,6 +224,169 @@ BLK_API int blh_sampler_draw(uint32_t seed, float temp, float top_p, int32_t top
         Sampler s(*none, sp);
         auto v = toVec(cand, n_cand);
         for (int32_t i = 0; i < n_draws; ++i) out[i] = s.sample(v, sorted != 0);
+    });
+}
+
+// ---- Server (reference server/code/server/Server.hpp:58-64): N workers = N replicas, requests are whole jobs ----------------------
+// models: handles from blh_model_create, one per replica (they stay owned by the caller and must outlive the server)
+BLK_API int blh_server_create(void* const* models, int n_models, uint32_t ctx_size, uint32_t batch_size, void** out) {
+    return guard([&] {
+        if (n_models <= 0) Raise{} << "a server needs at least one model replica";
+        std::vector<std::shared_ptr<Model>> reps;
+        for (int i = 0; i < n_models; ++i) reps.emplace_back(static_cast<Model*>(models[i]), [](Model*) {});
+        Instance::InitParams ip; ip.ctxSize = ctx_size; if (batch_size) ip.batchSize = batch_size;
+        auto box = std::make_unique<ServerBox>();
+        box->srv = std::make_unique<server::Server>(std::move(reps), ip);
+        ServerBox* raw = box.get();
+        box->srv->setErrorHandler([raw](const std::string& e) { std::lock_guard<std::mutex> lk(raw->mu); raw->lastWorkerError = e; });
+        *out = box.release();
+    });
+}
+BLK_API void blh_server_free(void* s) { delete static_cast<ServerBox*>(s); }
+BLK_API int blh_server_workers(void* s) { return int(static_cast<ServerBox*>(s)->srv->workerCount()); }
+BLK_API void blh_server_drain(void* s) { static_cast<ServerBox*>(s)->srv->drain(); }
+// text of the last exception a worker caught (empty when none)
+BLK_API int blh_server_last_worker_error(void* s, char* buf, int cap) {
+    auto* box = static_cast<ServerBox*>(s);
+    std::lock_guard<std::mutex> lk(box->mu);
+    const int n = int(box->lastWorkerError.size());
+    if (buf && cap > 0) { memcpy(buf, box->lastWorkerError.data(), size_t(n < cap ? n : cap)); }
+    return n;
+}
+// Server::completeText with the prompt already tokenised; *ticket identifies the pending answer
+BLK_API int blh_server_submit_complete(void* s, const int32_t* prompt, int n_prompt, uint32_t max_tokens, uint32_t seed, float temp, float top_p, int64_t* ticket) {
+    return guard([&] {
+        auto* box = static_cast<ServerBox*>(s);
+        auto [id, t] = box->open();
+        server::Server::CompleteRequestParams p; p.maxTokens = max_tokens; p.seed = seed; p.temperature = temp; p.topP = top_p;
+        box->srv->completeTokens(std::vector<int32_t>(prompt, prompt + n_prompt), std::move(p),
+                                 [box, t = t](server::Server::CompleteReponse r) { t->response = std::move(r); box->finish(t); });
+        *ticket = id;
+    });
+}
+// Server::verify with the prompt already tokenised and the response as [n][10] claimed blocks
+BLK_API int blh_server_submit_verify(void* s, const int32_t* prompt, int n_prompt, uint32_t seed, float temp, float top_p,
+                                     const int32_t* toks, int n, const blk_token_data* claimed, const int32_t* n_claimed, int64_t* ticket) {
+    return guard([&] {
+        auto* box = static_cast<ServerBox*>(s);
+        auto resp = responseOf(toks, n, claimed, n_claimed);
+        auto [id, t] = box->open();
+        server::Server::CompleteRequestParams p; p.seed = seed; p.temperature = temp; p.topP = top_p;
+        box->srv->verifyTokens(std::vector<int32_t>(prompt, prompt + n_prompt), std::move(p), std::move(resp),
+                               [box, t = t](float score) { t->score = score; box->finish(t); });
+        *ticket = id;
+    });
+}
+// the two HTTP bodies, text in / ticket out: POST /complete (HttpServerMain.cpp:312-318), POST /verify_completion (:328-337)
+BLK_API int blh_server_submit_complete_json(void* s, const char* body, int64_t* ticket) {
+    return guard([&] {
+        auto* box = static_cast<ServerBox*>(s);
+        auto params = server::wire::parseCompleteParams(body);
+        auto [id, t] = box->open();
+        box->srv->completeText(std::move(params), [box, t = t](server::Server::CompleteReponse r) { t->response = std::move(r); box->finish(t); });
+        *ticket = id;
+    });
+}
+BLK_API int blh_server_submit_verify_json(void* s, const char* body, int64_t* ticket) {
+    return guard([&] {
+        auto* box = static_cast<ServerBox*>(s);
+        auto vb = server::wire::parseVerifyBody(body);
+        auto [id, t] = box->open();
+        box->srv->verify(std::move(vb.request), std::move(vb.response), [box, t = t](float score) { t->score = score; box->finish(t); });
+        *ticket = id;
+    });
+}
+// blocks until the ticket's request has run.  out_top10: [cap][10]
+BLK_API int blh_server_wait_complete(void* s, int64_t ticket, int cap, int32_t* out_tokens, blk_token_data* out_top10, int32_t* out_n_logits, int32_t* out_n) {
+    return guard([&] {
+        auto t = static_cast<ServerBox*>(s)->wait(ticket);
+        const int n = int(std::min<size_t>(t->response.size(), size_t(cap < 0 ? 0 : cap)));
+        *out_n = int32_t(t->response.size());
+        for (int i = 0; i < n; ++i) {
+            const auto& td = t->response[size_t(i)];
+            out_tokens[i] = int32_t(td.tokenId);
+            out_n_logits[i] = int32_t(td.logits.size());
+            for (size_t j = 0; j < td.logits.size() && j < 10; ++j) out_top10[size_t(i) * 10 + j] = {int32_t(td.logits[j].tokenId), td.logits[j].logit};
+        }
+    });
+}
+BLK_API int blh_server_wait_verify(void* s, int64_t ticket, float* score) {
+    return guard([&] { *score = static_cast<ServerBox*>(s)->wait(ticket)->score; });
+}
+// the answer as the HTTP body the reference would send ({"text","tokenData"} or {"result"}); returns the length, copies <= cap bytes
+BLK_API int blh_server_wait_complete_json(void* s, int64_t ticket, char* buf, int cap, int* len) {
+    return guard([&] {
+        const std::string js = server::wire::completeResponseJson(static_cast<ServerBox*>(s)->wait(ticket)->response);
+        *len = int(js.size());
+        if (buf && cap > 0) memcpy(buf, js.data(), size_t(std::min<int>(cap, int(js.size()))));
+    });
+}
+BLK_API int blh_server_wait_verify_json(void* s, int64_t ticket, char* buf, int cap, int* len) {
+    return guard([&] {
+        const std::string js = server::wire::verifyResponseJson(static_cast<ServerBox*>(s)->wait(ticket)->score);
+        *len = int(js.size());
+        if (buf && cap > 0) memcpy(buf, js.data(), size_t(std::min<int>(cap, int(js.size()))));
+    });
+}
+BLK_API int blh_server_stats(void* s, int32_t* devices, uint64_t* requests, double* gpu_ms, int cap) {
+    const auto st = static_cast<ServerBox*>(s)->srv->workerStats();
+    for (size_t i = 0; i < st.size() && int(i) < cap; ++i) { devices[i] = st[i].device; requests[i] = st[i].requests; gpu_ms[i] = st[i].gpuMs; }
+    return int(st.size());
+}
+// HTTP front end on host:port (0 = any free port; the bound one comes back through *out_port)
+BLK_API int blh_server_http_start(void* s, const char* host, int port, int io_threads, int* out_port) {
+    return guard([&] {
+        auto* box = static_cast<ServerBox*>(s);
+        if (box->http) Raise{} << "the HTTP front end is already running";
+        box->http = std::make_unique<server::HttpFrontEnd>(*box->srv, host ? host : "0.0.0.0", uint16_t(port), io_threads > 0 ? io_threads : 4);
+        if (out_port) *out_port = box->http->port();
+    });
+}
+BLK_API void blh_server_http_stop(void* s) { static_cast<ServerBox*>(s)->http.reset(); }
+
+// ---- wire format, no device needed (tests pin the float text and the key order) ------------------------------------------------
+// dumps {"result": v}
+BLK_API int blh_wire_verify_json(float v, char* buf, int cap) {
+    const std::string js = server::wire::verifyResponseJson(v);
+    if (buf && cap > 0) memcpy(buf, js.data(), size_t(std::min<int>(cap, int(js.size()))));
+    return int(js.size());
+}
+// parse -> dump of any JSON document (normalises key order and number text exactly as the reference's nlohmann round trip does)
+BLK_API int blh_wire_json_roundtrip(const char* text, char* buf, int cap, int* len) {
+    return guard([&] {
+        const std::string js = json::parse(text).dump();
+        *len = int(js.size());
+        if (buf && cap > 0) memcpy(buf, js.data(), size_t(std::min<int>(cap, int(js.size()))));
+    });
+}
+// request body -> fields (HttpServerMain.cpp:85-94)
+BLK_API int blh_wire_parse_request(const char* body, char* prompt, int prompt_cap, uint32_t* max_tokens, uint32_t* seed, float* temp, float* top_p) {
+    return guard([&] {
+        const auto p = server::wire::parseCompleteParams(body);
+        snprintf(prompt, size_t(prompt_cap), "%s", p.prompt.c_str());
+        *max_tokens = p.maxTokens; *seed = p.seed; *temp = p.temperature; *top_p = p.topP;
+    });
+}
+// /verify_completion body -> the response's token ids and claimed logits ([cap][10] blocks); *n = tokens in the response
+BLK_API int blh_wire_parse_verify(const char* body, int cap, int32_t* toks, blk_token_data* claimed, int32_t* n_claimed, int32_t* n) {
+    return guard([&] {
+        const auto vb = server::wire::parseVerifyBody(body);
+        *n = int32_t(vb.response.size());
+        for (size_t i = 0; i < vb.response.size() && int(i) < cap; ++i) {
+            toks[i] = int32_t(vb.response[i].tokenId);
+            n_claimed[i] = int32_t(vb.response[i].logits.size());
+            for (size_t j = 0; j < vb.response[i].logits.size() && j < 10; ++j) claimed[i * 10 + j] = {int32_t(vb.response[i].logits[j].tokenId), vb.response[i].logits[j].logit};
+        }
+    });
+}
+// [n][10] blocks -> the /complete answer body
+BLK_API int blh_wire_complete_json(void* model, const int32_t* toks, int n, const blk_token_data* top10, const int32_t* n_logits, char* buf, int cap, int* len) {
+    return guard([&] {
+        server::Server::CompleteReponse resp = responseOf(toks, n, top10, n_logits);
+        if (model) for (auto& td : resp) td.tokenStr = static_cast<Model*>(model)->vocab().tokenToString(Token(td.tokenId));
+        const std::string js = server::wire::completeResponseJson(resp);
+        *len = int(js.size());
+        if (buf && cap > 0) memcpy(buf, js.data(), size_t(std::min<int>(cap, int(js.size()))));
     });
 }
 

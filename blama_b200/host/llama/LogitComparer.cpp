@@ -87,12 +87,20 @@ float LogitComparer::logitSimilarity(const TokenDataVector& data1, const TokenDa
     return weights > 0.0f ? weighted / weights : 0.0f;
 }
 
+ComparisonMetrics compareChecked(const TokenDataVector& data1, const TokenDataVector& data2) {
+    // LogitComparer::compare reads element 0 of both lists (reference :41): an empty list -- a response position without claimed
+    // logits, or one whose claimed ids are all outside the vocabulary -- is undefined behaviour there.  Such a position cannot be
+    // verified, so it scores as a complete mismatch instead of reading out of bounds.
+    if (data1.empty() || data2.empty()) return ComparisonMetrics{0.0f, 1.0f, 1.0f};
+    return LogitComparer::compare(data1, data2);
+}
+
 std::vector<ComparisonMetrics> compareAll(std::span<const TokenPredictionView> pairs) {
     std::vector<ComparisonMetrics> out(pairs.size());
     const size_t n = pairs.size();
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const size_t n_thr = n >= 256 ? std::min<size_t>({size_t(hw), size_t(8), n / 128}) : 1;
-    auto work = [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) out[i] = LogitComparer::compare(*pairs[i].a, *pairs[i].b); };
+    auto work = [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) out[i] = compareChecked(*pairs[i].a, *pairs[i].b); };
     if (n_thr <= 1) { work(0, n); return out; }
     std::vector<std::thread> thr;
     const size_t per = (n + n_thr - 1) / n_thr;

@@ -21,6 +21,9 @@ public:
 
 // LogitComparer::compare for every position of a verified response (prover's list vs verifier's list).  The positions are
 // independent, so long responses are compared on several host threads; each metric is the same float either way.
+// compare() for lists that come from the wire: an empty side gives {top1Match 0, distance 1, jsd 1} instead of the reference's
+// out-of-bounds read
+ComparisonMetrics compareChecked(const TokenDataVector& data1, const TokenDataVector& data2);
 struct TokenPredictionView { const TokenDataVector* a; const TokenDataVector* b; };
 std::vector<ComparisonMetrics> compareAll(std::span<const TokenPredictionView> pairs);
 

@@ -137,8 +137,12 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
     result.reserve(tokens.size());
     if (tokens.empty()) return result;
 
-    if (m_instance.model().prefixInputsWithBos()) {
-        // every pushPrompt would insert a BOS before its token (reference :129-132): keep the literal per-token loop
+    // the device gathers at most 10 ids per position in the batched form; the reference accepts any number of claimed logits
+    bool wide = false;
+    for (const auto& token : tokens) wide = wide || token.logits.size() > 10;
+    if (m_instance.model().prefixInputsWithBos() || wide) {
+        // every pushPrompt would insert a BOS before its token (reference :129-132) / more than 10 claimed ids somewhere:
+        // keep the reference's literal per-token loop
         for (const auto& token : tokens) {
             pushPrompt({&token.token, 1}, {});
             result.push_back({token.token, getLogitsFromCtx(token.logits)});
@@ -164,7 +168,6 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
         uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
         const int32_t nVocab = blk_model_n_vocab(m_instance.model().lmodel());
         uniq.erase(std::remove_if(uniq.begin(), uniq.end(), [&](Token t) { return t < 0 || t >= nVocab; }), uniq.end());
-        if (uniq.size() > 10) Raise{} << "at most 10 claimed logits per token are supported";
         nClaimed[i] = int32_t(uniq.size());
         std::copy(uniq.begin(), uniq.end(), claimed.begin() + long(i * 10));
     }

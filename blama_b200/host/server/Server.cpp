@@ -6,8 +6,11 @@
 #include "../llama/Model.hpp"
 #include "../llama/Session.hpp"
 
+#include <blama_b200.h>
+
 #include <condition_variable>
 #include <deque>
+#include <limits>
 #include <mutex>
 #include <thread>
 
@@ -18,21 +21,27 @@ struct Server::Impl {
         std::shared_ptr<Model> model;
         std::unique_ptr<Instance> instance;
         std::thread thread;
+        uint64_t requests = 0;      // guarded by Impl::mu
+        double gpuMs = 0;
     };
-    using Job = std::function<void(Worker&)>;
+    struct Job {
+        std::function<void(Worker&)> run;
+        std::function<void()> failed;      // delivers the request's "no result" answer to its callback
+    };
 
     std::vector<std::unique_ptr<Worker>> workers;
-    std::mutex mu;
+    mutable std::mutex mu;
     std::condition_variable cv, idleCv;
     std::deque<Job> queue;
     size_t running = 0;
     bool stopping = false;
+    std::function<void(const std::string&)> onError;
 
-    explicit Impl(std::vector<std::shared_ptr<Model>> replicas) {
+    Impl(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip) {
         for (auto& r : replicas) {
             auto w = std::make_unique<Worker>();
             w->model = std::move(r);
-            w->instance = std::make_unique<Instance>(*w->model, Instance::InitParams{});
+            w->instance = std::make_unique<Instance>(*w->model, ip);
             w->instance->warmup();
             workers.push_back(std::move(w));
         }
@@ -58,11 +67,28 @@ struct Server::Impl {
                 queue.pop_front();
                 ++running;
             }
-            // the reference lets exceptions escape its io_context and terminate; here a failing
-            // request is dropped after stopping its session so the worker survives
-            try { job(w); } catch (...) { w.instance->stopSession(); }
+            // CUDA events on the worker's own stream bracket the request: the GPU time of this replica, whatever the host did
+            blk_ctx* ctx = w.instance->lctx();
+            (void)blk_timer_start(ctx);
+            std::string error;
+            bool ok = true;
+            try { job.run(w); }
+            catch (const std::exception& e) { ok = false; error = e.what(); }
+            catch (...) { ok = false; error = "unknown error"; }
+            float ms = 0.0f;
+            (void)blk_timer_stop(ctx, &ms);
+            if (!ok) {
+                // the reference lets the exception escape its io_context and dies; here the session is
+                // stopped, the error reported and the request's callback answered, so that nobody waits forever
+                w.instance->stopSession();
+                std::function<void(const std::string&)> handler;
+                { std::lock_guard<std::mutex> lk(mu); handler = onError; }
+                try { if (handler) handler(error); } catch (...) {}
+                try { if (job.failed) job.failed(); } catch (...) {}
+            }
             {
                 std::lock_guard<std::mutex> lk(mu);
+                w.requests++; w.gpuMs += ms;
                 --running;
                 if (queue.empty() && running == 0) idleCv.notify_all();
             }
@@ -98,17 +124,24 @@ struct Server::Impl {
     }
 
     void complete(std::vector<int32_t> prompt, bool tokenize, CompleteRequestParams params, std::function<void(CompleteReponse)> cb) {
-        post([prompt = std::move(prompt), tokenize, params = std::move(params), cb = std::move(cb)](Worker& w) mutable {
+        auto cbp = std::make_shared<std::function<void(CompleteReponse)>>(std::move(cb));
+        Job job;
+        job.run = [prompt = std::move(prompt), tokenize, params = std::move(params), cbp](Worker& w) mutable {
             auto& session = w.instance->startSession({.seed = params.seed, .temperature = params.temperature, .topP = params.topP});
             if (tokenize) prompt = w.model->vocab().tokenize(params.prompt, true, true);
             session.setInitialPrompt(prompt);
             auto preds = session.complete({.prompt = {}, .suffix = {}, .maxTokens = int32_t(params.maxTokens)});
-            cb(marshal(*w.model, preds));
+            auto response = marshal(*w.model, preds);
             w.instance->stopSession();
-        });
+            (*cbp)(std::move(response));
+        };
+        job.failed = [cbp] { (*cbp)({}); };
+        post(std::move(job));
     }
     void verify(std::vector<int32_t> prompt, bool tokenize, CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb) {
-        post([prompt = std::move(prompt), tokenize, req = std::move(req), resp = std::move(resp), cb = std::move(cb)](Worker& w) mutable {
+        auto cbp = std::make_shared<std::function<void(float)>>(std::move(cb));
+        Job job;
+        job.run = [prompt = std::move(prompt), tokenize, req = std::move(req), resp = std::move(resp), cbp](Worker& w) mutable {
             auto& session = w.instance->startSession({.seed = req.seed, .temperature = req.temperature, .topP = req.topP});
             if (tokenize) prompt = w.model->vocab().tokenize(req.prompt, true, true);
             session.setInitialPrompt(prompt);
@@ -120,14 +153,18 @@ struct Server::Impl {
             for (size_t i = 0; i < orig.size(); i++) pairs[i] = {&orig[i].logits, &mine[i].logits};
             const std::vector<ComparisonMetrics> ms = compareAll(pairs);
             MetricsAggregator agg;
-            cb(ms.empty() ? 0.0f : agg.pushAndVerify(ms));
+            const float score = ms.empty() ? 0.0f : agg.pushAndVerify(ms);
             w.instance->stopSession();
-        });
+            (*cbp)(score);
+        };
+        job.failed = [cbp] { (*cbp)(std::numeric_limits<float>::quiet_NaN()); };
+        post(std::move(job));
     }
 };
 
-Server::Server(std::shared_ptr<Model> model) : m_impl(std::make_unique<Impl>(std::vector<std::shared_ptr<Model>>{std::move(model)})) {}
-Server::Server(std::vector<std::shared_ptr<Model>> replicas) : m_impl(std::make_unique<Impl>(std::move(replicas))) {}
+Server::Server(std::shared_ptr<Model> model) : m_impl(std::make_unique<Impl>(std::vector<std::shared_ptr<Model>>{std::move(model)}, Instance::InitParams{})) {}
+Server::Server(std::vector<std::shared_ptr<Model>> replicas) : m_impl(std::make_unique<Impl>(std::move(replicas), Instance::InitParams{})) {}
+Server::Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip) : m_impl(std::make_unique<Impl>(std::move(replicas), ip)) {}
 Server::~Server() = default;
 
 void Server::completeText(CompleteRequestParams params, std::function<void(CompleteReponse)> cb) {
@@ -141,6 +178,16 @@ void Server::completeTokens(std::vector<int32_t> prompt, CompleteRequestParams p
 }
 void Server::verifyTokens(std::vector<int32_t> prompt, CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb) {
     m_impl->verify(std::move(prompt), false, std::move(req), std::move(resp), std::move(cb));
+}
+void Server::setErrorHandler(std::function<void(const std::string&)> handler) {
+    std::lock_guard<std::mutex> lk(m_impl->mu);
+    m_impl->onError = std::move(handler);
+}
+std::vector<Server::WorkerStats> Server::workerStats() const {
+    std::lock_guard<std::mutex> lk(m_impl->mu);
+    std::vector<WorkerStats> out;
+    for (const auto& w : m_impl->workers) out.push_back({w->model->params().device, w->requests, w->gpuMs});
+    return out;
 }
 size_t Server::workerCount() const noexcept { return m_impl->workers.size(); }
 void Server::drain() { m_impl->drain(); }

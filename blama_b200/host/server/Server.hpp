@@ -5,6 +5,8 @@
 // one Instance and one worker thread per GPU, all pulling whole requests from a shared queue.  No collective is
 // involved.
 #pragma once
+#include "../llama/Instance.hpp"
+
 #include <cstdint>
 #include <functional>
 #include <memory>
@@ -19,6 +21,8 @@ class Server {
 public:
     explicit Server(std::shared_ptr<Model> model);                      // reference signature: one replica
     explicit Server(std::vector<std::shared_ptr<Model>> replicas);      // one replica per GPU
+    // extension: the Instance parameters of every worker (the reference passes {}: KV cache sized for the training context)
+    Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams instanceParams);
     ~Server();
     Server(const Server&) = delete;
     Server& operator=(const Server&) = delete;
@@ -49,6 +53,15 @@ public:
     // extension used by the benchmark harness: prompts given as token ids (no tokenizer on the path)
     void completeTokens(std::vector<int32_t> prompt, CompleteRequestParams params, std::function<void(CompleteReponse)> cb);
     void verifyTokens(std::vector<int32_t> prompt, CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb);
+
+    // A request that throws (malformed response, context overflow, ...) terminates the reference process (the exception escapes
+    // its io_context).  Here the worker survives: the request's callback is still invoked -- with an empty
+    // response / a NaN score -- after the handler set here has received the exception text (called on the worker thread).
+    void setErrorHandler(std::function<void(const std::string&)> handler);
+
+    // what a worker did, for the dispatcher benchmark: requests served and the CUDA-event time its GPU spent inside them
+    struct WorkerStats { int device = 0; uint64_t requests = 0; double gpuMs = 0; };
+    std::vector<WorkerStats> workerStats() const;
 
     size_t workerCount() const noexcept;
     void drain();     // blocks until every queued request has run

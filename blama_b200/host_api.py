@@ -38,6 +38,27 @@ HOST_SYMBOLS = {
     "blh_lc_similarity": (_f32, [_vp, _i32, _vp, _i32]),
     "blh_lc_score": (_f32, [_vp, _i32]),
     "blh_sampler_draw": (C.c_int, [_u32, _f32, _f32, _i32, _f32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "blh_server_create": (C.c_int, [_vp, C.c_int, _u32, _u32, C.POINTER(_vp)]),
+    "blh_server_free": (None, [_vp]),
+    "blh_server_workers": (C.c_int, [_vp]),
+    "blh_server_drain": (None, [_vp]),
+    "blh_server_last_worker_error": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "blh_server_submit_complete": (C.c_int, [_vp, _vp, C.c_int, _u32, _u32, _f32, _f32, C.POINTER(C.c_int64)]),
+    "blh_server_submit_verify": (C.c_int, [_vp, _vp, C.c_int, _u32, _f32, _f32, _vp, C.c_int, _vp, _vp, C.POINTER(C.c_int64)]),
+    "blh_server_submit_complete_json": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
+    "blh_server_submit_verify_json": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
+    "blh_server_wait_complete": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
+    "blh_server_wait_verify": (C.c_int, [_vp, C.c_int64, C.POINTER(_f32)]),
+    "blh_server_wait_complete_json": (C.c_int, [_vp, C.c_int64, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
+    "blh_server_wait_verify_json": (C.c_int, [_vp, C.c_int64, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
+    "blh_server_stats": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "blh_server_http_start": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "blh_server_http_stop": (None, [_vp]),
+    "blh_wire_verify_json": (C.c_int, [_f32, C.c_char_p, C.c_int]),
+    "blh_wire_json_roundtrip": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
+    "blh_wire_parse_request": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]),
+    "blh_wire_parse_verify": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, _vp, _vp]),
+    "blh_wire_complete_json": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
 }
 
 _bound = False
@@ -53,6 +74,11 @@ def lib() -> C.CDLL:
         l.blh_init()
         _bound = True
     return l
+
+
+def lib_nodevice() -> C.CDLL:
+    """the host-only entry points (verdict, sampler, wire format, tokenizer) need no CUDA device: same library, same binding"""
+    return lib()
 
 
 class HostError(RuntimeError):
@@ -205,3 +231,146 @@ def sampler_draw(cand, n_draws: int, seed: int = 0, temp: float = 0.8, top_p: fl
     out = np.zeros(n_draws, dtype=np.int32)
     _check(lib().blh_sampler_draw(seed, temp, top_p, top_k, min_p, min_keep, _p(c), len(c), int(is_sorted), n_draws, _p(out)))
     return out
+
+
+# ---- wire format (host only) ----------------------------------------------------------------------------------------------
+def _text_out(call, cap: int = 1 << 16) -> str:
+    """call(buf, cap, byref(len)) -> rc; grows the buffer once when the text is longer than cap"""
+    for _ in range(2):
+        buf = C.create_string_buffer(cap)
+        n = C.c_int(0)
+        rc = call(buf, cap, C.byref(n))
+        if rc:
+            raise HostError((lib_nodevice().blh_last_error() or b"").decode(errors="replace"))
+        if n.value <= cap:
+            return buf.raw[: n.value].decode("utf-8")
+        cap = n.value + 16
+    raise HostError("text did not fit")
+
+
+def wire_verify_json(score: float) -> str:
+    buf = C.create_string_buffer(256)
+    n = lib_nodevice().blh_wire_verify_json(score, buf, 256)
+    return buf.raw[:n].decode()
+
+
+def wire_json_roundtrip(text: str) -> str:
+    b = text.encode("utf-8")
+    return _text_out(lambda buf, cap, n: lib_nodevice().blh_wire_json_roundtrip(b, buf, cap, n), max(1 << 12, 2 * len(b)))
+
+
+def wire_parse_request(body: str):
+    pb = C.create_string_buffer(1 << 16)
+    mt, seed, temp, top_p = _u32(0), _u32(0), _f32(0), _f32(0)
+    rc = lib_nodevice().blh_wire_parse_request(body.encode(), pb, len(pb), C.byref(mt), C.byref(seed), C.byref(temp), C.byref(top_p))
+    if rc:
+        raise HostError((lib_nodevice().blh_last_error() or b"").decode(errors="replace"))
+    return {"prompt": pb.value.decode(), "max_tokens": mt.value, "seed": seed.value, "temp": temp.value, "top_p": top_p.value}
+
+
+def wire_parse_verify(body: str, cap: int = 4096):
+    toks = np.zeros(cap, dtype=np.int32); cl = np.zeros((cap, 10), dtype=TD_DTYPE); nc = np.zeros(cap, dtype=np.int32); n = _i32(0)
+    rc = lib_nodevice().blh_wire_parse_verify(body.encode(), cap, _p(toks), _p(cl), _p(nc), C.byref(n))
+    if rc:
+        raise HostError((lib_nodevice().blh_last_error() or b"").decode(errors="replace"))
+    return toks[: n.value].copy(), cl[: n.value].copy(), nc[: n.value].copy()
+
+
+def wire_complete_json(tokens, top10: np.ndarray, n_logits=None, model: Optional[Model] = None) -> str:
+    t = np.ascontiguousarray(tokens, dtype=np.int32)
+    n = len(t)
+    cl = np.ascontiguousarray(top10).reshape(n, 10)
+    nl = np.full(n, 10, dtype=np.int32) if n_logits is None else np.ascontiguousarray(n_logits, dtype=np.int32)
+    l = lib_nodevice()
+    return _text_out(lambda buf, cap, ln: l.blh_wire_complete_json(model.h if model else None, _p(t), n, _p(cl), _p(nl), buf, cap, ln), 1 << 20)
+
+
+# ---- Server: N replicas behind one request queue (reference server/code/server/Server.hpp) -----------------------------------
+class Server:
+    def __init__(self, models: Sequence[Model], ctx_size: int = 0, batch_size: int = 0):
+        arr = (_vp * len(models))(*[m.h for m in models])
+        h = _vp()
+        _check(lib().blh_server_create(arr, len(models), ctx_size, batch_size, C.byref(h)))
+        self.h = h
+        self.models = list(models)
+
+    def workers(self) -> int:
+        return lib().blh_server_workers(self.h)
+
+    def submit_complete(self, prompt: Sequence[int], max_tokens: int, seed: int = 0, temp: float = 0.8, top_p: float = 0.95) -> int:
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        t = C.c_int64(0)
+        _check(lib().blh_server_submit_complete(self.h, _p(p), len(p), max_tokens, seed, temp, top_p, C.byref(t)))
+        return t.value
+
+    def submit_verify(self, prompt: Sequence[int], tokens: Sequence[int], claimed: np.ndarray, n_claimed=None, seed: int = 0,
+                      temp: float = 0.8, top_p: float = 0.95) -> int:
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        tk = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = len(tk)
+        cl = np.ascontiguousarray(claimed).reshape(n, 10)
+        assert cl.dtype == TD_DTYPE
+        nc = np.full(n, 10, dtype=np.int32) if n_claimed is None else np.ascontiguousarray(n_claimed, dtype=np.int32)
+        t = C.c_int64(0)
+        _check(lib().blh_server_submit_verify(self.h, _p(p), len(p), seed, temp, top_p, _p(tk), n, _p(cl), _p(nc), C.byref(t)))
+        return t.value
+
+    def submit_complete_json(self, body: str) -> int:
+        t = C.c_int64(0)
+        _check(lib().blh_server_submit_complete_json(self.h, body.encode("utf-8"), C.byref(t)))
+        return t.value
+
+    def submit_verify_json(self, body: str) -> int:
+        t = C.c_int64(0)
+        _check(lib().blh_server_submit_verify_json(self.h, body.encode("utf-8"), C.byref(t)))
+        return t.value
+
+    def wait_complete(self, ticket: int, cap: int = 4096):
+        toks = np.zeros(cap, dtype=np.int32); top = np.zeros((cap, 10), dtype=TD_DTYPE); nl = np.zeros(cap, dtype=np.int32); n = _i32(0)
+        _check(lib().blh_server_wait_complete(self.h, ticket, cap, _p(toks), _p(top), _p(nl), C.byref(n)))
+        k = min(n.value, cap)
+        return toks[:k].copy(), top[:k].copy(), nl[:k].copy()
+
+    def wait_verify(self, ticket: int) -> float:
+        s = _f32(0)
+        _check(lib().blh_server_wait_verify(self.h, ticket, C.byref(s)))
+        return float(s.value)
+
+    def wait_complete_json(self, ticket: int) -> str:
+        # a ticket can be waited for once: size the buffer generously (a 2048-token answer is ~1.5 MB)
+        cap = 1 << 23
+        buf = C.create_string_buffer(cap); n = C.c_int(0)
+        _check(lib().blh_server_wait_complete_json(self.h, ticket, buf, cap, C.byref(n)))
+        return buf.raw[: min(n.value, cap)].decode("utf-8")
+
+    def wait_verify_json(self, ticket: int) -> str:
+        buf = C.create_string_buffer(256); n = C.c_int(0)
+        _check(lib().blh_server_wait_verify_json(self.h, ticket, buf, 256, C.byref(n)))
+        return buf.raw[: n.value].decode()
+
+    def drain(self):
+        lib().blh_server_drain(self.h)
+
+    def last_worker_error(self) -> str:
+        buf = C.create_string_buffer(4096)
+        n = lib().blh_server_last_worker_error(self.h, buf, 4096)
+        return buf.raw[: min(n, 4096)].decode(errors="replace")
+
+    def stats(self):
+        k = self.workers()
+        dev = np.zeros(k, dtype=np.int32); req = np.zeros(k, dtype=np.uint64); ms = np.zeros(k, dtype=np.float64)
+        lib().blh_server_stats(self.h, _p(dev), _p(req), _p(ms), k)
+        return [{"device": int(dev[i]), "requests": int(req[i]), "gpu_ms": float(ms[i])} for i in range(k)]
+
+    def http_start(self, host: str = "127.0.0.1", port: int = 0, io_threads: int = 4) -> int:
+        out = C.c_int(0)
+        _check(lib().blh_server_http_start(self.h, host.encode(), port, io_threads, C.byref(out)))
+        return out.value
+
+    def http_stop(self):
+        lib().blh_server_http_stop(self.h)
+
+    def close(self):
+        if self.h:
+            lib().blh_server_free(self.h)
+            self.h = None
