@@ -27,7 +27,13 @@ SYMBOLS = {
     "blk_device_count": (_i32, []),
     "blk_version": (C.c_char_p, []),
     "blk_model_load": (_vp, [C.c_char_p, _i32, PROGRESS_CB, _vp]),
+    "blk_model_load_vocab": (_vp, [C.c_char_p]),
     "blk_model_free": (None, [_vp]),
+    "blk_model_add_eos": (_i32, [_vp]),
+    "blk_model_vocab_only": (_i32, [_vp]),
+    "blk_model_token_type": (_i32, [_vp, _i32]),
+    "blk_model_n_merges": (_i32, [_vp]),
+    "blk_model_merge_text": (_i32, [_vp, _i32, C.c_char_p, _i32]),
     "blk_model_n_vocab": (_i32, [_vp]),
     "blk_model_n_ctx_train": (_i32, [_vp]),
     "blk_model_n_embd": (_i32, [_vp]),

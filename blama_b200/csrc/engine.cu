@@ -65,6 +65,7 @@ extern "C" const char* blk_version(void) { return "blama_b200 0.1 (sm_100a)"; }
 // model
 // ------------------------------------------------------------------------------------------------------------------
 blk_model::~blk_model() {
+    if (allocs.empty()) return;          // vocabulary-only models never touched a device
     cudaSetDevice(device);
     for (void* p : allocs) cudaFree(p);
 }
@@ -259,6 +260,62 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
 }
 } // namespace
 
+namespace {
+// hyper-parameters, special tokens and the vocabulary (what llama.cpp's llm_load_hparams / llama_vocab::load read).
+// vocab_only: the architecture is not restricted and no tensor geometry is needed.
+void load_metadata(blk_model* m, GgufFile& f, bool vocab_only) {
+    const std::string* arch = f.str("general.architecture");
+    if (!arch) throw BlkError(BLK_ERR_FORMAT, "gguf: no general.architecture");
+    m->arch = *arch;
+    if (!vocab_only) {
+        if (m->arch != "llama" && m->arch != "qwen2") throw BlkError(BLK_ERR_FORMAT, "unsupported architecture: " + m->arch);
+        auto hp = [&](const char* k) { return f.num_required(m->arch + "." + k); };
+        auto hpd = [&](const char* k, double d) { return f.num(m->arch + "." + k, d); };
+        auto pos_int = [&](double v, const char* what, double hi) -> int {
+            if (!(v >= 1 && v <= hi) || v != (double)(long long)v) throw BlkError(BLK_ERR_FORMAT, std::string("gguf: bad ") + what);
+            return (int)v;
+        };
+        m->n_embd = pos_int(hp("embedding_length"), "embedding_length", 1 << 20);
+        m->n_layer = pos_int(hp("block_count"), "block_count", 4096);
+        m->n_ff = pos_int(hp("feed_forward_length"), "feed_forward_length", 1 << 24);
+        m->n_head = pos_int(hp("attention.head_count"), "attention.head_count", 4096);
+        m->n_head_kv = pos_int(hpd("attention.head_count_kv", m->n_head), "attention.head_count_kv", 4096);
+        m->n_ctx_train = pos_int(hp("context_length"), "context_length", 1 << 30);
+        m->rms_eps = (float)hpd("attention.layer_norm_rms_epsilon", 1e-5);
+        m->rope_theta = (float)hpd("rope.freq_base", 10000.0);
+        if (m->n_embd % m->n_head) throw BlkError(BLK_ERR_FORMAT, "gguf: embedding_length is not a multiple of head_count");
+        m->d_head = m->n_embd / m->n_head;
+        m->n_rot = pos_int(hpd("rope.dimension_count", m->d_head), "rope.dimension_count", 1 << 16);
+        m->neox = (m->arch == "qwen2");
+        m->theta_scale = powf(m->rope_theta, -2.0f / (float)m->n_rot);
+        if (m->n_rot != m->d_head) throw BlkError(BLK_ERR_FORMAT, "partial rotary dimensions are not supported");
+        if (m->d_head != 64 && m->d_head != 128) throw BlkError(BLK_ERR_FORMAT, "head size must be 64 or 128");
+        if (m->n_head % m->n_head_kv || m->n_head / m->n_head_kv > MAX_GQ) throw BlkError(BLK_ERR_FORMAT, "unsupported GQA ratio");
+        if ((m->n_head * m->d_head) % 256 || m->n_embd % 256 || m->n_ff % 256) throw BlkError(BLK_ERR_FORMAT, "model widths must be multiples of 256");
+    }
+    m->vocab_only = vocab_only;
+    m->tok_bos = (int)f.num("tokenizer.ggml.bos_token_id", -1);
+    m->tok_eos = (int)f.num("tokenizer.ggml.eos_token_id", -1);
+    m->tok_eot = (int)f.num("tokenizer.ggml.eot_token_id", -1);
+    m->tok_eom = (int)f.num("tokenizer.ggml.eom_token_id", -1);
+    m->add_bos = f.num("tokenizer.ggml.add_bos_token", 0) != 0;
+    m->add_eos = f.num("tokenizer.ggml.add_eos_token", 0) != 0;
+    if (const auto* v = f.str_array("tokenizer.ggml.tokens")) m->vocab = *v;
+    if (const auto* v = f.str_array("tokenizer.ggml.merges")) m->merges = *v;
+    if (const auto* v = f.int_array("tokenizer.ggml.token_type")) { m->token_type.resize(v->size()); for (size_t i = 0; i < v->size(); i++) m->token_type[i] = (int32_t)(*v)[i]; }
+    if (m->token_type.size() != m->vocab.size()) m->token_type.assign(m->vocab.size(), 1);
+    for (const char* k : {"general.name", "general.architecture", "tokenizer.chat_template", "tokenizer.ggml.model", "tokenizer.ggml.pre"})
+        if (const std::string* s = f.str(k)) m->meta[k] = *s;
+    // End-of-generation set: the metadata ids plus the token texts llama.cpp's vocabulary loader recognises (llama-vocab.cpp,
+    // "special_eog_ids"): real Llama-3 / Qwen2 files mark <|eot_id|> / <|im_end|> only through their text.
+    m->eog.assign(m->vocab.size(), 0);
+    static const char* const eog_texts[] = {"<|eot_id|>", "<|im_end|>", "<|end|>", "<end_of_turn>", "<|endoftext|>", "<|eom_id|>", "<EOT>", "_<EOT>"};
+    for (size_t i = 0; i < m->vocab.size(); i++)
+        for (const char* t : eog_texts) if (m->vocab[i] == t) { m->eog[i] = 1; if (m->token_type[i] == 1) m->token_type[i] = 3; }
+    for (int id : {m->tok_eos, m->tok_eot, m->tok_eom}) if (id >= 0 && (size_t)id < m->eog.size()) m->eog[(size_t)id] = 1;
+}
+} // namespace
+
 extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progress_cb cb, void* user) {
     if (blk_init() != BLK_OK) return nullptr;
     if (device < 0 || device >= g_device_count) { fail(BLK_ERR_ARG, "bad device index"); return nullptr; }
@@ -272,36 +329,7 @@ extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progr
             throw BlkError(w.rfind("gguf:", 0) == 0 ? BLK_ERR_FORMAT : BLK_ERR_IO, w);
         }
         GgufFile& f = *fp;
-        const std::string* arch = f.str("general.architecture");
-        if (!arch) throw BlkError(BLK_ERR_FORMAT, "gguf: no general.architecture");
-        m->arch = *arch;
-        if (m->arch != "llama" && m->arch != "qwen2") throw BlkError(BLK_ERR_FORMAT, "unsupported architecture: " + m->arch);
-        auto hp = [&](const char* k) { return f.num_required(m->arch + "." + k); };
-        auto hpd = [&](const char* k, double d) { return f.num(m->arch + "." + k, d); };
-        m->n_embd = (int)hp("embedding_length");
-        m->n_layer = (int)hp("block_count");
-        m->n_ff = (int)hp("feed_forward_length");
-        m->n_head = (int)hp("attention.head_count");
-        m->n_head_kv = (int)hpd("attention.head_count_kv", m->n_head);
-        m->n_ctx_train = (int)hp("context_length");
-        m->rms_eps = (float)hpd("attention.layer_norm_rms_epsilon", 1e-5);
-        m->rope_theta = (float)hpd("rope.freq_base", 10000.0);
-        m->d_head = m->n_embd / m->n_head;
-        m->n_rot = (int)hpd("rope.dimension_count", m->d_head);
-        m->neox = (m->arch == "qwen2");
-        m->theta_scale = powf(m->rope_theta, -2.0f / (float)m->n_rot);
-        if (m->n_rot != m->d_head) throw BlkError(BLK_ERR_FORMAT, "partial rotary dimensions are not supported");
-        if (m->d_head != 64 && m->d_head != 128) throw BlkError(BLK_ERR_FORMAT, "head size must be 64 or 128");
-        if (m->n_head % m->n_head_kv || m->n_head / m->n_head_kv > MAX_GQ) throw BlkError(BLK_ERR_FORMAT, "unsupported GQA ratio");
-        if ((m->n_head * m->d_head) % 256 || m->n_embd % 256 || m->n_ff % 256) throw BlkError(BLK_ERR_FORMAT, "model widths must be multiples of 256");
-        m->tok_bos = (int)f.num("tokenizer.ggml.bos_token_id", -1);
-        m->tok_eos = (int)f.num("tokenizer.ggml.eos_token_id", -1);
-        m->tok_eot = (int)f.num("tokenizer.ggml.eot_token_id", -1);
-        m->tok_eom = (int)f.num("tokenizer.ggml.eom_token_id", -1);
-        m->add_bos = f.num("tokenizer.ggml.add_bos_token", 0) != 0;
-        if (const auto* v = f.str_array("tokenizer.ggml.tokens")) m->vocab = *v;
-        for (const char* k : {"general.name", "general.architecture", "tokenizer.chat_template", "tokenizer.ggml.model", "tokenizer.ggml.pre"})
-            if (const std::string* s = f.str(k)) m->meta[k] = *s;
+        load_metadata(m.get(), f, false);
 
         BLK_CUDA(cudaSetDevice(device));
         Uploader up; up.m = m.get();
@@ -421,6 +449,24 @@ extern "C" blk_model* blk_model_load(const char* path, int32_t device, blk_progr
     return m.release();
 }
 
+// Model::Params::vocabOnly (reference Model.hpp:30, test t-integration.cpp:25-43): metadata + vocabulary, no device, no weights.
+extern "C" blk_model* blk_model_load_vocab(const char* path) {
+    std::unique_ptr<blk_model> m(new blk_model());
+    m->device = -1;
+    blk_status st = guarded([&] {
+        std::unique_ptr<GgufFile> fp;
+        try { fp.reset(new GgufFile(path)); }
+        catch (const std::exception& e) {
+            const std::string w = e.what();
+            throw BlkError(w.rfind("gguf:", 0) == 0 ? BLK_ERR_FORMAT : BLK_ERR_IO, w);
+        }
+        load_metadata(m.get(), *fp, true);
+        m->n_vocab = (int)m->vocab.size();
+    });
+    if (st != BLK_OK) return nullptr;
+    return m.release();
+}
+
 extern "C" void blk_model_free(blk_model* m) { delete m; }
 extern "C" int32_t blk_model_n_vocab(const blk_model* m) { return m->n_vocab; }
 extern "C" int32_t blk_model_n_ctx_train(const blk_model* m) { return m->n_ctx_train; }
@@ -428,7 +474,22 @@ extern "C" int32_t blk_model_n_embd(const blk_model* m) { return m->n_embd; }
 extern "C" int32_t blk_model_n_layer(const blk_model* m) { return m->n_layer; }
 extern "C" int32_t blk_model_token_bos(const blk_model* m) { return m->tok_bos; }
 extern "C" int32_t blk_model_token_eos(const blk_model* m) { return m->tok_eos; }
-extern "C" int32_t blk_model_is_eog(const blk_model* m, int32_t t) { return t >= 0 && (t == m->tok_eos || t == m->tok_eot || t == m->tok_eom); }
+extern "C" int32_t blk_model_is_eog(const blk_model* m, int32_t t) {
+    if (t < 0) return 0;
+    if ((size_t)t < m->eog.size()) return m->eog[(size_t)t];
+    return t == m->tok_eos || t == m->tok_eot || t == m->tok_eom;
+}
+extern "C" int32_t blk_model_add_eos(const blk_model* m) { return m->add_eos ? 1 : 0; }
+extern "C" int32_t blk_model_token_type(const blk_model* m, int32_t t) { return (t >= 0 && (size_t)t < m->token_type.size()) ? m->token_type[(size_t)t] : 0; }
+extern "C" int32_t blk_model_n_merges(const blk_model* m) { return (int32_t)m->merges.size(); }
+extern "C" int32_t blk_model_merge_text(const blk_model* m, int32_t i, char* buf, int32_t cap) {
+    if (i < 0 || (size_t)i >= m->merges.size()) return 0;
+    const std::string& s = m->merges[(size_t)i];
+    const int n = (int)s.size();
+    if (buf && cap > 0) memcpy(buf, s.data(), (size_t)std::min(n, cap));
+    return n;
+}
+extern "C" int32_t blk_model_vocab_only(const blk_model* m) { return m->vocab_only ? 1 : 0; }
 extern "C" int32_t blk_model_add_bos(const blk_model* m) { return m->add_bos ? 1 : 0; }
 extern "C" int32_t blk_model_device(const blk_model* m) { return m->device; }
 extern "C" int64_t blk_model_weight_bytes_per_token(const blk_model* m) { return m->weight_bytes_per_token; }
@@ -1035,6 +1096,7 @@ void step(blk_ctx* c, int32_t tok, bool with_head) {
 
 extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch) {
     if (!m) { fail(BLK_ERR_ARG, "null model"); return nullptr; }
+    if (m->vocab_only) { fail(BLK_ERR_ARG, "Failed to create context: the model was loaded vocabulary-only"); return nullptr; }
     std::unique_ptr<blk_ctx> c(new blk_ctx());
     c->m = m;
     blk_status st = guarded([&] {

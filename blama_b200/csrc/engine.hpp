@@ -67,6 +67,11 @@ struct blk_model {
     const float* rope_freqs = nullptr;
     std::vector<void*> allocs;
     std::vector<std::string> vocab;
+    std::vector<int32_t> token_type;          // tokenizer.ggml.token_type (1 normal, 2 unknown, 3 control, 4 user defined, 5 unused, 6 byte)
+    std::vector<std::string> merges;          // tokenizer.ggml.merges ("left right", rank = index)
+    std::vector<uint8_t> eog;                 // per token: end-of-generation (ids from the metadata + the token texts llama.cpp recognises)
+    bool add_eos = false;
+    bool vocab_only = false;                  // metadata + vocabulary only: no device, no weights (Model::Params::vocabOnly)
     std::map<std::string, std::string> meta;
     int64_t weight_bytes_per_token = 0;
     int act_fmt = blk::ACT_F32;       // activation format of the layer mat-vecs

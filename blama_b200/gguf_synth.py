@@ -201,6 +201,80 @@ def _kv(key: str, vtype: int, value) -> bytes:
     return out + struct.pack(fmt[vtype], value)
 
 
+def bytes_to_unicode() -> List[str]:
+    """GPT-2's byte -> printable character table (byte-level BPE alphabet): index = byte value."""
+    keep = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    out, extra = [""] * 256, 0
+    for b in range(256):
+        if b in keep:
+            out[b] = chr(b)
+        else:
+            out[b] = chr(256 + extra)
+            extra += 1
+    return out
+
+
+_SEED_MERGES: Optional[List[Tuple[str, str]]] = None
+
+
+def _seed_merges() -> List[Tuple[str, str]]:
+    global _SEED_MERGES
+    if _SEED_MERGES is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bpe_seed_merges.txt")
+        with open(path, encoding="utf-8") as f:
+            _SEED_MERGES = [tuple(line.rstrip("\n").split(" ")) for line in f if line.strip()]
+    return _SEED_MERGES
+
+
+def synth_vocab(shape: "ModelShape | str", seed: int = 0xB1A4A) -> Tuple[List[str], List[int], List[str]]:
+    """(tokens, token types, merges) of a synthetic byte-level BPE vocabulary with shape.vocab entries, laid out like the real
+    Llama-3 / Qwen2 files: ids 0..255 the byte alphabet, then one token per merge in rank order (merge r creates id 256 + r), then
+    the CONTROL tokens from special_tokens()['bos' ...] upwards.  The first merges are trained on English text
+    (tools/gen_bpe_seed_merges.py), the rest are random concatenations of earlier tokens: every merge list is a valid BPE."""
+    if isinstance(shape, str):
+        shape = SHAPES[shape]
+    sp = special_tokens(shape)
+    base = min(sp.values())
+    assert base > 256, "vocabulary too small for a byte-level alphabet"
+    b2u = bytes_to_unicode()
+    keep = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    order = keep + [b for b in range(256) if b not in keep]
+    tokens = [b2u[b] for b in order]
+    have = set(tokens)
+    merges: List[str] = []
+    for a, b in _seed_merges():
+        if len(tokens) >= base:
+            break
+        if a in have and b in have and a + b not in have:
+            tokens.append(a + b); have.add(a + b); merges.append(f"{a} {b}")
+    rng = np.random.default_rng([seed, 0x70CAB])
+    short = [t for t in tokens if len(t) <= 6]          # both halves of a random merge: the result stays <= 12 characters
+    while len(tokens) < base:
+        need = base - len(tokens)
+        for ua, ub in rng.random((need + need // 8 + 64, 2)).tolist():
+            n = len(short)
+            a, b = short[int(ua * n)], short[int(ub * n)]
+            new = a + b
+            if new in have:
+                continue
+            tokens.append(new); have.add(new); merges.append(a + " " + b)
+            if len(new) <= 6:
+                short.append(new)
+            if len(tokens) >= base:
+                break
+    types = [1] * base
+    names = {"llama": {"bos": "<|begin_of_text|>", "eos": "<|end_of_text|>", "eot": "<|eot_id|>", "pad": "<|finetune_right_pad_id|>"},
+             "qwen2": {"bos": "<|endoftext|>", "eos": "<|im_end|>", "eot": "<|im_end|>", "pad": "<|endoftext|>"}}[shape.arch]
+    by_id = {}
+    for k in ("pad", "bos", "eot", "eos"):
+        by_id[sp[k]] = names[k]
+    for i in range(base, shape.vocab):
+        tokens.append(by_id.get(i, f"<|reserved_special_token_{i - base}|>"))
+        types.append(3)      # CONTROL
+    return tokens, types, merges
+
+
 def special_tokens(shape: ModelShape) -> Dict[str, int]:
     """bos / eos / eot ids placed where the real vocabularies keep them."""
     v = shape.vocab
@@ -256,17 +330,13 @@ def model_bytes(shape: ModelShape) -> int:
     return tot
 
 
-def write_gguf(path: str, shape: ModelShape | str, seed: int = 0xB1A4A, chunk_elems: int = 1 << 26) -> Dict[str, int]:
-    """Write a random-init GGUF for `shape`; returns the special-token ids."""
+def write_gguf(path: str, shape: ModelShape | str, seed: int = 0xB1A4A, chunk_elems: int = 1 << 26, pre: Optional[str] = None) -> Dict[str, int]:
+    """Write a random-init GGUF for `shape`; returns the special-token ids.  pre: tokenizer.ggml.pre override (tokenizer tests)."""
     if isinstance(shape, str):
         shape = SHAPES[shape]
     a = shape.arch
     sp = special_tokens(shape)
-    tokens = [f"<t{i}>" for i in range(shape.vocab)]
-    ttype = [1] * shape.vocab  # NORMAL
-    for k in ("bos", "eos", "eot", "pad"):
-        tokens[sp[k]] = f"<|{k}|>"
-        ttype[sp[k]] = 3      # CONTROL
+    tokens, ttype, merges = synth_vocab(shape, seed)
     ftype_id = {"F32": 0, "Q8_0": 7, "Q4_K_M": 15}[shape.ftype]
     kvs = [
         _kv("general.architecture", T_STR, a),
@@ -284,10 +354,10 @@ def write_gguf(path: str, shape: ModelShape | str, seed: int = 0xB1A4A, chunk_el
         _kv(f"{a}.rope.dimension_count", T_U32, shape.d_head),
         _kv(f"{a}.vocab_size", T_U32, shape.vocab),
         _kv("tokenizer.ggml.model", T_STR, "gpt2"),
-        _kv("tokenizer.ggml.pre", T_STR, "llama-bpe" if a == "llama" else "qwen2"),
+        _kv("tokenizer.ggml.pre", T_STR, pre or ("llama-bpe" if a == "llama" else "qwen2")),
         _kv("tokenizer.ggml.tokens", T_ARR, (T_STR, tokens)),
         _kv("tokenizer.ggml.token_type", T_ARR, (T_I32, ttype)),
-        _kv("tokenizer.ggml.merges", T_ARR, (T_STR, [])),
+        _kv("tokenizer.ggml.merges", T_ARR, (T_STR, merges)),
         _kv("tokenizer.ggml.bos_token_id", T_U32, sp["bos"]),
         _kv("tokenizer.ggml.eos_token_id", T_U32, sp["eos"]),
         _kv("tokenizer.ggml.eot_token_id", T_U32, sp["eot"]),

@@ -105,19 +105,32 @@ BLK_API int blh_model_create(const char* path, int device, int gpu, int prefix_b
         *out = new Model(path, p);
     });
 }
+// Model::Params::vocabOnly: tokenizer / detokenizer only, no device needed
+BLK_API int blh_model_create_vocab_only(const char* path, void** out) {
+    return guard([&] { Model::Params p; p.vocabOnly = true; *out = new Model(path, p); });
+}
 BLK_API void blh_model_free(void* m) { delete static_cast<Model*>(m); }
 BLK_API int blh_model_train_ctx(void* m) { return int(static_cast<Model*>(m)->trainCtxLength()); }
-BLK_API int blh_model_tokenize(void* m, const char* text, int add_special, int32_t* out, int cap) {
-    auto v = static_cast<Model*>(m)->vocab().tokenize(text, add_special != 0, true);
-    for (int i = 0; i < int(v.size()) && i < cap; ++i) out[i] = v[size_t(i)];
-    return int(v.size());
-}
-BLK_API int blh_model_token_to_string(void* m, int32_t tok, char* buf, int cap) {
-    auto s = static_cast<Model*>(m)->vocab().tokenToString(tok);
-    const int n = int(s.size());
-    memcpy(buf, s.data(), size_t(n < cap ? n : cap));
+// Vocab::tokenize over n_bytes of text (may contain NULs); returns the token count (may exceed cap), -1 on failure
+BLK_API int blh_model_tokenize(void* m, const char* text, int n_bytes, int add_special, int parse_special, int32_t* out, int cap) {
+    int n = -1;
+    guard([&] {
+        auto v = static_cast<Model*>(m)->vocab().tokenize(std::string_view(text, size_t(n_bytes)), add_special != 0, parse_special != 0);
+        for (int i = 0; i < int(v.size()) && i < cap; ++i) out[i] = v[size_t(i)];
+        n = int(v.size());
+    });
     return n;
 }
+BLK_API int blh_model_token_to_string(void* m, int32_t tok, int special, char* buf, int cap) {
+    int n = -1;
+    guard([&] {
+        auto s = static_cast<Model*>(m)->vocab().tokenToString(tok, special != 0);
+        n = int(s.size());
+        memcpy(buf, s.data(), size_t(n < cap ? n : cap));
+    });
+    return n;
+}
+BLK_API int blh_model_is_eog(void* m, int32_t tok) { return static_cast<Model*>(m)->vocab().isEog(tok) ? 1 : 0; }
 
 BLK_API int blh_instance_create(void* model, uint32_t ctx_size, uint32_t batch_size, void** out) {
     return guard([&] {

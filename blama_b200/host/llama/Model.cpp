@@ -13,8 +13,12 @@ int32_t progressTrampoline(float p, void* user) {
     return 1;
 }
 blk_model* load(const std::string& gguf, const Model::Params& params, ModelLoadProgressCb& pcb) {
+    if (params.vocabOnly) {      // metadata + vocabulary: no device involved (reference test "vocab only", t-integration.cpp:25-43)
+        blk_model* v = blk_model_load_vocab(gguf.c_str());
+        if (!v) Raise{} << "Failed to load model " << gguf << ": " << blk_last_error();
+        return v;
+    }
     if (!params.gpu) Raise{} << "blama_b200 has no CPU backend: Model::Params::gpu must be true";
-    if (params.vocabOnly) Raise{} << "vocabOnly models are not supported by this build";
     blk_model* m = blk_model_load(gguf.c_str(), params.device, pcb ? progressTrampoline : nullptr, &pcb);
     // the reference does not check for a null model (Model.cpp:50-53) and crashes later; fail here with the cause
     if (!m) Raise{} << "Failed to load model " << gguf << ": " << blk_last_error();
@@ -27,7 +31,7 @@ Model::Model(const std::string& gguf, Params params, ModelLoadProgressCb pcb)
 
 Model::~Model() = default;
 
-uint32_t Model::trainCtxLength() const noexcept { return uint32_t(blk_model_n_ctx_train(m_handle.get())); }
+uint32_t Model::trainCtxLength() const noexcept { return uint32_t(blk_model_n_ctx_train(m_handle.get())); }   // 0 for vocabOnly
 bool Model::shouldAddBosToken() const noexcept { return blk_model_add_bos(m_handle.get()) != 0; }
 
 std::string Model::getChatTemplateId() const {

@@ -17,7 +17,7 @@ public:
     struct Params {
         bool gpu = true;                  // the reference falls back to the CPU backend when false; this build has no
                                           // CPU backend: gpu = false is rejected
-        bool vocabOnly = false;           // not supported by this build (weights are always loaded)
+        bool vocabOnly = false;           // do not load the weights (tokenizer use only; needs no GPU)
         bool prefixInputsWithBos = false; // add bos token to interactive inputs (#13)
         int device = 0;                   // extension: which GPU holds this replica (one replica per GPU)
         bool operator==(const Params& other) const noexcept = default;

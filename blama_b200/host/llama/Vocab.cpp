@@ -1,10 +1,25 @@
 // Vocab.cpp -- reference inference/code/llama/Vocab.cpp:13-72 over the C ABI.
 #include "Vocab.hpp"
+#include "Errors.hpp"
 #include "Model.hpp"
+#include "Tokenizer.hpp"
 
 #include <blama_b200.h>
 
 namespace bl::llama {
+namespace {
+// a string-valued entry point called with the grow-and-retry protocol of the C ABI
+template <class F> std::string fetch(F&& call) {
+    std::string out(64, '\0');
+    int32_t len = call(out.data(), int32_t(out.size()));
+    if (len > int32_t(out.size())) {
+        out.resize(size_t(len));
+        len = call(out.data(), int32_t(out.size()));
+    }
+    out.resize(size_t(len < 0 ? 0 : len));
+    return out;
+}
+} // namespace
 
 Vocab::Vocab(const Model& model) : m_model(model) {}
 Vocab::~Vocab() = default;
@@ -14,49 +29,36 @@ Token Vocab::decoderStartToken() const noexcept { return blk_model_token_bos(m_m
 bool Vocab::isEog(Token token) const noexcept { return blk_model_is_eog(m_model.lmodel(), token) != 0; }
 int32_t Vocab::nTokens() const noexcept { return blk_model_n_vocab(m_model.lmodel()); }
 
-std::string Vocab::tokenToString(Token token, bool /*special*/) const {
-    std::string out(32, '\0');
-    int32_t len = blk_model_token_text(m_model.lmodel(), token, out.data(), int32_t(out.size()));
-    if (len > int32_t(out.size())) {
-        out.resize(size_t(len));
-        len = blk_model_token_text(m_model.lmodel(), token, out.data(), int32_t(out.size()));
-    }
-    out.resize(size_t(len < 0 ? 0 : len));
-    return out;
-}
-
-void Vocab::buildIndex() const {
-    if (m_indexed) return;
-    const int32_t n = nTokens();
-    m_byText.reserve(size_t(n));
-    for (Token t = 0; t < n; ++t) {
-        std::string s = tokenToString(t);
-        if (s.empty()) continue;
-        m_longest = std::max(m_longest, s.size());
-        m_byText.emplace(std::move(s), t);      // first id wins for duplicate texts
-    }
-    m_indexed = true;
-}
-
-std::vector<Token> Vocab::tokenize(std::string_view text, bool addSpecial, bool /*parseSpecial*/) const {
-    buildIndex();
-    std::vector<Token> out;
-    if (addSpecial && m_model.shouldAddBosToken()) out.push_back(blk_model_token_bos(m_model.lmodel()));
-    size_t pos = 0;
-    std::string probe;
-    while (pos < text.size()) {
-        size_t len = std::min(m_longest, text.size() - pos);
-        Token found = Token_Invalid;
-        for (; len > 0; --len) {
-            probe.assign(text.substr(pos, len));
-            const auto it = m_byText.find(probe);
-            if (it != m_byText.end()) { found = it->second; break; }
+const BpeTokenizer& Vocab::tokenizer() const {
+    std::call_once(m_once, [&] {
+        const blk_model* m = m_model.lmodel();
+        const std::string kind = fetch([&](char* b, int32_t c) { return blk_model_meta_str(m, "tokenizer.ggml.model", b, c); });
+        if (!kind.empty() && kind != "gpt2") Raise{} << "unsupported tokenizer model '" << kind << "' (only byte-level BPE, tokenizer.ggml.model = gpt2)";
+        BpeTokenizer::Config cfg;
+        const int32_t n = blk_model_n_vocab(m);
+        cfg.tokens.resize(size_t(n));
+        cfg.types.resize(size_t(n));
+        for (Token t = 0; t < n; ++t) {
+            cfg.tokens[size_t(t)] = fetch([&](char* b, int32_t c) { return blk_model_token_text(m, t, b, c); });
+            cfg.types[size_t(t)] = blk_model_token_type(m, t);
         }
-        if (found == Token_Invalid) { ++pos; continue; }   // bytes with no vocabulary entry are skipped
-        out.push_back(found);
-        pos += len;
-    }
-    return out;
+        const int32_t nm = blk_model_n_merges(m);
+        cfg.merges.resize(size_t(nm));
+        for (int32_t r = 0; r < nm; ++r) cfg.merges[size_t(r)] = fetch([&](char* b, int32_t c) { return blk_model_merge_text(m, r, b, c); });
+        cfg.pre = fetch([&](char* b, int32_t c) { return blk_model_meta_str(m, "tokenizer.ggml.pre", b, c); });
+        cfg.bos = blk_model_token_bos(m);
+        cfg.eos = blk_model_token_eos(m);
+        cfg.addBos = blk_model_add_bos(m) != 0;
+        cfg.addEos = blk_model_add_eos(m) != 0;
+        m_tokenizer = std::make_unique<BpeTokenizer>(std::move(cfg));
+    });
+    return *m_tokenizer;
 }
+
+std::vector<Token> Vocab::tokenize(std::string_view text, bool addSpecial, bool parseSpecial) const {
+    return tokenizer().tokenize(text, addSpecial, parseSpecial);
+}
+
+std::string Vocab::tokenToString(Token token, bool special) const { return tokenizer().tokenToPiece(token, special); }
 
 } // namespace bl::llama

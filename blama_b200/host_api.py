@@ -19,8 +19,10 @@ HOST_SYMBOLS = {
     "blh_model_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "blh_model_free": (None, [_vp]),
     "blh_model_train_ctx": (C.c_int, [_vp]),
-    "blh_model_tokenize": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, C.c_int]),
-    "blh_model_token_to_string": (C.c_int, [_vp, _i32, C.c_char_p, C.c_int]),
+    "blh_model_create_vocab_only": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "blh_model_tokenize": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, C.c_int]),
+    "blh_model_token_to_string": (C.c_int, [_vp, _i32, C.c_int, C.c_char_p, C.c_int]),
+    "blh_model_is_eog": (C.c_int, [_vp, _i32]),
     "blh_instance_create": (C.c_int, [_vp, _u32, _u32, C.POINTER(_vp)]),
     "blh_instance_free": (None, [_vp]),
     "blh_instance_warmup": (C.c_int, [_vp]),
@@ -104,23 +106,38 @@ def as_td(pairs) -> np.ndarray:
 
 
 class Model:
-    def __init__(self, path: str, device: int = 0, gpu: bool = True, prefix_bos: bool = False):
+    def __init__(self, path: str, device: int = 0, gpu: bool = True, prefix_bos: bool = False, vocab_only: bool = False):
         h = _vp()
-        _check(lib().blh_model_create(path.encode(), device, int(gpu), int(prefix_bos), C.byref(h)))
+        if vocab_only:
+            _check(lib().blh_model_create_vocab_only(path.encode(), C.byref(h)))
+        else:
+            _check(lib().blh_model_create(path.encode(), device, int(gpu), int(prefix_bos), C.byref(h)))
         self.h = h
+        self.path = path
 
     def train_ctx(self) -> int:
         return lib().blh_model_train_ctx(self.h)
 
-    def tokenize(self, text: str, add_special: bool = True) -> np.ndarray:
-        out = np.zeros(len(text) + 4, dtype=np.int32)
-        n = lib().blh_model_tokenize(self.h, text.encode(), int(add_special), _p(out), len(out))
+    def tokenize(self, text, add_special: bool = True, parse_special: bool = True) -> np.ndarray:
+        raw = text if isinstance(text, (bytes, bytearray)) else text.encode("utf-8")
+        out = np.zeros(len(raw) + 4, dtype=np.int32)
+        n = lib().blh_model_tokenize(self.h, bytes(raw), len(raw), int(add_special), int(parse_special), _p(out), len(out))
+        if n < 0:
+            raise HostError((lib().blh_last_error() or b"").decode(errors="replace"))
         return out[:n].copy()
 
-    def token_to_string(self, tok: int) -> str:
-        buf = C.create_string_buffer(256)
-        n = lib().blh_model_token_to_string(self.h, int(tok), buf, 256)
-        return buf.raw[:min(n, 256)].decode(errors="replace")
+    def token_to_bytes(self, tok: int, special: bool = True) -> bytes:
+        buf = C.create_string_buffer(512)
+        n = lib().blh_model_token_to_string(self.h, int(tok), int(special), buf, 512)
+        if n < 0:
+            raise HostError((lib().blh_last_error() or b"").decode(errors="replace"))
+        return buf.raw[:min(n, 512)]
+
+    def token_to_string(self, tok: int, special: bool = True) -> str:
+        return self.token_to_bytes(tok, special).decode(errors="replace")
+
+    def is_eog(self, tok: int) -> bool:
+        return bool(lib().blh_model_is_eog(self.h, int(tok)))
 
     def close(self):
         if self.h:

@@ -58,6 +58,9 @@ typedef int32_t (*blk_progress_cb)(float progress, void* user);           /* Mod
 /* Parses the GGUF, uploads every tensor to `device` as device-resident quant blocks (Q4_K/Q5_K/Q6_K/Q8_0/F16/F32),
  * re-tiled on the device into the split layout the kernels stream (DESIGN.md "Data layout"). */
 BLK_API blk_model* blk_model_load(const char* gguf_path, int32_t device, blk_progress_cb cb, void* user);
+/* Model::Params::vocabOnly (Model.hpp:30; llama_model_params.vocab_only, Model.cpp:33): metadata + vocabulary only.  Needs no
+ * CUDA device; such a model cannot back a context (n_ctx_train reads 0, as the reference's "vocab only" test expects). */
+BLK_API blk_model* blk_model_load_vocab(const char* gguf_path);
 BLK_API void       blk_model_free(blk_model*);
 BLK_API int32_t blk_model_n_vocab(const blk_model*);        /* llama_vocab_n_tokens    Session.cpp:27 */
 BLK_API int32_t blk_model_n_ctx_train(const blk_model*);    /* llama_model_n_ctx_train Model.cpp:59 */
@@ -67,6 +70,8 @@ BLK_API int32_t blk_model_token_bos(const blk_model*);      /* llama_vocab_bos  
 BLK_API int32_t blk_model_token_eos(const blk_model*);      /* llama_vocab_eos         Instance.cpp:94 */
 BLK_API int32_t blk_model_is_eog(const blk_model*, int32_t token);   /* llama_vocab_is_eog Vocab.cpp:30 */
 BLK_API int32_t blk_model_add_bos(const blk_model*);        /* llama_vocab_get_add_bos Model.cpp:63 */
+BLK_API int32_t blk_model_add_eos(const blk_model*);        /* llama_vocab_get_add_eos (llama_tokenize appends EOS when set) */
+BLK_API int32_t blk_model_vocab_only(const blk_model*);
 BLK_API int32_t blk_model_device(const blk_model*);
 /* bytes of weights one decoded token streams from HBM (all matmul tensors once + lm_head) */
 BLK_API int64_t blk_model_weight_bytes_per_token(const blk_model*);
@@ -74,6 +79,12 @@ BLK_API int64_t blk_model_weight_bytes_per_token(const blk_model*);
 BLK_API int64_t blk_model_kv_bytes_per_token(const blk_model*);
 /* token text (tokenizer.ggml.tokens[token]); returns length, copies at most cap bytes (llama_token_to_piece, Vocab.cpp:57) */
 BLK_API int32_t blk_model_token_text(const blk_model*, int32_t token, char* buf, int32_t cap);
+/* The vocabulary behind llama_tokenize / llama_token_to_piece (Vocab.cpp:40,57): token attribute (tokenizer.ggml.token_type:
+ * 1 normal, 2 unknown, 3 control, 4 user defined, 5 unused, 6 byte) and the BPE merge list in rank order ("left right").  The
+ * tokenizer itself is host code above this boundary (blama_b200/host/llama/Tokenizer.cpp). */
+BLK_API int32_t blk_model_token_type(const blk_model*, int32_t token);
+BLK_API int32_t blk_model_n_merges(const blk_model*);
+BLK_API int32_t blk_model_merge_text(const blk_model*, int32_t rank, char* buf, int32_t cap);
 /* metadata string lookup (llama_model_meta_val_str, Model.cpp:77); returns length or -1 */
 BLK_API int32_t blk_model_meta_str(const blk_model*, const char* key, char* buf, int32_t cap);
 

@@ -105,9 +105,14 @@ def test_streaming_equals_complete(host, hmodel):
     a.close(); b.close()
 
 
-def test_tokenizer_round_trip_on_synthetic_vocab(host, hmodel):
-    ids = hmodel.tokenize("<t5><t17><t4000>", add_special=False)
-    assert ids.tolist() == [5, 17, 4000]
-    assert hmodel.token_to_string(17) == "<t17>"
-    with_bos = hmodel.tokenize("<t5>", add_special=True)
-    assert len(with_bos) == 2 and with_bos[1] == 5
+def test_tokenizer_round_trip_on_the_loaded_model(host, hmodel):
+    # the BPE tokenizer itself is pinned host-side in tests/test_tokenizer.py; here: the same answers through a device-resident model
+    text = "The first man to walk on the moon, in July 1969."
+    ids = hmodel.tokenize(text, add_special=False)
+    assert b"".join(hmodel.token_to_bytes(int(t)) for t in ids).decode() == text
+    vo = host.Model(hmodel.path, vocab_only=True) if hasattr(hmodel, "path") else None
+    if vo is not None:
+        assert vo.tokenize(text, add_special=False).tolist() == ids.tolist()
+        vo.close()
+    with_bos = hmodel.tokenize(text, add_special=True)
+    assert len(with_bos) == len(ids) + 1 and with_bos[1:].tolist() == ids.tolist()
