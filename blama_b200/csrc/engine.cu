@@ -4,7 +4,7 @@
 // llama_decode / llama_get_logits_ith (reference call sites: Model.cpp:50-53, Instance.cpp:34-48, Session.cpp:388,
 // Session.cpp:24).  There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include "engine.hpp"
-#include "gemv_ring.cuh"
+#include "gemv_kernels.cuh"
 #include "gguf.hpp"
 #include "prefill.hpp"
 #include "prefill_kernels.cuh"
@@ -586,27 +586,14 @@ void prof_mark(blk_ctx* c, const char* name) {
 }
 
 // A mat-vec of the decode step: y = epilogue(W . act(in)) where act = (optional RMSNorm * norm_w) then the quantisation the
-// weight type needs.  Production shapes run the persistent TMA-ring kernel, whose prologue prepares the activations per CTA;
-// shapes the ring cannot take (rows that are not a whole number of 16 B-aligned super-block planes: the tiny test models)
-// run a separate act_prepare kernel followed by the register-staged kernel of gemv_kernels.cuh.
+// weight type needs: a separate act_prepare / act_quant kernel followed by the register-staged kernel of gemv_kernels.cuh.
+// (This per-op path serves F32 / F16 weights, shapes the persistent decode kernel does not take, and BLK_MEGA=0.)
 template <int EPI>
 void matvec(blk_ctx* c, GemvArgs& a, const float* in, const float* norm_w, const ActBuf& scratch, const char* name) {
     const int K = a.seg[0].W.K;
     const int ta = a.seg[0].W.type, tb = (a.nseg > 2) ? a.seg[2].W.type : ta;
     const int fmt = act_format_for(ta);
     a.act_fmt = fmt;
-    RingPlan plan = c->use_ring ? ring_plan(K, ta, tb, a.total_pairs, c->n_sms) : RingPlan{};
-    if (plan.ok) {
-        RingArgs ra{};
-        ra.g = a; ra.in = in; ra.norm_w = norm_w; ra.eps = c->m->rms_eps; ra.plan = plan;
-        cudaError_t e;
-        if (EPI == EPI_STORE) e = launch_ring_store(ra, c->stream);
-        else if (EPI == EPI_RESID) e = launch_ring_resid(ra, c->stream);
-        else if (EPI == EPI_QKV) e = launch_ring_qkv(ra, c->stream);
-        else e = launch_ring_swiglu(ra, c->stream);
-        if (e != cudaErrorInvalidValue) { BLK_CUDA(e); c->launches++; prof_mark(c, name); return; }
-        (void)cudaGetLastError();
-    }
     if (!norm_w && fmt != ACT_F32) {
         // quantise only: every 256-element block is independent -> one warp per block across several CTAs
         BLK_CUDA(launch_pdl(act_quant_kernel, dim3((K / 256 + 7) / 8), dim3(256), 0, c->stream, in, K, fmt, scratch));
@@ -869,9 +856,9 @@ void topk_of_logits(blk_ctx* c) {
 // causal flash attention of a prefill chunk: the query heads of a KV head share a CTA when the GQA ratio is a power of two
 template <int DH, int GQ>
 void launch_attn_gqa(const PrefillAttnArgs& pa, int n, int n_head_kv, cudaStream_t st) {
-    static bool attr_done = false;     // per process is enough: the attribute is per function, set before the first launch
     constexpr int smem = prefill_attn_gqa_smem<DH, GQ>();
-    if (!attr_done) { BLK_CUDA(cudaFuncSetAttribute(prefill_attn_gqa_kernel<DH, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done = true; }
+    // the opt-in is per (function, device) and several worker threads launch concurrently: set it on every launch (host-only, cheap)
+    BLK_CUDA(cudaFuncSetAttribute(prefill_attn_gqa_kernel<DH, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     constexpr int BQ = 128 / GQ;
     prefill_attn_gqa_kernel<DH, GQ><<<dim3((n + BQ - 1) / BQ, n_head_kv), 256, smem, st>>>(pa);
 }
@@ -1131,7 +1118,6 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         c->rope_cs = dalloc<float2>(c.get(), dh / 2);
         c->act_d = make_act(c.get(), d); c->act_q = make_act(c.get(), dq); c->act_q2 = make_act(c.get(), dq); c->act_ff = make_act(c.get(), ff);
         BLK_CUDA(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, m->device));
-        { const char* e = getenv("BLK_RING"); c->use_ring = (e && e[0] == '1'); }     // the TMA-ring mat-vec is opt-in (measured slower)
         {   // single-kernel cluster attention when one CTA's share of the scores fits in shared memory
             const int gq = m->n_head / m->n_head_kv;
             c->attn_cluster = 8;
@@ -1583,7 +1569,6 @@ extern "C" blk_status blk_test_gemv(int32_t device, int32_t type, const void* bl
         GemvArgs a{};
         a.nseg = 1; a.seg[0] = {tm.W, nullptr, 0, 0}; a.total_pairs = (int)(rows / 2); a.out = d_y;
         BLK_CUDA(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, device));
-        { const char* e = getenv("BLK_RING"); c.use_ring = (e && e[0] == '1'); }
         matvec<EPI_STORE>(&c, a, d_x, nullptr, act, "test");
         BLK_CUDA(cudaMemcpyAsync(y, d_y, rows * 4, cudaMemcpyDeviceToHost, c.stream));
         BLK_CUDA(cudaStreamSynchronize(c.stream));

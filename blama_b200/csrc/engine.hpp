@@ -105,7 +105,7 @@ struct blk_ctx {
     float* hbuf = nullptr;                // [n_ff]
     float2* rope_cs = nullptr;            // [d_head/2]
     blk::ActBuf act_d, act_q, act_q2, act_ff;
-    int n_sms = 148; bool use_ring = false;
+    int n_sms = 148;
     int attn_cluster = 0, attn_cap = 0;   // cluster size (0 = three-kernel fallback) and tokens per CTA
     float* part_o = nullptr; float* scores = nullptr;
     float* logits = nullptr;              // [n_vocab] of the last decoded token

@@ -24,7 +24,8 @@
 // quantize_row_q8_K / q8_0, integer dot products bit-identical to ggml_vec_dot_*, attention in ggml's order
 // (max -> expf -> sum in double -> p * (1/sum) -> f16 -> V.p).  Only the order of fp32 additions differs.
 #pragma once
-#include "gemv_ring.cuh"     // mbarrier / bulk-copy PTX wrappers
+#include "gemv_kernels.cuh"
+#include "tma_ptx.cuh"       // mbarrier / bulk-copy PTX wrappers
 #include "mega_decode.hpp"
 
 namespace blk {

@@ -239,11 +239,9 @@ bool encode_2d_f16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t 
 }
 template <int GQ, int GQS = GQ>
 cudaError_t launch_attn_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnTcArgs& a, int n_head_kv, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    {   // the opt-in is per (function, device): one replica per GPU in one process launches this on every device
         cudaError_t e = cudaFuncSetAttribute(prefill_attn_tc_kernel<GQ, GQS>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     constexpr int BQ = 128 / GQS;
     prefill_attn_tc_kernel<GQ, GQS><<<dim3((a.T + BQ - 1) / BQ, n_head_kv), AT_THREADS, AT_SMEM_BYTES, st>>>(mq, mk, mv, a);

@@ -17,7 +17,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
-#include "gemv_ring.cuh"   // mbarrier / bulk-copy wrappers, QMat
+#include "gemv_kernels.cuh"   // QMat
+#include "tma_ptx.cuh"        // mbarrier / bulk-copy wrappers
 
 namespace blk {
 

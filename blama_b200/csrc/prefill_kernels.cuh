@@ -5,6 +5,7 @@
 // the GEMMs); tolerances against the reference's int8 path are stated in tests/test_gpu_prefill.py.
 #pragma once
 #include <cuda_bf16.h>
+#include "tma_ptx.cuh"
 
 #include "decode_kernels.cuh"
 

@@ -1,0 +1,60 @@
+"""Parity bookkeeping shared by the GPU tests, smoke() and bench.py: pure numpy comparisons of two logit rows / top-10 lists
+(whoever calls this brings the reference values; nothing here imports the oracle).
+
+Terms: a decode step is CLEAN when the device row equals the reference row to fp32 summation noise, FLIPPED
+when one Q8_K / f16 rounding went the other way somewhere upstream (bounded by FLIP_TOL).  Top-10 ids must be identical at every
+rank whose gap to the next rank in the reference exceeds twice the row's measured deviation (an order can only change inside 2 x
+deviation); on clean rows that is practically every rank."""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+
+CLEAN_TOL = 2e-4      # absolute; logits have std ~2
+FLIP_TOL = 0.25       # measured worst flip: 0.175 (oracle against itself with the lane sums reversed), <= 0.2 GPU vs oracle
+
+
+def top_sorted(logits: np.ndarray, k: int):
+    """ids and values of the k largest logits, descending, ties by lower id (the device's order)"""
+    part = np.argpartition(-logits, k)[: k + 1] if k + 1 < len(logits) else np.arange(len(logits))
+    order = part[np.lexsort((part, -logits[part]))][:k]
+    return order.astype(np.int32), logits[order]
+
+
+class StepStats:
+    def __init__(self):
+        self.max_abs: List[float] = []
+        self.ids_equal: List[bool] = []
+        self.gap_ranks = 0          # ranks whose reference gap demanded an identical id ...
+        self.gap_ok = 0             # ... and got it
+        self.gaps: List[float] = []
+
+    def add(self, got: np.ndarray, want: np.ndarray, got_top_ids: np.ndarray):
+        err = float(np.abs(got - want).max())
+        self.max_abs.append(err)
+        ids11, val11 = top_sorted(want, 11)
+        self.ids_equal.append(bool(np.array_equal(got_top_ids[:10], ids11[:10])))
+        gaps = val11[:10] - val11[1:11]
+        self.gaps += [float(g) for g in gaps]
+        bad = []
+        # rank r is pinned when it is separated from both neighbours by more than 2 x the measured deviation
+        for r in range(10):
+            above = val11[r - 1] - val11[r] if r > 0 else np.inf
+            below = val11[r] - val11[r + 1]
+            if above > 2 * err + 1e-6 and below > 2 * err + 1e-6:
+                self.gap_ranks += 1
+                if int(got_top_ids[r]) == int(ids11[r]):
+                    self.gap_ok += 1
+                else:
+                    bad.append(r)
+        return err, bad
+
+    def summary(self) -> Dict[str, float]:
+        n = max(1, len(self.max_abs))
+        return {"steps": len(self.max_abs), "max_abs": max(self.max_abs) if self.max_abs else 0.0,
+                "clean_frac": sum(e <= CLEAN_TOL for e in self.max_abs) / n,
+                "top10_id_match_frac": sum(self.ids_equal) / n,
+                "pinned_ranks": self.gap_ranks, "pinned_ranks_ok": self.gap_ok,
+                "gap_median": float(np.median(self.gaps)) if self.gaps else 0.0,
+                "gap_p10": float(np.percentile(self.gaps, 10)) if self.gaps else 0.0}

@@ -394,6 +394,7 @@ struct orc_model {
     float rms_eps = 1e-5f, rope_theta = 10000.f;
     bool neox = false;
     int bos = -1, eos = -1, eot = -1, eom = -1;
+    std::vector<int> eog_by_text;           // tokens whose text llama.cpp's vocabulary loader treats as end-of-generation
     const Tensor* get(const std::string& n) const { auto it = tensors.find(n); return it == tensors.end() ? nullptr : &it->second; }
     ~orc_model() { if (base) munmap((void*)base, size); if (fd >= 0) close(fd); }
 };
@@ -418,7 +419,15 @@ void skip_value(Reader& r, uint32_t t, orc_model* m, const std::string& key) {
         case 9: {
             uint32_t et = r.get<uint32_t>(); uint64_t n = r.get<uint64_t>();
             m->num[key + ".count"] = (double)n;
-            if (et == 8) { for (uint64_t i = 0; i < n; i++) r.str(); }
+            if (et == 8) {
+                // llama-vocab.cpp (special_eog_ids): these token texts end a generation whatever the metadata ids say
+                static const char* const eog_texts[] = {"<|eot_id|>", "<|im_end|>", "<|end|>", "<end_of_turn>", "<|endoftext|>", "<|eom_id|>", "<EOT>", "_<EOT>"};
+                const bool toks = key == "tokenizer.ggml.tokens";
+                for (uint64_t i = 0; i < n; i++) {
+                    const std::string s = r.str();
+                    if (toks) for (const char* t : eog_texts) if (s == t) m->eog_by_text.push_back((int)i);
+                }
+            }
             else if (et < 13 && sz[et]) { r.p += n * sz[et]; }
             else throw std::runtime_error("gguf: nested arrays unsupported");
             break;
@@ -478,7 +487,12 @@ extern "C" int32_t orc_n_ctx_train(const orc_model* m) { return m->n_ctx_train; 
 extern "C" int32_t orc_n_embd(const orc_model* m) { return m->n_embd; }
 extern "C" int32_t orc_n_layer(const orc_model* m) { return m->n_layer; }
 extern "C" int32_t orc_token_bos(const orc_model* m) { return m->bos; }
-extern "C" int32_t orc_is_eog(const orc_model* m, int32_t t) { return t >= 0 && (t == m->eos || t == m->eot || t == m->eom); }
+extern "C" int32_t orc_is_eog(const orc_model* m, int32_t t) {
+    if (t < 0) return 0;
+    if (t == m->eos || t == m->eot || t == m->eom) return 1;
+    for (int e : m->eog_by_text) if (e == t) return 1;
+    return 0;
+}
 extern "C" int64_t orc_weight_bytes_per_token(const orc_model* m) {
     int64_t tot = 0;
     for (auto& kv : m->tensors) {

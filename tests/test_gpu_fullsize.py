@@ -1,82 +1,178 @@
-"""BASELINE.json full sizes (Llama-3.1-8B-arch Q4_K_M, random-init GGUF written to /dev/shm): the oracle cannot run these in
-seconds, so parity is checked through size-independent properties of the path (the reference's own structural tests,
-inference/test/t-integration.cpp:219-248 and t-LogitComparer.cpp:76-78):
-  * complete -> fillCtx on the same backend is bit-equal (sequential mode) and scores exactly 1;
-  * prover (batch-1 decode kernels) -> verifier (tcgen05 batched prefill) agree far inside the reference's 0.95 bar;
-  * both paths are bit-deterministic run to run; the device top-10 equals a host sort of the device logits."""
+"""BASELINE.json full sizes, GPU vs the CPU oracle on the same random-init GGUF (written to /dev/shm):
+  llama-3.2-1b-q8 (tied head), llama-3.1-8b-q4km, qwen2.5-7b-q8 (V = 152 064, biases, NEOX), llama-3.1-70b-q4km (Q5_K attn_v, GQA 8).
+Per model
+  * batch-1 decode (persistent kernel) vs oracle GGML mode: a 16-token prompt fed token by token + 8 teacher-forced steps -- every
+    row within FLIP_TOL, clean rows bit-close, top-10 ids identical at every rank the reference's gaps pin (parity_stats);
+  * batched verify prefill (tcgen05 path, >= 64 tokens) vs oracle BF16 mode: gathered logits at the claimed ids and the verifier's
+    own top-10;
+  * the reference's cross-backend test in both directions (inference/test/t-LogitComparer.cpp:41-79): GPU prover -> CPU verifier
+    and CPU prover -> GPU verifier (sequential and batched): avg similarity >= 0.98, score >= 0.95; same-backend fillCtx bit-equal
+    (t-integration.cpp:219-248).
+The 70B model does the decode comparison on 4 + 3 tokens (its oracle runs at ~1 token/s) and skips the BF16 oracle pass.
+BLAMA_SKIP_70B=1 skips it; a box without 60 GB free in /dev/shm skips it too."""
 import os
+import shutil
 
 import numpy as np
 import pytest
 
 from blama_b200 import gguf_synth as gs
+from blama_b200 import parity_stats as ps
 
 pytestmark = pytest.mark.gpu
-SHAPE = "llama-3.1-8b-q4km"
+MODELS = ["llama-3.2-1b-q8", "llama-3.1-8b-q4km", "qwen2.5-7b-q8", "llama-3.1-70b-q4km"]
+N_THREADS = os.cpu_count() or 8
 
 
-@pytest.fixture(scope="module")
-def big(tmp_path_factory):
+@pytest.fixture(scope="module", params=MODELS)
+def big(request, tmp_path_factory):
     from blama_b200 import host_api
 
     host_api.lib()
+    shape = request.param
+    need = gs.model_bytes(gs.SHAPES[shape])
     d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else str(tmp_path_factory.mktemp("big"))
-    path = os.path.join(d, f"blama_b200_test_{SHAPE}.gguf")
-    if not (os.path.exists(path) and os.path.getsize(path) == gs.model_bytes(gs.SHAPES[SHAPE])):
-        gs.write_gguf(path, SHAPE)
-    m = host_api.Model(path)
-    yield host_api, m, path
-    m.close()
+    if shape.startswith("llama-3.1-70b"):
+        if os.environ.get("BLAMA_SKIP_70B") == "1":
+            pytest.skip("BLAMA_SKIP_70B=1")
+        if shutil.disk_usage(d).free < need + (16 << 30):
+            pytest.skip("not enough room for the 70B GGUF")
+    path = os.path.join(d, f"blama_b200_test_{shape}.gguf")
+    gs.write_gguf(path, shape)
+    yield shape, path
     try:
         os.remove(path)
     except OSError:
         pass
 
 
-def test_fill_ctx_bit_equal_and_batched_verify_score(big):
-    host, m, _ = big
-    prompt = gs.synth_prompt(SHAPE, 48, 5)
-    a, b, c = host.Instance(m, 512), host.Instance(m, 512), host.Instance(m, 512)
-    a.start_session(seed=7).set_initial_prompt(prompt)
-    toks, top = a.complete(96)
-    assert len(toks) == 96
-    # same backend, sequential fillCtx: identical ids and logits, score exactly 1 (reference "filling ctx" test)
-    b.start_session(seed=7, sequential_verify=True).set_initial_prompt(prompt)
-    out, out_n = b.fill_ctx(toks, top)
-    assert np.all(out_n == 10)
-    assert np.array_equal(out["token"], top["token"]) and np.array_equal(out["logit"], top["logit"])
-    assert host.lc_score([host.lc_compare(top[i], out[i]) for i in range(len(toks))]) == 1.0
-    # batched tcgen05 prefill as the verifier: bf16 tensor-core arithmetic against the prover's int8 path
-    c.start_session(seed=7).set_initial_prompt(prompt)
-    s1 = c.verify(np.ascontiguousarray(toks, dtype=np.int32), np.ascontiguousarray(top))
-    c.stop_session()
-    c.start_session(seed=7).set_initial_prompt(prompt)
-    s2 = c.verify(np.ascontiguousarray(toks, dtype=np.int32), np.ascontiguousarray(top))
-    assert s1 == s2                                   # bit-deterministic
-    assert s1 >= 0.99                                 # reference bar: score >= 0.95 (t-LogitComparer.cpp:76-78)
-    for i in (a, b, c):
-        i.close()
+def sizes(shape):
+    if shape.startswith("llama-3.1-70b"):
+        return dict(prompt=4, steps=3, resp=3, verify=0)
+    return dict(prompt=16, steps=8, resp=20, verify=64)
 
 
-def test_decode_is_deterministic_and_topk_is_a_sort(big):
+def test_decode_matches_oracle(big, oracle):
     from blama_b200 import capi
 
-    _, _, path = big
+    shape, path = big
+    sz = sizes(shape)
+    om = oracle.Model(path)
+    oc = oracle.Ctx(om, 256, oracle.MODE_GGML, N_THREADS)
     m = capi.Model(path)
-    assert abs(m.weight_bytes_per_token / 1e9 - 4.617) < 0.01     # 4.617 GB of weights per token
-    runs = []
-    for _ in range(2):
-        c = capi.Ctx(m, 256)
-        assert c.persistent_decode
-        c.decode(gs.synth_prompt(SHAPE, 40, 9))       # tcgen05 prefill
-        ids = []
-        for _ in range(12):
-            tk = c.topk(10)
-            got = c.logits()
-            assert np.array_equal(tk["logit"], np.sort(got)[::-1][:10])
-            ids.append(int(tk["token"][0]))
-            c.decode([ids[-1]])
-        runs.append((ids, c.logits().copy()))
-        c.close()
-    assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1])
-    m.close()
+    c = capi.Ctx(m, 256)
+    assert c.persistent_decode, "the BASELINE shapes must run the persistent decode kernel"
+    assert m.weight_bytes_per_token == om.weight_bytes_per_token()
+    st = ps.StepStats()
+    toks = [int(t) for t in gs.synth_prompt(shape, sz["prompt"], 3)]
+    tok = None
+    for i in range(sz["prompt"] + sz["steps"]):
+        tok = toks[i] if i < sz["prompt"] else tok
+        want = oc.decode([tok])[0]
+        top = c.decode_topk(tok, 10)
+        got = c.logits()
+        assert np.array_equal(top["logit"], np.sort(got)[::-1][:10])                  # device top-k == sort of the device row
+        err, bad = st.add(got, want, top["token"])
+        assert err <= ps.FLIP_TOL, (shape, i, err)
+        assert not bad, (shape, i, "rank(s) pinned by the reference's gaps differ", bad, err)
+        if err <= ps.CLEAN_TOL:
+            ids, vals = ps.top_sorted(want, 10)
+            assert np.abs(top["logit"] - vals).max() <= ps.CLEAN_TOL
+        claimed = ps.top_sorted(want, 10)[0]
+        assert np.array_equal(c.gather(claimed), got[claimed])                         # claimed-id gather reads the same row
+        tok = int(np.argmax(want))                                                     # teacher forcing with the reference's arg-max
+    s = st.summary()
+    print(f"\n[parity {shape}] decode vs oracle(GGML): {s}")
+    assert s["pinned_ranks"] > 0 and s["pinned_ranks_ok"] == s["pinned_ranks"]
+    assert s["clean_frac"] >= 0.25, s              # measured: 8B 24/24 ... flips taint the rest of a sequence once they happen
+    c.close(); m.close(); oc.close(); om.close()
+
+
+def test_batched_verify_matches_oracle_bf16(big, oracle):
+    from blama_b200 import capi
+
+    shape, path = big
+    sz = sizes(shape)
+    if not sz["verify"]:
+        pytest.skip("the 70B oracle in BF16 mode needs minutes for a 64-token fill")
+    T = sz["verify"]
+    om = oracle.Model(path)
+    oc = oracle.Ctx(om, 256, oracle.MODE_BF16, N_THREADS)
+    m = capi.Model(path)
+    c = capi.Ctx(m, 256)
+    prompt = gs.synth_prompt(shape, 4, 5)
+    resp = gs.synth_prompt(shape, T, 6)
+    oc.decode(prompt)
+    want = oc.decode(resp, all_logits=True)                                            # [T][V]
+    claimed = np.stack([ps.top_sorted(want[i], 10)[0] for i in range(T)])
+    c.decode([int(t) for t in prompt])                                                 # 4 tokens: batch-1 path
+    g, top = c.verify_prefill(resp, claimed)                                           # T tokens: tcgen05 prefill path
+    ref = np.stack([want[i][claimed[i]] for i in range(T)])
+    err = np.abs(g - ref)
+    print(f"\n[parity {shape}] batched verify vs oracle(BF16): gathered max |d| {err.max():.4f}, mean {err.mean():.5f}")
+    assert err.max() <= 0.08, err.max()                                               # bf16 operand rounding, f32 accumulation
+    st = ps.StepStats()
+    for i in range(T):
+        row = want[i]
+        # the verifier's own top-10 against the reference row: deviation measured on the claimed ids of that row
+        d = max(float(err[i].max()), float(np.abs(top[i]["logit"] - row[top[i]["token"]]).max()))
+        ids11, val11 = ps.top_sorted(row, 11)
+        for r in range(10):
+            above = val11[r - 1] - val11[r] if r else np.inf
+            if above > 2 * d + 1e-3 and val11[r] - val11[r + 1] > 2 * d + 1e-3:
+                assert int(top[i]["token"][r]) == int(ids11[r]), (shape, i, r)
+        assert np.abs(top[i]["logit"] - val11[:10]).max() <= 0.08
+    c.close(); m.close(); oc.close(); om.close()
+
+
+def test_cross_backend_verdicts(big, oracle):
+    """t-LogitComparer.cpp:41-79 in both directions + t-integration.cpp:219-248 (same backend: bit-equal, score exactly 1)"""
+    from blama_b200 import host_api as H
+
+    shape, path = big
+    sz = sizes(shape)
+    n, prompt = sz["resp"], gs.synth_prompt(shape, sz["prompt"], 7)
+    hm = H.Model(path)
+    om = oracle.Model(path)
+    oc = oracle.Ctx(om, 256, oracle.MODE_GGML, N_THREADS)
+    prover, ver_seq, ver_bat = H.Instance(hm, 256), H.Instance(hm, 256), H.Instance(hm, 256)
+    # GPU prover
+    prover.start_session(seed=11).set_initial_prompt(prompt)
+    toks, top = prover.complete(n)
+    assert len(toks) == n
+    # ... same backend, sequential fill: bit-equal
+    ver_seq.start_session(seed=11, sequential_verify=True).set_initial_prompt(prompt)
+    out, out_n = ver_seq.fill_ctx(toks, top)
+    assert np.array_equal(out["token"], top["token"]) and np.array_equal(out["logit"], top["logit"])
+    assert H.lc_score([H.lc_compare(top[i], out[i]) for i in range(n)]) == 1.0
+    # ... CPU verifier (the reference's direction)
+    o_out, o_n = oc.fill_ctx(prompt, toks, top["token"])
+    sims = [H.lc_similarity(top[i], o_out[i][: o_n[i]]) for i in range(n)]
+    score_gc = H.lc_score([H.lc_compare(top[i], o_out[i][: o_n[i]]) for i in range(n)])
+    # CPU prover -> GPU verifiers
+    oc.clear()
+    c_toks, c_top = oc.complete(prompt, n, seed=11)
+    ver_seq.stop_session()
+    ver_seq.start_session(seed=11, sequential_verify=True).set_initial_prompt(prompt)
+    s_out, s_n = ver_seq.fill_ctx(c_toks, c_top)
+    score_cg = H.lc_score([H.lc_compare(c_top[i], s_out[i][: s_n[i]]) for i in range(len(c_toks))])
+    sims2 = [H.lc_similarity(c_top[i], s_out[i][: s_n[i]]) for i in range(len(c_toks))]
+    print(f"\n[parity {shape}] GPU prover -> CPU verifier: score {score_gc:.6f}, avg similarity {np.mean(sims):.6f}; "
+          f"CPU prover -> GPU verifier: score {score_cg:.6f}, avg similarity {np.mean(sims2):.6f}")
+    assert np.mean(sims) >= 0.98 and score_gc >= 0.95                                  # the reference's own bars
+    assert np.mean(sims2) >= 0.98 and score_cg >= 0.95
+    assert (score_gc >= 0.95) == (score_cg >= 0.95)                                    # same verdict at the reference's threshold
+    if n >= 16:
+        # batched tcgen05 verifier on a longer response of the GPU prover (>= prefill_min tokens take the prefill path)
+        prover.stop_session()
+        prover.start_session(seed=12).set_initial_prompt(prompt)
+        t2, top2 = prover.complete(48)
+        ver_bat.start_session(seed=12).set_initial_prompt(prompt)
+        s1 = ver_bat.verify(t2, top2)
+        ver_bat.stop_session()
+        ver_bat.start_session(seed=12).set_initial_prompt(prompt)
+        assert ver_bat.verify(t2, top2) == s1                                          # bit-deterministic
+        assert s1 >= 0.99
+    for i in (prover, ver_seq, ver_bat):
+        i.close()
+    hm.close(); oc.close(); om.close()

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from blama_b200 import gguf_synth as gs
+from blama_b200 import parity_stats as ps
 
 pytestmark = pytest.mark.gpu
 
@@ -14,7 +15,7 @@ MODELS = ["tiny-llama-q4km", "tiny-llama-q8", "tiny-qwen2-q8", "tiny-llama-f32",
 # different lane count shows the same, tests/test_oracle.py::test_summation_order_noise_floor).  So steps are either
 # CLEAN (fp32 noise only) or FLIPPED (bounded by the quantisation noise of the reference's own arithmetic).
 CLEAN_TOL = 1e-4          # absolute, logits have std ~2
-FLIP_TOL = 0.45           # ~ the Q8_K activation-quantisation noise of the reference arithmetic itself (see test_oracle)
+FLIP_TOL = ps.FLIP_TOL    # 0.25: the worst flip measured is 0.175 (oracle against itself with the lane sums reversed), <= 0.2 GPU vs oracle
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -27,18 +28,24 @@ def test_decode_logits_match_oracle(name, gguf_path, oracle):
     m = capi.Model(path)
     c = capi.Ctx(m, 256)
     assert m.n_vocab == om.n_vocab and m.weight_bytes_per_token == om.weight_bytes_per_token()
-    clean = total = 0
+    # the noise floor of THIS shape: the oracle against itself with the eight fp32 lane sums added in the opposite order
+    ob = oracle.Ctx(om, 256, oracle.MODE_GGML_ALT, 4)
+    clean = floor_clean = total = 0
+    st = ps.StepStats()
     for seq in range(6):                      # independent short sequences: a flip only taints its own sequence
         toks = gs.synth_prompt(name, 6, 100 + seq)
-        oc.clear(); c.clear()
+        oc.clear(); c.clear(); ob.clear()
         for i, t in enumerate(toks):
             want = oc.decode([t])[0]
+            floor_clean += float(np.abs(ob.decode([t])[0] - want).max()) <= CLEAN_TOL
             c.decode([int(t)])
             got = c.logits()
-            err = float(np.abs(got - want).max())
             total += 1
-            assert err <= FLIP_TOL, (seq, i, err)
             top_want, top_got = oracle.topk(want, 10), c.topk(10)
+            err, bad = st.add(got, want, top_got["token"])
+            assert err <= FLIP_TOL, (seq, i, err)
+            # top-10 ids identical at every rank the reference's gaps pin (more than 2 x the row's deviation to both neighbours)
+            assert not bad, (seq, i, bad, err)
             assert np.array_equal(c.topk(10)["logit"], np.sort(got)[::-1][:10])          # device top-k == sort of device logits
             ids = np.array([0, m.n_vocab - 1, int(top_want["token"][3]), 7], dtype=np.int32)
             assert np.array_equal(c.gather(ids), got[ids])
@@ -46,11 +53,11 @@ def test_decode_logits_match_oracle(name, gguf_path, oracle):
                 clean += 1
                 assert np.array_equal(top_got["token"], top_want["token"]), (seq, i, top_got, top_want)
                 assert np.abs(top_got["logit"] - top_want["logit"]).max() <= CLEAN_TOL
-            else:
-                assert top_got["token"][0] == top_want["token"][0] or (top_want["logit"][0] - top_want["logit"][1]) < 2 * err
-                assert len(set(top_got["token"]) & set(top_want["token"])) >= 7
-    assert clean >= 0.4 * total, (clean, total)
-    c.close(); m.close(); oc.close(); om.close()
+    s = st.summary()
+    print(f"\n[parity {name}] clean {clean}/{total} (oracle-vs-oracle floor {floor_clean}/{total}); {s}")
+    assert s["pinned_ranks"] > 0 and s["pinned_ranks_ok"] == s["pinned_ranks"]
+    assert clean >= floor_clean - 0.1 * total, (clean, floor_clean, total)      # no worse than the reference arithmetic against itself
+    c.close(); m.close(); oc.close(); ob.close(); om.close()
 
 
 @pytest.mark.parametrize("name", ["tiny-llama-q4km", "small-qwen2-q8"])

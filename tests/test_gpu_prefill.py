@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from blama_b200 import gguf_synth as gs
+from blama_b200 import parity_stats as ps
 
 pytestmark = pytest.mark.gpu
 
@@ -72,7 +73,13 @@ def test_batched_verify_against_oracle_and_prover(name, gguf_path, oracle):
     want = oc.decode(toks, all_logits=True)
     for i in range(90):
         assert np.abs(g[i] - want[i][claimed[i]]).max() <= 0.15, i      # prompt KV came from the int8 decode path on the GPU side
-        assert len(set(top[i]["token"]) & set(oracle.topk(want[i], 10)["token"])) >= 7
+        # the verifier's own top-10: identical ids at every rank the reference's gaps pin (2 x the row's measured deviation)
+        d = max(float(np.abs(g[i] - want[i][claimed[i]]).max()), float(np.abs(top[i]["logit"] - want[i][top[i]["token"]]).max()))
+        ids11, val11 = ps.top_sorted(want[i], 11)
+        for r in range(10):
+            above = val11[r - 1] - val11[r] if r else np.inf
+            if above > 2 * d + 1e-3 and val11[r] - val11[r + 1] > 2 * d + 1e-3:
+                assert int(top[i]["token"][r]) == int(ids11[r]), (i, r, d)
     # (b) prover (decode path) vs verifier (prefill path): the reference's own acceptance metric
     metrics, sims = [], []
     for i in range(90):
