@@ -157,6 +157,14 @@ def cpu_decode_sample(path: str, shape: str, budget_s: float, steps: int = 1, wa
         dt = time.time() - t0
         if s >= warmup:
             times.append(dt)
+    if keep:
+        # the noise floor of the reference arithmetic on the same tokens: the port against itself with the fp32 partial sums added
+        # in the opposite order (blama_b200/parity_stats.py)
+        alt = po.Ctx(m, 512, po.MODE_GGML_ALT, cores)
+        trace["floor_rows"] = [alt.decode(prompt)[0].copy()]
+        for tok, _ in trace["rows"][1:]:
+            trace["floor_rows"].append(alt.decode([tok])[0].copy())
+        alt.close()
     if cross:
         c.clear()
         trace["cpu_prover"] = c.complete(prompt, cross, seed=5)
@@ -183,9 +191,11 @@ def gpu_parity(hm, n_ctx: int, trace: dict) -> dict:
     for t in prompt[:-1]:
         ctx.decode([t])
     feed = prompt[-1]
-    for tok, want in trace["rows"]:
+    for k, (tok, want) in enumerate(trace["rows"]):
         top = ctx.decode_topk(feed if tok is None else tok, 10)
         st.add(ctx.logits(), want, top["token"])
+        if "floor_rows" in trace:
+            st.add_floor(trace["floor_rows"][k], want)
     out = st.summary()
     out["mode"] = "batch-1 decode kernel vs CPU port (ggml-cpu arithmetic), teacher-forced with the port's arg-max"
     if "cpu_prover" in trace:

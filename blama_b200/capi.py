@@ -52,8 +52,13 @@ SYMBOLS = {
     "blk_ctx_n_ctx": (_i32, [_vp]),
     "blk_ctx_n_batch": (_i32, [_vp]),
     "blk_ctx_n_past": (_i32, [_vp]),
+    "blk_ctx_model": (_vp, [_vp]),
     "blk_kv_clear": (_i32, [_vp]),
     "blk_sync": (_i32, [_vp]),
+    "blk_kv_shift": (_i32, [_vp, _i32, _i32]),
+    "blk_state_size": (_i64, [_vp]),
+    "blk_state_get": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "blk_state_set": (_i32, [_vp, _vp, _i64]),
     "blk_decode": (_i32, [_vp, _vp, _i32]),
     "blk_topk_last": (_i32, [_vp, _i32, _vp]),
     "blk_gather_last": (_i32, [_vp, _vp, _i32, _vp]),
@@ -171,6 +176,21 @@ class Ctx:
 
     def sync(self):
         _check(lib().blk_sync(self.h))
+
+    def kv_shift(self, p0: int, p1: int):
+        """drop the cells of positions [p0, p1), move the rest down (K re-rotated): reference Session.cpp:341-342"""
+        _check(lib().blk_kv_shift(self.h, p0, p1))
+
+    def state_get(self) -> np.ndarray:
+        n = int(lib().blk_state_size(self.h))
+        buf = np.zeros(n, dtype=np.uint8)
+        w = _i64(0)
+        _check(lib().blk_state_get(self.h, _p(buf), n, C.byref(w)))
+        return buf[: w.value]
+
+    def state_set(self, blob: np.ndarray):
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        _check(lib().blk_state_set(self.h, _p(b), len(b)))
 
     def decode(self, tokens: Sequence[int]):
         t = np.ascontiguousarray(tokens, dtype=np.int32)

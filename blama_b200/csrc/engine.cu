@@ -1110,7 +1110,11 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             std::vector<int32_t> pt(c->n_pages);
             for (int i = 0; i < c->n_pages; i++) pt[i] = i;
             BLK_CUDA(cudaMemcpy(c->page_table, pt.data(), pt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            c->page_table_host = pt;
         }
+        c->d_kpools = dalloc<__half*>(c.get(), m->n_layer); c->d_vpools = dalloc<__half*>(c.get(), m->n_layer);
+        BLK_CUDA(cudaMemcpy(c->d_kpools, c->k_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
+        BLK_CUDA(cudaMemcpy(c->d_vpools, c->v_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
         c->d_tok = dalloc<int32_t>(c.get(), 1); c->d_pos = dalloc<int32_t>(c.get(), 1);
         BLK_CUDA(cudaMemset(c->d_pos, 0, sizeof(int32_t)));
         c->h_tok = halloc<int32_t>(c.get(), blk_ctx::TOK_RING);
@@ -1167,10 +1171,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             auto ll = [&](size_t n) { uint2* p = dalloc<uint2>(c.get(), n); BLK_CUDA(cudaMemset(p, 0, n * sizeof(uint2))); return p; };
             P.x2 = ll(d); P.q2 = ll(dq); P.h2 = ll(ff); P.ao2 = ll(dq);
             P.sc2 = ll((size_t)m->n_head * P.score_stride); P.po2 = ll((size_t)P.max_split * dq); P.kvn2 = ll(2 * (size_t)dkv);
-            __half** kp = dalloc<__half*>(c.get(), m->n_layer); __half** vp = dalloc<__half*>(c.get(), m->n_layer);
-            BLK_CUDA(cudaMemcpy(kp, c->k_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
-            BLK_CUDA(cudaMemcpy(vp, c->v_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
-            P.k_pools = kp; P.v_pools = vp; P.page_table = c->page_table; P.kv_dim = dkv;
+            P.k_pools = c->d_kpools; P.v_pools = c->d_vpools; P.page_table = c->page_table; P.kv_dim = dkv;
             P.logits = c->logits; P.chunk_max = c->chunk_max; P.chunk_shift = c->chunk_shift;
             {   // a poll that times out reports here instead of hanging the GPU (mapped pinned host word)
                 void* hp = nullptr;
@@ -1208,6 +1209,7 @@ extern "C" void blk_ctx_free(blk_ctx* c) { delete c; }
 extern "C" int32_t blk_ctx_n_ctx(const blk_ctx* c) { return c->n_ctx; }
 extern "C" int32_t blk_ctx_n_batch(const blk_ctx* c) { return c->n_batch; }
 extern "C" int32_t blk_ctx_n_past(const blk_ctx* c) { return c->n_past; }
+extern "C" const blk_model* blk_ctx_model(const blk_ctx* c) { return c->m; }
 extern "C" int64_t blk_ctx_kernel_launches(const blk_ctx* c) { return c->launches; }
 extern "C" int32_t blk_ctx_persistent_decode(const blk_ctx* c) { return c->mega_on ? 1 : 0; }
 
@@ -1225,6 +1227,130 @@ extern "C" blk_status blk_kv_clear(blk_ctx* c) {
 }
 extern "C" blk_status blk_sync(blk_ctx* c) {
     return guarded([&] { BLK_CUDA(cudaSetDevice(c->m->device)); BLK_CUDA(cudaStreamSynchronize(c->stream)); check_mega(c); });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// context shift + state (reference Session.cpp:324-347 llama_kv_self_seq_rm / seq_add; :284-310 llama_state_get/set_data)
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+// Cache rows [src0, src0 + n) of every layer move to [dst0, dst0 + n) (the two ranges do not overlap within one launch).  K rows are
+// re-rotated by `delta` positions the way llama.cpp's K-shift does it (ggml rope on the F16 cache: f16 -> f32, rotate by
+// theta_i = delta * theta_scale^i / freq_factor_i, f32 -> f16); V rows are copied.  grid = (n, n_layer), block = 128.
+__global__ void __launch_bounds__(128) kv_shift_kernel(__half* const* __restrict__ k_pools, __half* const* __restrict__ v_pools,
+                                                       const int32_t* __restrict__ page_table, int kv_dim, int d_head, int neox, int src0, int dst0,
+                                                       int delta, float theta_scale, const float* __restrict__ freq_factors) {
+    __shared__ float2 cs[64];
+    const int half_rot = d_head / 2;
+    rope_table_fill(cs, half_rot, delta, theta_scale, freq_factors);
+    __syncthreads();
+    const int ts = src0 + (int)blockIdx.x, td = dst0 + (int)blockIdx.x;
+    const size_t rs = ((size_t)page_table[ts / KV_PAGE] * KV_PAGE + (ts % KV_PAGE)) * kv_dim;
+    const size_t rd = ((size_t)page_table[td / KV_PAGE] * KV_PAGE + (td % KV_PAGE)) * kv_dim;
+    const __half* ks = k_pools[blockIdx.y] + rs; __half* kd = k_pools[blockIdx.y] + rd;
+    const __half* vs = v_pools[blockIdx.y] + rs; __half* vd = v_pools[blockIdx.y] + rd;
+    for (int p = threadIdx.x; p < kv_dim / 2; p += blockDim.x) {
+        const int h = p / half_rot, i = p - h * half_rot;
+        const int e0 = neox ? h * d_head + i : h * d_head + 2 * i;
+        const int e1 = neox ? e0 + half_rot : e0 + 1;
+        const float x0 = __half2float(ks[e0]), x1 = __half2float(ks[e1]);
+        const float2 c = cs[i];
+        kd[e0] = __float2half_rn(__fsub_rn(__fmul_rn(x0, c.x), __fmul_rn(x1, c.y)));
+        kd[e1] = __float2half_rn(__fadd_rn(__fmul_rn(x0, c.y), __fmul_rn(x1, c.x)));
+    }
+    for (int e = threadIdx.x; e < kv_dim / 8; e += blockDim.x) reinterpret_cast<uint4*>(vd)[e] = reinterpret_cast<const uint4*>(vs)[e];
+}
+
+constexpr uint32_t STATE_MAGIC = 0x534B4C42u;      // "BLKS"
+struct StateHeader { uint32_t magic, version; int32_t n_layer, kv_dim, n_vocab, n_past, have_logits, reserved; };
+size_t state_bytes(const blk_ctx* c, int n_past) {
+    const blk_model* m = c->m;
+    const size_t kv_dim = (size_t)m->n_head_kv * m->d_head;
+    return sizeof(StateHeader) + (size_t)m->n_vocab * 4 + TOPK_MAX * 8 + 2 * (size_t)m->n_layer * (size_t)n_past * kv_dim * 2;
+}
+} // namespace
+
+extern "C" blk_status blk_kv_shift(blk_ctx* c, int32_t p0, int32_t p1) {
+    if (!c || p0 < 0 || p1 <= p0 || p1 > c->n_past) return fail(BLK_ERR_ARG, "blk_kv_shift: bad range");
+    return guarded([&] {
+        blk_model* m = c->m;
+        BLK_CUDA(cudaSetDevice(m->device));
+        const int d = p1 - p0, dkv = m->n_head_kv * m->d_head;
+        // front to back in chunks of at most d rows: a chunk's destination never overlaps its source, and what it overwrites has been
+        // moved already
+        for (int t = p1; t < c->n_past; t += d) {
+            const int n = std::min(d, c->n_past - t);
+            kv_shift_kernel<<<dim3((unsigned)n, (unsigned)m->n_layer), 128, 0, c->stream>>>(c->d_kpools, c->d_vpools, c->page_table, dkv, m->d_head, m->neox ? 1 : 0,
+                                                                                                t, t - d, -d, m->theta_scale, m->rope_freqs);
+            BLK_CUDA(cudaGetLastError());
+            c->launches++;
+        }
+        c->n_past -= d;
+        int32_t np = c->n_past;
+        BLK_CUDA(cudaMemcpyAsync(c->d_pos, &np, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        BLK_CUDA(cudaStreamSynchronize(c->stream));      // np is a stack variable
+    });
+}
+
+extern "C" int64_t blk_state_size(const blk_ctx* c) { return c ? (int64_t)state_bytes(c, c->n_past) : 0; }
+
+extern "C" blk_status blk_state_get(blk_ctx* c, void* dst, int64_t cap, int64_t* written) {
+    if (!c || !dst || !written) return fail(BLK_ERR_ARG, "blk_state_get: bad arguments");
+    return guarded([&] {
+        blk_model* m = c->m;
+        BLK_CUDA(cudaSetDevice(m->device));
+        const size_t need = state_bytes(c, c->n_past);
+        if ((size_t)cap < need) throw BlkError(BLK_ERR_ARG, "blk_state_get: buffer too small");
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        check_mega(c);
+        uint8_t* out = static_cast<uint8_t*>(dst);
+        const int kv_dim = m->n_head_kv * m->d_head;
+        StateHeader h{STATE_MAGIC, 1u, m->n_layer, kv_dim, m->n_vocab, c->n_past, c->have_logits ? 1 : 0, 0};
+        memcpy(out, &h, sizeof(h)); out += sizeof(h);
+        BLK_CUDA(cudaMemcpy(out, c->logits, (size_t)m->n_vocab * 4, cudaMemcpyDeviceToHost)); out += (size_t)m->n_vocab * 4;
+        memcpy(out, c->h_top_ids, TOPK_MAX * 4); out += TOPK_MAX * 4;
+        memcpy(out, c->h_top_logits, TOPK_MAX * 4); out += TOPK_MAX * 4;
+        const size_t row = (size_t)kv_dim * 2;
+        for (int l = 0; l < m->n_layer; l++)
+            for (const __half* pool : {c->k_pool[l], c->v_pool[l]})
+                for (int t0 = 0; t0 < c->n_past; t0 += KV_PAGE) {
+                    const int n = std::min(KV_PAGE, c->n_past - t0);
+                    BLK_CUDA(cudaMemcpy(out, pool + (size_t)c->page_table_host[t0 / KV_PAGE] * KV_PAGE * kv_dim, n * row, cudaMemcpyDeviceToHost));
+                    out += n * row;
+                }
+        *written = (int64_t)need;
+    });
+}
+
+extern "C" blk_status blk_state_set(blk_ctx* c, const void* src, int64_t size) {
+    if (!c || !src || size < (int64_t)sizeof(StateHeader)) return fail(BLK_ERR_ARG, "blk_state_set: bad arguments");
+    return guarded([&] {
+        blk_model* m = c->m;
+        BLK_CUDA(cudaSetDevice(m->device));
+        const uint8_t* in = static_cast<const uint8_t*>(src);
+        StateHeader h;
+        memcpy(&h, in, sizeof(h)); in += sizeof(h);
+        const int kv_dim = m->n_head_kv * m->d_head;
+        if (h.magic != STATE_MAGIC || h.version != 1u) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: not a state blob of this engine");
+        if (h.n_layer != m->n_layer || h.kv_dim != kv_dim || h.n_vocab != m->n_vocab) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: the state belongs to another model");
+        if (h.n_past < 0 || h.n_past > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "blk_state_set: the state does not fit this context");
+        if ((size_t)size != state_bytes(c, h.n_past)) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: truncated state");
+        BLK_CUDA(cudaStreamSynchronize(c->stream));
+        BLK_CUDA(cudaMemcpy(c->logits, in, (size_t)m->n_vocab * 4, cudaMemcpyHostToDevice)); in += (size_t)m->n_vocab * 4;
+        memcpy(c->h_top_ids, in, TOPK_MAX * 4); in += TOPK_MAX * 4;
+        memcpy(c->h_top_logits, in, TOPK_MAX * 4); in += TOPK_MAX * 4;
+        BLK_CUDA(cudaMemcpy(c->top_ids, c->h_top_ids, TOPK_MAX * 4, cudaMemcpyHostToDevice));
+        BLK_CUDA(cudaMemcpy(c->top_logits, c->h_top_logits, TOPK_MAX * 4, cudaMemcpyHostToDevice));
+        const size_t row = (size_t)kv_dim * 2;
+        for (int l = 0; l < m->n_layer; l++)
+            for (__half* pool : {c->k_pool[l], c->v_pool[l]})
+                for (int t0 = 0; t0 < h.n_past; t0 += KV_PAGE) {
+                    const int n = std::min(KV_PAGE, h.n_past - t0);
+                    BLK_CUDA(cudaMemcpy(pool + (size_t)c->page_table_host[t0 / KV_PAGE] * KV_PAGE * kv_dim, in, n * row, cudaMemcpyHostToDevice));
+                    in += n * row;
+                }
+        c->n_past = h.n_past; c->have_logits = h.have_logits != 0;
+        BLK_CUDA(cudaMemcpy(c->d_pos, &h.n_past, sizeof(int32_t), cudaMemcpyHostToDevice));
+    });
 }
 
 extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {

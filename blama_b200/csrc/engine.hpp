@@ -94,7 +94,9 @@ struct blk_ctx {
     std::vector<void*> host_allocs;
     // KV pages
     std::vector<__half*> k_pool, v_pool;
+    __half** d_kpools = nullptr; __half** d_vpools = nullptr;      // device arrays of the per-layer pool pointers
     int32_t* page_table = nullptr;
+    std::vector<int32_t> page_table_host;                          // host copy of the page table (state save / restore)
     // decode-step state
     int32_t* d_tok = nullptr; int32_t* d_pos = nullptr;
     static constexpr int TOK_RING = 256;

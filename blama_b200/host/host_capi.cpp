@@ -209,8 +209,25 @@ BLK_API int blh_session_verify(void* i, const int32_t* toks, int n, const blk_to
         *score = ms.empty() ? 0.0f : agg.pushAndVerify(ms);
     });
 }
-BLK_API int blh_session_get_state(void* i) { return guard([&] { (void)static_cast<InstanceBox*>(i)->session->getState(); }); }
-BLK_API int blh_session_set_state(void* i) { return guard([&] { (void)static_cast<InstanceBox*>(i)->session->setState({}); }); }
+// Session::getState into buf (cap bytes); *size = bytes of the state (call with cap 0 to learn it -- the state is then dropped)
+BLK_API int blh_session_get_state(void* i, uint8_t* buf, int64_t cap, int64_t* size) {
+    return guard([&] {
+        auto st = static_cast<InstanceBox*>(i)->session->getState();
+        *size = int64_t(st.size());
+        if (buf && cap >= int64_t(st.size())) memcpy(buf, st.data(), st.size());
+    });
+}
+BLK_API int blh_session_set_state(void* i, uint8_t* buf, int64_t size) {
+    return guard([&] { (void)static_cast<InstanceBox*>(i)->session->setState({buf, size_t(size < 0 ? 0 : size)}); });
+}
+BLK_API int blh_session_start_ex(void* i, uint32_t seed, float temp, float top_p, int sequential_verify, int infinite_context) {
+    return guard([&] {
+        auto* box = static_cast<InstanceBox*>(i);
+        Session::InitParams sp; sp.seed = seed; sp.temperature = temp; sp.topP = top_p; sp.sequentialVerify = sequential_verify != 0;
+        sp.infiniteContext = infinite_context != 0;
+        box->session = &box->inst->startSession(sp);
+    });
+}
 
 // ---- verdict -------------------------------------------------------------------------------------------------------
 BLK_API void blh_lc_compare(const blk_token_data* a, int32_t na, const blk_token_data* b, int32_t nb, float* out3) {

@@ -140,7 +140,9 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
     // the device gathers at most 10 ids per position in the batched form; the reference accepts any number of claimed logits
     bool wide = false;
     for (const auto& token : tokens) wide = wide || token.logits.size() > 10;
-    if (m_instance.model().prefixInputsWithBos() || wide) {
+    // a fill that does not fit the context shifts it token by token exactly like the reference's loop
+    const bool overflows = m_numPast + tokens.size() >= uint32_t(blk_ctx_n_ctx(m_ctx));
+    if (m_instance.model().prefixInputsWithBos() || wide || overflows) {
         // every pushPrompt would insert a BOS before its token (reference :129-132) / more than 10 claimed ids somewhere:
         // keep the reference's literal per-token loop
         for (const auto& token : tokens) {
@@ -155,7 +157,6 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
     m_sampler->reset();
 
     const size_t n = tokens.size();
-    if (m_numPast + n >= uint32_t(blk_ctx_n_ctx(m_ctx))) Raise{} << "context limit of " << blk_ctx_n_ctx(m_ctx) << " reached";
     std::vector<Token> ids(n);
     std::vector<int32_t> claimed(n * 10, 0), nClaimed(n, 0);
     for (size_t i = 0; i < n; ++i) {
@@ -232,14 +233,22 @@ TokenDataVector Session::getLogitsFromCtx(TokenDataVector tokens) {
 std::vector<uint8_t> Session::getState() {
     requireStarted(false);
     flushPendingState();
-    Raise{} << "Failed to get state";       // state save / restore is outside this build's scope
-    return {};
+    const auto size = blk_state_size(m_ctx);
+    std::vector<uint8_t> state(static_cast<size_t>(size));
+    int64_t written = 0;
+    if (blk_state_get(m_ctx, state.data(), size, &written) != BLK_OK || written != size) Raise{} << "Failed to get state";
+    return state;
 }
 
-bool Session::setState(std::span<uint8_t>) {
+bool Session::setState(std::span<uint8_t> state) {
     if (m_phase != Phase::Initial) Raise{} << "Session already started";
-    Raise{} << "Failed to set state";
-    return false;
+    if (blk_state_set(m_ctx, state.data(), int64_t(state.size())) != BLK_OK) Raise{} << "Failed to set state";
+    // llama.cpp keeps the positions inside its context; here the session's counters follow the restored cache
+    m_numPast = uint32_t(blk_ctx_n_past(m_ctx));
+    m_numKeep = std::min(m_numPast, m_maxTokens);
+    refreshCandidates();
+    m_phase = Phase::Generating;
+    return true;
 }
 
 void Session::doDecode(std::span<const Token> tokens, Source src) {
@@ -250,8 +259,17 @@ void Session::doDecode(std::span<const Token> tokens, Source src) {
     }
     const auto ctxLen = uint32_t(blk_ctx_n_ctx(m_ctx));
     if (m_numPast + tokens.size() >= ctxLen) {
-        // the reference would shift the context here (:324-347); K-shift on the paged cache is not built yet
-        Raise{} << "context limit of " << ctxLen << " reached";
+        // infinite text generation via context shifting (reference :324-347): keep the first numKeep tokens (the initial prompt),
+        // drop half of the rest, move what remains down -- blk_kv_shift re-rotates the K rows like llama.cpp's K-shift
+        if (!m_params.infiniteContext) Raise{} << "context limit of " << ctxLen << " reached";
+        const auto numLeft = m_numPast - m_numKeep;
+        const int numDiscard = int(numLeft / 2);
+        if (numDiscard <= 0) Raise{} << "context limit of " << ctxLen << " reached";
+        logLine(LogLevel::Debug, "Context is full. Swapping: past = " + std::to_string(m_numPast) + ", numLeft: " + std::to_string(numLeft) +
+                                     ", ctxLen: " + std::to_string(ctxLen) + ", numKeep: " + std::to_string(m_numKeep) + ", numDiscard: " + std::to_string(numDiscard));
+        throwIfFailed(blk_kv_shift(m_ctx, int32_t(m_numKeep), int32_t(m_numKeep) + numDiscard), "context shift");
+        m_numPast -= uint32_t(numDiscard);
+        logLine(LogLevel::Info, "Context full mitigation performed: past = " + std::to_string(m_numPast) + ", tokens = " + std::to_string(tokens.size()));
     }
     for (auto t : tokens) m_sampler->accept(t, src == Source::Generated);
 

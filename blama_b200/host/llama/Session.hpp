@@ -29,7 +29,7 @@ public:
     struct InitParams {
         uint32_t gaFactor = 1;          // group-attention (Self-Extend) factor; only 1 is supported by this build
         uint32_t gaWidth = 512;
-        bool infiniteContext = true;    // context shifting is not supported by this build: a full context throws
+        bool infiniteContext = true;    // a full context drops half of the non-prompt past and shifts the rest (false: throws)
         uint32_t seed = 0;
         std::string grammar;
         float temperature = 0.80f;
@@ -48,8 +48,9 @@ public:
     // prefill path, the last position's logits come from the decode mat-vec.  Throws "Session already started" /
     // "Initial prompt too long. Got N tokens, max: M" with the reference's texts.
     void setInitialPrompt(std::span<const Token> prompt);
-    // Context save / restore (Session.cpp:284-310) is outside the scope of this build: both throw after the reference's own
-    // state checks ("Session already started" / "Session hasn't started yet").
+    // Context save / restore (Session.cpp:284-310): the KV rows, the pending logits and their top-k as one blob; the sampler's
+    // RNG is not part of it (as in the reference).  Same state checks and texts ("Session already started" / "Session hasn't
+    // started yet" / "Failed to set state").
     bool setState(std::span<uint8_t> state);
 
     struct CompleteParams {

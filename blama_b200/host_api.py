@@ -34,8 +34,9 @@ HOST_SYMBOLS = {
     "blh_session_stream": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "blh_session_fill_ctx": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "blh_session_verify": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.POINTER(_f32)]),
-    "blh_session_get_state": (C.c_int, [_vp]),
-    "blh_session_set_state": (C.c_int, [_vp]),
+    "blh_session_get_state": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
+    "blh_session_set_state": (C.c_int, [_vp, _vp, C.c_int64]),
+    "blh_session_start_ex": (C.c_int, [_vp, _u32, _f32, _f32, C.c_int, C.c_int]),
     "blh_lc_compare": (None, [_vp, _i32, _vp, _i32, _vp]),
     "blh_lc_similarity": (_f32, [_vp, _i32, _vp, _i32]),
     "blh_lc_score": (_f32, [_vp, _i32]),
@@ -159,14 +160,17 @@ class Instance:
 
     def raw_ctx(self) -> "capi.Ctx":
         """non-owning capi.Ctx view of this instance's C-ABI context (timers, launch counters)"""
+        import types
+
         c = capi.Ctx.__new__(capi.Ctx)
-        c.m = None
         c.h = lib().blh_instance_ctx(self.h)
+        c.m = types.SimpleNamespace(n_vocab=int(capi.lib().blk_model_n_vocab(capi.lib().blk_ctx_model(c.h))))
         c.close = lambda: None
         return c
 
-    def start_session(self, seed: int = 0, temperature: float = 0.8, top_p: float = 0.95, sequential_verify: bool = False):
-        _check(lib().blh_session_start(self.h, seed, temperature, top_p, int(sequential_verify)))
+    def start_session(self, seed: int = 0, temperature: float = 0.8, top_p: float = 0.95, sequential_verify: bool = False,
+                      infinite_context: bool = True):
+        _check(lib().blh_session_start_ex(self.h, seed, temperature, top_p, int(sequential_verify), int(infinite_context)))
         return self
 
     def stop_session(self):
@@ -213,11 +217,16 @@ class Instance:
         _check(lib().blh_session_verify(self.h, _p(t), n, _p(cl), _p(nc), C.byref(score)))
         return float(score.value)
 
-    def get_state(self):
-        _check(lib().blh_session_get_state(self.h))
+    def get_state(self) -> np.ndarray:
+        cap = int(capi.lib().blk_state_size(lib().blh_instance_ctx(self.h))) + (1 << 16)
+        buf = np.zeros(cap, dtype=np.uint8)
+        n = C.c_int64(0)
+        _check(lib().blh_session_get_state(self.h, _p(buf), cap, C.byref(n)))
+        return buf[: n.value].copy()
 
-    def set_state(self):
-        _check(lib().blh_session_set_state(self.h))
+    def set_state(self, blob=None):
+        b = np.zeros(0, dtype=np.uint8) if blob is None else np.ascontiguousarray(blob, dtype=np.uint8)
+        _check(lib().blh_session_set_state(self.h, _p(b) if len(b) else None, len(b)))
 
     def close(self):
         if self.h:

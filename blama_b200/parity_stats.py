@@ -12,7 +12,14 @@ from typing import Dict, List
 import numpy as np
 
 CLEAN_TOL = 2e-4      # absolute; logits have std ~2
-FLIP_TOL = 0.25       # measured worst flip: 0.175 (oracle against itself with the lane sums reversed), <= 0.2 GPU vs oracle
+FLIP_TOL = 0.25       # small test models (V <= 5000): measured worst flip 0.175 (oracle against itself with the fp32 partial sums added
+                      # in the opposite order), <= 0.2 GPU vs oracle.
+# At the BASELINE sizes nothing stays clean: with d = 4096, 32 layers and 128 256 logits per row some Q8_K / f16 rounding flips in
+# every token, and the oracle against ITSELF (ORC_MODE_GGML vs ORC_MODE_GGML_ALT, same integer arithmetic, opposite fp32 summation
+# order) differs by rms 0.05-0.08 / max 0.26-0.41 per row on the 8B model from the first token on (measured, tools/noise_floor.py).
+# Full-size comparisons are therefore made RELATIVE to that floor, measured on the same tokens: the device row must be no further
+# from the reference than FLOOR_FACTOR x what a second faithful implementation of the reference arithmetic is.
+FLOOR_FACTOR = 1.5
 
 
 def top_sorted(logits: np.ndarray, k: int):
@@ -25,14 +32,25 @@ def top_sorted(logits: np.ndarray, k: int):
 class StepStats:
     def __init__(self):
         self.max_abs: List[float] = []
+        self.rms: List[float] = []
+        self.floor_max_abs: List[float] = []
+        self.floor_rms: List[float] = []
         self.ids_equal: List[bool] = []
         self.gap_ranks = 0          # ranks whose reference gap demanded an identical id ...
         self.gap_ok = 0             # ... and got it
         self.gaps: List[float] = []
 
+    def add_floor(self, alt: np.ndarray, want: np.ndarray):
+        """deviation of a second faithful implementation of the reference arithmetic on the same row (the noise floor)"""
+        d = alt - want
+        self.floor_max_abs.append(float(np.abs(d).max()))
+        self.floor_rms.append(float(np.sqrt(np.mean(d.astype(np.float64) ** 2))))
+
     def add(self, got: np.ndarray, want: np.ndarray, got_top_ids: np.ndarray):
-        err = float(np.abs(got - want).max())
+        d = got - want
+        err = float(np.abs(d).max())
         self.max_abs.append(err)
+        self.rms.append(float(np.sqrt(np.mean(d.astype(np.float64) ** 2))))
         ids11, val11 = top_sorted(want, 11)
         self.ids_equal.append(bool(np.array_equal(got_top_ids[:10], ids11[:10])))
         gaps = val11[:10] - val11[1:11]
@@ -52,7 +70,12 @@ class StepStats:
 
     def summary(self) -> Dict[str, float]:
         n = max(1, len(self.max_abs))
-        return {"steps": len(self.max_abs), "max_abs": max(self.max_abs) if self.max_abs else 0.0,
+        floor = {}
+        if self.floor_max_abs:
+            floor = {"floor_max_abs": max(self.floor_max_abs), "floor_rms": max(self.floor_rms),
+                     "within_floor": bool(max(self.max_abs) <= FLOOR_FACTOR * max(self.floor_max_abs) + 0.02 and
+                                          max(self.rms) <= FLOOR_FACTOR * max(self.floor_rms) + 1e-3)}
+        return {"steps": len(self.max_abs), "max_abs": max(self.max_abs) if self.max_abs else 0.0, "rms": max(self.rms) if self.rms else 0.0, **floor,
                 "clean_frac": sum(e <= CLEAN_TOL for e in self.max_abs) / n,
                 "top10_id_match_frac": sum(self.ids_equal) / n,
                 "pinned_ranks": self.gap_ranks, "pinned_ranks_ok": self.gap_ok,

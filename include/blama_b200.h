@@ -95,8 +95,20 @@ BLK_API void       blk_ctx_free(blk_ctx*);
 BLK_API int32_t    blk_ctx_n_ctx(const blk_ctx*);           /* llama_n_ctx   Session.cpp:57 */
 BLK_API int32_t    blk_ctx_n_batch(const blk_ctx*);         /* llama_n_batch Session.cpp:381 */
 BLK_API int32_t    blk_ctx_n_past(const blk_ctx*);
+BLK_API const blk_model* blk_ctx_model(const blk_ctx*);     /* llama_get_model Session.cpp:26 */
 BLK_API blk_status blk_kv_clear(blk_ctx*);                  /* llama_kv_self_clear Session.cpp:53 */
 BLK_API blk_status blk_sync(blk_ctx*);                      /* llama_synchronize   Session.cpp:54 */
+/* Context shift (Session.cpp:341-342): llama_kv_self_seq_rm(ctx, 0, p0, p1) followed by llama_kv_self_seq_add(ctx, 0, p1, n_past,
+ * -(p1 - p0)).  The cells of positions [p0, p1) are dropped, the cells behind them move down by p1 - p0 and their K rows are
+ * re-rotated by that position change exactly as llama.cpp's K-shift does (RoPE applied to the f16 cache row); n_past shrinks by
+ * p1 - p0. */
+BLK_API blk_status blk_kv_shift(blk_ctx*, int32_t p0, int32_t p1);
+/* llama_state_get_size / llama_state_get_data / llama_state_set_data (Session.cpp:291-304): the KV rows of every layer, the
+ * last logits row and its top-k list, as one blob (engine-specific layout, not llama.cpp's).  The sampler's RNG is not part of
+ * it, as in the reference (t-integration.cpp:371-376). */
+BLK_API int64_t    blk_state_size(const blk_ctx*);
+BLK_API blk_status blk_state_get(blk_ctx*, void* dst, int64_t cap, int64_t* written);
+BLK_API blk_status blk_state_set(blk_ctx*, const void* src, int64_t size);
 
 /* ---- decode (Session.cpp:388 llama_decode on a llama_batch_get_one batch) -------------------------------- */
 /* Appends n tokens at positions n_past.. ; afterwards the logits of the LAST token are resident on the device

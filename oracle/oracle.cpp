@@ -255,7 +255,8 @@ void quantize_q8_0(const float* x, int64_t k, int8_t* qs, float* dout) {
     }
 }
 
-// ORC_MODE_GGML_ALT: identical integer arithmetic, but the eight fp32 lane sums are added in the opposite order.
+// ORC_MODE_GGML_ALT: identical integer arithmetic, but the eight fp32 lane sums (K-quants) / the block products (Q8_0) are
+// added in the opposite order.
 // Exists only to measure how far two faithful implementations of the reference arithmetic drift apart
 // (tests/test_oracle.py::test_summation_order_noise_floor).
 static bool g_alt_order = false;
@@ -360,7 +361,8 @@ float vec_dot_q6_K_q8_K(int64_t k, const uint8_t* w, const int8_t* aq, const flo
 float vec_dot_q8_0_q8_0(int64_t k, const uint8_t* w, const int8_t* aq, const float* ad) {
     const int64_t nb = k / 32;
     float sumf = 0;
-    for (int64_t i = 0; i < nb; i++) {
+    for (int64_t ii = 0; ii < nb; ii++) {
+        const int64_t i = g_alt_order ? nb - 1 - ii : ii;      // noise-floor probe: the same block products added back to front
         const uint8_t* blk = w + i * 34;
         uint16_t dh; memcpy(&dh, blk, 2);
         const int8_t* q = (const int8_t*)(blk + 2);
@@ -698,6 +700,31 @@ extern "C" orc_ctx* orc_ctx_create(orc_model* m, int32_t n_ctx, int32_t mode, in
 }
 extern "C" void orc_ctx_free(orc_ctx* c) { delete c; }
 extern "C" void orc_kv_clear(orc_ctx* c) { c->n_past = 0; }
+
+// Context shift (reference Session.cpp:341-342): llama_kv_self_seq_rm(ctx, 0, p0, p1) drops the cells of positions [p0, p1);
+// llama_kv_self_seq_add(ctx, 0, p1, n_past, -(p1 - p0)) moves the positions of the cells behind them down, which llama.cpp applies
+// before the next decode as a K-shift: ggml_rope_ext_inplace on the F16 K cache with the position DELTA of every cell
+// (llama-context.cpp build_rope_shift; ggml-cpu rope on F16: f16 -> f32, rotate, f32 -> f16).  V rows only move.
+extern "C" int32_t orc_kv_shift(orc_ctx* c, int32_t p0, int32_t p1) {
+    if (p0 < 0 || p1 <= p0 || p1 > c->n_past) return 1;
+    const orc_model* m = c->m;
+    const int d = p1 - p0, dh = m->d_head, nkv = m->n_head_kv, dkv = nkv * dh;
+    const Tensor* rf = m->get("rope_freqs.weight");
+    const float* ffac = rf ? (const float*)rf->data : nullptr;
+    std::vector<float> row(dkv);
+    for (int l = 0; l < m->n_layer; l++) {
+        for (int t = p1; t < c->n_past; t++) {
+            const uint16_t* src = &c->kc[l][(size_t)t * dkv];
+            for (int i = 0; i < dkv; i++) row[i] = h2f(src[i]);
+            rope(row.data(), nkv, dh, m->n_rot, -d, m->rope_theta, ffac, m->neox);
+            uint16_t* dst = &c->kc[l][(size_t)(t - d) * dkv];
+            for (int i = 0; i < dkv; i++) dst[i] = f2h(row[i]);
+            memcpy(&c->vc[l][(size_t)(t - d) * dkv], &c->vc[l][(size_t)t * dkv], (size_t)dkv * 2);
+        }
+    }
+    c->n_past -= d;
+    return 0;
+}
 extern "C" int32_t orc_n_past(const orc_ctx* c) { return c->n_past; }
 extern "C" int32_t orc_decode(orc_ctx* c, const int32_t* tokens, int32_t n, int32_t all_logits) {
     try { return forward(c, tokens, n, all_logits != 0); }

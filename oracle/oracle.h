@@ -48,6 +48,9 @@ int64_t    orc_weight_bytes_per_token(const orc_model*);
 orc_ctx* orc_ctx_create(orc_model*, int32_t n_ctx, int32_t mode, int32_t n_threads);
 void     orc_ctx_free(orc_ctx*);
 void     orc_kv_clear(orc_ctx*);
+/* llama_kv_self_seq_rm(p0, p1) + llama_kv_self_seq_add(p1, n_past, -(p1 - p0)) + the K-shift llama.cpp applies before the next decode
+ * (reference Session.cpp:341-342) */
+int32_t  orc_kv_shift(orc_ctx*, int32_t p0, int32_t p1);
 int32_t  orc_n_past(const orc_ctx*);
 /* decode n tokens at positions n_past..; all_logits!=0 keeps logits of every position. returns 0 on success */
 int32_t  orc_decode(orc_ctx*, const int32_t* tokens, int32_t n, int32_t all_logits);

@@ -40,6 +40,7 @@ def _load() -> C.CDLL:
         "orc_n_vocab": (i32, [vp]), "orc_n_ctx_train": (i32, [vp]), "orc_n_embd": (i32, [vp]), "orc_n_layer": (i32, [vp]),
         "orc_token_bos": (i32, [vp]), "orc_is_eog": (i32, [vp, i32]), "orc_weight_bytes_per_token": (i64, [vp]),
         "orc_ctx_create": (vp, [vp, i32, i32, i32]), "orc_ctx_free": (None, [vp]), "orc_kv_clear": (None, [vp]),
+        "orc_kv_shift": (i32, [vp, i32, i32]),
         "orc_n_past": (i32, [vp]), "orc_decode": (i32, [vp, vp, i32, i32]),
         "orc_get_logits": (C.POINTER(C.c_float), [vp, i32]), "orc_get_hidden": (C.POINTER(C.c_float), [vp, i32]),
         "orc_topk": (None, [vp, i32, i32, vp]), "orc_gather_sorted": (i32, [vp, i32, vp, i32, vp]),
@@ -116,6 +117,14 @@ class Ctx:
 
     def clear(self):
         lib().orc_kv_clear(self.h)
+
+    def kv_shift(self, p0: int, p1: int):
+        if lib().orc_kv_shift(self.h, p0, p1):
+            raise RuntimeError("orc_kv_shift: bad range")
+
+    @property
+    def n_past(self) -> int:
+        return lib().orc_n_past(self.h)
 
     def decode(self, tokens: Sequence[int], all_logits: bool = False) -> np.ndarray:
         t = np.ascontiguousarray(tokens, dtype=np.int32)
