@@ -13,7 +13,15 @@ HOST_SRCS := $(wildcard $(HOST)/llama/*.cpp) $(wildcard $(HOST)/server/*.cpp) $(
 HOST_OBJS := $(patsubst $(HOST)/%.cpp,$(OBJDIR)/host/%.o,$(HOST_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(HOST)/llama/*.hpp) $(wildcard $(HOST)/server/*.hpp) $(wildcard $(HOST)/*.hpp) include/blama_b200.h
 
-all: $(LIBDIR)/libblama_b200.so oracle
+BINDIR    := blama_b200/bin
+
+all: $(LIBDIR)/libblama_b200.so $(BINDIR)/blama-server oracle
+
+# the server executable (reference server/code/http/HttpServerMain.cpp main): links the library, configured by BLAMA_* variables
+# (the C++ host classes are not exported from the library -- its boundary is the C ABI -- so the executable links their objects)
+$(BINDIR)/blama-server: $(HOST)/server/main/HttpServerMain.cpp $(LIBDIR)/libblama_b200.so $(HDRS)
+	@mkdir -p $(BINDIR)
+	g++ -O2 -std=c++20 -Wall -I$(HOST) -Iinclude $< $(filter-out $(OBJDIR)/host/host_capi.o,$(HOST_OBJS)) -o $@ -L$(LIBDIR) -lblama_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(dir $@)
@@ -31,5 +39,5 @@ oracle:
 	$(MAKE) -s -C oracle
 
 clean:
-	rm -rf $(OBJDIR) $(LIBDIR)/libblama_b200.so
+	rm -rf $(OBJDIR) $(LIBDIR)/libblama_b200.so $(BINDIR)/blama-server
 .PHONY: all oracle clean

@@ -162,6 +162,15 @@ bool mega_geometry(int K, int& W, int& L, int& rpc) {
     return W <= MG_WARPS;
 }
 
+// QKV of a 4096-wide model: 3072 row pairs over 148 x 16 warps is 1.3 pairs per warp -- a third of the warps carry two pairs = four
+// chunks, one more than the ring holds, so the phase waits for an HBM round trip.  With two warps per pair every warp has two or
+// three (half as long) chunks, all prefetched.  (0 = keep the geometry of mega_geometry)
+int mega_default_w_qkv(int K) {
+    static const int forced = [] { const char* e = getenv("BLK_MEGA_W_QKV_DEFAULT"); return e ? atoi(e) : -1; }();
+    if (forced >= 0) return forced;
+    return 0;
+}
+
 MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
     MegaPlan pl;
     blk_mega_model& mg = m->mega;
@@ -177,6 +186,18 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
     auto add_phase = [&](int layer, int K, int src, std::initializer_list<std::tuple<std::string, int, int, int, int>> segs /*tensor, n_pairs, kind, rowmap, ab*/) {
         MegaPhase ph{};
         if (!mega_geometry(K, ph.W, ph.L, ph.rpc)) { bad = true; return; }
+        {   // finer K split of a phase (more, shorter chunks per row pair: every warp's share fits its ring, smaller remainder):
+            // BLK_MEGA_W_QKV / _WO / _GU / _DOWN / _HEAD = warps per row pair
+            const int kind0 = std::get<2>(*segs.begin());
+            const char* key = kind0 == MK_Q ? "BLK_MEGA_W_QKV" : kind0 == MK_SWIGLU ? "BLK_MEGA_W_GU" : kind0 == MK_LOGITS ? "BLK_MEGA_W_HEAD" :
+                              (src == MSRC_ATTN ? "BLK_MEGA_W_WO" : "BLK_MEGA_W_DOWN");
+            const char* e = getenv(key);
+            int w = e ? atoi(e) : (kind0 == MK_Q ? mega_default_w_qkv(K) : 0);
+            const int halfs = K / 128;
+            if (w > ph.W && w <= MG_WARPS && (MG_WARPS % w) == 0 && halfs % (2 * w) == 0) {
+                ph.W = w; ph.L = halfs / w; ph.rpc = (2 * ph.L <= 32) ? 2 : 1;
+            }
+        }
         ph.K = K; ph.src = src; ph.layer = layer; ph.nseg = 0;
         const int NGtot = n_sms * (MG_WARPS / ph.W);
         int items = 0;
@@ -1171,6 +1192,8 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             auto ll = [&](size_t n) { uint2* p = dalloc<uint2>(c.get(), n); BLK_CUDA(cudaMemset(p, 0, n * sizeof(uint2))); return p; };
             P.x2 = ll(d); P.q2 = ll(dq); P.h2 = ll(ff); P.ao2 = ll(dq);
             P.sc2 = ll((size_t)m->n_head * P.score_stride); P.po2 = ll((size_t)P.max_split * dq); P.kvn2 = ll(2 * (size_t)dkv);
+            P.st2 = ll((size_t)m->n_head * P.max_split * 2);
+            { const char* e = getenv("BLK_ATTN_LOCAL"); P.attn_local = (e && e[0] == '0') ? 0 : 1; }
             P.k_pools = c->d_kpools; P.v_pools = c->d_vpools; P.page_table = c->page_table; P.kv_dim = dkv;
             P.logits = c->logits; P.chunk_max = c->chunk_max; P.chunk_shift = c->chunk_shift;
             {   // a poll that times out reports here instead of hanging the GPU (mapped pinned host word)

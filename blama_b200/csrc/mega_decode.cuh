@@ -394,6 +394,9 @@ __device__ __forceinline__ void mg_attn_setup(const MegaParams& P, int n_kv, con
     const int per = (n_kv + n_split - 1) / n_split;
     const int t0 = split * per;
     S.misc[1] = hk; S.misc[2] = split; S.misc[3] = n_split; S.misc[4] = t0; S.misc[5] = max(0, min(n_kv, t0 + per) - t0); S.misc[6] = split < n_split ? 1 : 0;
+    // every slice fits one shared-memory tile (contexts up to max_split * ts_cap tokens): the soft-max runs on the CTA's own scores
+    // (local maximum and sum, merged by the combiner) and the scores never leave the CTA
+    S.misc[8] = (per <= P.ts_cap && P.attn_local) ? 1 : 0;
 }
 __device__ __forceinline__ size_t mg_kv_row(const MegaParams& P, int hk, int t) {
     return ((size_t)P.page_table[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * P.kv_dim + (size_t)hk * P.d_head;
@@ -508,10 +511,119 @@ __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int 
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v = __fmul_rn(v, P.attn_scale);
             if (tl < cn && ld == 0) {
-                ll_st(P.sc2 + (size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl, v, tag_out);
+                if (!S.misc[8]) ll_st(P.sc2 + (size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl, v, tag_out);
                 if (c0 == 0) s.sc[gI * P.ts_cap + tl] = v;
             }
         }
+    }
+}
+
+// stage 2, local form (every context slice is one shared-memory tile): soft-max over the CTA's OWN scores.
+//   one slice (n_split == 1): that is the whole row -- ggml's order exactly (max -> expf -> sum in double -> p * (1/sum) -> f16 -> V.p),
+//     the result goes straight to the attention output;
+//   several slices: flash-style -- p = f16(expf(s - m_local)), o = sum p v, and (m_local, l_local) travel with the partial; the CTA of
+//     split 0 merges: M = max m_s, w_s = expf(m_s - M), out = (sum_s w_s o_s) / (sum_s w_s l_s).  Against ggml this moves the f16
+//     rounding of the probabilities in front of the normalisation (a 2^-11 relative change per probability, the size of every other
+//     rounding difference between two implementations of this arithmetic); it removes the all-to-all exchange of the scores and the
+//     statistics pass over the whole row (13 -> ~6 us per layer on the 8B model).
+template <int GQ, bool TR>
+__device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, const MgSmem& S) {
+    const MgAttn a = mg_attn_get(S);
+    if (!a.on) return;
+    const MgAttnSmem s = mg_attn_carve(P, S.attn);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, dh = P.d_head, gq = P.n_head / P.n_head_kv;
+    const uint32_t tag_po = mg_tag(P.seq, phi, 2), tag_ao = mg_tag(P.seq, phi, 3);
+    const int TG = MG_THREADS / dh;
+    const int d = tid & (dh - 1), tg = dh == 128 ? tid >> 7 : tid >> 6;
+    const int cn = a.nt;
+    const bool single = a.n_split == 1;
+    float acc[GQ];
+#pragma unroll
+    for (int gI = 0; gI < GQ; gI++) acc[gI] = 0.0f;
+    if (cn > 0) {
+        if (warp < gq) {                                   // warp g: statistics and probabilities of query head g
+            float* row = s.sc + warp * P.ts_cap;
+            float m = -INFINITY;
+            for (int tl = lane; tl < cn; tl += 32) m = fmaxf(m, row[tl]);
+            m = warp_max(m);
+            double sum = 0.0;
+            for (int tl = lane; tl < cn; tl += 32) { const float e = expf(row[tl] - m); row[tl] = e; sum += (double)e; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            __syncwarp();
+            if (single) {
+                const float inv = (float)(1.0 / sum);
+                for (int tl = lane; tl < cn; tl += 32) row[tl] = __half2float(__float2half_rn(__fmul_rn(row[tl], inv)));
+            } else {
+                for (int tl = lane; tl < cn; tl += 32) row[tl] = __half2float(__float2half_rn(row[tl]));
+                if (lane == 0) ll_st2(P.st2 + ((size_t)(a.hk * gq + warp) * P.max_split + a.split) * 2, m, (float)sum, tag_po);
+            }
+        }
+        __syncthreads();
+        mg_tr<TR>(P, S, 13);
+        for (int tl = tg; tl < cn; tl += TG) {
+            const float v = __half2float(s.v[(size_t)tl * dh + d]);
+#pragma unroll
+            for (int gI = 0; gI < GQ; gI++) if (gI < gq) acc[gI] += s.sc[gI * P.ts_cap + tl] * v;
+        }
+    } else if (!single && warp < gq && lane == 0) {
+        ll_st2(P.st2 + ((size_t)(a.hk * gq + warp) * P.max_split + a.split) * 2, -INFINITY, 0.0f, tag_po);
+    }
+    __syncthreads();
+    mg_tr<TR>(P, S, 14);
+#pragma unroll
+    for (int gI = 0; gI < GQ; gI++) if (gI < gq) s.red[(tg * gq + gI) * dh + d] = acc[gI];
+    __syncthreads();
+    const int E = gq * dh, NO = P.n_head * dh;
+    for (int e = tid; e < E; e += MG_THREADS) {
+        float o = 0.0f;
+        for (int k = 0; k < TG; k++) o += s.red[k * E + e];
+        if (single) ll_st(P.ao2 + (size_t)a.hk * E + e, o, tag_ao);
+        else ll_st(P.po2 + (size_t)a.split * NO + a.hk * E + e, o, tag_po);
+    }
+    mg_tr<TR>(P, S, 15);
+    if (single || a.split != 0) return;
+    // ---- the CTA of split 0 merges the slices of its KV head ----
+    float* wgt = reinterpret_cast<float*>(S.redd);          // [gq <= 8][32] merge weights (the double reduction scratch: 256 floats)
+    if (warp < gq) {
+        const uint2* sp = P.st2 + (size_t)(a.hk * gq + warp) * P.max_split * 2;
+        float m = -INFINITY, l = 0.0f;
+        int spins = 0;
+        bool ok;
+        do {
+            ok = true;
+            if (lane < a.n_split) { const uint4 w = ll_ld2(sp + lane * 2); m = __uint_as_float(w.x); l = __uint_as_float(w.z); ok = w.y == tag_po && w.w == tag_po; }
+            if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 2); break; }
+        } while (!__all_sync(0xffffffffu, ok));
+        const float M = warp_max(lane < a.n_split ? m : -INFINITY);
+        const float w = lane < a.n_split ? expf(m - M) : 0.0f;
+        float L = w * l;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+        if (lane < a.n_split) wgt[warp * 32 + lane] = w;
+        if (lane == 0) S.stat[warp] = __fdiv_rn(1.0f, L);
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += MG_THREADS) {
+        const int g = dh == 128 ? e >> 7 : e >> 6;
+        const uint2* pp = P.po2 + a.hk * E + e;
+        float o = 0.0f;
+        for (int s0 = 0; s0 < a.n_split; s0 += 8) {        // batches of 8 polled together, added in split order
+            float pv[8];
+            int spins = 0;
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (s0 + i < a.n_split) { const uint2 w = ll_ld(pp + (size_t)(s0 + i) * NO); pv[i] = __uint_as_float(w.x); ok = ok && w.y == tag_po; } else pv[i] = 0.0f;
+                }
+                if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 3); break; }
+            } while (!ok);
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (s0 + i < a.n_split) o += wgt[g * 32 + s0 + i] * pv[i];
+        }
+        ll_st(P.ao2 + (size_t)a.hk * E + e, o * S.stat[g], tag_ao);
     }
 }
 
@@ -519,6 +631,7 @@ __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int 
 // partial V.p -> LL words; the CTA of split 0 sums the split partials in split order.
 template <int GQ, bool TR>
 __device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int phi, int n_kv, const MgSmem& S) {
+    if (S.misc[8]) { mg_attn_pv_local<GQ, TR>(P, phi, S); return; }      // slices of one tile: soft-max on the CTA's own scores
     const MgAttn a = mg_attn_get(S);
     if (!a.on) return;
     const MgAttnSmem s = mg_attn_carve(P, S.attn);

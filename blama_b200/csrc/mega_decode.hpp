@@ -81,7 +81,9 @@ struct MegaParams {
     // cross-CTA vectors as LL words {value bits, epoch tag} (mega_decode.cuh): residual stream, q, SwiGLU output, attention output,
     // scores [n_head][score_stride], split partials [max_split][n_head * d_head], the new token's K | V rows [2][kv_dim]
     uint2* x2; uint2* q2; uint2* h2; uint2* ao2; uint2* sc2; uint2* po2; uint2* kvn2;
+    uint2* st2;              // soft-max statistics of the split partials [n_head][max_split] x {local max, local sum} (local attention form)
     int score_stride; int max_split;
+    int attn_local;          // 1: slices that fit one tile run the soft-max on their own scores (BLK_ATTN_LOCAL=0 switches back)
     uint32_t seq;            // launch counter of the context (epoch base of every tag)
     int* err;                // mapped host word: set when a poll timed out
     __half* const* k_pools; __half* const* v_pools; const int32_t* page_table; int kv_dim;
