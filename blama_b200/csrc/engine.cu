@@ -1054,6 +1054,15 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     c->have_logits = true;
 }
 
+// tokens per chunk when n tokens do not fit one logical batch: equal chunks (rounded up to whole 64-token tiles) instead of full
+// batches plus a small remainder -- a 32-token tail would run the few-token GEMM form and cost as much as a quarter of a full chunk
+int balanced_chunk(int n, int n_batch) {
+    if (n <= n_batch) return n;
+    const int chunks = (n + n_batch - 1) / n_batch;
+    const int per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
+    return std::min(per, n_batch);
+}
+
 void build_graphs(blk_ctx* c) {
     for (int which = 0; which < 3; which++) {
         const bool head = (which != 1);
@@ -1194,6 +1203,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
             P.sc2 = ll((size_t)m->n_head * P.score_stride); P.po2 = ll((size_t)P.max_split * dq); P.kvn2 = ll(2 * (size_t)dkv);
             P.st2 = ll((size_t)m->n_head * P.max_split * 2);
             { const char* e = getenv("BLK_ATTN_LOCAL"); P.attn_local = (e && e[0] == '0') ? 0 : 1; }
+
             P.k_pools = c->d_kpools; P.v_pools = c->d_vpools; P.page_table = c->page_table; P.kv_dim = dkv;
             P.logits = c->logits; P.chunk_max = c->chunk_max; P.chunk_shift = c->chunk_shift;
             {   // a poll that times out reports here instead of hanging the GPU (mapped pinned host word)
@@ -1383,7 +1393,8 @@ extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
         if (c->n_past + n > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
         for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= c->m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
         if (n >= c->prefill_min) {
-            for (int off = 0; off < n; off += c->n_batch) prefill_chunk(c, tokens + off, std::min(c->n_batch, n - off), nullptr, 0);
+            const int per = balanced_chunk(n, c->n_batch);
+            for (int off = 0; off < n; off += per) prefill_chunk(c, tokens + off, std::min(per, n - off), nullptr, 0);
             return;
         }
         for (int i = 0; i < n; i++) step(c, tokens[i], i == n - 1);
@@ -1467,7 +1478,8 @@ extern "C" blk_status blk_verify_prefill(blk_ctx* c, const int32_t* tokens, int3
         for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= c->m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
         if (c->verify_mode == 0 && n >= c->prefill_min) {
             VerifyIo io{claimed, n_claimed, gathered, top};
-            for (int off = 0; off < n; off += c->n_batch) prefill_chunk(c, tokens + off, std::min(c->n_batch, n - off), &io, off);
+            const int per = balanced_chunk(n, c->n_batch);
+            for (int off = 0; off < n; off += per) prefill_chunk(c, tokens + off, std::min(per, n - off), &io, off);
             return;
         }
         // sequential form of the context fill: one batch-1 decode per response token (Session.cpp:235-241), logits gathered

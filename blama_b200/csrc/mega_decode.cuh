@@ -525,7 +525,10 @@ __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int 
 //     split 0 merges: M = max m_s, w_s = expf(m_s - M), out = (sum_s w_s o_s) / (sum_s w_s l_s).  Against ggml this moves the f16
 //     rounding of the probabilities in front of the normalisation (a 2^-11 relative change per probability, the size of every other
 //     rounding difference between two implementations of this arithmetic); it removes the all-to-all exchange of the scores and the
-//     statistics pass over the whole row (13 -> ~6 us per layer on the 8B model).
+//     statistics pass over the whole row (measured on the 8B model: the partials are published 1.9 us earlier per layer; the split
+//     merge then waits on two dependent L2 round trips, statistics and partials.  Fetching both as one batch of 8 / 12 slices per
+//     thread made the kernel 3 % SLOWER overall -- the wider register footprint of this function costs the caller three spilled
+//     registers -- so the two-step merge stays; profiles/r2_decode_experiments.md).
 template <int GQ, bool TR>
 __device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, const MgSmem& S) {
     const MgAttn a = mg_attn_get(S);
@@ -540,6 +543,7 @@ __device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, cons
     float acc[GQ];
 #pragma unroll
     for (int gI = 0; gI < GQ; gI++) acc[gI] = 0.0f;
+    __syncthreads();                                       // the scores of stage 1 (written by the token's lane group) are in shared memory
     if (cn > 0) {
         if (warp < gq) {                                   // warp g: statistics and probabilities of query head g
             float* row = s.sc + warp * P.ts_cap;

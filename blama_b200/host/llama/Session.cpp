@@ -190,6 +190,58 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
     return result;
 }
 
+std::vector<TokenPrediction> Session::setInitialPromptAndFill(std::span<const Token> prompt, std::span<TokenPrediction> tokens) {
+    if (m_phase != Phase::Initial) Raise{} << "Session already started";
+    bool wide = false;
+    for (const auto& token : tokens) wide = wide || token.logits.size() > 10;
+    const size_t total = std::max<size_t>(prompt.size(), 1) + tokens.size();
+    const bool batched = !tokens.empty() && !m_instance.model().prefixInputsWithBos() && !wide && !m_params.sequentialVerify &&
+                         m_params.gaFactor == 1 && total < m_maxTokens && total < size_t(blk_ctx_n_ctx(m_ctx));
+    if (!batched) {
+        setInitialPrompt(prompt);
+        return fillCtx(tokens);
+    }
+    Token single;
+    m_numKeep = std::min(uint32_t(prompt.size()), m_maxTokens);
+    if (prompt.empty()) {
+        single = blk_model_token_bos(m_instance.model().lmodel());
+        prompt = {&single, 1};
+    }
+    const size_t np = prompt.size(), n = tokens.size();
+    std::vector<Token> ids(np + n);
+    std::vector<int32_t> claimed((np + n) * 10, 0), nClaimed(np + n, 0);
+    for (size_t i = 0; i < np; ++i) { ids[i] = prompt[i]; m_sampler->accept(prompt[i], false); }
+    m_sampler->reset();                                   // pushPrompt: previous inputs must not influence the generation
+    const int32_t nVocab = blk_model_n_vocab(m_instance.model().lmodel());
+    for (size_t i = 0; i < n; ++i) {
+        ids[np + i] = tokens[i].token;
+        m_sampler->accept(tokens[i].token, false);
+        std::vector<Token> uniq;
+        for (const auto& td : tokens[i].logits) uniq.push_back(td.token);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        uniq.erase(std::remove_if(uniq.begin(), uniq.end(), [&](Token t) { return t < 0 || t >= nVocab; }), uniq.end());
+        nClaimed[np + i] = int32_t(uniq.size());
+        std::copy(uniq.begin(), uniq.end(), claimed.begin() + long((np + i) * 10));
+    }
+    std::vector<float> gathered((np + n) * 10, 0.0f);
+    throwIfFailed(blk_ctx_set_verify_mode(m_ctx, 0), "verify mode");
+    if (blk_verify_prefill(m_ctx, ids.data(), int32_t(np + n), claimed.data(), nClaimed.data(), gathered.data(), nullptr) != BLK_OK)
+        Raise{} << "Failed to decode tokens";
+    m_numPast += uint32_t(np + n);
+    m_phase = Phase::Generating;
+    std::vector<TokenPrediction> result;
+    result.reserve(n);
+    for (size_t i = np; i < np + n; ++i) {
+        TokenDataVector v(size_t(nClaimed[i]));
+        for (int32_t j = 0; j < nClaimed[i]; ++j) v[size_t(j)] = {claimed[i * 10 + size_t(j)], gathered[i * 10 + size_t(j)]};
+        std::sort(v.begin(), v.end(), [](const TokenData& a, const TokenData& b) { return a.logit > b.logit; });
+        result.push_back({ids[i], std::move(v)});
+    }
+    refreshCandidates();
+    return result;
+}
+
 void Session::refreshCandidates() {
     m_candidates.resize(size_t(Sampler::MaxDeviceCandidates));
     static_assert(sizeof(TokenData) == sizeof(blk_token_data));

@@ -83,6 +83,10 @@ public:
     // model's logits at the claimed ids sorted by logit.  ONE causal prefill here (or N single-token decodes when
     // InitParams::sequentialVerify is set: bit-identical to complete()).
     std::vector<TokenPrediction> fillCtx(std::span<TokenPrediction> tokens);
+    // Extension for Server::verify: setInitialPrompt(prompt) followed by fillCtx(tokens) as ONE causal prefill over [prompt | response]
+    // (a short prompt run on its own streams every weight once for a handful of tokens: 7 ms of a 35 ms request on the 8B model).
+    // Same checks, texts and results layout as the two calls; falls back to them whenever fillCtx itself would not batch.
+    std::vector<TokenPrediction> setInitialPromptAndFill(std::span<const Token> prompt, std::span<TokenPrediction> tokens);
     std::vector<uint8_t> getState();
     // New sampler chain for the rest of the session (Session.cpp:403-405); the KV cache is kept.
     void resetSampler(const Sampler::Params& params);

@@ -144,9 +144,9 @@ struct Server::Impl {
         job.run = [prompt = std::move(prompt), tokenize, req = std::move(req), resp = std::move(resp), cbp](Worker& w) mutable {
             auto& session = w.instance->startSession({.seed = req.seed, .temperature = req.temperature, .topP = req.topP});
             if (tokenize) prompt = w.model->vocab().tokenize(req.prompt, true, true);
-            session.setInitialPrompt(prompt);
             auto orig = unmarshal(resp);
-            auto mine = session.fillCtx(orig);
+            // setInitialPrompt + fillCtx (reference :135, :149) as one causal prefill over [prompt | response]
+            auto mine = session.setInitialPromptAndFill(prompt, orig);
             // the reference pushes one metric at a time and re-sums the history on every push (Server.cpp:153-156); only the last
             // push's value is reported, which is the in-order double sum over all metrics: one push of the whole span
             std::vector<TokenPredictionView> pairs(orig.size());
