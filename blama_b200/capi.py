@@ -66,6 +66,7 @@ SYMBOLS = {
     "blk_get_logits_last": (_i32, [_vp, _vp]),
     "blk_decode_topk": (_i32, [_vp, _i32, _i32, _vp]),
     "blk_decode_loop": (_i32, [_vp, _i32, _i32, C.POINTER(_i32)]),
+    "blk_decode_batch": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "blk_verify_prefill": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "blk_ctx_set_verify_mode": (_i32, [_vp, _i32]),
     "blk_timer_start": (_i32, [_vp]),
@@ -119,6 +120,16 @@ def _p(a: np.ndarray):
 
 def init() -> None:
     _check(lib().blk_init())
+
+
+def decode_batch(ws: "Ctx", ctxs: Sequence["Ctx"], tokens: Sequence[int], k: int = 40) -> np.ndarray:
+    """one forward pass for len(ctxs) sequences, one new token each (blk_decode_batch); returns [n][k] top-k lists"""
+    n = len(ctxs)
+    arr = (_vp * n)(*[c.h for c in ctxs])
+    t = np.ascontiguousarray(tokens, dtype=np.int32)
+    out = np.zeros((n, k), dtype=TD_DTYPE)
+    _check(lib().blk_decode_batch(ws.h, arr, _p(t), n, k, _p(out)))
+    return out
 
 
 def device_count() -> int:

@@ -8,6 +8,7 @@
 #include "gguf.hpp"
 #include "prefill.hpp"
 #include "prefill_kernels.cuh"
+#include "batch_decode.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1398,6 +1399,102 @@ extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
             return;
         }
         for (int i = 0; i < n; i++) step(c, tokens[i], i == n - 1);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batched decode step: n sequences, one new token each, ONE pass over the weights (continuous batching)
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct BatchDesc {       // layout of blk_ctx::bd_host / bd_dev
+    int32_t tokens[BATCH_MAX];
+    int32_t pos[BATCH_MAX];
+    const int32_t* page_table[BATCH_MAX];
+    __half* const* k_pools[BATCH_MAX];
+    __half* const* v_pools[BATCH_MAX];
+    int32_t* pos_ptr[BATCH_MAX];
+};
+} // namespace
+
+extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const int32_t* tokens, int32_t n, int32_t k, blk_token_data* out) {
+    if (!ws || !ctxs || !tokens || !out || n <= 0 || n > BATCH_MAX || k <= 0 || k > TOPK_MAX) return fail(BLK_ERR_ARG, "blk_decode_batch: bad arguments");
+    return guarded([&] {
+        blk_model* m = ws->m;
+        BLK_CUDA(cudaSetDevice(m->device));
+        const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff, V = m->n_vocab;
+        for (int i = 0; i < n; i++) {
+            blk_ctx* c = ctxs[i];
+            if (!c || c->m != m) throw BlkError(BLK_ERR_ARG, "blk_decode_batch: every context must belong to the workspace's model");
+            for (int j = 0; j < i; j++) if (ctxs[j] == c) throw BlkError(BLK_ERR_ARG, "blk_decode_batch: a context appears twice");
+            if (tokens[i] < 0 || tokens[i] >= V) throw BlkError(BLK_ERR_ARG, "token id out of range");
+            if (c->n_past + 1 > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+            BLK_CUDA(cudaStreamSynchronize(c->stream));          // its prompt prefill / previous step ran on its own stream
+        }
+        ensure_prefill_bufs(ws, n);
+        if (!ws->bd_host) {
+            ws->bd_host = reinterpret_cast<uint8_t*>(halloc<BatchDesc>(ws, 1));
+            ws->bd_dev = reinterpret_cast<uint8_t*>(dalloc<BatchDesc>(ws, 1));
+            ws->bd_top_ids = dalloc<int32_t>(ws, BATCH_MAX * TOPK_MAX); ws->bd_top_logits = dalloc<float>(ws, BATCH_MAX * TOPK_MAX);
+            ws->bd_h_top_ids = halloc<int32_t>(ws, BATCH_MAX * TOPK_MAX); ws->bd_h_top_logits = halloc<float>(ws, BATCH_MAX * TOPK_MAX);
+        }
+        cudaStream_t st = ws->stream;
+        BLK_CUDA(cudaStreamSynchronize(st));                      // the staging block is reused every step
+        BatchDesc* h = reinterpret_cast<BatchDesc*>(ws->bd_host);
+        const BatchDesc* dv = reinterpret_cast<const BatchDesc*>(ws->bd_dev);
+        for (int i = 0; i < n; i++) {
+            h->tokens[i] = tokens[i]; h->pos[i] = ctxs[i]->n_past; h->page_table[i] = ctxs[i]->page_table;
+            h->k_pools[i] = ctxs[i]->d_kpools; h->v_pools[i] = ctxs[i]->d_vpools; h->pos_ptr[i] = ctxs[i]->d_pos;
+        }
+        BLK_CUDA(cudaMemcpyAsync(ws->bd_dev, ws->bd_host, sizeof(BatchDesc), cudaMemcpyHostToDevice, st));
+        embed_rows_kernel<<<n, 256, 0, st>>>(m->tok_embd, dv->tokens, dv->pos, ws->pf_x, ws->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
+        BLK_CUDA(cudaGetLastError()); ws->launches++;
+        const long long ldq = dq + 2 * dkv;
+        const SplitKWs sk{ws->pf_splitk, ws->pf_splitk_elems};
+        for (int l = 0; l < m->n_layer; l++) {
+            const LayerWeights& L = m->layers[l];
+            rmsnorm_bf16_launch(ws->pf_x, L.attn_norm, d, m->rms_eps, ws->pf_xn, n, st);
+            const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
+            BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, ws->pf_xn, n, ws->pf_qkv, ldq, st, nullptr, false, &sk));
+            QkvPostBatchArgs qa{};
+            qa.base.qkv = ws->pf_qkv; qa.base.ld = ldq; qa.base.rope_cs = ws->pf_rope; qa.base.q_out = ws->pf_q;
+            qa.base.dq = dq; qa.base.dkv = dkv; qa.base.d_head = dh; qa.base.neox = m->neox ? 1 : 0;
+            qa.pos = dv->pos; qa.page_table = dv->page_table; qa.k_pools = dv->k_pools; qa.v_pools = dv->v_pools; qa.layer = l;
+            qkv_post_batch_kernel<<<n, 256, 0, st>>>(qa);
+            BatchAttnArgs aa{};
+            aa.q = ws->pf_q; aa.pos = dv->pos; aa.page_table = dv->page_table; aa.k_pools = dv->k_pools; aa.v_pools = dv->v_pools; aa.out = ws->pf_ao;
+            aa.layer = l; aa.n_head = m->n_head; aa.n_head_kv = m->n_head_kv; aa.kv_dim = dkv; aa.scale = 1.0f / sqrtf((float)dh);
+            if (dh == 128) decode_attn_batch_kernel<128><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
+            else decode_attn_batch_kernel<64><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
+            BLK_CUDA(cudaGetLastError());
+            BLK_CUDA(prefill_gemm(L.wo, ws->pf_ao, n, ws->pf_x, d, nullptr, 1, st, nullptr, false, &sk));
+            rmsnorm_bf16_launch(ws->pf_x, L.ffn_norm, d, m->rms_eps, ws->pf_xn, n, st);
+            BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, ws->pf_xn, n, ws->pf_h, ff, st, nullptr, false, &sk));
+            BLK_CUDA(prefill_gemm(L.down, ws->pf_h, n, ws->pf_x, d, nullptr, 1, st, nullptr, false, &sk));
+            ws->launches += 8;
+        }
+        rmsnorm_bf16_launch(ws->pf_x, m->out_norm, d, m->rms_eps, ws->pf_xn, n, st);
+        BLK_CUDA(prefill_gemm(m->output, ws->pf_xn, n, ws->pf_logits, V, nullptr, 0, st, nullptr, false));
+        ws->launches += 2;
+        // per row: threshold top-64 (the selector of the batch-1 path, one row at a time)
+        for (int i = 0; i < n; i++) {
+            const float* row = ws->pf_logits + (size_t)i * V;
+            chunk_max_kernel<<<ws->n_chunks, 256, 0, st>>>(row, V, ws->chunk_shift, ws->chunk_max);
+            TopkArgs tk{};
+            tk.logits = row; tk.n = V; tk.chunk_max = ws->chunk_max; tk.n_chunks = ws->n_chunks;
+            tk.cand_l = ws->cand_l; tk.cand_i = ws->cand_i; tk.cap = ws->cand_cap; tk.count = ws->counters + 1; tk.done = ws->counters + 2;
+            tk.out_ids = ws->bd_top_ids + (size_t)i * TOPK_MAX; tk.out_logits = ws->bd_top_logits + (size_t)i * TOPK_MAX;
+            topk_select_kernel<<<16, 1024, 0, st>>>(tk);
+            BLK_CUDA(cudaGetLastError()); ws->launches += 2;
+        }
+        advance_many_kernel<<<1, BATCH_MAX, 0, st>>>(dv->pos_ptr, n);
+        BLK_CUDA(cudaGetLastError()); ws->launches++;
+        BLK_CUDA(cudaMemcpyAsync(ws->bd_h_top_ids, ws->bd_top_ids, (size_t)n * TOPK_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BLK_CUDA(cudaMemcpyAsync(ws->bd_h_top_logits, ws->bd_top_logits, (size_t)n * TOPK_MAX * sizeof(float), cudaMemcpyDeviceToHost, st));
+        BLK_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; i++) {
+            ctxs[i]->n_past++; ctxs[i]->have_logits = false;
+            for (int j = 0; j < k; j++) { out[(size_t)i * k + j].token = ws->bd_h_top_ids[i * TOPK_MAX + j]; out[(size_t)i * k + j].logit = ws->bd_h_top_logits[i * TOPK_MAX + j]; }
+        }
     });
 }
 

@@ -139,6 +139,9 @@ struct blk_ctx {
     // scratch for gather / verify
     int32_t* d_ids = nullptr; float* d_gath = nullptr; int ids_cap = 0;
     void* flush_buf = nullptr; size_t flush_bytes = 0;
+    // batched decode step (blk_decode_batch): per-row descriptors (pinned host staging + device copy) and per-row top-k lists
+    uint8_t* bd_host = nullptr; uint8_t* bd_dev = nullptr;
+    int32_t* bd_top_ids = nullptr; float* bd_top_logits = nullptr; int32_t* bd_h_top_ids = nullptr; float* bd_h_top_logits = nullptr;
     // persistent decode kernel (one cooperative launch per token instead of the per-op graph)
     bool mega_on = false;
     blk::MegaParams mega_params{};

@@ -80,16 +80,16 @@ __device__ __forceinline__ uint2 pack_h4(float a, float b, float c, float d) {
     uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
     return o;
 }
-__global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
-    const int t = blockIdx.x, tid = threadIdx.x;
+// row t of the batch at cache position `pos` of the sequence whose pools / page table are given
+__device__ __forceinline__ void qkv_post_row(const QkvPostArgs& a, int t, int pos, __half* k_pool, __half* v_pool, const int32_t* page_table) {
+    const int tid = threadIdx.x;
     const float* row = a.qkv + (size_t)t * a.ld;
     const float2* cs = a.rope_cs + (size_t)t * (a.d_head / 2);
-    const int pos = a.pos0[0] + t;
-    const size_t base = ((size_t)a.page_table[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * a.dkv;
+    const size_t base = ((size_t)page_table[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * a.dkv;
     const int dh = a.d_head, hd = dh >> 1;               // d_head is 64 or 128 (checked at load)
     const int nqk = a.dq + a.dkv;                        // q then k: contiguous in the row, both whole heads
     __half* qdst = a.q_out + (size_t)t * a.dq;
-    __half* kdst = a.k_pool + base;
+    __half* kdst = k_pool + base;
     if (!a.neox) {
         // NORM pairs (2i, 2i+1): four consecutive elements are two pairs
         for (int e = tid * 4; e < nqk; e += 1024) {
@@ -116,8 +116,11 @@ __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
     }
     for (int e = tid * 4; e < a.dkv; e += 1024) {
         const float4 x = *reinterpret_cast<const float4*>(row + nqk + e);
-        *reinterpret_cast<uint2*>(a.v_pool + base + e) = pack_h4(x.x, x.y, x.z, x.w);
+        *reinterpret_cast<uint2*>(v_pool + base + e) = pack_h4(x.x, x.y, x.z, x.w);
     }
+}
+__global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
+    qkv_post_row(a, blockIdx.x, a.pos0[0] + (int)blockIdx.x, a.k_pool, a.v_pool, a.page_table);
 }
 
 // ---- SwiGLU: h = silu(g) * u -> bf16 ------------------------------------------------------------------------------------------

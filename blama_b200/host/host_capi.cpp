@@ -259,14 +259,20 @@ BLK_API int blh_sampler_draw(uint32_t seed, float temp, float top_p, int32_t top
 
 // ---- Server (reference server/code/server/Server.hpp:58-64): N workers = N replicas, requests are whole jobs ----------------------
 // models: handles from blh_model_create, one per replica (they stay owned by the caller and must outlive the server)
+BLK_API int blh_server_create_ex(void* const* models, int n_models, uint32_t ctx_size, uint32_t batch_size, uint32_t max_batch, void** out);
 BLK_API int blh_server_create(void* const* models, int n_models, uint32_t ctx_size, uint32_t batch_size, void** out) {
+    return blh_server_create_ex(models, n_models, ctx_size, batch_size, 1, out);
+}
+// max_batch > 1: continuous batching, up to max_batch /complete requests in flight per replica (Server.hpp)
+BLK_API int blh_server_create_ex(void* const* models, int n_models, uint32_t ctx_size, uint32_t batch_size, uint32_t max_batch, void** out) {
     return guard([&] {
         if (n_models <= 0) Raise{} << "a server needs at least one model replica";
         std::vector<std::shared_ptr<Model>> reps;
         for (int i = 0; i < n_models; ++i) reps.emplace_back(static_cast<Model*>(models[i]), [](Model*) {});
         Instance::InitParams ip; ip.ctxSize = ctx_size; if (batch_size) ip.batchSize = batch_size;
         auto box = std::make_unique<ServerBox>();
-        box->srv = std::make_unique<server::Server>(std::move(reps), ip);
+        if (max_batch > 64) Raise{} << "at most 64 requests per batched step";
+        box->srv = std::make_unique<server::Server>(std::move(reps), ip, max_batch < 1 ? 1u : max_batch);
         ServerBox* raw = box.get();
         box->srv->setErrorHandler([raw](const std::string& e) { std::lock_guard<std::mutex> lk(raw->mu); raw->lastWorkerError = e; });
         *out = box.release();

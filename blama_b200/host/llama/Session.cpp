@@ -242,6 +242,27 @@ std::vector<TokenPrediction> Session::setInitialPromptAndFill(std::span<const To
     return result;
 }
 
+Token Session::sampleNext() {
+    requireStarted(true);
+    flushPendingState();
+    const int32_t need = m_sampler->candidatesNeeded();
+    if (need <= 0) Raise{} << "batched decoding needs a sampler chain that starts with top-k (the device returns the top " << Sampler::MaxDeviceCandidates << ")";
+    const Token t = m_sampler->sample({m_candidates.data(), std::min<size_t>(m_candidates.size(), size_t(need))}, true);
+    if (m_instance.model().vocab().isEog(t)) return Token_Invalid;
+    ensureRoom(1);
+    return t;
+}
+
+TokenPrediction Session::acceptDecoded(Token token, std::span<const TokenData> candidates) {
+    m_sampler->accept(token, true);
+    m_numPast += 1;
+    m_candidates.assign(candidates.begin(), candidates.end());
+    TokenPrediction out;
+    out.token = token;
+    out.logits.assign(m_candidates.begin(), m_candidates.begin() + std::min<size_t>(m_candidates.size(), size_t(kReportedTop)));
+    return out;
+}
+
 void Session::refreshCandidates() {
     m_candidates.resize(size_t(Sampler::MaxDeviceCandidates));
     static_assert(sizeof(TokenData) == sizeof(blk_token_data));
@@ -303,14 +324,9 @@ bool Session::setState(std::span<uint8_t> state) {
     return true;
 }
 
-void Session::doDecode(std::span<const Token> tokens, Source src) {
-    if (tokens.size() > m_maxTokens) {
-        const auto skipped = tokens.size() - m_maxTokens;
-        tokens = tokens.first(m_maxTokens);
-        logLine(LogLevel::Warning, "Input too long. Skipping " + std::to_string(skipped) + " tokens");
-    }
+void Session::ensureRoom(size_t nTokens) {
     const auto ctxLen = uint32_t(blk_ctx_n_ctx(m_ctx));
-    if (m_numPast + tokens.size() >= ctxLen) {
+    if (m_numPast + nTokens >= ctxLen) {
         // infinite text generation via context shifting (reference :324-347): keep the first numKeep tokens (the initial prompt),
         // drop half of the rest, move what remains down -- blk_kv_shift re-rotates the K rows like llama.cpp's K-shift
         if (!m_params.infiniteContext) Raise{} << "context limit of " << ctxLen << " reached";
@@ -321,8 +337,17 @@ void Session::doDecode(std::span<const Token> tokens, Source src) {
                                      ", ctxLen: " + std::to_string(ctxLen) + ", numKeep: " + std::to_string(m_numKeep) + ", numDiscard: " + std::to_string(numDiscard));
         throwIfFailed(blk_kv_shift(m_ctx, int32_t(m_numKeep), int32_t(m_numKeep) + numDiscard), "context shift");
         m_numPast -= uint32_t(numDiscard);
-        logLine(LogLevel::Info, "Context full mitigation performed: past = " + std::to_string(m_numPast) + ", tokens = " + std::to_string(tokens.size()));
+        logLine(LogLevel::Info, "Context full mitigation performed: past = " + std::to_string(m_numPast) + ", tokens = " + std::to_string(nTokens));
     }
+}
+
+void Session::doDecode(std::span<const Token> tokens, Source src) {
+    if (tokens.size() > m_maxTokens) {
+        const auto skipped = tokens.size() - m_maxTokens;
+        tokens = tokens.first(m_maxTokens);
+        logLine(LogLevel::Warning, "Input too long. Skipping " + std::to_string(skipped) + " tokens");
+    }
+    ensureRoom(tokens.size());
     for (auto t : tokens) m_sampler->accept(t, src == Source::Generated);
 
     if (tokens.size() == 1) {

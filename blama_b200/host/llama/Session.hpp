@@ -87,6 +87,12 @@ public:
     // (a short prompt run on its own streams every weight once for a handful of tokens: 7 ms of a 35 ms request on the 8B model).
     // Same checks, texts and results layout as the two calls; falls back to them whenever fillCtx itself would not batch.
     std::vector<TokenPrediction> setInitialPromptAndFill(std::span<const Token> prompt, std::span<TokenPrediction> tokens);
+    // Extension for a batching server: the two halves of getToken() around a decode that somebody else runs
+    // for several sessions at once (blk_decode_batch).  sampleNext() draws from the current distribution (Token_Invalid at an
+    // end-of-generation token; shifts the context first when it is full, like doDecode); acceptDecoded() records that `token` has
+    // been decoded into this session's cache and installs the new distribution's top-k.  Returns what getToken() would have.
+    Token sampleNext();
+    TokenPrediction acceptDecoded(Token token, std::span<const TokenData> candidates);
     std::vector<uint8_t> getState();
     // New sampler chain for the rest of the session (Session.cpp:403-405); the KV cache is kept.
     void resetSampler(const Sampler::Params& params);
@@ -99,6 +105,7 @@ private:
     void pushPrompt(std::span<const Token> prompt, std::span<const Token> postfix = {});
     TokenPrediction getToken();
     void doDecode(std::span<const Token> tokens, Source src);
+    void ensureRoom(size_t nTokens);      // context shift when nTokens more do not fit (reference :324-347)
     void flushPendingState();
     TokenDataVector getLogitsFromCtx(int32_t topK);
     TokenDataVector getLogitsFromCtx(TokenDataVector tokens);

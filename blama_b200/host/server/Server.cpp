@@ -19,15 +19,29 @@ namespace bl::llama::server {
 struct Server::Impl {
     struct Worker {
         std::shared_ptr<Model> model;
-        std::unique_ptr<Instance> instance;
+        std::unique_ptr<Instance> instance;                 // slot 0; also the workspace of the batched steps
+        std::vector<std::unique_ptr<Instance>> extra;       // slots 1 .. maxBatch - 1 (continuous batching)
         std::thread thread;
         uint64_t requests = 0;      // guarded by Impl::mu
         double gpuMs = 0;
+        Instance& slot(size_t i) { return i == 0 ? *instance : *extra[i - 1]; }
     };
     struct Job {
-        std::function<void(Worker&)> run;
+        std::function<void(Worker&, size_t)> run;      // (worker, slot): slot 0 unless the worker batches
         std::function<void()> failed;      // delivers the request's "no result" answer to its callback
+        // a /complete request in a form the batching worker can advance token by token
+        bool isComplete = false;
+        std::vector<int32_t> prompt; bool tokenize = false; CompleteRequestParams params;
+        std::shared_ptr<std::function<void(CompleteReponse)>> completeCb;
     };
+    struct Generation {              // a /complete request in flight on one slot
+        size_t slotIndex;
+        Session* session;
+        uint32_t maxTokens;
+        std::vector<TokenPrediction> preds;
+        std::shared_ptr<std::function<void(CompleteReponse)>> cb;
+    };
+    unsigned maxBatch = 1;
 
     std::vector<std::unique_ptr<Worker>> workers;
     mutable std::mutex mu;
@@ -37,15 +51,16 @@ struct Server::Impl {
     bool stopping = false;
     std::function<void(const std::string&)> onError;
 
-    Impl(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip) {
+    Impl(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip, unsigned batch) : maxBatch(batch < 1 ? 1 : batch) {
         for (auto& r : replicas) {
             auto w = std::make_unique<Worker>();
             w->model = std::move(r);
             w->instance = std::make_unique<Instance>(*w->model, ip);
             w->instance->warmup();
+            for (unsigned i = 1; i < maxBatch; ++i) w->extra.push_back(std::make_unique<Instance>(*w->model, ip));
             workers.push_back(std::move(w));
         }
-        for (auto& w : workers) w->thread = std::thread([this, wp = w.get()] { loop(*wp); });
+        for (auto& w : workers) w->thread = std::thread([this, wp = w.get()] { if (maxBatch > 1) batchLoop(*wp); else loop(*wp); });
     }
     ~Impl() {
         { std::lock_guard<std::mutex> lk(mu); stopping = true; }
@@ -72,7 +87,7 @@ struct Server::Impl {
             (void)blk_timer_start(ctx);
             std::string error;
             bool ok = true;
-            try { job.run(w); }
+            try { job.run(w, 0); }
             catch (const std::exception& e) { ok = false; error = e.what(); }
             catch (...) { ok = false; error = "unknown error"; }
             float ms = 0.0f;
@@ -92,6 +107,119 @@ struct Server::Impl {
                 --running;
                 if (queue.empty() && running == 0) idleCv.notify_all();
             }
+        }
+    }
+    // ---- continuous batching: up to maxBatch /complete requests advance together, one blk_decode_batch step per token ----
+    void reportFailure(const std::string& error) {
+        std::function<void(const std::string&)> handler;
+        { std::lock_guard<std::mutex> lk(mu); handler = onError; }
+        try { if (handler) handler(error); } catch (...) {}
+    }
+    void finish(Worker& w, Generation& g) {
+        auto response = marshal(*w.model, g.preds);
+        w.slot(g.slotIndex).stopSession();
+        try { (*g.cb)(std::move(response)); } catch (...) {}
+        std::lock_guard<std::mutex> lk(mu);
+        w.requests++;
+    }
+    void batchLoop(Worker& w) {
+        std::vector<Generation> active;
+        std::vector<char> busy(maxBatch, 0);
+        blk_ctx* ws = w.instance->lctx();
+        for (;;) {
+            // 1. admit: block only when nothing is in flight
+            std::vector<Job> admitted;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (active.empty()) cv.wait(lk, [&] { return stopping || !queue.empty(); });
+                if (queue.empty() && active.empty()) { if (stopping) return; continue; }
+                size_t freeSlots = maxBatch - active.size();
+                while (!queue.empty()) {
+                    if (queue.front().isComplete) { if (freeSlots == 0) break; --freeSlots; }
+                    else if (!active.empty() && freeSlots == 0) break;          // a verify needs a slot of its own, too
+                    else if (freeSlots > 0) --freeSlots;
+                    admitted.push_back(std::move(queue.front()));
+                    queue.pop_front();
+                    ++running;
+                }
+            }
+            for (Job& job : admitted) {
+                size_t si = 0;
+                while (si < maxBatch && busy[si]) ++si;
+                float ms = 0.0f;
+                blk_ctx* ctx = w.slot(si).lctx();
+                (void)blk_timer_start(ctx);
+                try {
+                    if (!job.isComplete) {                    // e.g. a verify: one prefill on a free slot, between two steps
+                        job.run(w, si);
+                    } else {
+                        auto& session = w.slot(si).startSession({.seed = job.params.seed, .temperature = job.params.temperature, .topP = job.params.topP});
+                        if (job.tokenize) job.prompt = w.model->vocab().tokenize(job.params.prompt, true, true);
+                        session.setInitialPrompt(job.prompt);
+                        busy[si] = 1;
+                        active.push_back({si, &session, job.params.maxTokens, {}, job.completeCb});
+                    }
+                } catch (const std::exception& e) {
+                    w.slot(si).stopSession();
+                    reportFailure(e.what());
+                    try { if (job.failed) job.failed(); } catch (...) {}
+                }
+                (void)blk_timer_stop(ctx, &ms);
+                std::lock_guard<std::mutex> lk(mu);
+                w.gpuMs += ms;
+                if (!job.isComplete) { w.requests++; --running; }
+            }
+            // 2. requests that are done (token budget reached) leave
+            auto retire = [&](size_t i, bool failed, const std::string& why) {
+                Generation g = std::move(active[i]);
+                active.erase(active.begin() + long(i));
+                busy[g.slotIndex] = 0;
+                if (failed) { w.slot(g.slotIndex).stopSession(); reportFailure(why); try { (*g.cb)({}); } catch (...) {} std::lock_guard<std::mutex> lk(mu); w.requests++; }
+                else finish(w, g);
+                std::lock_guard<std::mutex> lk(mu);
+                --running;
+                if (queue.empty() && running == 0) idleCv.notify_all();
+            };
+            for (size_t i = active.size(); i-- > 0;) if (active[i].preds.size() >= active[i].maxTokens) retire(i, false, {});
+            if (active.empty()) { std::lock_guard<std::mutex> lk(mu); if (queue.empty() && running == 0) idleCv.notify_all(); continue; }
+            // 3. one token for everybody in flight
+            float ms = 0.0f;
+            (void)blk_timer_start(ws);
+            if (active.size() == 1) {
+                // a lone request: the batch-1 decode kernel (the reference's arithmetic), exactly Session::complete's step
+                Generation& g = active[0];
+                try {
+                    auto preds = g.session->complete({.prompt = {}, .suffix = {}, .maxTokens = 1});
+                    if (preds.empty()) g.maxTokens = uint32_t(g.preds.size());        // end of generation
+                    else g.preds.push_back(std::move(preds[0]));
+                } catch (const std::exception& e) { (void)blk_timer_stop(ws, &ms); retire(0, true, e.what()); continue; }
+            } else {
+                std::vector<blk_ctx*> ctxs; std::vector<Token> toks; std::vector<size_t> who;
+                for (size_t i = active.size(); i-- > 0;) {
+                    try {
+                        const Token t = active[i].session->sampleNext();
+                        if (t == Token_Invalid) { active[i].maxTokens = uint32_t(active[i].preds.size()); continue; }      // leaves at the next round
+                        ctxs.push_back(w.slot(active[i].slotIndex).lctx()); toks.push_back(t); who.push_back(i);
+                    } catch (const std::exception& e) { retire(i, true, e.what()); for (auto& x : who) if (x > i) --x; }
+                }
+                if (!ctxs.empty()) {
+                    std::vector<blk_token_data> top(ctxs.size() * size_t(Sampler::MaxDeviceCandidates));
+                    if (blk_decode_batch(ws, ctxs.data(), toks.data(), int32_t(ctxs.size()), Sampler::MaxDeviceCandidates, top.data()) != BLK_OK) {
+                        const std::string why = std::string("Failed to decode tokens: ") + blk_last_error();
+                        (void)blk_timer_stop(ws, &ms);
+                        while (!active.empty()) retire(active.size() - 1, true, why);
+                        continue;
+                    }
+                    using LlamaTokenData = bl::llama::TokenData;      // (Server::TokenData is the marshalled form)
+                    static_assert(sizeof(LlamaTokenData) == sizeof(blk_token_data));
+                    for (size_t j = 0; j < who.size(); ++j) {
+                        const LlamaTokenData* cand = reinterpret_cast<const LlamaTokenData*>(top.data() + j * size_t(Sampler::MaxDeviceCandidates));
+                        active[who[j]].preds.push_back(active[who[j]].session->acceptDecoded(toks[j], std::span<const LlamaTokenData>(cand, size_t(Sampler::MaxDeviceCandidates))));
+                    }
+                }
+            }
+            (void)blk_timer_stop(ws, &ms);
+            { std::lock_guard<std::mutex> lk(mu); w.gpuMs += ms; }
         }
     }
     void drain() {
@@ -126,7 +254,8 @@ struct Server::Impl {
     void complete(std::vector<int32_t> prompt, bool tokenize, CompleteRequestParams params, std::function<void(CompleteReponse)> cb) {
         auto cbp = std::make_shared<std::function<void(CompleteReponse)>>(std::move(cb));
         Job job;
-        job.run = [prompt = std::move(prompt), tokenize, params = std::move(params), cbp](Worker& w) mutable {
+        job.isComplete = true; job.prompt = prompt; job.tokenize = tokenize; job.params = params; job.completeCb = cbp;
+        job.run = [prompt = std::move(prompt), tokenize, params = std::move(params), cbp](Worker& w, size_t) mutable {
             auto& session = w.instance->startSession({.seed = params.seed, .temperature = params.temperature, .topP = params.topP});
             if (tokenize) prompt = w.model->vocab().tokenize(params.prompt, true, true);
             session.setInitialPrompt(prompt);
@@ -141,8 +270,9 @@ struct Server::Impl {
     void verify(std::vector<int32_t> prompt, bool tokenize, CompleteRequestParams req, CompleteReponse resp, std::function<void(float)> cb) {
         auto cbp = std::make_shared<std::function<void(float)>>(std::move(cb));
         Job job;
-        job.run = [prompt = std::move(prompt), tokenize, req = std::move(req), resp = std::move(resp), cbp](Worker& w) mutable {
-            auto& session = w.instance->startSession({.seed = req.seed, .temperature = req.temperature, .topP = req.topP});
+        job.run = [prompt = std::move(prompt), tokenize, req = std::move(req), resp = std::move(resp), cbp](Worker& w, size_t slot) mutable {
+            Instance& inst = w.slot(slot);
+            auto& session = inst.startSession({.seed = req.seed, .temperature = req.temperature, .topP = req.topP});
             if (tokenize) prompt = w.model->vocab().tokenize(req.prompt, true, true);
             auto orig = unmarshal(resp);
             // setInitialPrompt + fillCtx (reference :135, :149) as one causal prefill over [prompt | response]
@@ -154,7 +284,7 @@ struct Server::Impl {
             const std::vector<ComparisonMetrics> ms = compareAll(pairs);
             MetricsAggregator agg;
             const float score = ms.empty() ? 0.0f : agg.pushAndVerify(ms);
-            w.instance->stopSession();
+            inst.stopSession();
             (*cbp)(score);
         };
         job.failed = [cbp] { (*cbp)(std::numeric_limits<float>::quiet_NaN()); };
@@ -162,9 +292,10 @@ struct Server::Impl {
     }
 };
 
-Server::Server(std::shared_ptr<Model> model) : m_impl(std::make_unique<Impl>(std::vector<std::shared_ptr<Model>>{std::move(model)}, Instance::InitParams{})) {}
-Server::Server(std::vector<std::shared_ptr<Model>> replicas) : m_impl(std::make_unique<Impl>(std::move(replicas), Instance::InitParams{})) {}
-Server::Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip) : m_impl(std::make_unique<Impl>(std::move(replicas), ip)) {}
+Server::Server(std::shared_ptr<Model> model) : m_impl(std::make_unique<Impl>(std::vector<std::shared_ptr<Model>>{std::move(model)}, Instance::InitParams{}, 1u)) {}
+Server::Server(std::vector<std::shared_ptr<Model>> replicas) : m_impl(std::make_unique<Impl>(std::move(replicas), Instance::InitParams{}, 1u)) {}
+Server::Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip) : m_impl(std::make_unique<Impl>(std::move(replicas), ip, 1u)) {}
+Server::Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams ip, unsigned maxBatch) : m_impl(std::make_unique<Impl>(std::move(replicas), ip, maxBatch)) {}
 Server::~Server() = default;
 
 void Server::completeText(CompleteRequestParams params, std::function<void(CompleteReponse)> cb) {

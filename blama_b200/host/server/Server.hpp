@@ -23,6 +23,11 @@ public:
     explicit Server(std::vector<std::shared_ptr<Model>> replicas);      // one replica per GPU
     // extension: the Instance parameters of every worker (the reference passes {}: KV cache sized for the training context)
     Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams instanceParams);
+    // extension (continuous batching): every worker keeps up to maxBatch /complete requests in flight and
+    // advances them together, one blk_decode_batch step per token (weights streamed once for all of them); requests join and leave
+    // between steps.  1 = the reference's behaviour (a worker serves one request at a time, batch-1 decode kernel).  With more than
+    // one request in flight a step runs in the bf16 arithmetic of the verify prefill; a lone request runs the batch-1 kernel.
+    Server(std::vector<std::shared_ptr<Model>> replicas, Instance::InitParams instanceParams, unsigned maxBatch);
     ~Server();
     Server(const Server&) = delete;
     Server& operator=(const Server&) = delete;

@@ -42,6 +42,7 @@ HOST_SYMBOLS = {
     "blh_lc_score": (_f32, [_vp, _i32]),
     "blh_sampler_draw": (C.c_int, [_u32, _f32, _f32, _i32, _f32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "blh_server_create": (C.c_int, [_vp, C.c_int, _u32, _u32, C.POINTER(_vp)]),
+    "blh_server_create_ex": (C.c_int, [_vp, C.c_int, _u32, _u32, _u32, C.POINTER(_vp)]),
     "blh_server_free": (None, [_vp]),
     "blh_server_workers": (C.c_int, [_vp]),
     "blh_server_drain": (None, [_vp]),
@@ -313,10 +314,11 @@ def wire_complete_json(tokens, top10: np.ndarray, n_logits=None, model: Optional
 
 # ---- Server: N replicas behind one request queue (reference server/code/server/Server.hpp) -----------------------------------
 class Server:
-    def __init__(self, models: Sequence[Model], ctx_size: int = 0, batch_size: int = 0):
+    def __init__(self, models: Sequence[Model], ctx_size: int = 0, batch_size: int = 0, max_batch: int = 1):
+        """max_batch > 1: continuous batching -- up to max_batch /complete requests in flight per replica, one batched step per token"""
         arr = (_vp * len(models))(*[m.h for m in models])
         h = _vp()
-        _check(lib().blh_server_create(arr, len(models), ctx_size, batch_size, C.byref(h)))
+        _check(lib().blh_server_create_ex(arr, len(models), ctx_size, batch_size, max_batch, C.byref(h)))
         self.h = h
         self.models = list(models)
 

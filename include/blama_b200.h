@@ -130,6 +130,15 @@ BLK_API blk_status blk_get_logits_last(blk_ctx*, float* out);
  * distribution in one device->host copy. */
 BLK_API blk_status blk_decode_topk(blk_ctx*, int32_t token, int32_t k, blk_token_data* out);
 
+/* Continuous batching (not in the reference, whose Server serialises requests: server/code/server/Server.cpp:36; SURVEY.md 8f
+ * item 4): ONE forward pass for n <= 64 sequences, one new token each.  ctxs[i] are distinct contexts of the workspace context's
+ * model; tokens[i] is appended to ctxs[i] at that context's own position, into its own KV pages.  The weights are streamed once for
+ * all rows through the tcgen05 GEMM path (bf16 operand arithmetic: that of the verify prefill, not the int8 arithmetic of the
+ * batch-1 kernel).  out[i * k .. i * k + k - 1] = top-k of sequence i's new distribution, descending.  `ws` lends its stream and
+ * prefill workspaces and may or may not be one of ctxs.  The contexts' "last logits" are not kept (blk_topk_last / blk_gather_last
+ * need a blk_decode first). */
+BLK_API blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const int32_t* tokens, int32_t n, int32_t k, blk_token_data* out);
+
 /* Device-resident greedy decode loop (measurement aid for bench.py's `value`): n_steps decode steps back to back with the
  * arg-max token fed back ON THE DEVICE, no host round trip inside the loop.  Asynchronous unless last_token != NULL. */
 BLK_API blk_status blk_decode_loop(blk_ctx*, int32_t first_token, int32_t n_steps, int32_t* last_token);
