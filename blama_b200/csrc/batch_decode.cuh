@@ -49,8 +49,12 @@ struct BatchAttnArgs {
 };
 template <int DH>
 __global__ void __launch_bounds__(256) decode_attn_batch_kernel(const BatchAttnArgs a) {
+    constexpr int HP = DH / 2;                       // dimension pairs per head
+    constexpr int SLOTS = 256 / HP;                  // query heads served per pass of the P.V stage (4 for d_head 128, 8 for 64)
+    constexpr int NH = (MAX_GQ + SLOTS - 1) / SLOTS; // passes
     __shared__ float q_s[MAX_GQ * DH];
     __shared__ float s_s[MAX_GQ][BD_TK];
+    __shared__ int off_s[BD_TK];                     // cache row offset (in halfs) of every token of the tile
     __shared__ float red[MAX_GQ][8];
     __shared__ float m_run[MAX_GQ], l_run[MAX_GQ], corr[MAX_GQ];
     const int hk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -60,17 +64,19 @@ __global__ void __launch_bounds__(256) decode_attn_batch_kernel(const BatchAttnA
     const __half* vp = a.v_pools[b][a.layer] + (size_t)hk * DH;
     for (int i = tid; i < gq * DH; i += 256) q_s[i] = __half2float(a.q[(size_t)b * a.n_head * DH + (size_t)hk * gq * DH + i]);
     if (tid < MAX_GQ) { m_run[tid] = -INFINITY; l_run[tid] = 0.0f; }
-    // output element(s) of this thread: e = tid, tid + 256, ... < gq * DH
-    float acc[(MAX_GQ * DH + 255) / 256];
+    const int dp = tid % HP, g0 = tid / HP;          // this thread's dimension pair and first query head
+    float2 acc[NH];
 #pragma unroll
-    for (int i = 0; i < (MAX_GQ * DH + 255) / 256; i++) acc[i] = 0.0f;
+    for (int i = 0; i < NH; i++) acc[i] = make_float2(0.0f, 0.0f);
     __syncthreads();
     for (int t0 = 0; t0 < n_kv; t0 += BD_TK) {
         const int cn = min(BD_TK, n_kv - t0);
         // scores of the tile: one thread per token
         for (int j = tid; j < cn; j += 256) {
             const int t = t0 + j;
-            const uint4* kr = reinterpret_cast<const uint4*>(kp + ((size_t)pt[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * a.kv_dim);
+            const int off = (pt[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * a.kv_dim;
+            off_s[j] = off;
+            const uint4* kr = reinterpret_cast<const uint4*>(kp + off);
             float sc[MAX_GQ];
 #pragma unroll
             for (int g = 0; g < MAX_GQ; g++) sc[g] = 0.0f;
@@ -119,16 +125,18 @@ __global__ void __launch_bounds__(256) decode_attn_batch_kernel(const BatchAttnA
             for (int w = 0; w < 8; w++) l += red[tid][w];
             l_run[tid] = l_run[tid] * corr[tid] + l;
         }
-        // P.V of the tile
+        // P.V of the tile: a thread owns one dimension pair of up to NH query heads; V rows are read as half2, coalesced over dp
 #pragma unroll
-        for (int i = 0; i < (MAX_GQ * DH + 255) / 256; i++) {
-            const int e = tid + i * 256;
-            if (e < gq * DH) {
-                const int g = e / DH, d = e % DH;
-                float o = acc[i] * corr[g];
+        for (int i = 0; i < NH; i++) {
+            const int g = g0 + i * SLOTS;
+            if (g < gq) {
+                float2 o = make_float2(acc[i].x * corr[g], acc[i].y * corr[g]);
+                const float* pr = s_s[g];
+#pragma unroll 4
                 for (int j = 0; j < cn; j++) {
-                    const int t = t0 + j;
-                    o += s_s[g][j] * __half2float(vp[((size_t)pt[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * a.kv_dim + d]);
+                    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(vp + off_s[j] + 2 * dp));
+                    const float p = pr[j];
+                    o.x += p * v.x; o.y += p * v.y;
                 }
                 acc[i] = o;
             }
@@ -136,9 +144,13 @@ __global__ void __launch_bounds__(256) decode_attn_batch_kernel(const BatchAttnA
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < (MAX_GQ * DH + 255) / 256; i++) {
-        const int e = tid + i * 256;
-        if (e < gq * DH) a.out[(size_t)b * a.n_head * DH + (size_t)hk * gq * DH + e] = __float2bfloat16(acc[i] / l_run[e / DH]);
+    for (int i = 0; i < NH; i++) {
+        const int g = g0 + i * SLOTS;
+        if (g < gq) {
+            const float inv = 1.0f / l_run[g];
+            __nv_bfloat162 o = __floats2bfloat162_rn(acc[i].x * inv, acc[i].y * inv);
+            *reinterpret_cast<__nv_bfloat162*>(a.out + (size_t)b * a.n_head * DH + (size_t)(hk * gq + g) * DH + 2 * dp) = o;
+        }
     }
 }
 

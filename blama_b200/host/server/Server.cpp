@@ -8,7 +8,10 @@
 
 #include <blama_b200.h>
 
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <deque>
 #include <limits>
 #include <mutex>
@@ -123,6 +126,13 @@ struct Server::Impl {
         w.requests++;
     }
     void batchLoop(Worker& w) {
+        // BLAMA_SERVER_PROFILE=1: host-side time per part of the loop, printed when the worker stops
+        const bool prof = std::getenv("BLAMA_SERVER_PROFILE") != nullptr;
+        double tAdmit = 0, tSample = 0, tStep = 0, tAccept = 0, tRetire = 0; uint64_t nSteps = 0, nRows = 0;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        struct Report { bool on; double& a; double& b; double& c; double& d; double& e; uint64_t& n; uint64_t& r;
+            ~Report() { if (on) std::fprintf(stderr, "[server profile] steps %llu rows %llu | admit %.1f ms, sample %.1f, step %.1f, accept %.1f, retire %.1f\n",
+                                             (unsigned long long)n, (unsigned long long)r, a, b, c, d, e); } } report{prof, tAdmit, tSample, tStep, tAccept, tRetire, nSteps, nRows};
         std::vector<Generation> active;
         std::vector<char> busy(maxBatch, 0);
         blk_ctx* ws = w.instance->lctx();
@@ -143,6 +153,7 @@ struct Server::Impl {
                     ++running;
                 }
             }
+            const double ta0 = now();
             for (Job& job : admitted) {
                 size_t si = 0;
                 while (si < maxBatch && busy[si]) ++si;
@@ -169,6 +180,8 @@ struct Server::Impl {
                 w.gpuMs += ms;
                 if (!job.isComplete) { w.requests++; --running; }
             }
+            tAdmit += now() - ta0;
+            const double tr0 = now();
             // 2. requests that are done (token budget reached) leave
             auto retire = [&](size_t i, bool failed, const std::string& why) {
                 Generation g = std::move(active[i]);
@@ -181,6 +194,7 @@ struct Server::Impl {
                 if (queue.empty() && running == 0) idleCv.notify_all();
             };
             for (size_t i = active.size(); i-- > 0;) if (active[i].preds.size() >= active[i].maxTokens) retire(i, false, {});
+            tRetire += now() - tr0;
             if (active.empty()) { std::lock_guard<std::mutex> lk(mu); if (queue.empty() && running == 0) idleCv.notify_all(); continue; }
             // 3. one token for everybody in flight
             float ms = 0.0f;
@@ -195,6 +209,7 @@ struct Server::Impl {
                 } catch (const std::exception& e) { (void)blk_timer_stop(ws, &ms); retire(0, true, e.what()); continue; }
             } else {
                 std::vector<blk_ctx*> ctxs; std::vector<Token> toks; std::vector<size_t> who;
+                const double ts0 = now();
                 for (size_t i = active.size(); i-- > 0;) {
                     try {
                         const Token t = active[i].session->sampleNext();
@@ -202,7 +217,9 @@ struct Server::Impl {
                         ctxs.push_back(w.slot(active[i].slotIndex).lctx()); toks.push_back(t); who.push_back(i);
                     } catch (const std::exception& e) { retire(i, true, e.what()); for (auto& x : who) if (x > i) --x; }
                 }
+                tSample += now() - ts0;
                 if (!ctxs.empty()) {
+                    const double tb0 = now();
                     std::vector<blk_token_data> top(ctxs.size() * size_t(Sampler::MaxDeviceCandidates));
                     if (blk_decode_batch(ws, ctxs.data(), toks.data(), int32_t(ctxs.size()), Sampler::MaxDeviceCandidates, top.data()) != BLK_OK) {
                         const std::string why = std::string("Failed to decode tokens: ") + blk_last_error();
@@ -210,12 +227,15 @@ struct Server::Impl {
                         while (!active.empty()) retire(active.size() - 1, true, why);
                         continue;
                     }
+                    const double tc0 = now();
+                    tStep += tc0 - tb0; nSteps++; nRows += ctxs.size();
                     using LlamaTokenData = bl::llama::TokenData;      // (Server::TokenData is the marshalled form)
                     static_assert(sizeof(LlamaTokenData) == sizeof(blk_token_data));
                     for (size_t j = 0; j < who.size(); ++j) {
                         const LlamaTokenData* cand = reinterpret_cast<const LlamaTokenData*>(top.data() + j * size_t(Sampler::MaxDeviceCandidates));
                         active[who[j]].preds.push_back(active[who[j]].session->acceptDecoded(toks[j], std::span<const LlamaTokenData>(cand, size_t(Sampler::MaxDeviceCandidates))));
                     }
+                    tAccept += now() - tc0;
                 }
             }
             (void)blk_timer_stop(ws, &ms);
