@@ -229,8 +229,10 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
-        "config": {"workload": f"{args.shape} /complete decode, bounded sample on host cores", "shape": args.shape,
-                   "sample_new_tokens": n_new},
+        "config": {"workload": f"{args.shape}: {args.prompt}-token prompt + {args.new} new tokens per request (BASELINE configs[1]), "
+                               "one replica per GPU, independent requests", "shape": args.shape, "prompt_tokens": args.prompt,
+                   "new_tokens": args.new, "sample": f"bounded: 16-token prompt + {n_new} decode steps per step on the host cores (the full "
+                                                     "512 + 256 request takes minutes on the CPU); shorter context favours the CPU arm"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

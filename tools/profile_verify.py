@@ -9,7 +9,8 @@ nv = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 path = ensure_model(shape, 0, lambda: None)
 m = capi.Model(path); c = capi.Ctx(m, nv + 64)
 toks = gguf_synth.synth_prompt(shape, nv, 2)
-for rep in range(2):
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+for rep in range(reps):
     c.clear(); c.decode(gguf_synth.synth_prompt(shape, 32, 1))
     rpt = c.profile_verify(toks)
 print(rpt)
