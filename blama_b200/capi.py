@@ -57,6 +57,9 @@ SYMBOLS = {
     "blk_kv_clear": (_i32, [_vp]),
     "blk_sync": (_i32, [_vp]),
     "blk_kv_shift": (_i32, [_vp, _i32, _i32]),
+    "blk_kv_seq_add": (_i32, [_vp, _i32, _i32, _i32]),
+    "blk_kv_seq_div": (_i32, [_vp, _i32, _i32, _i32]),
+    "blk_ctx_next_pos": (_i32, [_vp]),
     "blk_state_size": (_i64, [_vp]),
     "blk_state_get": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "blk_state_set": (_i32, [_vp, _vp, _i64]),
@@ -192,6 +195,16 @@ class Ctx:
     def kv_shift(self, p0: int, p1: int):
         """drop the cells of positions [p0, p1), move the rest down (K re-rotated): reference Session.cpp:341-342"""
         _check(lib().blk_kv_shift(self.h, p0, p1))
+
+    def kv_seq_add(self, p0: int, p1: int, delta: int):
+        _check(lib().blk_kv_seq_add(self.h, p0, p1, delta))
+
+    def kv_seq_div(self, p0: int, p1: int, d: int):
+        _check(lib().blk_kv_seq_div(self.h, p0, p1, d))
+
+    @property
+    def next_pos(self) -> int:
+        return int(lib().blk_ctx_next_pos(self.h))
 
     def state_get(self) -> np.ndarray:
         n = int(lib().blk_state_size(self.h))

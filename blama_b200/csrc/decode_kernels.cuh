@@ -58,7 +58,7 @@ __global__ void embed_kernel(QMat E, const int32_t* __restrict__ tokens, const i
     pdl_launch_dependents(); pdl_wait();
     const int t = blockIdx.x;
     dequant_row_cta(E, tokens[t], x + (size_t)t * E.K);
-    rope_table_fill(rope_cs + (size_t)t * half_rot, half_rot, pos0[0] + t, theta_scale, freq_factors);
+    rope_table_fill(rope_cs + (size_t)t * half_rot, half_rot, pos0[0] + pos0[1] + t, theta_scale, freq_factors);      // pos0 = {cell index, rotary offset}
 }
 
 // =================================================================================================================

@@ -801,6 +801,111 @@ void enqueue_step(blk_ctx* c, bool with_head, bool feedback = false) {
     }
 }
 
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// cell positions other than the cell index (Self-Extend: llama_kv_self_seq_add / seq_div, reference Session.cpp:348-368)
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+// K rows of cells [cell0, cell0 + n) of every layer rotated IN PLACE by each cell's own position delta (llama.cpp's K-shift after
+// llama_kv_self_seq_add / seq_div: ggml rope on the F16 cache).  grid = (n, n_layer), block = 128.
+__global__ void __launch_bounds__(128) kv_rerope_kernel(__half* const* __restrict__ k_pools, const int32_t* __restrict__ page_table, int kv_dim, int d_head,
+                                                        int neox, int cell0, const int32_t* __restrict__ delta, float theta_scale,
+                                                        const float* __restrict__ freq_factors) {
+    __shared__ float2 cs[64];
+    const int cell = cell0 + (int)blockIdx.x;
+    const int dl = delta[cell];
+    if (dl == 0) return;
+    const int half_rot = d_head / 2;
+    rope_table_fill(cs, half_rot, dl, theta_scale, freq_factors);
+    __syncthreads();
+    __half* k = k_pools[blockIdx.y] + ((size_t)page_table[cell / KV_PAGE] * KV_PAGE + (cell % KV_PAGE)) * kv_dim;
+    for (int p = threadIdx.x; p < kv_dim / 2; p += blockDim.x) {
+        const int h = p / half_rot, i = p - h * half_rot;
+        const int e0 = neox ? h * d_head + i : h * d_head + 2 * i;
+        const int e1 = neox ? e0 + half_rot : e0 + 1;
+        const float x0 = __half2float(k[e0]), x1 = __half2float(k[e1]);
+        const float2 c = cs[i];
+        k[e0] = __float2half_rn(__fsub_rn(__fmul_rn(x0, c.x), __fmul_rn(x1, c.y)));
+        k[e1] = __float2half_rn(__fadd_rn(__fmul_rn(x0, c.y), __fmul_rn(x1, c.x)));
+    }
+}
+
+// positions of the cells as a host vector (created on the first Self-Extend call)
+void materialise_positions(blk_ctx* c) {
+    if (!c->cell_pos.empty() || c->n_past == 0) { if (c->cell_pos.empty()) { c->cell_pos.assign((size_t)c->n_ctx, 0); c->cell_shift.assign((size_t)c->n_ctx, 0); } return; }
+    c->cell_pos.resize((size_t)c->n_ctx); c->cell_shift.assign((size_t)c->n_ctx, 0);
+    for (int i = 0; i < c->n_ctx; i++) c->cell_pos[(size_t)i] = i;
+}
+// after a position change: the next token's rotary position is one past the largest cell position (llama_batch_allocr, pos == nullptr)
+void refresh_rope_offset(blk_ctx* c) {
+    int mx = -1;
+    for (int i = 0; i < c->n_past; i++) mx = std::max(mx, c->cell_pos[(size_t)i]);
+    c->rope_off = (mx + 1) - c->n_past;
+    const int32_t both[2] = {c->n_past, c->rope_off};
+    BLK_CUDA(cudaMemcpyAsync(c->d_pos, both, sizeof(both), cudaMemcpyHostToDevice, c->stream));
+    BLK_CUDA(cudaStreamSynchronize(c->stream));
+}
+// new cells [n_past, n_past + n) take the positions the kernels used for them
+void note_new_cells(blk_ctx* c, int n) {
+    if (c->cell_pos.empty()) return;
+    for (int i = 0; i < n; i++) { c->cell_pos[(size_t)(c->n_past + i)] = c->n_past + c->rope_off + i; c->cell_shift[(size_t)(c->n_past + i)] = 0; }
+}
+// the accumulated position changes reach the K rows before anything reads them (llama.cpp applies its K-shift at the next decode)
+void flush_pos_shift(blk_ctx* c) {
+    if (!c->shift_pending) return;
+    blk_model* m = c->m;
+    int32_t* d_delta = nullptr;
+    BLK_CUDA(cudaMalloc(&d_delta, (size_t)c->n_past * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpyAsync(d_delta, c->cell_shift.data(), (size_t)c->n_past * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        kv_rerope_kernel<<<dim3((unsigned)c->n_past, (unsigned)m->n_layer), 128, 0, c->stream>>>(c->d_kpools, c->page_table, m->n_head_kv * m->d_head, m->d_head,
+                                                                                                   m->neox ? 1 : 0, 0, d_delta, m->theta_scale, m->rope_freqs);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_delta);
+    BLK_CUDA(e);
+    std::fill(c->cell_shift.begin(), c->cell_shift.begin() + c->n_past, 0);
+    c->shift_pending = false;
+}
+} // namespace
+
+// llama_kv_self_seq_add(ctx, 0, p0, p1, delta) (reference Session.cpp:359, 361): cells whose POSITION lies in [p0, p1) move by delta
+extern "C" blk_status blk_kv_seq_add(blk_ctx* c, int32_t p0, int32_t p1, int32_t delta) {
+    if (!c || p0 < 0 || p1 < p0) return fail(BLK_ERR_ARG, "blk_kv_seq_add: bad range");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (delta == 0 || p0 == p1) return;
+        materialise_positions(c);
+        for (int i = 0; i < c->n_past; i++) {
+            int32_t& p = c->cell_pos[(size_t)i];
+            if (p >= p0 && p < p1) { p += delta; c->cell_shift[(size_t)i] += delta; c->shift_pending = true; if (p < 0) throw BlkError(BLK_ERR_ARG, "blk_kv_seq_add: negative position"); }
+        }
+        refresh_rope_offset(c);
+    });
+}
+// llama_kv_self_seq_div(ctx, 0, p0, p1, d) (reference Session.cpp:360): positions in [p0, p1) are divided by d
+extern "C" blk_status blk_kv_seq_div(blk_ctx* c, int32_t p0, int32_t p1, int32_t d) {
+    if (!c || p0 < 0 || p1 < p0 || d <= 0) return fail(BLK_ERR_ARG, "blk_kv_seq_div: bad arguments");
+    return guarded([&] {
+        BLK_CUDA(cudaSetDevice(c->m->device));
+        if (d == 1 || p0 == p1) return;
+        materialise_positions(c);
+        for (int i = 0; i < c->n_past; i++) {
+            int32_t& p = c->cell_pos[(size_t)i];
+            if (p >= p0 && p < p1) { const int32_t old = p; p /= d; c->cell_shift[(size_t)i] += p - old; c->shift_pending = true; }
+        }
+        refresh_rope_offset(c);
+    });
+}
+// rotary position the next token will get (one past the largest cell position; = n_past unless Self-Extend moved positions)
+extern "C" int32_t blk_ctx_next_pos(const blk_ctx* c) { return c->n_past + c->rope_off; }
+
+
+namespace {
+
 // ------------------------------------------------------------------------------------------------------------------
 // multi-token prefill (tcgen05 GEMM path)
 // ------------------------------------------------------------------------------------------------------------------
@@ -918,6 +1023,8 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     blk_model* m = c->m;
     const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff, V = m->n_vocab;
     ensure_prefill_bufs(c, n);
+    flush_pos_shift(c);
+    note_new_cells(c, n);
     cudaStream_t st = c->stream;
     // many tokens: dequantise every matrix ONCE into the bf16 panel and run the GEMMs TMA-fed on both operands; few tokens: the
     // fused form (weights dequantised inside the GEMM, once per 256 tokens) moves fewer bytes
@@ -1095,6 +1202,8 @@ void step(blk_ctx* c, int32_t tok, bool with_head) {
     blk_model* m = c->m;
     if (tok < 0 || tok >= m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
     if (c->n_past + 1 > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+    flush_pos_shift(c);
+    note_new_cells(c, 1);
     // pinned ring of token slots: a slot is only rewritten after the stream has drained once per lap
     if (c->tok_slot == 0) BLK_CUDA(cudaStreamSynchronize(c->stream));
     int32_t* slot = c->h_tok + c->tok_slot;
@@ -1146,8 +1255,8 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         c->d_kpools = dalloc<__half*>(c.get(), m->n_layer); c->d_vpools = dalloc<__half*>(c.get(), m->n_layer);
         BLK_CUDA(cudaMemcpy(c->d_kpools, c->k_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
         BLK_CUDA(cudaMemcpy(c->d_vpools, c->v_pool.data(), m->n_layer * sizeof(__half*), cudaMemcpyHostToDevice));
-        c->d_tok = dalloc<int32_t>(c.get(), 1); c->d_pos = dalloc<int32_t>(c.get(), 1);
-        BLK_CUDA(cudaMemset(c->d_pos, 0, sizeof(int32_t)));
+        c->d_tok = dalloc<int32_t>(c.get(), 1); c->d_pos = dalloc<int32_t>(c.get(), 2);
+        BLK_CUDA(cudaMemset(c->d_pos, 0, 2 * sizeof(int32_t)));
         c->h_tok = halloc<int32_t>(c.get(), blk_ctx::TOK_RING);
         c->x = dalloc<float>(c.get(), d); c->qbuf = dalloc<float>(c.get(), dq); c->hbuf = dalloc<float>(c.get(), ff);
         c->rope_cs = dalloc<float2>(c.get(), dh / 2);
@@ -1255,8 +1364,9 @@ extern "C" blk_status blk_ctx_set_verify_mode(blk_ctx* c, int32_t mode) {
 extern "C" blk_status blk_kv_clear(blk_ctx* c) {
     return guarded([&] {
         BLK_CUDA(cudaSetDevice(c->m->device));
-        BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, sizeof(int32_t), c->stream));
+        BLK_CUDA(cudaMemsetAsync(c->d_pos, 0, 2 * sizeof(int32_t), c->stream));
         c->n_past = 0; c->have_logits = false;
+        c->cell_pos.clear(); c->cell_shift.clear(); c->rope_off = 0; c->shift_pending = false;
     });
 }
 extern "C" blk_status blk_sync(blk_ctx* c) {
@@ -1296,10 +1406,11 @@ __global__ void __launch_bounds__(128) kv_shift_kernel(__half* const* __restrict
 
 constexpr uint32_t STATE_MAGIC = 0x534B4C42u;      // "BLKS"
 struct StateHeader { uint32_t magic, version; int32_t n_layer, kv_dim, n_vocab, n_past, have_logits, reserved; };
-size_t state_bytes(const blk_ctx* c, int n_past) {
+size_t state_bytes(const blk_ctx* c, int n_past, bool with_positions) {
     const blk_model* m = c->m;
     const size_t kv_dim = (size_t)m->n_head_kv * m->d_head;
-    return sizeof(StateHeader) + (size_t)m->n_vocab * 4 + TOPK_MAX * 8 + 2 * (size_t)m->n_layer * (size_t)n_past * kv_dim * 2;
+    return sizeof(StateHeader) + (size_t)m->n_vocab * 4 + TOPK_MAX * 8 + (with_positions ? 4 + (size_t)n_past * 4 : 0) +
+           2 * (size_t)m->n_layer * (size_t)n_past * kv_dim * 2;
 }
 } // namespace
 
@@ -1308,6 +1419,7 @@ extern "C" blk_status blk_kv_shift(blk_ctx* c, int32_t p0, int32_t p1) {
     return guarded([&] {
         blk_model* m = c->m;
         BLK_CUDA(cudaSetDevice(m->device));
+        if (!c->cell_pos.empty()) throw BlkError(BLK_ERR_ARG, "blk_kv_shift: not available once Self-Extend has moved cell positions (blk_kv_seq_add / blk_kv_seq_div)");
         const int d = p1 - p0, dkv = m->n_head_kv * m->d_head;
         // front to back in chunks of at most d rows: a chunk's destination never overlaps its source, and what it overwrites has been
         // moved already
@@ -1325,24 +1437,31 @@ extern "C" blk_status blk_kv_shift(blk_ctx* c, int32_t p0, int32_t p1) {
     });
 }
 
-extern "C" int64_t blk_state_size(const blk_ctx* c) { return c ? (int64_t)state_bytes(c, c->n_past) : 0; }
+extern "C" int64_t blk_state_size(const blk_ctx* c) { return c ? (int64_t)state_bytes(c, c->n_past, !c->cell_pos.empty()) : 0; }
 
 extern "C" blk_status blk_state_get(blk_ctx* c, void* dst, int64_t cap, int64_t* written) {
     if (!c || !dst || !written) return fail(BLK_ERR_ARG, "blk_state_get: bad arguments");
     return guarded([&] {
         blk_model* m = c->m;
         BLK_CUDA(cudaSetDevice(m->device));
-        const size_t need = state_bytes(c, c->n_past);
+        const bool with_pos = !c->cell_pos.empty();
+        const size_t need = state_bytes(c, c->n_past, with_pos);
         if ((size_t)cap < need) throw BlkError(BLK_ERR_ARG, "blk_state_get: buffer too small");
+        flush_pos_shift(c);
         BLK_CUDA(cudaStreamSynchronize(c->stream));
         check_mega(c);
         uint8_t* out = static_cast<uint8_t*>(dst);
         const int kv_dim = m->n_head_kv * m->d_head;
-        StateHeader h{STATE_MAGIC, 1u, m->n_layer, kv_dim, m->n_vocab, c->n_past, c->have_logits ? 1 : 0, 0};
+        StateHeader h{STATE_MAGIC, 1u, m->n_layer, kv_dim, m->n_vocab, c->n_past, c->have_logits ? 1 : 0, with_pos ? 1 : 0};
         memcpy(out, &h, sizeof(h)); out += sizeof(h);
         BLK_CUDA(cudaMemcpy(out, c->logits, (size_t)m->n_vocab * 4, cudaMemcpyDeviceToHost)); out += (size_t)m->n_vocab * 4;
         memcpy(out, c->h_top_ids, TOPK_MAX * 4); out += TOPK_MAX * 4;
         memcpy(out, c->h_top_logits, TOPK_MAX * 4); out += TOPK_MAX * 4;
+        if (with_pos) {      // Self-Extend moved cell positions: they are part of the state
+            const int32_t off = c->rope_off;
+            memcpy(out, &off, 4); out += 4;
+            memcpy(out, c->cell_pos.data(), (size_t)c->n_past * 4); out += (size_t)c->n_past * 4;
+        }
         const size_t row = (size_t)kv_dim * 2;
         for (int l = 0; l < m->n_layer; l++)
             for (const __half* pool : {c->k_pool[l], c->v_pool[l]})
@@ -1367,13 +1486,21 @@ extern "C" blk_status blk_state_set(blk_ctx* c, const void* src, int64_t size) {
         if (h.magic != STATE_MAGIC || h.version != 1u) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: not a state blob of this engine");
         if (h.n_layer != m->n_layer || h.kv_dim != kv_dim || h.n_vocab != m->n_vocab) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: the state belongs to another model");
         if (h.n_past < 0 || h.n_past > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "blk_state_set: the state does not fit this context");
-        if ((size_t)size != state_bytes(c, h.n_past)) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: truncated state");
+        if ((size_t)size != state_bytes(c, h.n_past, h.reserved != 0)) throw BlkError(BLK_ERR_FORMAT, "blk_state_set: truncated state");
         BLK_CUDA(cudaStreamSynchronize(c->stream));
         BLK_CUDA(cudaMemcpy(c->logits, in, (size_t)m->n_vocab * 4, cudaMemcpyHostToDevice)); in += (size_t)m->n_vocab * 4;
         memcpy(c->h_top_ids, in, TOPK_MAX * 4); in += TOPK_MAX * 4;
         memcpy(c->h_top_logits, in, TOPK_MAX * 4); in += TOPK_MAX * 4;
         BLK_CUDA(cudaMemcpy(c->top_ids, c->h_top_ids, TOPK_MAX * 4, cudaMemcpyHostToDevice));
         BLK_CUDA(cudaMemcpy(c->top_logits, c->h_top_logits, TOPK_MAX * 4, cudaMemcpyHostToDevice));
+        c->cell_pos.clear(); c->cell_shift.clear(); c->rope_off = 0; c->shift_pending = false;
+        if (h.reserved != 0) {
+            int32_t off = 0;
+            memcpy(&off, in, 4); in += 4;
+            c->cell_pos.assign((size_t)c->n_ctx, 0); c->cell_shift.assign((size_t)c->n_ctx, 0);
+            memcpy(c->cell_pos.data(), in, (size_t)h.n_past * 4); in += (size_t)h.n_past * 4;
+            c->rope_off = off;
+        }
         const size_t row = (size_t)kv_dim * 2;
         for (int l = 0; l < m->n_layer; l++)
             for (__half* pool : {c->k_pool[l], c->v_pool[l]})
@@ -1383,7 +1510,8 @@ extern "C" blk_status blk_state_set(blk_ctx* c, const void* src, int64_t size) {
                     in += n * row;
                 }
         c->n_past = h.n_past; c->have_logits = h.have_logits != 0;
-        BLK_CUDA(cudaMemcpy(c->d_pos, &h.n_past, sizeof(int32_t), cudaMemcpyHostToDevice));
+        const int32_t both[2] = {h.n_past, c->rope_off};
+        BLK_CUDA(cudaMemcpy(c->d_pos, both, sizeof(both), cudaMemcpyHostToDevice));
     });
 }
 
@@ -1408,7 +1536,8 @@ extern "C" blk_status blk_decode(blk_ctx* c, const int32_t* tokens, int32_t n) {
 namespace {
 struct BatchDesc {       // layout of blk_ctx::bd_host / bd_dev
     int32_t tokens[BATCH_MAX];
-    int32_t pos[BATCH_MAX];
+    int32_t pos[BATCH_MAX];          // cell index of the new token
+    int32_t rpos[BATCH_MAX];         // its rotary position (differs after Self-Extend)
     const int32_t* page_table[BATCH_MAX];
     __half* const* k_pools[BATCH_MAX];
     __half* const* v_pools[BATCH_MAX];
@@ -1429,6 +1558,7 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
             if (tokens[i] < 0 || tokens[i] >= V) throw BlkError(BLK_ERR_ARG, "token id out of range");
             if (c->n_past + 1 > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
             BLK_CUDA(cudaStreamSynchronize(c->stream));          // its prompt prefill / previous step ran on its own stream
+            flush_pos_shift(c);
         }
         ensure_prefill_bufs(ws, n);
         if (!ws->bd_host) {
@@ -1442,11 +1572,12 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
         BatchDesc* h = reinterpret_cast<BatchDesc*>(ws->bd_host);
         const BatchDesc* dv = reinterpret_cast<const BatchDesc*>(ws->bd_dev);
         for (int i = 0; i < n; i++) {
-            h->tokens[i] = tokens[i]; h->pos[i] = ctxs[i]->n_past; h->page_table[i] = ctxs[i]->page_table;
+            h->tokens[i] = tokens[i]; h->pos[i] = ctxs[i]->n_past; h->rpos[i] = ctxs[i]->n_past + ctxs[i]->rope_off; h->page_table[i] = ctxs[i]->page_table;
+            note_new_cells(ctxs[i], 1);
             h->k_pools[i] = ctxs[i]->d_kpools; h->v_pools[i] = ctxs[i]->d_vpools; h->pos_ptr[i] = ctxs[i]->d_pos;
         }
         BLK_CUDA(cudaMemcpyAsync(ws->bd_dev, ws->bd_host, sizeof(BatchDesc), cudaMemcpyHostToDevice, st));
-        embed_rows_kernel<<<n, 256, 0, st>>>(m->tok_embd, dv->tokens, dv->pos, ws->pf_x, ws->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
+        embed_rows_kernel<<<n, 256, 0, st>>>(m->tok_embd, dv->tokens, dv->rpos, ws->pf_x, ws->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
         BLK_CUDA(cudaGetLastError()); ws->launches++;
         const long long ldq = dq + 2 * dkv;
         const SplitKWs sk{ws->pf_splitk, ws->pf_splitk_elems};
@@ -1505,6 +1636,8 @@ extern "C" blk_status blk_decode_loop(blk_ctx* c, int32_t first_token, int32_t n
         BLK_CUDA(cudaSetDevice(m->device));
         if (first_token < 0 || first_token >= m->n_vocab) throw BlkError(BLK_ERR_ARG, "token id out of range");
         if (c->n_past + n_steps > c->n_ctx) throw BlkError(BLK_ERR_CTX_FULL, "context is full");
+        flush_pos_shift(c);
+        note_new_cells(c, n_steps);
         BLK_CUDA(cudaStreamSynchronize(c->stream));
         c->h_tok[0] = first_token; c->tok_slot = 1;
         BLK_CUDA(cudaMemcpyAsync(c->d_tok, c->h_tok, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));

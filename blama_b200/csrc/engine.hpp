@@ -98,7 +98,13 @@ struct blk_ctx {
     int32_t* page_table = nullptr;
     std::vector<int32_t> page_table_host;                          // host copy of the page table (state save / restore)
     // decode-step state
-    int32_t* d_tok = nullptr; int32_t* d_pos = nullptr;
+    int32_t* d_tok = nullptr;
+    int32_t* d_pos = nullptr;             // device [2]: {cells in the cache = cell index of the next token, rotary position of the next token MINUS that}
+    // Self-Extend (llama_kv_self_seq_add / seq_div, reference Session.cpp:348-368): cell positions other than the cell index.
+    // Materialised on the first such call; empty = every cell's position is its index (the normal case, nothing is touched).
+    std::vector<int32_t> cell_pos, cell_shift;      // position of every cell; rotation delta not yet applied to its K row
+    int rope_off = 0;                               // rotary position of the next token - n_past
+    bool shift_pending = false;
     static constexpr int TOK_RING = 256;
     int32_t* h_tok = nullptr;             // pinned ring [TOK_RING]
     int tok_slot = 0;

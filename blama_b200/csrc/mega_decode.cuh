@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 
     mg_tr<TR>(P, S, 1);
     mg_embed(P);
-    rope_table_fill(S.rope, P.d_head / 2, pos, P.theta_scale, P.rope_freqs);
+    rope_table_fill(S.rope, P.d_head / 2, pos + P.pos[1], P.theta_scale, P.rope_freqs);      // P.pos = {cell index, rotary offset (Self-Extend)}
     __syncthreads();
 
     // ================================= the token: one stream phase per iteration =================================

@@ -220,6 +220,14 @@ BLK_API int blh_session_get_state(void* i, uint8_t* buf, int64_t cap, int64_t* s
 BLK_API int blh_session_set_state(void* i, uint8_t* buf, int64_t size) {
     return guard([&] { (void)static_cast<InstanceBox*>(i)->session->setState({buf, size_t(size < 0 ? 0 : size)}); });
 }
+// Self-Extend session (Session::InitParams::gaFactor / gaWidth)
+BLK_API int blh_session_start_ga(void* i, uint32_t seed, float temp, float top_p, uint32_t ga_factor, uint32_t ga_width) {
+    return guard([&] {
+        auto* box = static_cast<InstanceBox*>(i);
+        Session::InitParams sp; sp.seed = seed; sp.temperature = temp; sp.topP = top_p; sp.gaFactor = ga_factor; sp.gaWidth = ga_width;
+        box->session = &box->inst->startSession(sp);
+    });
+}
 BLK_API int blh_session_start_ex(void* i, uint32_t seed, float temp, float top_p, int sequential_verify, int infinite_context) {
     return guard([&] {
         auto* box = static_cast<InstanceBox*>(i);

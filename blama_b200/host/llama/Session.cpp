@@ -59,9 +59,10 @@ void Session::setInitialPrompt(std::span<const Token> initialPrompt) {
     if (initialPrompt.size() > m_maxTokens)
         Raise{} << "Initial prompt too long. Got " << initialPrompt.size() << " tokens, max: " << ctxLen - 4;
     if (m_params.gaFactor != 1) {
-        if (m_params.gaWidth % m_params.gaFactor != 0)
+        if (m_params.gaFactor == 0 || m_params.gaWidth % m_params.gaFactor != 0)
             Raise{} << "Group-attention width " << m_params.gaWidth << " must be a multiple of group-attention factor " << m_params.gaFactor;
-        Raise{} << "Self-Extend (gaFactor != 1) is not supported by this build";
+        logLine(LogLevel::Info, "self-extend: train = " + std::to_string(m_instance.model().trainCtxLength()) + ", gaFactor = " +
+                                    std::to_string(m_params.gaFactor) + ", gaWidth = " + std::to_string(m_params.gaWidth));
     }
     doDecode(initialPrompt, Source::InitialPrompt);
     m_phase = Phase::Generating;
@@ -142,7 +143,7 @@ std::vector<TokenPrediction> Session::fillCtx(std::span<TokenPrediction> tokens)
     for (const auto& token : tokens) wide = wide || token.logits.size() > 10;
     // a fill that does not fit the context shifts it token by token exactly like the reference's loop
     const bool overflows = m_numPast + tokens.size() >= uint32_t(blk_ctx_n_ctx(m_ctx));
-    if (m_instance.model().prefixInputsWithBos() || wide || overflows) {
+    if (m_instance.model().prefixInputsWithBos() || wide || overflows || m_params.gaFactor != 1) {      // (Self-Extend regroups between tokens)
         // every pushPrompt would insert a BOS before its token (reference :129-132) / more than 10 claimed ids somewhere:
         // keep the reference's literal per-token loop
         for (const auto& token : tokens) {
@@ -317,7 +318,7 @@ bool Session::setState(std::span<uint8_t> state) {
     if (m_phase != Phase::Initial) Raise{} << "Session already started";
     if (blk_state_set(m_ctx, state.data(), int64_t(state.size())) != BLK_OK) Raise{} << "Failed to set state";
     // llama.cpp keeps the positions inside its context; here the session's counters follow the restored cache
-    m_numPast = uint32_t(blk_ctx_n_past(m_ctx));
+    m_numPast = uint32_t(blk_ctx_next_pos(m_ctx));
     m_numKeep = std::min(m_numPast, m_maxTokens);
     refreshCandidates();
     m_phase = Phase::Generating;
@@ -325,6 +326,25 @@ bool Session::setState(std::span<uint8_t> state) {
 }
 
 void Session::ensureRoom(size_t nTokens) {
+    if (m_params.gaFactor != 1) {
+        // context extension via Self-Extend (reference :348-368): whenever a whole group-attention window lies behind gaIndex, its
+        // positions are divided by gaFactor and everything after it moves up close -- positions only, the cells stay; the engine
+        // re-rotates the K rows by the position change (llama.cpp's K-shift) before the next decode
+        const int gaFactor = int(m_params.gaFactor), gaWidth = int(m_params.gaWidth);
+        while (int(m_numPast) >= int(m_gaIndex) + gaWidth) {
+            const int ib = (gaFactor * int(m_gaIndex)) / gaWidth;
+            const int bd = (gaWidth / gaFactor) * (gaFactor - 1);
+            const int dd = (gaWidth / gaFactor) - ib * bd - gaWidth;
+            logLine(LogLevel::Debug, "Group attention shift: ib = " + std::to_string(ib) + ", bd = " + std::to_string(bd) + ", dd = " + std::to_string(dd));
+            throwIfFailed(blk_kv_seq_add(m_ctx, int32_t(m_gaIndex), int32_t(m_numPast), ib * bd), "group attention shift");
+            throwIfFailed(blk_kv_seq_div(m_ctx, int32_t(m_gaIndex) + ib * bd, int32_t(m_gaIndex) + ib * bd + gaWidth, gaFactor), "group attention shift");
+            throwIfFailed(blk_kv_seq_add(m_ctx, int32_t(m_gaIndex) + ib * bd + gaWidth, int32_t(m_numPast) + ib * bd, dd), "group attention shift");
+            m_numPast -= uint32_t(bd);
+            m_gaIndex += uint32_t(gaWidth / gaFactor);
+            logLine(LogLevel::Info, "Context full mitigation performed: past = " + std::to_string(m_numPast) + ", tokens = " + std::to_string(nTokens));
+        }
+        return;
+    }
     const auto ctxLen = uint32_t(blk_ctx_n_ctx(m_ctx));
     if (m_numPast + nTokens >= ctxLen) {
         // infinite text generation via context shifting (reference :324-347): keep the first numKeep tokens (the initial prompt),

@@ -27,8 +27,8 @@ struct TokenPrediction {
 class Session {
 public:
     struct InitParams {
-        uint32_t gaFactor = 1;          // group-attention (Self-Extend) factor; only 1 is supported by this build
-        uint32_t gaWidth = 512;
+        uint32_t gaFactor = 1;          // group-attention (Self-Extend) factor
+        uint32_t gaWidth = 512;         // group-attention width (a multiple of gaFactor)
         bool infiniteContext = true;    // a full context drops half of the non-prompt past and shifts the rest (false: throws)
         uint32_t seed = 0;
         std::string grammar;
@@ -121,7 +121,8 @@ private:
     Token m_currToken = Token_Invalid;      // sampled but not yet decoded
     unsigned m_maxTokens = 0;
     unsigned m_numKeep = 0;
-    uint32_t m_numPast = 0;
+    uint32_t m_numPast = 0;                 // position of the next token (= cells in the cache unless Self-Extend regrouped positions)
+    uint32_t m_gaIndex = 0;                 // number of grouped KV tokens (only used if gaFactor > 1)
     TokenDataVector m_candidates;           // device top-k of the current logits, descending
 };
 

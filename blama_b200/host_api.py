@@ -37,6 +37,7 @@ HOST_SYMBOLS = {
     "blh_session_get_state": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
     "blh_session_set_state": (C.c_int, [_vp, _vp, C.c_int64]),
     "blh_session_start_ex": (C.c_int, [_vp, _u32, _f32, _f32, C.c_int, C.c_int]),
+    "blh_session_start_ga": (C.c_int, [_vp, _u32, _f32, _f32, _u32, _u32]),
     "blh_lc_compare": (None, [_vp, _i32, _vp, _i32, _vp]),
     "blh_lc_similarity": (_f32, [_vp, _i32, _vp, _i32]),
     "blh_lc_score": (_f32, [_vp, _i32]),
@@ -172,6 +173,11 @@ class Instance:
     def start_session(self, seed: int = 0, temperature: float = 0.8, top_p: float = 0.95, sequential_verify: bool = False,
                       infinite_context: bool = True):
         _check(lib().blh_session_start_ex(self.h, seed, temperature, top_p, int(sequential_verify), int(infinite_context)))
+        return self
+
+    def start_session_self_extend(self, ga_factor: int, ga_width: int, seed: int = 0, temperature: float = 0.8, top_p: float = 0.95):
+        """Session with group attention (Self-Extend, reference Session.cpp:348-368)"""
+        _check(lib().blh_session_start_ga(self.h, seed, temperature, top_p, ga_factor, ga_width))
         return self
 
     def stop_session(self):

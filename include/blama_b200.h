@@ -103,6 +103,13 @@ BLK_API blk_status blk_sync(blk_ctx*);                      /* llama_synchronize
  * re-rotated by that position change exactly as llama.cpp's K-shift does (RoPE applied to the f16 cache row); n_past shrinks by
  * p1 - p0. */
 BLK_API blk_status blk_kv_shift(blk_ctx*, int32_t p0, int32_t p1);
+/* Self-Extend group attention (Session.cpp:348-368): llama_kv_self_seq_add(ctx, 0, p0, p1, delta) and llama_kv_self_seq_div(ctx, 0, p0,
+ * p1, d).  Cells whose POSITION lies in [p0, p1) get position + delta / position / d; the cells stay where they are, their K rows
+ * are re-rotated by the accumulated position change before the next decode (llama.cpp's K-shift), and the next token takes the
+ * position one past the largest one (blk_ctx_next_pos), which from then on differs from the number of cells (blk_ctx_n_past). */
+BLK_API blk_status blk_kv_seq_add(blk_ctx*, int32_t p0, int32_t p1, int32_t delta);
+BLK_API blk_status blk_kv_seq_div(blk_ctx*, int32_t p0, int32_t p1, int32_t d);
+BLK_API int32_t    blk_ctx_next_pos(const blk_ctx*);
 /* llama_state_get_size / llama_state_get_data / llama_state_set_data (Session.cpp:291-304): the KV rows of every layer, the
  * last logits row and its top-k list, as one blob (engine-specific layout, not llama.cpp's).  The sampler's RNG is not part of
  * it, as in the reference (t-integration.cpp:371-376). */

@@ -517,6 +517,9 @@ struct orc_ctx {
         if (pool) pool->run(total, grain, fn); else fn(0, total);
     }
     std::vector<std::vector<uint16_t>> kc, vc;     // per layer [n_ctx][n_head_kv*d_head] f16
+    // Self-Extend: position of every cell (empty = its index) and the rotation not yet applied to its K row; rope_off = position of
+    // the next token - n_past (llama_batch_allocr gives a batch without positions pos_max + 1 ...)
+    std::vector<int> cell_pos, cell_shift; int rope_off = 0;
     std::vector<float> logits; int n_logit_rows = 0; int last_n = 0;
     std::vector<float> hidden;
 };
@@ -606,12 +609,36 @@ void rope(float* v, int n_heads, int d_head, int n_rot, int pos, float theta_bas
     }
 }
 
+// llama.cpp's K-shift: before the next decode every cell whose position changed gets its K row rotated by the accumulated delta
+void orc_apply_pos_shift(orc_ctx* c) {
+    if (c->cell_shift.empty()) return;
+    const orc_model* m = c->m;
+    const int dh = m->d_head, nkv = m->n_head_kv, dkv = nkv * dh;
+    const Tensor* rf = m->get("rope_freqs.weight");
+    const float* ffac = rf ? (const float*)rf->data : nullptr;
+    std::vector<float> row(dkv);
+    for (int t = 0; t < c->n_past; t++) {
+        const int dl = c->cell_shift[t];
+        if (!dl) continue;
+        for (int l = 0; l < m->n_layer; l++) {
+            uint16_t* k = &c->kc[l][(size_t)t * dkv];
+            for (int i = 0; i < dkv; i++) row[i] = h2f(k[i]);
+            rope(row.data(), nkv, dh, m->n_rot, dl, m->rope_theta, ffac, m->neox);
+            for (int i = 0; i < dkv; i++) k[i] = f2h(row[i]);
+        }
+        c->cell_shift[t] = 0;
+    }
+}
+
 int forward(orc_ctx* c, const int32_t* tokens, int n, bool all_logits) {
     orc_model* m = c->m;
     if (n <= 0 || c->n_past + n > c->n_ctx) return 1;
     for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m->n_vocab) return 2;
     const int d = m->n_embd, dh = m->d_head, nh = m->n_head, nkv = m->n_head_kv, dq = nh * dh, dkv = nkv * dh, ff = m->n_ff;
-    const int pos0 = c->n_past;
+    const int pos0 = c->n_past;                      // cell index of the first new token
+    const int rpos0 = c->n_past + c->rope_off;       // its rotary position
+    orc_apply_pos_shift(c);
+    if (!c->cell_pos.empty()) for (int t = 0; t < n; t++) { c->cell_pos[pos0 + t] = rpos0 + t; c->cell_shift[pos0 + t] = 0; }
     const Tensor* te = m->get("token_embd.weight");
     std::vector<float> X((size_t)n * d), H((size_t)n * d), Q((size_t)n * dq), Kc((size_t)n * dkv), Vc((size_t)n * dkv), A((size_t)n * dq),
         X2((size_t)n * d), G((size_t)n * ff), U((size_t)n * ff), T((size_t)n * std::max(d, dq));
@@ -631,8 +658,8 @@ int forward(orc_ctx* c, const int32_t* tokens, int n, bool all_logits) {
         if (const Tensor* b = m->get(p + "attn_k.bias")) for (int t = 0; t < n; t++) for (int i = 0; i < dkv; i++) Kc[(size_t)t * dkv + i] += ((const float*)b->data)[i];
         if (const Tensor* b = m->get(p + "attn_v.bias")) for (int t = 0; t < n; t++) for (int i = 0; i < dkv; i++) Vc[(size_t)t * dkv + i] += ((const float*)b->data)[i];
         for (int t = 0; t < n; t++) {
-            rope(Q.data() + (size_t)t * dq, nh, dh, m->n_rot, pos0 + t, m->rope_theta, ffac, m->neox);
-            rope(Kc.data() + (size_t)t * dkv, nkv, dh, m->n_rot, pos0 + t, m->rope_theta, ffac, m->neox);
+            rope(Q.data() + (size_t)t * dq, nh, dh, m->n_rot, rpos0 + t, m->rope_theta, ffac, m->neox);
+            rope(Kc.data() + (size_t)t * dkv, nkv, dh, m->n_rot, rpos0 + t, m->rope_theta, ffac, m->neox);
         }
         // KV cache store: f32 -> f16 (ggml_cpy)
         for (int t = 0; t < n; t++) for (int i = 0; i < dkv; i++) {
@@ -699,7 +726,37 @@ extern "C" orc_ctx* orc_ctx_create(orc_model* m, int32_t n_ctx, int32_t mode, in
     return c;
 }
 extern "C" void orc_ctx_free(orc_ctx* c) { delete c; }
-extern "C" void orc_kv_clear(orc_ctx* c) { c->n_past = 0; }
+extern "C" void orc_kv_clear(orc_ctx* c) { c->n_past = 0; c->cell_pos.clear(); c->cell_shift.clear(); c->rope_off = 0; }
+
+// Self-Extend (reference Session.cpp:348-368): llama_kv_self_seq_add / seq_div on the POSITIONS of the cells (llama-kv-cache.cpp:
+// pos += delta / pos /= d, the change accumulated in cell.delta and applied to K by the next decode's K-shift)
+namespace {
+void orc_positions(orc_ctx* c) {
+    if (!c->cell_pos.empty()) return;
+    c->cell_pos.resize(c->n_ctx); c->cell_shift.assign(c->n_ctx, 0);
+    for (int i = 0; i < c->n_ctx; i++) c->cell_pos[i] = i;
+}
+void orc_refresh_off(orc_ctx* c) {
+    int mx = -1;
+    for (int i = 0; i < c->n_past; i++) mx = std::max(mx, c->cell_pos[i]);
+    c->rope_off = mx + 1 - c->n_past;
+}
+} // namespace
+extern "C" int32_t orc_kv_seq_add(orc_ctx* c, int32_t p0, int32_t p1, int32_t delta) {
+    if (p0 < 0 || p1 < p0) return 1;
+    orc_positions(c);
+    for (int i = 0; i < c->n_past; i++) if (c->cell_pos[i] >= p0 && c->cell_pos[i] < p1) { c->cell_pos[i] += delta; c->cell_shift[i] += delta; }
+    orc_refresh_off(c);
+    return 0;
+}
+extern "C" int32_t orc_kv_seq_div(orc_ctx* c, int32_t p0, int32_t p1, int32_t d) {
+    if (p0 < 0 || p1 < p0 || d <= 0) return 1;
+    orc_positions(c);
+    for (int i = 0; i < c->n_past; i++) if (c->cell_pos[i] >= p0 && c->cell_pos[i] < p1) { const int old = c->cell_pos[i]; c->cell_pos[i] /= d; c->cell_shift[i] += c->cell_pos[i] - old; }
+    orc_refresh_off(c);
+    return 0;
+}
+extern "C" int32_t orc_next_pos(const orc_ctx* c) { return c->n_past + c->rope_off; }
 
 // Context shift (reference Session.cpp:341-342): llama_kv_self_seq_rm(ctx, 0, p0, p1) drops the cells of positions [p0, p1);
 // llama_kv_self_seq_add(ctx, 0, p1, n_past, -(p1 - p0)) moves the positions of the cells behind them down, which llama.cpp applies

@@ -52,6 +52,10 @@ void     orc_kv_clear(orc_ctx*);
  * (reference Session.cpp:341-342) */
 int32_t  orc_kv_shift(orc_ctx*, int32_t p0, int32_t p1);
 int32_t  orc_n_past(const orc_ctx*);
+/* llama_kv_self_seq_add / llama_kv_self_seq_div on cell positions (Self-Extend, reference Session.cpp:359-361) */
+int32_t  orc_kv_seq_add(orc_ctx*, int32_t p0, int32_t p1, int32_t delta);
+int32_t  orc_kv_seq_div(orc_ctx*, int32_t p0, int32_t p1, int32_t d);
+int32_t  orc_next_pos(const orc_ctx*);
 /* decode n tokens at positions n_past..; all_logits!=0 keeps logits of every position. returns 0 on success */
 int32_t  orc_decode(orc_ctx*, const int32_t* tokens, int32_t n, int32_t all_logits);
 /* logits of the i-th token of the last decode (-1 = last); pointer valid until the next decode */

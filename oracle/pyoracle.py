@@ -40,7 +40,8 @@ def _load() -> C.CDLL:
         "orc_n_vocab": (i32, [vp]), "orc_n_ctx_train": (i32, [vp]), "orc_n_embd": (i32, [vp]), "orc_n_layer": (i32, [vp]),
         "orc_token_bos": (i32, [vp]), "orc_is_eog": (i32, [vp, i32]), "orc_weight_bytes_per_token": (i64, [vp]),
         "orc_ctx_create": (vp, [vp, i32, i32, i32]), "orc_ctx_free": (None, [vp]), "orc_kv_clear": (None, [vp]),
-        "orc_kv_shift": (i32, [vp, i32, i32]),
+        "orc_kv_shift": (i32, [vp, i32, i32]), "orc_kv_seq_add": (i32, [vp, i32, i32, i32]), "orc_kv_seq_div": (i32, [vp, i32, i32, i32]),
+        "orc_next_pos": (i32, [vp]),
         "orc_n_past": (i32, [vp]), "orc_decode": (i32, [vp, vp, i32, i32]),
         "orc_get_logits": (C.POINTER(C.c_float), [vp, i32]), "orc_get_hidden": (C.POINTER(C.c_float), [vp, i32]),
         "orc_topk": (None, [vp, i32, i32, vp]), "orc_gather_sorted": (i32, [vp, i32, vp, i32, vp]),
@@ -121,6 +122,18 @@ class Ctx:
     def kv_shift(self, p0: int, p1: int):
         if lib().orc_kv_shift(self.h, p0, p1):
             raise RuntimeError("orc_kv_shift: bad range")
+
+    def kv_seq_add(self, p0: int, p1: int, delta: int):
+        if lib().orc_kv_seq_add(self.h, p0, p1, delta):
+            raise RuntimeError("orc_kv_seq_add: bad range")
+
+    def kv_seq_div(self, p0: int, p1: int, d: int):
+        if lib().orc_kv_seq_div(self.h, p0, p1, d):
+            raise RuntimeError("orc_kv_seq_div: bad arguments")
+
+    @property
+    def next_pos(self) -> int:
+        return lib().orc_next_pos(self.h)
 
     @property
     def n_past(self) -> int:

@@ -139,3 +139,85 @@ def test_states(gguf_path):
     for i in (inst, other, small):
         i.close()
     hm.close()
+
+
+def _regroup(ctxs, n_pos, ga_i, F, W):
+    """Session::ensureRoom's Self-Extend loop (reference Session.cpp:348-368) applied to every context in `ctxs`"""
+    while n_pos >= ga_i + W:
+        ib = (F * ga_i) // W
+        bd = (W // F) * (F - 1)
+        dd = (W // F) - ib * bd - W
+        for c in ctxs:
+            c.kv_seq_add(ga_i, n_pos, ib * bd)
+            c.kv_seq_div(ga_i + ib * bd, ga_i + ib * bd + W, F)
+            c.kv_seq_add(ga_i + ib * bd + W, n_pos + ib * bd, dd)
+        n_pos -= bd
+        ga_i += W // F
+    return n_pos, ga_i
+
+
+@pytest.mark.parametrize("name,F,W", [("small-llama-q4km", 2, 32), ("small-qwen2-q8", 4, 32), ("tiny-llama-q8", 2, 16)])
+def test_self_extend_positions_match_oracle(name, F, W, gguf_path, oracle):
+    """llama_kv_self_seq_add / seq_div on cell positions + the K-shift, against the oracle's restatement, driven by the reference's
+    schedule; the next token's rotary position is one past the largest cell position"""
+    from blama_b200 import capi
+
+    path = gguf_path(name)
+    om = oracle.Model(path); oc = oracle.Ctx(om, 256, oracle.MODE_GGML, 4)
+    m = capi.Model(path); c = capi.Ctx(m, 256)
+    toks = [int(t) for t in gs.synth_prompt(name, 140, 61)]
+    n_pos, ga_i, worst, regroups = 0, 0, 0.0, 0
+    # a 40-token prompt in one call (the tcgen05 prefill on the GPU), then token by token
+    oc.decode(toks[:40]); c.decode(toks[:40])
+    n_pos = 40
+    for i, t in enumerate(toks[40:]):
+        before = ga_i
+        n_pos, ga_i = _regroup([c, oc], n_pos, ga_i, F, W)
+        regroups += ga_i != before
+        assert c.next_pos == oc.next_pos == n_pos and c.n_past == 40 + i
+        want = oc.decode([t])[0]
+        c.decode([t])
+        n_pos += 1
+        err = float(np.abs(c.logits() - want).max())
+        worst = max(worst, err)
+        # the prompt went through the bf16 prefill on the GPU and the int8 path in the oracle: quantisation-noise bound
+        assert err <= 0.5, (i, err)
+    print(f"\n[self-extend {name} F={F} W={W}] {regroups} regroupings over 100 tokens, max |dlogit| = {worst:.3g}")
+    assert regroups >= 3
+    # the state blob carries the positions: a second context continues identically
+    c2 = capi.Ctx(m, 256)
+    c2.state_set(c.state_get())
+    assert c2.next_pos == c.next_pos and c2.n_past == c.n_past
+    c.decode([toks[0]]); c2.decode([toks[0]])
+    assert np.array_equal(c.logits(), c2.logits())
+    with pytest.raises(capi.BlkError):
+        c.kv_shift(2, 5)                                   # compaction is not defined once positions have been regrouped
+    c.close(); c2.close(); m.close(); oc.close(); om.close()
+
+
+def test_self_extend_session_follows_the_reference_schedule(gguf_path, oracle):
+    from blama_b200 import host_api as H
+
+    name, F, W = "small-llama-q4km", 2, 32
+    path = gguf_path(name)
+    prompt = [int(t) for t in gs.synth_prompt(name, 10, 8)]
+    hm = H.Model(path)
+    inst = H.Instance(hm, 256)
+    inst.start_session_self_extend(F, W, seed=6).set_initial_prompt(prompt)
+    toks, top = inst.complete(120)
+    assert len(toks) == 120
+    inst.stop_session()
+    with pytest.raises(H.HostError, match="^Group-attention width 33 must be a multiple of group-attention factor 2$"):
+        inst.start_session_self_extend(2, 33).set_initial_prompt(prompt)
+    inst.close()
+    om = oracle.Model(path); oc = oracle.Ctx(om, 256, oracle.MODE_GGML, 4)
+    oc.decode(prompt)
+    n_pos, ga_i, worst = len(prompt), 0, 0.0
+    for i, t in enumerate(toks):
+        n_pos, ga_i = _regroup([oc], n_pos, ga_i, F, W)
+        row = oc.decode([int(t)])[0]
+        n_pos += 1
+        worst = max(worst, float(np.abs(row[top[i]["token"]] - top[i]["logit"]).max()))
+    print(f"\n[self-extend session] ga index {ga_i} after 120 tokens, max |dlogit| on the reported top-10 = {worst:.3g}")
+    assert ga_i >= 3 * (W // F) and worst <= ps.FLIP_TOL, (ga_i, worst)
+    oc.close(); om.close(); hm.close()
