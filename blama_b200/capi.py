@@ -85,6 +85,9 @@ SYMBOLS = {
     "blk_test_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
     "blk_bench_gemm": (_i32, [_i32, _i32, _vp, _i64, _i64, _i64, _i32, _f32p]),
     "blk_test_dequant": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp]),
+    "blk_test_rmsnorm": (_i32, [_i32, _vp, _vp, _i32, _i32, C.c_float, _vp]),
+    "blk_test_qkv_post": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp, _vp]),
+    "blk_test_prefill_attn": (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, C.POINTER(_i32)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -123,6 +126,34 @@ def _p(a: np.ndarray):
 
 def init() -> None:
     _check(lib().blk_init())
+
+
+def test_rmsnorm(x: np.ndarray, w: np.ndarray, eps: float, device: int = 0) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32); w = np.ascontiguousarray(w, dtype=np.float32)
+    out = np.zeros_like(x)
+    _check(lib().blk_test_rmsnorm(device, _p(x), _p(w), x.shape[0], x.shape[1], eps, _p(out)))
+    return out
+
+
+def test_qkv_post(qkv: np.ndarray, n_head: int, n_head_kv: int, d_head: int, neox: bool, pos0: int, theta: float, freq_factors=None, device: int = 0):
+    qkv = np.ascontiguousarray(qkv, dtype=np.float32)
+    T = qkv.shape[0]
+    q = np.zeros((T, n_head * d_head), dtype=np.float32); k = np.zeros((T, n_head_kv * d_head), dtype=np.float32); v = np.zeros_like(k)
+    ff = None if freq_factors is None else np.ascontiguousarray(freq_factors, dtype=np.float32)
+    _check(lib().blk_test_qkv_post(device, _p(qkv), T, n_head, n_head_kv, d_head, int(neox), pos0, theta, _p(ff) if ff is not None else None, _p(q), _p(k), _p(v)))
+    return q, k, v
+
+
+def test_prefill_attn(q: np.ndarray, k: np.ndarray, v: np.ndarray, pos0: int, n_head: int, n_head_kv: int, d_head: int, device: int = 0):
+    q = np.ascontiguousarray(q, dtype=np.float32); k = np.ascontiguousarray(k, dtype=np.float32); v = np.ascontiguousarray(v, dtype=np.float32)
+    T = q.shape[0]
+    out = np.zeros_like(q)
+    tc = _i32(0)
+    _check(lib().blk_test_prefill_attn(device, _p(q), _p(k), _p(v), T, pos0, n_head, n_head_kv, d_head, _p(out), C.byref(tc)))
+    return out, bool(tc.value)
+
+
+test_rmsnorm.__test__ = test_qkv_post.__test__ = test_prefill_attn.__test__ = False      # (not pytest tests)
 
 
 def decode_batch(ws: "Ctx", ctxs: Sequence["Ctx"], tokens: Sequence[int], k: int = 40) -> np.ndarray:

@@ -2007,3 +2007,133 @@ extern "C" blk_status blk_bench_gemm(int32_t device, int32_t type, const void* b
         *avg_ms = ms / (float)iters;
     });
 }
+
+// ---- unit entry points of the non-GEMM prefill kernels (tests/test_gpu_prefill_units.py: float64 numpy on the rounded operands) ----
+namespace {
+struct Scratch {        // device allocations of one test call
+    std::vector<void*> ptrs;
+    template <class T> T* get(size_t n) { void* p = nullptr; BLK_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); ptrs.push_back(p); return reinterpret_cast<T*>(p); }
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+};
+__global__ void f32_to_f16_kernel(const float* x, __half* y, size_t n) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = __float2half_rn(x[i]); }
+__global__ void f16_to_f32_kernel(const __half* x, float* y, size_t n) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = __half2float(x[i]); }
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* x, float* y, size_t n) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = __bfloat162float(x[i]); }
+__global__ void rope_rows_kernel(float2* rope_cs, int half_rot, int pos0, float theta_scale, const float* ff) {
+    rope_table_fill(rope_cs + (size_t)blockIdx.x * half_rot, half_rot, pos0 + (int)blockIdx.x, theta_scale, ff);
+}
+unsigned grid_of(size_t n) { return (unsigned)((n + 255) / 256); }
+} // namespace
+
+// y[t][:] = bf16(rms_norm(x[t][:]) * w) through rmsnorm_bf16_kernel; out as f32 (exactly the bf16 values)
+extern "C" blk_status blk_test_rmsnorm(int32_t device, const float* x, const float* w, int32_t T, int32_t K, float eps, float* out) {
+    return guarded([&] {
+        if (blk_init() != BLK_OK) throw BlkError(BLK_ERR_NO_DEVICE, g_last_error);
+        if (T <= 0 || K <= 0 || K % 8 || K > 8192) throw BlkError(BLK_ERR_ARG, "blk_test_rmsnorm: bad shape");
+        BLK_CUDA(cudaSetDevice(device));
+        Scratch sc;
+        float* dx = sc.get<float>((size_t)T * K); float* dw = sc.get<float>(K); float* dout = sc.get<float>((size_t)T * K);
+        __nv_bfloat16* dy = sc.get<__nv_bfloat16>((size_t)T * K);
+        BLK_CUDA(cudaMemcpy(dx, x, (size_t)T * K * 4, cudaMemcpyHostToDevice));
+        BLK_CUDA(cudaMemcpy(dw, w, (size_t)K * 4, cudaMemcpyHostToDevice));
+        rmsnorm_bf16_launch(dx, dw, K, eps, dy, T, nullptr);
+        bf16_to_f32_kernel<<<grid_of((size_t)T * K), 256>>>(dy, dout, (size_t)T * K);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(cudaMemcpy(out, dout, (size_t)T * K * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+// qkv_post_kernel on T rows at positions pos0 .. : q_out [T][dq], k_out / v_out [T][dkv] (the f16 values as f32); freq_factors may be NULL
+extern "C" blk_status blk_test_qkv_post(int32_t device, const float* qkv, int32_t T, int32_t n_head, int32_t n_head_kv, int32_t d_head, int32_t neox,
+                                        int32_t pos0, float rope_theta, const float* freq_factors, float* q_out, float* k_out, float* v_out) {
+    return guarded([&] {
+        if (blk_init() != BLK_OK) throw BlkError(BLK_ERR_NO_DEVICE, g_last_error);
+        if (T <= 0 || pos0 < 0 || (d_head != 64 && d_head != 128) || n_head <= 0 || n_head_kv <= 0) throw BlkError(BLK_ERR_ARG, "blk_test_qkv_post: bad shape");
+        BLK_CUDA(cudaSetDevice(device));
+        const int dq = n_head * d_head, dkv = n_head_kv * d_head, ld = dq + 2 * dkv, half = d_head / 2;
+        const int n_pages = (pos0 + T + KV_PAGE - 1) / KV_PAGE;
+        Scratch sc;
+        float* dqkv = sc.get<float>((size_t)T * ld);
+        float2* rope = sc.get<float2>((size_t)T * half);
+        float* dff = freq_factors ? sc.get<float>(half) : nullptr;
+        __half* dq16 = sc.get<__half>((size_t)T * dq);
+        __half* kp = sc.get<__half>((size_t)n_pages * KV_PAGE * dkv); __half* vp = sc.get<__half>((size_t)n_pages * KV_PAGE * dkv);
+        int32_t* pt = sc.get<int32_t>(n_pages); int32_t* dpos = sc.get<int32_t>(2);
+        float* fq = sc.get<float>((size_t)T * dq); float* fk = sc.get<float>((size_t)T * dkv); float* fv = sc.get<float>((size_t)T * dkv);
+        // a REVERSED page table: the kernel must go through it
+        std::vector<int32_t> hpt(n_pages);
+        for (int i = 0; i < n_pages; i++) hpt[i] = n_pages - 1 - i;
+        const int32_t hpos[2] = {pos0, 0};
+        BLK_CUDA(cudaMemcpy(dqkv, qkv, (size_t)T * ld * 4, cudaMemcpyHostToDevice));
+        BLK_CUDA(cudaMemcpy(pt, hpt.data(), (size_t)n_pages * 4, cudaMemcpyHostToDevice));
+        BLK_CUDA(cudaMemcpy(dpos, hpos, sizeof(hpos), cudaMemcpyHostToDevice));
+        if (dff) BLK_CUDA(cudaMemcpy(dff, freq_factors, (size_t)half * 4, cudaMemcpyHostToDevice));
+        rope_rows_kernel<<<T, 64>>>(rope, half, pos0, powf(rope_theta, -2.0f / (float)d_head), dff);
+        QkvPostArgs qa{};
+        qa.qkv = dqkv; qa.ld = ld; qa.rope_cs = rope; qa.pos0 = dpos; qa.q_out = dq16; qa.k_pool = kp; qa.v_pool = vp; qa.page_table = pt;
+        qa.dq = dq; qa.dkv = dkv; qa.d_head = d_head; qa.neox = neox ? 1 : 0;
+        qkv_post_kernel<<<T, 256>>>(qa);
+        BLK_CUDA(cudaGetLastError());
+        f16_to_f32_kernel<<<grid_of((size_t)T * dq), 256>>>(dq16, fq, (size_t)T * dq);
+        BLK_CUDA(cudaMemcpy(q_out, fq, (size_t)T * dq * 4, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < T; t++) {        // rows come back through the same page table
+            const int pos = pos0 + t;
+            const size_t row = ((size_t)hpt[pos / KV_PAGE] * KV_PAGE + (pos % KV_PAGE)) * dkv;
+            f16_to_f32_kernel<<<grid_of(dkv), 256>>>(kp + row, fk + (size_t)t * dkv, dkv);
+            f16_to_f32_kernel<<<grid_of(dkv), 256>>>(vp + row, fv + (size_t)t * dkv, dkv);
+        }
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(cudaMemcpy(k_out, fk, (size_t)T * dkv * 4, cudaMemcpyDeviceToHost));
+        BLK_CUDA(cudaMemcpy(v_out, fv, (size_t)T * dkv * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+// Causal prefill attention of T query rows at positions pos0 .. over a cache of pos0 + T keys: q [T][n_head*dh], k / v [pos0+T][n_head_kv*dh]
+// (rounded to f16 on the way in, like the cache); out [T][n_head*dh] = the kernel's bf16 output as f32.  *used_tc = 1 when the tcgen05
+// kernel ran (d_head 128), 0 for the mma.sync fallbacks.
+extern "C" blk_status blk_test_prefill_attn(int32_t device, const float* q, const float* k, const float* v, int32_t T, int32_t pos0, int32_t n_head,
+                                            int32_t n_head_kv, int32_t d_head, float* out, int32_t* used_tc) {
+    return guarded([&] {
+        if (blk_init() != BLK_OK) throw BlkError(BLK_ERR_NO_DEVICE, g_last_error);
+        if (T <= 0 || pos0 < 0 || (d_head != 64 && d_head != 128) || n_head <= 0 || n_head_kv <= 0 || n_head % n_head_kv) throw BlkError(BLK_ERR_ARG, "blk_test_prefill_attn: bad shape");
+        BLK_CUDA(cudaSetDevice(device));
+        const int dq = n_head * d_head, dkv = n_head_kv * d_head, n_keys = pos0 + T;
+        blk_model mm; mm.device = device; mm.n_head = n_head; mm.n_head_kv = n_head_kv; mm.d_head = d_head;
+        blk_ctx c; c.m = &mm;
+        BLK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.n_pages = (n_keys + KV_PAGE - 1) / KV_PAGE; c.n_past = pos0;
+        const size_t pool = (size_t)c.n_pages * KV_PAGE * dkv;
+        float* fq = dalloc<float>(&c, (size_t)T * dq); float* fkv = dalloc<float>(&c, (size_t)n_keys * dkv);
+        __half* q16 = dalloc<__half>(&c, (size_t)T * dq); __half* kp = dalloc<__half>(&c, pool); __half* vp = dalloc<__half>(&c, pool);
+        __nv_bfloat16* o = dalloc<__nv_bfloat16>(&c, (size_t)T * dq); float* fo = dalloc<float>(&c, (size_t)T * dq);
+        c.page_table = dalloc<int32_t>(&c, c.n_pages); c.d_pos = dalloc<int32_t>(&c, 2);
+        std::vector<int32_t> hpt(c.n_pages);
+        for (int i = 0; i < c.n_pages; i++) hpt[i] = i;
+        const int32_t hpos[2] = {pos0, 0};
+        BLK_CUDA(cudaMemcpyAsync(c.page_table, hpt.data(), (size_t)c.n_pages * 4, cudaMemcpyHostToDevice, c.stream));
+        BLK_CUDA(cudaMemcpyAsync(c.d_pos, hpos, sizeof(hpos), cudaMemcpyHostToDevice, c.stream));
+        BLK_CUDA(cudaMemsetAsync(kp, 0, pool * 2, c.stream)); BLK_CUDA(cudaMemsetAsync(vp, 0, pool * 2, c.stream));
+        BLK_CUDA(cudaMemcpyAsync(fq, q, (size_t)T * dq * 4, cudaMemcpyHostToDevice, c.stream));
+        f32_to_f16_kernel<<<grid_of((size_t)T * dq), 256, 0, c.stream>>>(fq, q16, (size_t)T * dq);
+        BLK_CUDA(cudaMemcpyAsync(fkv, k, (size_t)n_keys * dkv * 4, cudaMemcpyHostToDevice, c.stream));
+        f32_to_f16_kernel<<<grid_of((size_t)n_keys * dkv), 256, 0, c.stream>>>(fkv, kp, (size_t)n_keys * dkv);
+        BLK_CUDA(cudaStreamSynchronize(c.stream));
+        BLK_CUDA(cudaMemcpyAsync(fkv, v, (size_t)n_keys * dkv * 4, cudaMemcpyHostToDevice, c.stream));
+        f32_to_f16_kernel<<<grid_of((size_t)n_keys * dkv), 256, 0, c.stream>>>(fkv, vp, (size_t)n_keys * dkv);
+        const bool tc = prefill_attn_tc_supported(d_head, n_head, n_head_kv);
+        if (tc) { c.pf_vt_pad = (c.n_pages * KV_PAGE + 127) / 128 * 128; c.pf_vt = dalloc<__half>(&c, (size_t)n_head_kv * 128 * c.pf_vt_pad); }
+        BLK_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * (128 + 8) * 2));
+        BLK_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * (64 + 8) * 2));
+        PrefillAttnArgs pa{};
+        pa.q = q16; pa.k_pool = kp; pa.v_pool = vp; pa.page_table = c.page_table; pa.pos0 = c.d_pos; pa.out = o; pa.T = T;
+        pa.n_head = n_head; pa.n_head_kv = n_head_kv; pa.kv_dim = dkv; pa.scale = 1.0f / sqrtf((float)d_head);
+        launch_prefill_attn(&c, pa, T, c.stream);
+        bf16_to_f32_kernel<<<grid_of((size_t)T * dq), 256, 0, c.stream>>>(o, fo, (size_t)T * dq);
+        BLK_CUDA(cudaGetLastError());
+        BLK_CUDA(cudaMemcpyAsync(out, fo, (size_t)T * dq * 4, cudaMemcpyDeviceToHost, c.stream));
+        BLK_CUDA(cudaStreamSynchronize(c.stream));
+        if (used_tc) {
+            static const bool no_tc = [] { const char* e = getenv("BLK_ATTN_TC"); return e && e[0] == '0'; }();
+            *used_tc = (tc && !no_tc) ? 1 : 0;
+        }
+    });
+}

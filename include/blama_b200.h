@@ -200,6 +200,14 @@ BLK_API blk_status blk_test_gemm(int32_t device, int32_t type, const void* w_blo
                                  const float* x, int64_t n_tok, float* y);
 /* average duration of the prefill GEMM on the given weights with n_tok resident bf16 activations (CUDA events) */
 BLK_API blk_status blk_bench_gemm(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k, int64_t n_tok, int32_t iters, float* avg_ms);
+/* The non-GEMM kernels of the prefill path, one at a time (host buffers in / out; f16 / bf16 results come back as the exact values in
+ * f32): rmsnorm_bf16_kernel; qkv_post_kernel (RoPE on q and k, q -> f16, k / v -> the f16 cache rows, read back through a reversed
+ * page table); the causal prefill attention (tcgen05 kernel for d_head 128, *used_tc tells) over a cache of pos0 + T keys. */
+BLK_API blk_status blk_test_rmsnorm(int32_t device, const float* x, const float* w, int32_t T, int32_t K, float eps, float* out);
+BLK_API blk_status blk_test_qkv_post(int32_t device, const float* qkv, int32_t T, int32_t n_head, int32_t n_head_kv, int32_t d_head, int32_t neox,
+                                     int32_t pos0, float rope_theta, const float* freq_factors, float* q_out, float* k_out, float* v_out);
+BLK_API blk_status blk_test_prefill_attn(int32_t device, const float* q, const float* k, const float* v, int32_t T, int32_t pos0, int32_t n_head,
+                                         int32_t n_head_kv, int32_t d_head, float* out, int32_t* used_tc);
 /* dequantise through the device re-tile + dequant kernels */
 BLK_API blk_status blk_test_dequant(int32_t device, int32_t type, const void* w_blocks, int64_t rows, int64_t k, float* out);
 
