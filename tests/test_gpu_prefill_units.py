@@ -8,8 +8,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-BF16_ULP = 2.0 ** -8          # relative spacing of bf16 (8 significand bits)
-F16_ULP = 2.0 ** -11 * 2      # relative spacing of f16 (11 significand bits)
+BF16_ULP = 2.0 ** -7          # relative spacing of bf16 at the bottom of a binade (8 significand bits): half an ulp = 2^-8 = 3.9e-3
+F16_ULP = 2.0 ** -10          # ... of f16 (11 significand bits): half an ulp = 4.9e-4
 
 
 @pytest.mark.parametrize("T,K", [(5, 256), (64, 2048), (33, 4096), (7, 8192)])
