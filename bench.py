@@ -517,7 +517,8 @@ def run_dispatcher(args):
     sh = gguf_synth.SHAPES[args.shape]
     p0 = 32
     v_max = args.verify if args.mode == "stream" else 64 if args.mode == "batch" else min(args.verify, 1024)
-    srv = host_api.Server(models, ctx_size=p0 + max(v_max, args.new) + 64, batch_size=4096, max_batch=args.max_batch if args.mode == "batch" else 1)
+    workers = [m for m in models for _ in range(max(1, args.workers_per_gpu))]      # several Instances may share one Model (t-integration.cpp:220-224)
+    srv = host_api.Server(workers, ctx_size=p0 + max(v_max, args.new) + 64, batch_size=4096, max_batch=args.max_batch if args.mode == "batch" else 1)
     prompt = gguf_synth.synth_prompt(args.shape, p0, 1)
     # the prover's side (not timed): ONE /complete of v_max tokens through the same Server; the queued verify requests re-fill
     # prefixes of that response (lengths spread over [v_max / 2, v_max]) -- the cost of a verify depends on its length only
@@ -536,7 +537,7 @@ def run_dispatcher(args):
     def wait(i, t):
         return srv.wait_verify(t) if kinds[i] == "verify" else len(srv.wait_complete(t, cap=args.new)[0])
 
-    for t in [srv.submit_verify(prompt, toks[: lens[0]], top[: lens[0]], nl[: lens[0]], seed=1) for _ in range(2 * n_gpus)]:      # warm-up: every worker
+    for t in [srv.submit_verify(prompt, toks[: lens[0]], top[: lens[0]], nl[: lens[0]], seed=1) for _ in range(2 * len(workers))]:      # warm-up: every worker
         srv.wait_verify(t)
     srv.drain()
     sampler = ClockSampler(0)
@@ -550,7 +551,7 @@ def run_dispatcher(args):
     st1 = srv.stats()
     sampler.stop_flag.set()
     per_worker = [{"device": b["device"], "requests": b["requests"] - a["requests"], "gpu_ms": b["gpu_ms"] - a["gpu_ms"]} for a, b in zip(st0, st1)]
-    dev_s = max(w["gpu_ms"] for w in per_worker) / 1e3            # device clock (CUDA events around every request), max over the replicas
+    dev_s = max(w["gpu_ms"] for w in per_worker) / 1e3            # device clock (CUDA events around every request), max over the workers
     v_tokens = sum(lens[i] for i in range(R) if kinds[i] == "verify")
     d_tokens = sum(int(results[i]) for i in range(R) if kinds[i] == "complete")
     scores = [float(results[i]) for i in range(R) if kinds[i] == "verify"]
@@ -575,7 +576,7 @@ def run_dispatcher(args):
                    "responses": "prefixes of one prover run (a /complete of the longest length through the same Server)",
                    "l2": "per-request weight stream >> 126 MB L2"},
         "timing": "CUDA events on every replica's stream around each request, summed per replica; value = tokens / max over replicas",
-        "wall_s": wall, "value_wall": v_tokens / wall, "dispatch_efficiency": busy / (n_gpus * wall),
+        "wall_s": wall, "value_wall": v_tokens / wall, "dispatch_efficiency": busy / (len(workers) * wall), "workers_per_gpu": max(1, args.workers_per_gpu),
         "decode_tokens": d_tokens, "decode_tok_s_wall": d_tokens / wall if d_tokens else None,
         "per_worker": per_worker, "score_min": min(scores) if scores else None, "score_max": max(scores) if scores else None,
         "roofline": {"bound": "tensor", "achieved": flops / dev_s / 1e12 / n_gpus, "peak": tf_peak, "unit": "TFLOP/s per GPU",
@@ -627,6 +628,8 @@ def main():
                     help="step: the contract's per-GPU replica benchmark; stream: queued /verify_completion requests through ONE Server with "
                          "--gpus replicas in one process (BASELINE configs[4]); mix: alternating /complete and /verify_completion requests (configs[3])")
     ap.add_argument("--requests", type=int, default=64, help="queued requests of --mode stream / mix")
+    ap.add_argument("--workers-per-gpu", type=int, default=1, help="--mode stream / mix: Server workers (Instances) sharing each replica: with 2, "
+                    "one request's host work (claimed-id preparation, LogitComparer) overlaps the other's prefill")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

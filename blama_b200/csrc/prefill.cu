@@ -1,5 +1,6 @@
 // prefill.cu -- launchers of the multi-token prefill path (tcgen05 GEMM + helpers).
 #include "prefill.hpp"
+#include <cstdlib>
 #include "prefill_gemm.cuh"
 #include "prefill_attn_tc.cuh"
 
@@ -114,6 +115,10 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
 
 // first pass of the two-pass form: W -> panel rows [row0, row0 + W.N)
 cudaError_t panel_dequant(const QMat& W, __nv_bfloat16* panel, long long row0, cudaStream_t st) {
+    // BLK_PANEL_NOFILL=1 (measurement only, results are garbage): skip the de-quantisation pass so that the GEMMs read whatever the
+    // panel holds -- the difference in wall time is what the panel fills (their HBM traffic and power) cost a verify
+    static const bool nofill = [] { const char* e = getenv("BLK_PANEL_NOFILL"); return e && e[0] == '1'; }();
+    if (nofill) return cudaSuccess;
     const long long total = (long long)W.N * (W.K >> 6);
     const unsigned grid = (unsigned)((total + 255) / 256);
     __nv_bfloat16* dst = panel + (size_t)row0 * W.K;
