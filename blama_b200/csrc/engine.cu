@@ -69,6 +69,7 @@ blk_model::~blk_model() {
     if (allocs.empty()) return;          // vocabulary-only models never touched a device
     cudaSetDevice(device);
     for (void* p : allocs) cudaFree(p);
+    for (void* p : panels.allocs) cudaFree(p);
 }
 
 namespace {
@@ -181,6 +182,11 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
     auto ttype = [&](const std::string& n) -> int { const GgufTensor* t = f.find(n); return t ? t->type : -1; };
     const bool tied = f.find("output.weight") == nullptr;
     mg.n_cta = n_sms;
+    {   // BLK_MEGA_CTAS: CTAs of the persistent kernel (<= SMs).  Fewer CTAs than SMs can divide the row pairs of every phase evenly
+        // (4096 / 14336-wide models: 128 CTAs x 16 warps = 2048 warps -> 3 / 1 / 7 / 4 items per warp group, no remainder round)
+        const char* e = getenv("BLK_MEGA_CTAS");
+        if (e && atoi(e) >= m->n_head_kv && atoi(e) <= n_sms) mg.n_cta = atoi(e);
+    }
     int64_t rot_acc = 0;
     int max_items = 1, slot = 0, kmax = 0;
     bool bad = false;
@@ -200,7 +206,7 @@ MegaPlan mega_plan(blk_model* m, GgufFile& f, int n_sms) {
             }
         }
         ph.K = K; ph.src = src; ph.layer = layer; ph.nseg = 0;
-        const int NGtot = n_sms * (MG_WARPS / ph.W);
+        const int NGtot = mg.n_cta * (MG_WARPS / ph.W);
         int items = 0;
         // The segments of a phase occupy consecutive warp groups, starting so that the chain ENDS at the last group: the groups that
         // carry one pair more than the others are the highest CTAs.  CTAs 0 .. n_head_kv * n_split - 1 run the attention stages (and
@@ -909,6 +915,82 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------------
 // multi-token prefill (tcgen05 GEMM path)
 // ------------------------------------------------------------------------------------------------------------------
+// Per-context streaming panels of the two-pass GEMM form (matrices that are not resident in the model's panel cache): one bf16
+// panel per GEMM kind, so the de-quantisation of the NEXT matrix (second stream) runs while the current GEMM does:
+//   [0] QKV   [1] Wo   [2] gate+up | lm_head   [3] down
+void ensure_stream_panels(blk_ctx* c) {
+    if (c->panel_tried) return;
+    c->panel_tried = true;
+    blk_model* m = c->m;
+    const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+    auto rows = [](int n) { return (size_t)((n + 255) / 256) * 256; };
+    const size_t pe[4] = {(rows(dq) + 2 * rows(dkv)) * (size_t)d, rows(d) * (size_t)dq,
+                          std::max(2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d, rows(m->n_vocab) * (size_t)d), rows(d) * (size_t)ff};
+    bool ok = true;
+    for (int i = 0; i < 4 && ok; i++) {
+        void* p = nullptr;
+        ok = cudaMalloc(&p, pe[i] * sizeof(__nv_bfloat16)) == cudaSuccess;
+        if (ok) { c->allocs.push_back(p); c->pf_panel[i] = reinterpret_cast<__nv_bfloat16*>(p); }
+    }
+    if (!ok) { (void)cudaGetLastError(); for (int i = 0; i < 4; i++) c->pf_panel[i] = nullptr; }
+    else for (int i = 0; i < 4; i++) {
+        BLK_CUDA(cudaEventCreateWithFlags(&c->pn_filled[i], cudaEventDisableTiming));
+        BLK_CUDA(cudaEventCreateWithFlags(&c->pn_start[i], cudaEventDisableTiming));
+    }
+}
+
+// fill of one op's panel (QKV | Wo | gate+up | down of layer l, or the lm_head); false: the combination takes the fused GEMM form
+bool fill_panel_op(blk_model* m, int i, __nv_bfloat16* panel, cudaStream_t ss, cudaError_t* err) {
+    const int dq = m->n_head * m->d_head, dkv = m->n_head_kv * m->d_head;
+    const int l = i >> 2, k = i & 3;
+    if (l >= m->n_layer) { const GemmPart o[1] = {{&m->output, nullptr, 0}}; return prefill_panel_fill(o, 1, panel, ss, err); }
+    const LayerWeights& L = m->layers[l];
+    if (k == 0) { const GemmPart q[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}}; return prefill_panel_fill(q, 3, panel, ss, err); }
+    if (k == 1) { const GemmPart o[1] = {{&L.wo, nullptr, 0}}; return prefill_panel_fill(o, 1, panel, ss, err); }
+    if (k == 2) return prefill_panel_fill_swiglu(L.gate, L.up, panel, ss, err);
+    const GemmPart o[1] = {{&L.down, nullptr, 0}};
+    return prefill_panel_fill(o, 1, panel, ss, err);
+}
+
+// The model's resident panel cache (engine.hpp), built by the first multi-token pass: layer by layer while device memory beyond
+// the reserve lasts.  Every later pass only reads it, so nothing but this build needs the lock.
+const std::vector<__nv_bfloat16*>& model_panels(blk_ctx* c) {
+    blk_model* m = c->m;
+    blk_model::PanelCache& pc = m->panels;
+    std::lock_guard<std::mutex> lk(pc.mu);
+    if (pc.built) return pc.op;
+    pc.built = true;
+    const int n_ops = 4 * m->n_layer + 1;
+    pc.op.assign(n_ops, nullptr);
+    double cap_gb = 1e9;
+    { const char* e = getenv("BLK_PANEL_CACHE_GB"); if (e) cap_gb = atof(e); }
+    if (cap_gb <= 0.0) return pc.op;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return pc.op; }
+    // reserve: later contexts (KV pages, prefill workspaces) and other users of the device must still find room
+    const size_t reserve = std::max((size_t)16 << 30, total_b / 6);
+    size_t budget = free_b > reserve ? free_b - reserve : 0;
+    budget = (size_t)std::min((double)budget, cap_gb * 1e9);
+    const int d = m->n_embd, dh = m->d_head, dq = m->n_head * dh, dkv = m->n_head_kv * dh, ff = m->n_ff;
+    auto rows = [](int n) { return (size_t)((n + 255) / 256) * 256; };
+    const size_t pe[5] = {(rows(dq) + 2 * rows(dkv)) * (size_t)d, rows(d) * (size_t)dq, 2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d,
+                          rows(d) * (size_t)ff, rows(m->n_vocab) * (size_t)d};
+    cudaStream_t ss = c->pf_stream;
+    for (int i = 0; i < n_ops; i++) {
+        const size_t bytes = pe[i >= 4 * m->n_layer ? 4 : (i & 3)] * sizeof(__nv_bfloat16);
+        if (pc.bytes + bytes > budget) break;
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); break; }
+        cudaError_t err = cudaSuccess;
+        const bool ok = fill_panel_op(m, i, reinterpret_cast<__nv_bfloat16*>(p), ss, &err);
+        if (!ok || err != cudaSuccess) { (void)cudaGetLastError(); cudaStreamSynchronize(ss); cudaFree(p); if (err != cudaSuccess) break; continue; }   // a type without a panel form: fused GEMM
+        pc.allocs.push_back(p); pc.op[i] = reinterpret_cast<__nv_bfloat16*>(p); pc.bytes += bytes; pc.n_resident++;
+    }
+    BLK_CUDA(cudaStreamSynchronize(ss));
+    log_msg(1, "resident bf16 panels: " + std::to_string(pc.n_resident) + " of " + std::to_string(n_ops) + " matrices, " + std::to_string(pc.bytes >> 20) + " MiB");
+    return pc.op;
+}
+
 void ensure_prefill_bufs(blk_ctx* c, int T) {
     if (T <= c->pf_cap) return;
     blk_model* m = c->m;
@@ -931,29 +1013,6 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
     }
     c->pf_logit_rows = 512;     // rows of one lm_head chunk: two M tiles share every weight tile through L2
     c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
-    {   // bf16 weight panel of the two-pass GEMM form (largest single launch: QKV | Wo | gate+up | down | lm_head)
-        // one panel per GEMM kind, so the dequantisation of the NEXT matrix (second stream) runs while the current GEMM does:
-        //   [0] QKV   [1] Wo   [2] gate+up | lm_head   [3] down
-        auto rows = [](int n) { return (size_t)((n + 255) / 256) * 256; };
-        const size_t pe[4] = {(rows(dq) + 2 * rows(dkv)) * (size_t)d, rows(d) * (size_t)dq,
-                              std::max(2 * (size_t)((ff + 127) / 128) * 128 * (size_t)d, rows(m->n_vocab) * (size_t)d), rows(d) * (size_t)ff};
-        const char* pm = getenv("BLK_PANEL_MIN");
-        c->panel_min = pm ? atoi(pm) : 257;      // measured (tools/prefill_sweep.py, both forms with split-K): up to one 256-token M tile the fused
-        //                                          form wins (no 14 GB bf16 panel to write and read back), beyond it the two-pass form
-        if (c->panel_min > 0 && cap >= c->panel_min) {
-            bool ok = true;
-            for (int i = 0; i < 4 && ok; i++) {
-                void* p = nullptr;
-                ok = cudaMalloc(&p, pe[i] * sizeof(__nv_bfloat16)) == cudaSuccess;
-                if (ok) { c->allocs.push_back(p); c->pf_panel[i] = reinterpret_cast<__nv_bfloat16*>(p); }
-            }
-            if (!ok) { (void)cudaGetLastError(); for (int i = 0; i < 4; i++) c->pf_panel[i] = nullptr; }
-            else for (int i = 0; i < 4; i++) {
-                BLK_CUDA(cudaEventCreateWithFlags(&c->pn_filled[i], cudaEventDisableTiming));
-                BLK_CUDA(cudaEventCreateWithFlags(&c->pn_start[i], cudaEventDisableTiming));
-            }
-        }
-    }
     if (prefill_attn_tc_supported(dh, m->n_head, m->n_head_kv)) {      // transposed-V scratch of the tcgen05 attention (one layer at a time)
         c->pf_vt_pad = (c->n_pages * KV_PAGE + 127) / 128 * 128;
         c->pf_vt = dalloc<__half>(c, (size_t)m->n_head_kv * 128 * c->pf_vt_pad);
@@ -1026,9 +1085,6 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     flush_pos_shift(c);
     note_new_cells(c, n);
     cudaStream_t st = c->stream;
-    // many tokens: dequantise every matrix ONCE into the bf16 panel and run the GEMMs TMA-fed on both operands; few tokens: the
-    // fused form (weights dequantised inside the GEMM, once per 256 tokens) moves fewer bytes
-    const bool panel = c->pf_panel[0] && c->panel_min > 0 && n >= c->panel_min;
     BLK_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     embed_kernel<<<n, 256, 0, st>>>(m->tok_embd, c->pf_tokens, c->d_pos, c->pf_x, c->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
     BLK_CUDA(cudaGetLastError()); c->launches++;
@@ -1042,38 +1098,44 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     static const bool full_head_env = [] { const char* e = getenv("BLK_VERIFY_FULL_HEAD"); return e && e[0] == '1'; }();
     const bool sparse_head = verify && !verify->top && !full_head_env && m->output.type != QT_F32 && m->output.type != QT_F16 && (d % 64) == 0;
     const int n_ops = 4 * m->n_layer + (verify && !sparse_head ? 1 : 0);
+    // GEMM form per matrix: resident bf16 panel (model cache) -> TMA-fed GEMM at every batch size; otherwise many tokens: the matrix is
+    // de-quantised ONCE into a streaming panel (second stream, one GEMM ahead); few tokens: the fused form (weights de-quantised
+    // inside the GEMM, once per 256 tokens) moves fewer bytes
+    const std::vector<__nv_bfloat16*>& res = model_panels(c);
+    auto res_op = [&](int i) -> __nv_bfloat16* { return i < (int)res.size() ? res[i] : nullptr; };
+    bool all_res = true;
+    for (int i = 0; i < n_ops; i++) all_res = all_res && res_op(i);
+    if (!all_res && c->panel_min > 0 && n >= c->panel_min) ensure_stream_panels(c);
+    const bool panel = !all_res && c->pf_panel[0] && c->panel_min > 0 && n >= c->panel_min;
     std::vector<char> op_panel(n_ops + 1, 0);
     auto panel_of = [&](int i) { return i >= 4 * m->n_layer ? 2 : (i & 3); };
     auto fill_op = [&](int i) {      // enqueue the fill of op i on the side stream
-        if (!panel || i >= n_ops) return;
-        const int b = panel_of(i), l = i >> 2, k = i & 3;
-        cudaStream_t ss = c->pf_stream;
-        cudaError_t err = cudaSuccess; bool ok = false;
-        if (l >= m->n_layer) { const GemmPart o[1] = {{&m->output, nullptr, 0}}; ok = prefill_panel_fill(o, 1, c->pf_panel[b], ss, &err); }
-        else {
-            const LayerWeights& L = m->layers[l];
-            if (k == 0) { const GemmPart q[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}}; ok = prefill_panel_fill(q, 3, c->pf_panel[b], ss, &err); }
-            else if (k == 1) { const GemmPart o[1] = {{&L.wo, nullptr, 0}}; ok = prefill_panel_fill(o, 1, c->pf_panel[b], ss, &err); }
-            else if (k == 2) ok = prefill_panel_fill_swiglu(L.gate, L.up, c->pf_panel[b], ss, &err);
-            else { const GemmPart o[1] = {{&L.down, nullptr, 0}}; ok = prefill_panel_fill(o, 1, c->pf_panel[b], ss, &err); }
-        }
+        if (!panel || i >= n_ops || res_op(i)) return;
+        const int b = panel_of(i);
+        cudaError_t err = cudaSuccess;
+        const bool ok = fill_panel_op(m, i, c->pf_panel[b], c->pf_stream, &err);
         BLK_CUDA(err);
         op_panel[i] = ok ? 1 : 0;
-        BLK_CUDA(cudaEventRecord(c->pn_filled[b], ss));
+        BLK_CUDA(cudaEventRecord(c->pn_filled[b], c->pf_stream));
         c->launches += ok ? 2 : 0;
     };
     auto before_gemm = [&](int i) -> __nv_bfloat16* {      // main stream, right before GEMM i; returns its panel (nullptr: fused form)
-        if (!panel) return nullptr;
         const int b = panel_of(i);
-        BLK_CUDA(cudaEventRecord(c->pn_start[b], st));                      // GEMM i is about to start ...
-        BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[b], 0));     // ... so is the fill of op i + 1 (other panel)
-        BLK_CUDA(cudaStreamWaitEvent(st, c->pn_filled[b], 0));
-        __nv_bfloat16* mine = op_panel[i] ? c->pf_panel[b] : nullptr;
-        fill_op(i + 1);
+        const bool next_fill = panel && i + 1 < n_ops && !res_op(i + 1);
+        if (next_fill) {
+            BLK_CUDA(cudaEventRecord(c->pn_start[b], st));                      // GEMM i is about to start ...
+            BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[b], 0));     // ... so is the fill of op i + 1 (other panel; its last reader, GEMM i - 3, is done)
+        }
+        __nv_bfloat16* mine = res_op(i);
+        if (!mine && panel) {
+            BLK_CUDA(cudaStreamWaitEvent(st, c->pn_filled[b], 0));
+            mine = op_panel[i] ? c->pf_panel[b] : nullptr;
+        }
+        if (next_fill) fill_op(i + 1);
         return mine;
     };
     auto after_gemm = [&](int) {};
-    if (panel) { BLK_CUDA(cudaEventRecord(c->pn_start[0], st)); BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[0], 0)); }   // after whatever ran before
+    if (panel && !res_op(0)) { BLK_CUDA(cudaEventRecord(c->pn_start[0], st)); BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[0], 0)); }   // after whatever ran before
     fill_op(0);
     const SplitKWs sk{c->pf_splitk, c->pf_splitk_elems};
     for (int l = 0; l < m->n_layer; l++) {
@@ -1232,6 +1294,7 @@ extern "C" blk_ctx* blk_ctx_create(blk_model* m, int32_t n_ctx, int32_t n_batch)
         c->n_ctx = n_ctx > 0 ? n_ctx : m->n_ctx_train;
         c->n_batch = n_batch > 0 ? n_batch : 2048;
         { const char* e = getenv("BLK_PREFILL_MIN"); if (e) c->prefill_min = std::max(2, atoi(e)); }
+        { const char* e = getenv("BLK_PANEL_MIN"); if (e) c->panel_min = atoi(e); }
         BLK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         BLK_CUDA(cudaEventCreate(&c->ev0)); BLK_CUDA(cudaEventCreate(&c->ev1));
         BLK_CUDA(cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
@@ -1581,11 +1644,15 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
         BLK_CUDA(cudaGetLastError()); ws->launches++;
         const long long ldq = dq + 2 * dkv;
         const SplitKWs sk{ws->pf_splitk, ws->pf_splitk_elems};
+        // matrices with a resident bf16 panel (model cache) take the TMA-fed GEMM: the step then streams the panels at HBM speed
+        // instead of waiting for the de-quantising producers of the fused form
+        const std::vector<__nv_bfloat16*>& res = model_panels(ws);
+        auto res_op = [&](int i) -> __nv_bfloat16* { return i < (int)res.size() ? res[i] : nullptr; };
         for (int l = 0; l < m->n_layer; l++) {
             const LayerWeights& L = m->layers[l];
             rmsnorm_bf16_launch(ws->pf_x, L.attn_norm, d, m->rms_eps, ws->pf_xn, n, st);
             const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
-            BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, ws->pf_xn, n, ws->pf_qkv, ldq, st, nullptr, false, &sk));
+            BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, ws->pf_xn, n, ws->pf_qkv, ldq, st, res_op(4 * l), false, &sk));
             QkvPostBatchArgs qa{};
             qa.base.qkv = ws->pf_qkv; qa.base.ld = ldq; qa.base.rope_cs = ws->pf_rope; qa.base.q_out = ws->pf_q;
             qa.base.dq = dq; qa.base.dkv = dkv; qa.base.d_head = dh; qa.base.neox = m->neox ? 1 : 0;
@@ -1597,14 +1664,14 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
             if (dh == 128) decode_attn_batch_kernel<128><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
             else decode_attn_batch_kernel<64><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
             BLK_CUDA(cudaGetLastError());
-            BLK_CUDA(prefill_gemm(L.wo, ws->pf_ao, n, ws->pf_x, d, nullptr, 1, st, nullptr, false, &sk));
+            BLK_CUDA(prefill_gemm(L.wo, ws->pf_ao, n, ws->pf_x, d, nullptr, 1, st, res_op(4 * l + 1), false, &sk));
             rmsnorm_bf16_launch(ws->pf_x, L.ffn_norm, d, m->rms_eps, ws->pf_xn, n, st);
-            BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, ws->pf_xn, n, ws->pf_h, ff, st, nullptr, false, &sk));
-            BLK_CUDA(prefill_gemm(L.down, ws->pf_h, n, ws->pf_x, d, nullptr, 1, st, nullptr, false, &sk));
+            BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, ws->pf_xn, n, ws->pf_h, ff, st, res_op(4 * l + 2), false, &sk));
+            BLK_CUDA(prefill_gemm(L.down, ws->pf_h, n, ws->pf_x, d, nullptr, 1, st, res_op(4 * l + 3), false, &sk));
             ws->launches += 8;
         }
         rmsnorm_bf16_launch(ws->pf_x, m->out_norm, d, m->rms_eps, ws->pf_xn, n, st);
-        BLK_CUDA(prefill_gemm(m->output, ws->pf_xn, n, ws->pf_logits, V, nullptr, 0, st, nullptr, false));
+        BLK_CUDA(prefill_gemm(m->output, ws->pf_xn, n, ws->pf_logits, V, nullptr, 0, st, res_op(4 * m->n_layer), false));
         ws->launches += 2;
         // per row: threshold top-64 (the selector of the batch-1 path, one row at a time)
         for (int i = 0; i < n; i++) {

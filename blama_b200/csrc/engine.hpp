@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <mutex>
 
 #include "../../include/blama_b200.h"
 #include <cuda_bf16.h>
@@ -76,6 +77,11 @@ struct blk_model {
     int64_t weight_bytes_per_token = 0;
     int act_fmt = blk::ACT_F32;       // activation format of the layer mat-vecs
     int act_fmt_out = blk::ACT_F32;   // ... of the lm_head
+    // Resident bf16 copies ("panels") of the layer matrices for the TMA-fed tcgen05 GEMMs of the multi-token paths (prompt prefill,
+    // verify, batched decode): B200 has 180 GB, an 8B model's panels are 14 GB.  Filled once, by the first multi-token pass that
+    // wants them, into whatever device memory is free beyond a reserve (BLK_PANEL_CACHE_GB caps it, 0 = off); op index
+    // 4 l + {0 QKV, 1 Wo, 2 gate+up, 3 down}, 4 n_layer = lm_head; nullptr = not resident (streamed through the per-context panels).
+    struct PanelCache { std::mutex mu; bool built = false; std::vector<__nv_bfloat16*> op; std::vector<void*> allocs; size_t bytes = 0; int n_resident = 0; } panels;
     ~blk_model();
 };
 
@@ -139,7 +145,9 @@ struct blk_ctx {
     float* pf_splitk = nullptr; size_t pf_splitk_elems = 0;               // partial sums of the split-K prefill GEMMs (few-token batches)
     __nv_bfloat16* pf_panel[4] = {nullptr, nullptr, nullptr, nullptr};     // bf16 weight panels of the two-pass GEMM form, one per GEMM kind
     cudaEvent_t pn_filled[4] = {nullptr, nullptr, nullptr, nullptr}, pn_start[4] = {nullptr, nullptr, nullptr, nullptr};
-    int panel_min = 32;   // two-pass GEMM form from this many tokens per chunk on (0 = never)
+    int panel_min = 257;  // matrices that are NOT resident (model panel cache): streamed two-pass GEMM form from this many tokens per chunk on
+                          // (0 = never); measured (tools/prefill_sweep.py): up to one 256-token M tile the fused form wins, beyond it the two-pass form
+    bool panel_tried = false;
     int32_t* pf_claimed = nullptr; int32_t* pf_nclaimed = nullptr; float* pf_gath = nullptr; int32_t* pf_topi = nullptr; float* pf_topl = nullptr;
     int prefill_min = 32;                  // blk_decode / blk_verify_prefill use the tcgen05 path from this many tokens on
     // scratch for gather / verify

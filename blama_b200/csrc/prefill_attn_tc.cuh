@@ -10,8 +10,9 @@
 //   pass 1: S = Q.K^T -> row max m
 //   pass 2: S again, P = exp2(s - m) -> f16 (row sum l alongside), O += P.V^T in TMEM (never rescaled); O / l at the end.
 // Q.K^T is done twice (1.5x the MMA work of one pass), which is cheap next to keeping O out of the register file.
-// Warp roles: warp 0 = TMA, warp 1 = MMA issue (one elected thread), warps 2-9 = soft-max / epilogue: two threads per row
-// (= TMEM lane), 64 key columns each.  The exponentials (MUFU, 16 / clk / SM) are the floor of this kernel, so they are
+// Warp roles: warp 0 = TMA, warp 1 = MMA issue (one elected thread), warps 2-17 = soft-max / epilogue: four threads per row
+// (= TMEM lane), 32 key columns each (16 warps = 4 per scheduler: with 8 warps the kernel issued one instruction per 10 cycles and
+// warp -- TMEM load and MUFU latency exposed -- and the tensor pipe idled two thirds of the time).  The exponentials (MUFU, 16 / clk / SM) are the floor of this kernel, so they are
 // evaluated once: pass 1 only takes the row maximum, pass 2 computes P and the row sum together.
 // Arithmetic as the mma.sync kernel (prefill_kernels.cuh): f16 operands, f32 accumulation, P rounded to f16 before P.V.
 #pragma once
@@ -19,7 +20,9 @@
 
 namespace blk {
 
-constexpr int AT_THREADS = 320;                            // warp 0 TMA, warp 1 MMA, warps 2-9 soft-max (two threads per row)
+constexpr int AT_SM_WARPS = 16;                            // soft-max warps: four per TMEM lane quarter
+constexpr int AT_SM_THREADS = 32 * AT_SM_WARPS;
+constexpr int AT_THREADS = 64 + AT_SM_THREADS;             // warp 0 TMA, warp 1 MMA, warps 2-17 soft-max (four threads per row)
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;                 // one [128][64] f16 K block = 16 KB
 constexpr int AT_SMEM_BYTES = (2 + 2 * 2 + 2 * 2 + 2 * 2) * AT_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row statistics*/;      // Q, K x2, V x2, P x2
 
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     uint64_t* kv_full = bars + 1;       // [2]
     uint64_t* kv_empty = bars + 3;      // [2]
     uint64_t* s_full = bars + 5;        // [2]
-    uint64_t* s_empty = bars + 7;       // [2]  256 soft-max threads
-    uint64_t* p_full = bars + 9;        // [2]  256 soft-max threads
+    uint64_t* s_empty = bars + 7;       // [2]  all soft-max threads
+    uint64_t* p_full = bars + 9;        // [2]  all soft-max threads
     uint64_t* p_empty = bars + 11;      // [2]  tcgen05.commit
     uint64_t* o_full = bars + 13;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
@@ -89,8 +92,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); mbar_init(s_full + s, 1); mbar_init(s_empty + s, 256); }
-        for (int s = 0; s < 2; s++) { mbar_init(p_full + s, 256); mbar_init(p_empty + s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); mbar_init(s_full + s, 1); mbar_init(s_empty + s, AT_SM_THREADS); }
+        for (int s = 0; s < 2; s++) { mbar_init(p_full + s, AT_SM_THREADS); mbar_init(p_empty + s, 1); }
         mbar_init(o_full, 1);
         mbar_fence_init();
     }
@@ -187,10 +190,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
             tc_commit(o_full);
         }
     } else {
-        // ===================== soft-max / epilogue: two threads per row (= TMEM lane), 64 key columns each =====================
-        float* s_x = reinterpret_cast<float*>(tmem_slot + 4);   // [2 halves][128 rows] exchange of row maxima, then row sums
+        // ===================== soft-max / epilogue: four threads per row (= TMEM lane), 32 key columns each =====================
+        // row statistics are exchanged through the P buffers: before pass 2 nothing has been written there, and after o_full every
+        // MMA that read them has completed
+        float* s_x = reinterpret_cast<float*>(sP);          // [4 parts][128 rows]
         const int row = 32 * (warp & 3) + lane;             // warp w may touch TMEM lanes 32 (w % 4) .. +31
-        const int half = warp >= 6 ? 1 : 0;                 // key columns [64 half, 64 half + 64) of every tile
+        const int part = (warp - 2) >> 2;                   // key columns [32 part, 32 part + 32) of every tile
         const int g = row / BQ, tok = q0 + (row % BQ);
         const bool row_ok = tok < a.T && g < GQ;
         const int last_key = pos0 + tok;                    // causal: keys <= last_key
@@ -203,50 +208,55 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
             const int b = si & 1;
             mbar_wait(s_full + b, (si >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 2; c++) {
-                uint32_t v[32];
-                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + half * 64 + c * 32) + lane_off, v);
-                tc_wait_ld();
-                const int key0 = t * 128 + half * 64 + c * 32;
-                if (row_ok && key0 + 31 <= last_key) {      // no key of this chunk is masked (every tile but the diagonal one)
-#pragma unroll
-                    for (int j = 0; j < 32; j++) m = fmaxf(m, __uint_as_float(v[j]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) if (row_ok && key0 + j <= last_key) m = fmaxf(m, __uint_as_float(v[j]));
-                }
-            }
+            uint32_t v[32];
+            tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + part * 32) + lane_off, v);
+            tc_wait_ld();
             tc_fence_before();
-            mbar_arrive(s_empty + b);
+            mbar_arrive(s_empty + b);                       // the scores are in registers: S[b] is free
+            const int key0 = t * 128 + part * 32;
+            if (row_ok && key0 + 31 <= last_key) {          // no key of this chunk is masked (every tile but the diagonal one)
+                float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(v[j])); m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(v[j + 2])); m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                }
+                m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (row_ok && key0 + j <= last_key) m = fmaxf(m, __uint_as_float(v[j]));
+            }
         }
-        s_x[half * 128 + row] = m;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        m = fmaxf(s_x[row], s_x[128 + row]) * sl2;          // scale > 0: max commutes with the scaling
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        s_x[part * 128 + row] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");
+        m = fmaxf(fmaxf(s_x[row], s_x[128 + row]), fmaxf(s_x[256 + row], s_x[384 + row])) * sl2;      // scale > 0: max commutes with the scaling
+        asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");
         // ---- pass 2: P = exp2(s - m), row sum alongside ----
-        unsigned char* prow0 = sP + half * AT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        unsigned char* prow0 = sP + (part >> 1) * AT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
         for (int t = 0; t < n_tiles; t++, si++) {
             const int b = si & 1;
             mbar_wait(s_full + b, (si >> 1) & 1);
             tc_fence_after();
-            uint32_t pk[32];
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
+            uint32_t pk[16];
+            {
                 uint32_t v[32];
-                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + half * 64 + c * 32) + lane_off, v);
+                tc_ld_32x32b_x32(tmem + (uint32_t)(b * 128 + part * 32) + lane_off, v);
                 tc_wait_ld();
-                const int key0 = t * 128 + half * 64 + c * 32;
+                tc_fence_before();
+                mbar_arrive(s_empty + b);                   // S[b] is free for the scores of tile t + 2
+                const int key0 = t * 128 + part * 32;
                 if (row_ok && key0 + 31 <= last_key) {      // unmasked chunk
-                    float l0 = 0.0f, l1 = 0.0f;
+                    float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
+                    for (int j = 0; j < 32; j += 4) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -m)), p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -m));
-                        l0 += p0; l1 += p1;
-                        __half2 h = __floats2half2_rn(p0, p1);
-                        pk[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+                        const float p2 = ex2_approx(fmaf(__uint_as_float(v[j + 2]), sl2, -m)), p3 = ex2_approx(fmaf(__uint_as_float(v[j + 3]), sl2, -m));
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        __half2 h0 = __floats2half2_rn(p0, p1), h1 = __floats2half2_rn(p2, p3);
+                        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+                        pk[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
                     }
-                    l += l0 + l1;
+                    l += (l0 + l1) + (l2 + l3);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
@@ -254,32 +264,31 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
                         const float p1 = (row_ok && key0 + j + 1 <= last_key) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -m)) : 0.0f;
                         l += p0 + p1;
                         __half2 h = __floats2half2_rn(p0, p1);
-                        pk[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+                        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(s_empty + b);                       // S[b] is free for the scores of tile t + 2
             mbar_wait(p_empty + (t & 1), ((t >> 1) & 1) ^ 1);   // the P.V of tile t - 2 has read this P buffer
             unsigned char* prow = prow0 + (t & 1) * 2 * AT_TILE_BYTES;
 #pragma unroll
-            for (int q = 0; q < 8; q++)                     // this thread's 64 keys = the eight 16-byte chunks of its row in key block `half`
-                *reinterpret_cast<uint4*>(prow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            for (int q = 0; q < 4; q++) {                   // this thread's 32 keys = four 16-byte chunks of its row in key block part / 2
+                const int ch = (part & 1) * 4 + q;
+                *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
             fence_proxy_async();
             mbar_arrive(p_full + (t & 1));
         }
-        s_x[half * 128 + row] = l;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        l = s_x[row] + s_x[128 + row];
-        // ---- epilogue: O / l -> bf16, this thread's 64 of the 128 head dims ----
-        mbar_wait(o_full, 0);
+        // ---- epilogue: O / l -> bf16, this thread's 32 of the 128 head dims ----
+        mbar_wait(o_full, 0);                               // every MMA has completed: the P buffers are free for the row sums
         tc_fence_after();
+        s_x[part * 128 + row] = l;
+        asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");
+        l = (s_x[row] + s_x[128 + row]) + (s_x[256 + row] + s_x[384 + row]);
         const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-        __nv_bfloat16* dst = a.out + (size_t)tok * ((size_t)a.n_head * 128) + (size_t)(hk * GQ + g) * 128 + half * 64;
-#pragma unroll 1
-        for (int c = 0; c < 2; c++) {
+        __nv_bfloat16* dst = a.out + (size_t)tok * ((size_t)a.n_head * 128) + (size_t)(hk * GQ + g) * 128 + part * 32;
+        {
             uint32_t v[32];
-            tc_ld_32x32b_x32(tO + (uint32_t)(half * 64 + c * 32) + lane_off, v);
+            tc_ld_32x32b_x32(tO + (uint32_t)(part * 32) + lane_off, v);
             tc_wait_ld();
             if (row_ok) {
 #pragma unroll
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
                     o.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
                     o.z = pack_bf16x2(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
                     o.w = pack_bf16x2(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + c * 32 + j) = o;
+                    *reinterpret_cast<uint4*>(dst + j) = o;
                 }
             }
         }
