@@ -18,6 +18,7 @@ random-init Llama-3.1-8B-arch Q4_K_M weights.  Printed JSON line (rank 0):
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -401,6 +402,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 traffic_v = nv["dram__bytes_read"] + nv["dram__bytes_write"]
         except (OSError, ValueError, KeyError):
             pass
+        try:      # resident bf16 panels of the multi-token GEMMs (built by the first prefill; blama_b200.h blk_model_panel_bytes)
+            nr, nm = C.c_int32(0), C.c_int32(0)
+            pb = int(capi.lib().blk_model_panel_bytes(capi.lib().blk_ctx_model(ctx.h), C.byref(nr), C.byref(nm)))
+            verify["weights_bf16_resident"] = {"bytes": pb, "matrices": int(nr.value), "of": int(nm.value),
+                                               "note": "de-quantised once at the first multi-token pass and kept in HBM; BLK_PANEL_CACHE_GB=0 streams them per request instead"}
+        except Exception as e:      # noqa: BLE001
+            verify["weights_bf16_resident"] = {"error": str(e)}
         verify["roofline"] = {"bound": "tensor", "achieved": flops / t_v / 1e12, "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / t_v / 1e12 / tf_peak,
                               "flops": flops, "flops_if_full_vocab_head": flops_full_head, "peak_source": tf_src, "traffic": traffic_v,
                               "traffic_source": "profiles/r2_ncu_verify_summary.json (sum of dram__bytes over the kernels of one verify prefill)" if traffic_v else None,
@@ -539,6 +547,9 @@ def run_dispatcher(args):
 
     for t in [srv.submit_verify(prompt, toks[: lens[0]], top[: lens[0]], nl[: lens[0]], seed=1) for _ in range(2 * len(workers))]:      # warm-up: every worker
         srv.wait_verify(t)
+    if args.mode == "batch":      # ... and every slot of the batching worker (first-use allocations of its context, the batched-step scratch)
+        for t in [srv.submit_complete(gguf_synth.synth_prompt(args.shape, p0, 900 + i), 4, seed=i) for i in range(args.max_batch)]:
+            srv.wait_complete(t, cap=4)
     srv.drain()
     sampler = ClockSampler(0)
     sampler.start()

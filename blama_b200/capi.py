@@ -46,6 +46,7 @@ SYMBOLS = {
     "blk_model_device": (_i32, [_vp]),
     "blk_model_weight_bytes_per_token": (_i64, [_vp]),
     "blk_model_kv_bytes_per_token": (_i64, [_vp]),
+    "blk_model_panel_bytes": (_i64, [_vp, _vp, _vp]),
     "blk_model_token_text": (_i32, [_vp, _i32, C.c_char_p, _i32]),
     "blk_model_meta_str": (_i32, [_vp, C.c_char_p, C.c_char_p, _i32]),
     "blk_ctx_create": (_vp, [_vp, _i32, _i32]),
@@ -192,6 +193,12 @@ class Model:
 
     def is_eog(self, tok: int) -> bool:
         return bool(lib().blk_model_is_eog(self.h, int(tok)))
+
+    def panel_cache(self):
+        """(bytes, resident matrices, matrices) of the resident bf16 panels (0 before the first multi-token pass)"""
+        nr, nm = C.c_int32(0), C.c_int32(0)
+        b = lib().blk_model_panel_bytes(self.h, C.byref(nr), C.byref(nm))
+        return int(b), int(nr.value), int(nm.value)
 
     def token_text(self, tok: int) -> str:
         buf = C.create_string_buffer(256)

@@ -563,10 +563,17 @@ struct TopkArgs {
     unsigned int* count; unsigned int* done;
     int32_t* out_ids; float* out_logits;
     int32_t* feed_tok;          // optional: receives the arg-max (greedy on-device feedback of the decode loop)
+    long long ld;               // rows of a batch (blockIdx.y): logits ld floats apart; every per-row array below is laid out row-major:
+                                // chunk_max [row][256], cand_l / cand_i [row][cap], count / done [row][2], out_* [row][TOPK_MAX]
 };
 
-__global__ void __launch_bounds__(1024) topk_select_kernel(const TopkArgs a) {
+__global__ void __launch_bounds__(1024) topk_select_kernel(TopkArgs a) {
     pdl_launch_dependents(); pdl_wait();
+    if (blockIdx.y) {       // batched rows
+        const size_t r = blockIdx.y;
+        a.logits += r * (size_t)a.ld; a.chunk_max += r * 256; a.cand_l += r * (size_t)a.cap; a.cand_i += r * (size_t)a.cap;
+        a.count += 2 * r; a.done += 2 * r; a.out_ids += r * TOPK_MAX; a.out_logits += r * TOPK_MAX;
+    }
     __shared__ float key[2048];
     __shared__ int idx[2048];
     __shared__ unsigned int s_last, s_n;

@@ -521,6 +521,13 @@ extern "C" int32_t blk_model_vocab_only(const blk_model* m) { return m->vocab_on
 extern "C" int32_t blk_model_add_bos(const blk_model* m) { return m->add_bos ? 1 : 0; }
 extern "C" int32_t blk_model_device(const blk_model* m) { return m->device; }
 extern "C" int64_t blk_model_weight_bytes_per_token(const blk_model* m) { return m->weight_bytes_per_token; }
+extern "C" int64_t blk_model_panel_bytes(blk_model* m, int32_t* n_resident, int32_t* n_matrices) {
+    if (!m) return 0;
+    std::lock_guard<std::mutex> lk(m->panels.mu);
+    if (n_resident) *n_resident = m->panels.n_resident;
+    if (n_matrices) *n_matrices = 4 * m->n_layer + 1;
+    return (int64_t)m->panels.bytes;
+}
 extern "C" int64_t blk_model_kv_bytes_per_token(const blk_model* m) { return (int64_t)m->n_layer * m->n_head_kv * m->d_head * 2 * 2; }
 extern "C" int32_t blk_model_token_text(const blk_model* m, int32_t tok, char* buf, int32_t cap) {
     if (tok < 0 || tok >= (int)m->vocab.size()) return 0;
@@ -1629,6 +1636,12 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
             ws->bd_dev = reinterpret_cast<uint8_t*>(dalloc<BatchDesc>(ws, 1));
             ws->bd_top_ids = dalloc<int32_t>(ws, BATCH_MAX * TOPK_MAX); ws->bd_top_logits = dalloc<float>(ws, BATCH_MAX * TOPK_MAX);
             ws->bd_h_top_ids = halloc<int32_t>(ws, BATCH_MAX * TOPK_MAX); ws->bd_h_top_logits = halloc<float>(ws, BATCH_MAX * TOPK_MAX);
+            // per-row scratch of the batched threshold selector
+            ws->bd_chunk_max = dalloc<int>(ws, BATCH_MAX * 256);
+            { std::vector<int> init(BATCH_MAX * 256, (int)0x80000000); BLK_CUDA(cudaMemcpy(ws->bd_chunk_max, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice)); }
+            ws->bd_cand_l = dalloc<float>(ws, (size_t)BATCH_MAX * ws->cand_cap); ws->bd_cand_i = dalloc<int>(ws, (size_t)BATCH_MAX * ws->cand_cap);
+            ws->bd_counters = dalloc<unsigned int>(ws, 2 * BATCH_MAX);
+            BLK_CUDA(cudaMemset(ws->bd_counters, 0, 2 * BATCH_MAX * sizeof(unsigned int)));
         }
         cudaStream_t st = ws->stream;
         BLK_CUDA(cudaStreamSynchronize(st));                      // the staging block is reused every step
@@ -1673,15 +1686,14 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
         rmsnorm_bf16_launch(ws->pf_x, m->out_norm, d, m->rms_eps, ws->pf_xn, n, st);
         BLK_CUDA(prefill_gemm(m->output, ws->pf_xn, n, ws->pf_logits, V, nullptr, 0, st, res_op(4 * m->n_layer), false));
         ws->launches += 2;
-        // per row: threshold top-64 (the selector of the batch-1 path, one row at a time)
-        for (int i = 0; i < n; i++) {
-            const float* row = ws->pf_logits + (size_t)i * V;
-            chunk_max_kernel<<<ws->n_chunks, 256, 0, st>>>(row, V, ws->chunk_shift, ws->chunk_max);
+        // threshold top-64 of every row (the selector of the batch-1 path, blockIdx.y = row): two launches for the whole batch
+        {
+            chunk_max_kernel<<<dim3(ws->n_chunks, n), 256, 0, st>>>(ws->pf_logits, V, ws->chunk_shift, ws->bd_chunk_max, (long long)V);
             TopkArgs tk{};
-            tk.logits = row; tk.n = V; tk.chunk_max = ws->chunk_max; tk.n_chunks = ws->n_chunks;
-            tk.cand_l = ws->cand_l; tk.cand_i = ws->cand_i; tk.cap = ws->cand_cap; tk.count = ws->counters + 1; tk.done = ws->counters + 2;
-            tk.out_ids = ws->bd_top_ids + (size_t)i * TOPK_MAX; tk.out_logits = ws->bd_top_logits + (size_t)i * TOPK_MAX;
-            topk_select_kernel<<<16, 1024, 0, st>>>(tk);
+            tk.logits = ws->pf_logits; tk.n = V; tk.ld = V; tk.chunk_max = ws->bd_chunk_max; tk.n_chunks = ws->n_chunks;
+            tk.cand_l = ws->bd_cand_l; tk.cand_i = ws->bd_cand_i; tk.cap = ws->cand_cap; tk.count = ws->bd_counters; tk.done = ws->bd_counters + 1;
+            tk.out_ids = ws->bd_top_ids; tk.out_logits = ws->bd_top_logits;
+            topk_select_kernel<<<dim3(16, n), 1024, 0, st>>>(tk);
             BLK_CUDA(cudaGetLastError()); ws->launches += 2;
         }
         advance_many_kernel<<<1, BATCH_MAX, 0, st>>>(dv->pos_ptr, n);

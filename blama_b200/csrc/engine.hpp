@@ -156,6 +156,7 @@ struct blk_ctx {
     // batched decode step (blk_decode_batch): per-row descriptors (pinned host staging + device copy) and per-row top-k lists
     uint8_t* bd_host = nullptr; uint8_t* bd_dev = nullptr;
     int32_t* bd_top_ids = nullptr; float* bd_top_logits = nullptr; int32_t* bd_h_top_ids = nullptr; float* bd_h_top_logits = nullptr;
+    int* bd_chunk_max = nullptr; float* bd_cand_l = nullptr; int* bd_cand_i = nullptr; unsigned int* bd_counters = nullptr;      // [row][...] scratch of the batched top-k
     // persistent decode kernel (one cooperative launch per token instead of the per-op graph)
     bool mega_on = false;
     blk::MegaParams mega_params{};

@@ -565,6 +565,7 @@ __device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, cons
         }
         __syncthreads();
         mg_tr<TR>(P, S, 13);
+#pragma unroll 4
         for (int tl = tg; tl < cn; tl += TG) {
             const float v = __half2float(s.v[(size_t)tl * dh + d]);
 #pragma unroll
@@ -586,47 +587,53 @@ __device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, cons
         else ll_st(P.po2 + (size_t)a.split * NO + a.hk * E + e, o, tag_po);
     }
     mg_tr<TR>(P, S, 15);
-    if (single || a.split != 0) return;
-    // ---- the CTA of split 0 merges the slices of its KV head ----
+    if (single) return;
+    // ---- merge, spread over the CTAs of the KV head: split s owns elements [s per, s per + per) of the head group's output.  One
+    //      thread per (element, slice) pair, statistics and partials polled TOGETHER (one L2 round trip behind the slowest slice
+    //      instead of the split-0 CTA's three dependent ones); the sum runs in split order as before (bit-identical). ----
+    const int ns = a.n_split;
+    const int per = (E + ns - 1) / ns;
+    const int e0 = a.split * per, ne = max(0, min(E, e0 + per) - e0);
+    const int n_items = ne * ns;
     float* wgt = reinterpret_cast<float*>(S.redd);          // [gq <= 8][32] merge weights (the double reduction scratch: 256 floats)
-    if (warp < gq) {
-        const uint2* sp = P.st2 + (size_t)(a.hk * gq + warp) * P.max_split * 2;
-        float m = -INFINITY, l = 0.0f;
+    float* wp = s.red;                                      // [ne][ns] partials of this CTA's elements (the reduction scratch is dead after the sync below)
+    {
+        const uint2* sp = P.st2 + (size_t)(a.hk * gq + min(warp, gq - 1)) * P.max_split * 2;
+        const bool st_on = warp < gq && lane < ns;
+        int el[3], sl[3];                                 // n_items <= E + ns - 1 <= 8 * 128 + 31 < 3 * MG_THREADS
+#pragma unroll
+        for (int r = 0; r < 3; r++) { const int it = tid + r * MG_THREADS; el[r] = it / ns; sl[r] = it - el[r] * ns; }
+        float m = -INFINITY, l = 0.0f, pv[3] = {0.0f, 0.0f, 0.0f};
         int spins = 0;
         bool ok;
         do {
             ok = true;
-            if (lane < a.n_split) { const uint4 w = ll_ld2(sp + lane * 2); m = __uint_as_float(w.x); l = __uint_as_float(w.z); ok = w.y == tag_po && w.w == tag_po; }
-            if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 2); break; }
-        } while (!__all_sync(0xffffffffu, ok));
-        const float M = warp_max(lane < a.n_split ? m : -INFINITY);
-        const float w = lane < a.n_split ? expf(m - M) : 0.0f;
-        float L = w * l;
+            if (st_on) { const uint4 w = ll_ld2(sp + lane * 2); m = __uint_as_float(w.x); l = __uint_as_float(w.z); ok = w.y == tag_po && w.w == tag_po; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
-        if (lane < a.n_split) wgt[warp * 32 + lane] = w;
-        if (lane == 0) S.stat[warp] = __fdiv_rn(1.0f, L);
+            for (int r = 0; r < 3; r++) if (tid + r * MG_THREADS < n_items) {
+                const uint2 w = ll_ld(P.po2 + (size_t)sl[r] * NO + a.hk * E + e0 + el[r]);
+                pv[r] = __uint_as_float(w.x); ok = ok && w.y == tag_po;
+            }
+            if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 2); break; }
+        } while (!__syncthreads_and(ok));
+        if (warp < gq) {
+            const float M = warp_max(lane < ns ? m : -INFINITY);
+            const float w = lane < ns ? expf(m - M) : 0.0f;
+            float L = w * l;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+            if (lane < ns) wgt[warp * 32 + lane] = w;
+            if (lane == 0) S.stat[warp] = __fdiv_rn(1.0f, L);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) if (tid + r * MG_THREADS < n_items) wp[tid + r * MG_THREADS] = pv[r];
     }
     __syncthreads();
-    for (int e = tid; e < E; e += MG_THREADS) {
+    if (tid < ne) {
+        const int e = e0 + tid;
         const int g = dh == 128 ? e >> 7 : e >> 6;
-        const uint2* pp = P.po2 + a.hk * E + e;
         float o = 0.0f;
-        for (int s0 = 0; s0 < a.n_split; s0 += 8) {        // batches of 8 polled together, added in split order
-            float pv[8];
-            int spins = 0;
-            bool ok;
-            do {
-                ok = true;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (s0 + i < a.n_split) { const uint2 w = ll_ld(pp + (size_t)(s0 + i) * NO); pv[i] = __uint_as_float(w.x); ok = ok && w.y == tag_po; } else pv[i] = 0.0f;
-                }
-                if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 3); break; }
-            } while (!ok);
-#pragma unroll
-            for (int i = 0; i < 8; i++) if (s0 + i < a.n_split) o += wgt[g * 32 + s0 + i] * pv[i];
-        }
+        for (int s0 = 0; s0 < ns; s0++) o += wgt[g * 32 + s0] * wp[tid * ns + s0];
         ll_st(P.ao2 + (size_t)a.hk * E + e, o * S.stat[g], tag_ao);
     }
 }

@@ -376,13 +376,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                 // panel rows of the two 128-row halves of the B tile
                 const int w0 = a.mode == PG_SWIGLU ? nt * 128 : nt * PG_BN;
                 const int w1 = a.mode == PG_SWIGLU ? a.panel_up_row0 + nt * 128 : nt * PG_BN + 128;
+                const bool two = m0 + 128 < a.T;                   // token rows 128-255 of the tile exist (few-token batches: one M half only)
                 for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % PG_STAGES;
                     mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
                     unsigned char* sa = smem + s * PG_STAGE_BYTES;
-                    mbar_expect_tx(full + s, PANEL ? PG_A_BYTES + PG_B_BYTES : PG_A_BYTES);
+                    mbar_expect_tx(full + s, (PANEL ? PG_A_BYTES + PG_B_BYTES : PG_A_BYTES) - (two ? 0 : PG_A_BYTES / 2));
                     tma_load_2d(sa, &tmap_x, kb * PG_BK, m0, full + s);
-                    tma_load_2d(sa + PG_A_BYTES / 2, &tmap_x, kb * PG_BK, m0 + 128, full + s);
+                    if (two) tma_load_2d(sa + PG_A_BYTES / 2, &tmap_x, kb * PG_BK, m0 + 128, full + s);
                     if (PANEL) {
                         tma_load_2d(sa + PG_A_BYTES, &tmap_w, kb * PG_BK, w0, full + s);
                         tma_load_2d(sa + PG_A_BYTES + PG_B_BYTES / 2, &tmap_w, kb * PG_BK, w1, full + s);
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
                 const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
                 const int kb0 = w.kb0, kb1 = w.kb1;
+                const bool two = (w.tile % m_tiles) * PG_BM + 128 < a.T;      // the second accumulator's token rows exist
                 mbar_wait(tmem_empty, (tile_i & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
                 for (int kb = kb0; kb < kb1; kb++, it++) {
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                         const uint64_t koff = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 B along K inside the swizzle atom
                         const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
                         tc_mma_bf16(tmem_base, da0 + koff, db + koff, idesc, acc);
-                        tc_mma_bf16(tmem_base + PG_BN, da1 + koff, db + koff, idesc, acc);
+                        if (two) tc_mma_bf16(tmem_base + PG_BN, da1 + koff, db + koff, idesc, acc);
                     }
                     tc_commit(empty + s);                         // frees the stage when these MMAs have read it
                 }
@@ -483,7 +485,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                     const int h = warp >> 2;
                     const int trow = m0 + h * 128 + q * 32 + lane;
                     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * PG_BN);
-                    if (w.part) {
+                    if (m0 + h * 128 >= a.T) {
+                        // this accumulator's token rows do not exist (few-token batch): nothing was accumulated, nothing to drain
+                    } else if (w.part) {
                         // a K split: the raw partial sums of the tile go to the workspace (row-major 256 x 256), nothing else
                         float* wt = a.ws + ((size_t)(tile - n_whole) * n_split + w.split) * (size_t)(PG_BM * PG_BN) + (size_t)(h * 128 + q * 32 + lane) * PG_BN;
 #pragma unroll 1

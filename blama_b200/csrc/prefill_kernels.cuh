@@ -512,7 +512,9 @@ __global__ void __launch_bounds__(256) row_topk_gather_kernel(const RowTopkArgs 
 }
 
 // per-chunk maxima of a logits row (feeds topk_select_kernel when the row was not produced by the decode lm_head mat-vec)
-__global__ void __launch_bounds__(256) chunk_max_kernel(const float* __restrict__ logits, int n, int chunk_shift, int* chunk_max) {
+// blockIdx.y = row of a batch (rows ld floats apart, 256 chunk maxima per row)
+__global__ void __launch_bounds__(256) chunk_max_kernel(const float* __restrict__ logits, int n, int chunk_shift, int* chunk_max, long long ld = 0) {
+    logits += (size_t)blockIdx.y * (size_t)ld; chunk_max += blockIdx.y * 256;
     const int c = blockIdx.x, begin = c << chunk_shift, end = min(n, begin + (1 << chunk_shift));
     float m = -INFINITY;
     for (int i = begin + threadIdx.x; i < end; i += 256) m = fmaxf(m, logits[i]);

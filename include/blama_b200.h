@@ -77,6 +77,10 @@ BLK_API int32_t blk_model_device(const blk_model*);
 BLK_API int64_t blk_model_weight_bytes_per_token(const blk_model*);
 /* KV bytes per context token (K+V, all layers, f16) */
 BLK_API int64_t blk_model_kv_bytes_per_token(const blk_model*);
+/* Bytes of the resident bf16 weight panels (the multi-token GEMMs' B operands, built by the first prefill of >= 32 tokens into
+   free device memory beyond a reserve; BLK_PANEL_CACHE_GB caps it, 0 disables) and how many of the 4 n_layer + 1 matrices they
+   cover (n_resident may be NULL).  0 before the first multi-token pass.  No llama.cpp counterpart: ggml keeps quantised weights only. */
+BLK_API int64_t blk_model_panel_bytes(blk_model*, int32_t* n_resident, int32_t* n_matrices);
 /* token text (tokenizer.ggml.tokens[token]); returns length, copies at most cap bytes (llama_token_to_piece, Vocab.cpp:57) */
 BLK_API int32_t blk_model_token_text(const blk_model*, int32_t token, char* buf, int32_t cap);
 /* The vocabulary behind llama_tokenize / llama_token_to_piece (Vocab.cpp:40,57): token attribute (tokenizer.ggml.token_type:

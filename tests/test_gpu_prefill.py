@@ -17,14 +17,17 @@ MODELS = ["tiny-llama-q4km", "tiny-qwen2-q8", "small-llama-q4km", "small-qwen2-q
 
 
 @pytest.mark.parametrize("name", MODELS)
-@pytest.mark.parametrize("form", ["two-pass", "fused"])
+@pytest.mark.parametrize("form", ["resident", "two-pass", "fused"])
 def test_prompt_prefill_matches_bf16_oracle(name, form, gguf_path, oracle, monkeypatch):
-    """form: the GEMMs read a bf16 weight panel dequantised once per matrix (default above 256 tokens) / dequantise inside the GEMM;
-    both with the deterministic split-K that few-token batches get"""
+    """form: the GEMMs read the model's resident bf16 panels (default) / a streaming panel de-quantised once per matrix and request
+    (default above 256 tokens for matrices that are not resident) / de-quantise inside the GEMM; all with the deterministic split-K
+    that few-token batches get"""
     from blama_b200 import capi
 
-    # (the default switches form at 257 tokens: pick explicitly so that both are covered at this size)
-    monkeypatch.setenv("BLK_PANEL_MIN", "0" if form == "fused" else "32")
+    # (without resident panels the default switches form at 257 tokens: pick explicitly so that both are covered at this size)
+    if form != "resident":
+        monkeypatch.setenv("BLK_PANEL_CACHE_GB", "0")
+        monkeypatch.setenv("BLK_PANEL_MIN", "0" if form == "fused" else "32")
 
     path = gguf_path(name)
     toks = gs.synth_prompt(name, 75, 11)                     # 75 >= prefill_min and not a multiple of any tile size
@@ -36,6 +39,11 @@ def test_prompt_prefill_matches_bf16_oracle(name, form, gguf_path, oracle, monke
     c.decode(toks)
     got = c.logits()
     assert np.abs(got - want[-1]).max() <= PREFILL_TOL
+    pbytes, n_res, n_mat = m.panel_cache()
+    if form == "resident" and "f32" not in name:
+        assert n_res == n_mat and pbytes > 0                 # every layer matrix and the lm_head
+    if form != "resident":
+        assert n_res == 0 and pbytes == 0
     top = c.topk(10)
     assert np.array_equal(top["logit"], np.sort(got)[::-1][:10])
     # the KV cache written by the prefill is usable by the decode path: next-token logits stay close to the oracle's
@@ -140,3 +148,25 @@ def test_sparse_claimed_logits_equal_the_full_head(name, gguf_path):
     ta, tb = a.topk(10), b.topk(10)
     assert ta["token"][0] == tb["token"][0] or abs(ta["logit"][0] - ta["logit"][1]) < 0.2
     a.close(); b.close(); m.close()
+
+
+@pytest.mark.parametrize("name", ["small-llama-q4km", "small-qwen2-q8"])
+@pytest.mark.parametrize("T", [48, 300])
+def test_resident_panels_give_the_streamed_forms_logits(name, T, gguf_path, monkeypatch):
+    """the resident panels hold exactly what the streamed two-pass form de-quantises per request: the logits of a prefill are
+    bit-identical between the two, below and above the 256-token switch (same GEMM kernel, same tiles, same split-K)"""
+    from blama_b200 import capi
+
+    path = gguf_path(name)
+    toks = gs.synth_prompt(name, T, 5)
+    rows = []
+    for cache in ("default", "0"):
+        if cache == "0":
+            monkeypatch.setenv("BLK_PANEL_CACHE_GB", "0")
+            monkeypatch.setenv("BLK_PANEL_MIN", "32")
+        m = capi.Model(path); c = capi.Ctx(m, 512)
+        c.decode(toks); rows.append(c.logits().copy())
+        c.clear(); c.decode(toks)                            # second pass: the cache is warm / the stream panels are reused
+        assert np.array_equal(rows[-1], c.logits())
+        c.close(); m.close()
+    assert np.array_equal(rows[0], rows[1])
