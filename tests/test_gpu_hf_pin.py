@@ -1,0 +1,56 @@
+"""The PRODUCT against Hugging Face transformers directly (golden vectors of tools/gen_hf_forward_golden.py: HF's own GGUF loader and
+Llama / Qwen2 models on the same synthetic GGUF, float32): both arithmetic paths of the engine, without the oracle in between.
+
+  * prefill path (bf16 tensor-core GEMMs, f16 attention): within PREFILL_TOL of the float32 logits, arg-max identical wherever Hugging
+    Face's own top-2 gap exceeds twice the tolerance;
+  * decode path (ggml's int8 activation arithmetic): within the quantisation noise of Q8_K / Q8_0 activations (the same bound the
+    oracle's GGML mode meets against these vectors on the CPU, tests/test_oracle_hf_pin.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from blama_b200 import gguf_synth as gs
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "hf_forward_golden.npz"))
+SHAPES = sorted({k.split("/")[0] for k in GOLD.files if k.endswith("/last_logits")})
+PREFILL_TOL = 0.1           # bf16 operands (2^-9 relative) through 2-8 layers, logits of standard deviation 2.1
+DECODE_MAX, DECODE_RMS = 0.5, 0.1
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_prefill_path_matches_hf(shape, gguf_path, monkeypatch):
+    from blama_b200 import capi
+
+    monkeypatch.setenv("BLK_PREFILL_MIN", "8")             # the 24-token prompt takes the tcgen05 prefill path
+    toks = GOLD[shape + "/tokens"]
+    last = GOLD[shape + "/last_logits"]
+    m = capi.Model(gguf_path(shape)); c = capi.Ctx(m, 256)
+    for r in range(len(last)):                             # the last positions one by one: prefill of the prefix that ends there
+        n = len(toks) - len(last) + r + 1
+        c.clear(); c.decode(toks[:n])
+        got = c.logits()
+        assert np.abs(got - last[r]).max() <= PREFILL_TOL
+        top2 = np.sort(last[r])[::-1][:2]
+        if top2[0] - top2[1] > 2 * PREFILL_TOL:
+            assert int(got.argmax()) == int(GOLD[shape + "/argmax"][n - 1])
+    c.close(); m.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_decode_path_stays_within_quantisation_noise_of_hf(shape, gguf_path, monkeypatch):
+    from blama_b200 import capi
+
+    monkeypatch.setenv("BLK_PREFILL_MIN", "1000000")       # token by token through the batch-1 decode kernel
+    toks = GOLD[shape + "/tokens"]
+    last = GOLD[shape + "/last_logits"]
+    m = capi.Model(gguf_path(shape)); c = capi.Ctx(m, 256)
+    rows = []
+    for t in toks:
+        c.decode([int(t)]); rows.append(c.logits().copy())
+    d = np.abs(np.stack(rows[-len(last):]) - last)
+    assert d.max() <= DECODE_MAX and np.sqrt((d ** 2).mean()) <= DECODE_RMS, (d.max(), np.sqrt((d ** 2).mean()))
+    c.close(); m.close()

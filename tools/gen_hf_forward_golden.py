@@ -23,7 +23,8 @@ sys.path.insert(0, ROOT)
 from blama_b200 import gguf_synth as gs  # noqa: E402
 
 SHAPES = ["small-llama-q4km", "small-qwen2-q8", "tiny-llama-q8", "small-llama70-q4km", "small-llama-gq3"]
-N_TOK, KEEP = 24, 4
+BIG_SHAPES = ["llama-3.2-1b-q8"]       # BASELINE configs[0] at full size: only the top-32 of the last positions is kept (128 256 logits per row)
+N_TOK, KEEP, TOPK = 24, 4, 32
 
 
 def hf_logits(path: str, tokens):
@@ -64,7 +65,7 @@ def main():
     tmp = "/tmp/blama_hf_golden"
     os.makedirs(tmp, exist_ok=True)
     out = {}
-    for shape in SHAPES:
+    for shape in SHAPES + BIG_SHAPES:
         path = os.path.join(tmp, shape + ".gguf")
         gs.write_gguf(path, shape)
         toks = np.array([int(t) for t in gs.synth_prompt(shape, N_TOK, 1)], dtype=np.int32)
@@ -77,7 +78,13 @@ def main():
         out[shape + "/tokens"] = toks
         out[shape + "/sha256"] = np.frombuffer(bytes.fromhex(sha256(path)), dtype=np.uint8)
         out[shape + "/argmax"] = lg.argmax(1).astype(np.int32)
-        out[shape + "/last_logits"] = lg[-KEEP:]
+        if shape in BIG_SHAPES:
+            ids = np.argsort(-lg[-KEEP:], axis=1, kind="stable")[:, :TOPK].astype(np.int32)
+            out[shape + "/top_ids"] = ids
+            out[shape + "/top_logits"] = np.take_along_axis(lg[-KEEP:], ids, axis=1)
+            os.remove(path)
+        else:
+            out[shape + "/last_logits"] = lg[-KEEP:]
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hf_forward_golden.npz"), **out)
 
 
