@@ -75,13 +75,8 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     tmap_w = tmap;
-    if (panel) {
-        const cuuint64_t wdim[2] = {(cuuint64_t)a.K, (cuuint64_t)panel_rows};
-        r = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(panel), wdim, gstride, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    }
+    a.panel = reinterpret_cast<const unsigned char*>(panel);      // tile images, fetched with plain bulk copies (no tensor map)
+    (void)panel_rows;
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -119,14 +114,15 @@ cudaError_t panel_dequant(const QMat& W, __nv_bfloat16* panel, long long row0, c
     // panel holds -- the difference in wall time is what the panel fills (their HBM traffic and power) cost a verify
     static const bool nofill = [] { const char* e = getenv("BLK_PANEL_NOFILL"); return e && e[0] == '1'; }();
     if (nofill) return cudaSuccess;
-    const long long total = (long long)W.N * (W.K >> 6);
+    if (row0 % 128) return cudaErrorInvalidValue;
+    const long long total = (long long)((W.N + 127) / 128) * 128 * (W.K >> 6);
     const unsigned grid = (unsigned)((total + 255) / 256);
-    __nv_bfloat16* dst = panel + (size_t)row0 * W.K;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(panel);
     switch (W.type) {
-        case QT_Q4_K: panel_dequant_kernel<QT_Q4_K><<<grid, 256, 0, st>>>(W, dst); break;
-        case QT_Q5_K: panel_dequant_kernel<QT_Q5_K><<<grid, 256, 0, st>>>(W, dst); break;
-        case QT_Q6_K: panel_dequant_kernel<QT_Q6_K><<<grid, 256, 0, st>>>(W, dst); break;
-        case QT_Q8_0: panel_dequant_kernel<QT_Q8_0><<<grid, 256, 0, st>>>(W, dst); break;
+        case QT_Q4_K: panel_dequant_kernel<QT_Q4_K><<<grid, 256, 0, st>>>(W, dst, row0); break;
+        case QT_Q5_K: panel_dequant_kernel<QT_Q5_K><<<grid, 256, 0, st>>>(W, dst, row0); break;
+        case QT_Q6_K: panel_dequant_kernel<QT_Q6_K><<<grid, 256, 0, st>>>(W, dst, row0); break;
+        case QT_Q8_0: panel_dequant_kernel<QT_Q8_0><<<grid, 256, 0, st>>>(W, dst, row0); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -27,7 +27,7 @@ constexpr int AT_THREADS = 64 + AT_SM_THREADS;             // warp 0 TMA, warp 1
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;                 // one [128][64] f16 K block = 16 KB
 constexpr int AT_MX_BYTES = 2 * 4 * 128 * 2;              // tile maxima of the four threads of a row, f16, double-buffered
 constexpr int AT_USED_BYTES = (2 + 2 * 2 + 2 * 2 + 2 * 2) * AT_TILE_BYTES + 256 /*barriers*/ + AT_MX_BYTES;      // Q, K x2, V x2, P x2
-constexpr int AT_SMEM_BYTES = 227 * 1024;                  // everything an SM has: 768 bytes of slack for the 1024-byte alignment of the tiles (checked in the kernel)
+constexpr int AT_SMEM_BYTES = AT_USED_BYTES;               // the dynamic shared memory starts 1024-aligned (checked in the kernel)
 
 __device__ __forceinline__ void tc_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
                                                                         const __grid_constant__ CUtensorMap tmap_vt, const AttnTcArgs a) {
     constexpr int BQ = 128 / GQS;
     extern __shared__ __align__(1024) unsigned char at_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = at_smem_raw;      // 1024-aligned (checked below); no integer cast, so that the accesses stay LDS / STS
     unsigned char* sQ = smem;                                   // 2 K blocks
     unsigned char* sK = sQ + 2 * AT_TILE_BYTES;                 // 2 stages x 2 K blocks
     unsigned char* sV = sK + 4 * AT_TILE_BYTES;                 // 2 stages x 2 key blocks
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     uint64_t* o_full = bars + 17;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
     __half* s_mx = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(bars) + 256);      // [2][4 parts][128 rows]
-    if (threadIdx.x == 0 && (smem - at_smem_raw) + AT_USED_BYTES > AT_SMEM_BYTES) __trap();     // the launch's dynamic shared memory starts less aligned than assumed
+    if (threadIdx.x == 0 && (smem_u32(at_smem_raw) & 1023u)) __trap();      // the tiles need 1024-byte alignment (SWIZZLE_128B atoms)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = (int)gridDim.x - 1 - (int)blockIdx.x, hk = blockIdx.y;      // late (long) query tiles first

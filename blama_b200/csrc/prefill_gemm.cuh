@@ -23,7 +23,9 @@
 namespace blk {
 
 constexpr int PG_BM = 256, PG_BN = 256, PG_BK = 64;
-constexpr int PG_STAGES = 3;
+constexpr int PG_STAGES = 3;                              // full tiles: three 64 KB stages (A 32 KB + B 32 KB)
+constexpr int PG_STAGES_FEW = 4;                          // batches of at most 128 tokens (one M half): four 48 KB stages (A 16 KB + B 32 KB) in the
+                                                          // same 192 KB -- a third more weight bytes in flight per SM, which is what bounds a few-token GEMM
 constexpr int PG_PRODUCER_THREADS = 256;
 constexpr int PG_THREADS = PG_PRODUCER_THREADS + 64;      // + TMA warp + MMA warp
 constexpr int PG_A_BYTES = PG_BM * PG_BK * 2;             // 32 KB (two 128-row boxes)
@@ -50,6 +52,11 @@ struct PrefillGemmArgs {
     int n_tiles;                // total column tiles over all segments
     int mode;
     int panel_up_row0;          // QT_PANEL + PG_SWIGLU: panel row of ffn_up row 0 (ffn_gate starts at panel row 0)
+    // QT_PANEL: the bf16 weights as TILE IMAGES -- block (rb, kb) = rows 128 rb .. +127, columns 64 kb .. +63 is 16 KB at
+    // panel + (rb * K / 64 + kb) * 16384 bytes, laid out exactly as the K-major SWIZZLE_128B shared-memory tile (row r at
+    // (r >> 3) * 1024 + (r & 7) * 128, 16-byte chunk c at position c ^ (r & 7)): one contiguous cp.async.bulk per half tile instead of a
+    // 2-D tensor-map box of 128 pieces of 128 bytes at an 8-16 KB stride (which touched 128 DRAM pages for 16 KB)
+    const unsigned char* panel;
     // deterministic split-K of the LAST, partial wave of tiles (and of every tile when the batch has fewer tiles than SMs): tiles
     // [0, n_whole) are computed whole; each tile t >= n_whole becomes k_splits work items, item (t, s) stores its partial sums as a
     // 256 x 256 f32 tile at ws + ((t - n_whole) * k_splits + s) * 65536 and splitk_reduce_kernel adds the partials in split order and
@@ -334,18 +341,27 @@ __device__ __forceinline__ PgItem pg_item(int item, int n_whole, int n_split, in
 template <int TA, int TB>
 __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const PrefillGemmArgs a) {
     constexpr bool PANEL = (TA == QT_PANEL);
-    extern __shared__ unsigned char pg_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_smem_raw) + 1023) & ~uintptr_t(1023));
+    // The tiles need 1024-byte alignment (SWIZZLE_128B atoms).  The dynamic shared memory of a kernel without static shared memory
+    // starts 1024-aligned on this part; it is checked, not assumed, and NOT re-aligned through an integer cast -- that hides the
+    // address space from the compiler, and every shared-memory access of the producers became a generic ST.E / LD.E.
+    extern __shared__ __align__(1024) unsigned char pg_smem_raw[];
+    unsigned char* smem = pg_smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(pg_smem_raw) & 1023u)) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PG_STAGES * PG_STAGE_BYTES);
-    uint64_t* full = bars;                          // [PG_STAGES]  TMA bytes + 8 producer-warp arrivals
-    uint64_t* empty = bars + PG_STAGES;             // [PG_STAGES]  tcgen05.commit
-    uint64_t* tmem_full = bars + 2 * PG_STAGES;     // accumulators complete
-    uint64_t* tmem_empty = bars + 2 * PG_STAGES + 1;    // epilogue drained them (8 warps)
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * PG_STAGES + 2);
+    uint64_t* full = bars;                          // [n_st]  TMA bytes + 8 producer-warp arrivals
+    uint64_t* empty = bars + PG_STAGES_FEW;         // [n_st]  tcgen05.commit
+    uint64_t* tmem_full = bars + 2 * PG_STAGES_FEW;     // accumulators complete
+    uint64_t* tmem_empty = bars + 2 * PG_STAGES_FEW + 1;    // epilogue drained them (8 warps)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * PG_STAGES_FEW + 2);
+    // stage geometry: kernel-uniform (few = every tile has one M half only)
+    const bool few = a.T <= 128;
+    const int n_st = few ? PG_STAGES_FEW : PG_STAGES;
+    const int a_bytes = few ? PG_A_BYTES / 2 : PG_A_BYTES;
+    const int st_bytes = a_bytes + PG_B_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PG_STAGES; s++) { mbar_init(full + s, PANEL ? 1 : 1 + PG_PRODUCER_THREADS / 32); mbar_init(empty + s, 1); }
+        for (int s = 0; s < PG_STAGES_FEW; s++) { mbar_init(full + s, PANEL ? 1 : 1 + PG_PRODUCER_THREADS / 32); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 8);
         mbar_fence_init();
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     if (warp == 8) {
         // ===================== TMA producer (activations) =====================
         if (lane == 0) {
-            int it = 0;
+            int s = 0; uint32_t ph = 0;                        // stage and its phase
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
                 const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
                 const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
@@ -377,17 +393,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                 const int w0 = a.mode == PG_SWIGLU ? nt * 128 : nt * PG_BN;
                 const int w1 = a.mode == PG_SWIGLU ? a.panel_up_row0 + nt * 128 : nt * PG_BN + 128;
                 const bool two = m0 + 128 < a.T;                   // token rows 128-255 of the tile exist (few-token batches: one M half only)
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const int s = it % PG_STAGES;
-                    mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
-                    unsigned char* sa = smem + s * PG_STAGE_BYTES;
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(empty + s, ph ^ 1);
+                    unsigned char* sa = smem + s * st_bytes;
                     mbar_expect_tx(full + s, (PANEL ? PG_A_BYTES + PG_B_BYTES : PG_A_BYTES) - (two ? 0 : PG_A_BYTES / 2));
                     tma_load_2d(sa, &tmap_x, kb * PG_BK, m0, full + s);
                     if (two) tma_load_2d(sa + PG_A_BYTES / 2, &tmap_x, kb * PG_BK, m0 + 128, full + s);
                     if (PANEL) {
-                        tma_load_2d(sa + PG_A_BYTES, &tmap_w, kb * PG_BK, w0, full + s);
-                        tma_load_2d(sa + PG_A_BYTES + PG_B_BYTES / 2, &tmap_w, kb * PG_BK, w1, full + s);
+                        bulk_g2s(sa + a_bytes, a.panel + (((size_t)(w0 >> 7) * k_blocks_all + kb) << 14), PG_B_BYTES / 2, full + s);
+                        bulk_g2s(sa + a_bytes + PG_B_BYTES / 2, a.panel + (((size_t)(w1 >> 7) * k_blocks_all + kb) << 14), PG_B_BYTES / 2, full + s);
                     }
+                    if (++s == n_st) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -395,19 +411,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, PG_BN);
-            int it = 0, tile_i = 0;
+            int s = 0, tile_i = 0; uint32_t ph = 0;
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
                 const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
                 const int kb0 = w.kb0, kb1 = w.kb1;
                 const bool two = (w.tile % m_tiles) * PG_BM + 128 < a.T;      // the second accumulator's token rows exist
                 mbar_wait(tmem_empty, (tile_i & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const int s = it % PG_STAGES;
-                    mbar_wait(full + s, (it / PG_STAGES) & 1);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(full + s, ph);
                     tc_fence_after();
-                    unsigned char* sa = smem + s * PG_STAGE_BYTES;
-                    unsigned char* sb = sa + PG_A_BYTES;
+                    unsigned char* sa = smem + s * st_bytes;
+                    unsigned char* sb = sa + a_bytes;
                     const uint64_t da0 = umma_desc_sw128(sa), da1 = umma_desc_sw128(sa + PG_A_BYTES / 2), db = umma_desc_sw128(sb);
 #pragma unroll
                     for (int k = 0; k < PG_BK / 16; k++) {
@@ -417,6 +432,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                         if (two) tc_mma_bf16(tmem_base + PG_BN, da1 + koff, db + koff, idesc, acc);
                     }
                     tc_commit(empty + s);                         // frees the stage when these MMAs have read it
+                    if (++s == n_st) { s = 0; ph ^= 1; }
                 }
                 tc_commit(tmem_full);                             // accumulators of this tile are final
             }
@@ -424,7 +440,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     } else {
         // ===================== dequant producers (warps 0-7); warps 4-7 also run the epilogue =====================
         const int r = threadIdx.x;                                // B-tile row handled by this thread
-        int it = 0, tile_i = 0;
+        int s = 0, tile_i = 0; uint32_t ph = 0;
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, tile_i++) {
             const PgItem w = pg_item(item, n_whole, n_split, k_per, k_blocks_all);
             const int tile = w.tile, kb0 = w.kb0, kb1 = w.kb1;
@@ -446,12 +462,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                 constexpr bool DEEP = sizeof(Raw) <= 64;           // small raw slices (Q4_K): three in flight; large ones: two
                 Raw cur, nxt, nx2;
                 if (row_ok) { cur.load(Sg.W, row, kb0); if (DEEP && kb0 + 1 < kb1) nxt.load(Sg.W, row, kb0 + 1); }
-                for (int kb = kb0; kb < kb1; kb++, it++) {
-                    const int s = it % PG_STAGES;
+                for (int kb = kb0; kb < kb1; kb++) {
                     if (DEEP) { if (row_ok && kb + 2 < kb1) nx2.load(Sg.W, row, kb + 2); }      // loads fly while the current slice is expanded
                     else { if (row_ok && kb + 1 < kb1) nxt.load(Sg.W, row, kb + 1); }
-                    mbar_wait(empty + s, ((it / PG_STAGES) & 1) ^ 1);
-                    unsigned char* srow = smem + s * PG_STAGE_BYTES + PG_A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                    mbar_wait(empty + s, ph ^ 1);
+                    unsigned char* srow = smem + s * st_bytes + a_bytes + (r >> 3) * 1024 + (r & 7) * 128;
                     if (row_ok) cur.expand(srow, r, kb);
                     else {
 #pragma unroll
@@ -462,6 +477,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
                     if (lane == 0) mbar_arrive(full + s);
                     cur = nxt;
                     if (DEEP) nxt = nx2;
+                    if (++s == n_st) { s = 0; ph ^= 1; }
                 }
             };
             if constexpr (!PANEL) { if (TA != TB && si == 2) produce(RawK64<TB>{}); else produce(RawK64<TA>{}); }
@@ -632,34 +648,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const PrefillGemmArg
     }
 }
 
-// ---- first pass of the two-pass form: one weight matrix -> bf16 panel rows [N][K] (row stride K), same values the fused
-// producers write into shared memory (bf16 of ggml's dequantised f32) ----------------------------------------------------
+// ---- one weight matrix -> bf16 tile images of the panel (PrefillGemmArgs::panel): the same values the fused producers write into
+// shared memory (bf16 of ggml's dequantised f32), in the same swizzled tile layout.  One thread expands one 64-element slice of a
+// row (128 bytes); consecutive threads take consecutive rows of the same (row block, K block), so a warp writes 4 KB contiguous.
+// row0 = panel row of W's row 0 (a multiple of 128) -------------------------------------------------------------------------------
 template <int TYPE>
-__global__ void __launch_bounds__(256) panel_dequant_kernel(const QMat W, __nv_bfloat16* __restrict__ dst) {
-    // one thread expands one 64-element slice (128 B of bf16) into its warp's staging rows in shared memory; the warp then writes
-    // its 32 slices (4 KB, contiguous in the panel: consecutive threads = consecutive slices of a row, rows back to back) with
-    // fully coalesced 512-byte stores -- storing straight from the expander would issue 16-byte pieces at a 128-byte stride
-    __shared__ __align__(16) unsigned char stage[8][32 * 144];     // 144 B row pitch: 4-way instead of 32-way bank conflicts
+__global__ void __launch_bounds__(256) panel_dequant_kernel(const QMat W, unsigned char* __restrict__ panel, long long row0) {
     const int kbs = W.K >> 6;
-    const int64_t total = (int64_t)W.N * kbs;
+    const int64_t n_rb = (W.N + 127) >> 7;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* mine = stage[warp] + lane * 144;
-    if (idx < total) {
-        const int64_t row = idx / kbs; const int kb = (int)(idx - row * kbs);
-        RawK64<TYPE> raw;
-        raw.load(W, row, kb);
-        raw.expand(mine, 0, kb);                                    // r = 0: no swizzle, 8 x 16 B in order
-    }
-    __syncwarp();
-    const int64_t idx0 = idx - lane;                                // first slice of this warp
-    unsigned char* out = reinterpret_cast<unsigned char*>(dst) + idx0 * 128;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int j = i * 32 + lane;                                // 16-byte chunk j of the warp's 4 KB
-        if (idx0 + (j >> 3) < total)
-            *reinterpret_cast<uint4*>(out + (size_t)j * 16) = *reinterpret_cast<const uint4*>(stage[warp] + (j >> 3) * 144 + (j & 7) * 16);
-    }
+    if (idx >= n_rb * kbs * 128) return;
+    const int r = (int)(idx & 127);
+    const int64_t bk = idx >> 7;
+    const int64_t rb = bk / kbs; const int kb = (int)(bk - rb * kbs);
+    const int64_t row = rb * 128 + r;
+    if (row >= W.N) return;
+    RawK64<TYPE> raw;
+    raw.load(W, row, kb);
+    unsigned char* dst = panel + ((((size_t)(row0 >> 7) + (size_t)rb) * kbs + kb) << 14) + (r >> 3) * 1024 + (r & 7) * 128;
+    raw.expand(dst, r, kb);
 }
 
 } // namespace blk

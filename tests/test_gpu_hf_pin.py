@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "hf_forward_golden.npz"))
 SHAPES = sorted({k.split("/")[0] for k in GOLD.files if k.endswith("/last_logits")})
-PREFILL_TOL = 0.1           # bf16 operands (2^-9 relative) through 2-8 layers, logits of standard deviation 2.1
+PREFILL_TOL, PREFILL_RMS = 0.15, 0.03      # bf16 operands (2^-9 relative) through 2-8 layers, logits of standard deviation 2.1; the CPU
+                                           # restatement of this arithmetic (oracle BF16 mode) sits at max 0.03-0.07, rms 0.007-0.017 from the same vectors
 DECODE_MAX, DECODE_RMS = 0.5, 0.1
 
 
@@ -33,7 +34,8 @@ def test_prefill_path_matches_hf(shape, gguf_path, monkeypatch):
         n = len(toks) - len(last) + r + 1
         c.clear(); c.decode(toks[:n])
         got = c.logits()
-        assert np.abs(got - last[r]).max() <= PREFILL_TOL
+        d = np.abs(got - last[r])
+        assert d.max() <= PREFILL_TOL and np.sqrt((d ** 2).mean()) <= PREFILL_RMS, (shape, r, float(d.max()), float(np.sqrt((d ** 2).mean())))
         top2 = np.sort(last[r])[::-1][:2]
         if top2[0] - top2[1] > 2 * PREFILL_TOL:
             assert int(got.argmax()) == int(GOLD[shape + "/argmax"][n - 1])
