@@ -51,6 +51,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- LL exchange: every value that crosses CTAs travels with an epoch tag in ONE 8-byte store; readers poll the data itself.
 // Measured on B200 (tools/micro/lat.cu): store -> visible -> read = ~900 cycles, against ~3500 for grid barrier + read.
@@ -394,9 +395,8 @@ __device__ __forceinline__ void mg_attn_setup(const MegaParams& P, int n_kv, con
     const int per = (n_kv + n_split - 1) / n_split;
     const int t0 = split * per;
     S.misc[1] = hk; S.misc[2] = split; S.misc[3] = n_split; S.misc[4] = t0; S.misc[5] = max(0, min(n_kv, t0 + per) - t0); S.misc[6] = split < n_split ? 1 : 0;
-    // every slice fits one shared-memory tile (contexts up to max_split * ts_cap tokens): the soft-max runs on the CTA's own scores
-    // (local maximum and sum, merged by the combiner) and the scores never leave the CTA
-    S.misc[8] = (per <= P.ts_cap && P.attn_local) ? 1 : 0;
+    // the soft-max runs on the CTA's OWN scores (local maximum and sum, merged by the CTAs of the head): the scores never leave the CTA
+    S.misc[8] = P.attn_local ? 1 : 0;      // (a slice longer than one tile is walked tile by tile with a running maximum, mg_attn_pv_local)
 }
 __device__ __forceinline__ size_t mg_kv_row(const MegaParams& P, int hk, int t) {
     return ((size_t)P.page_table[t / KV_PAGE] * KV_PAGE + (t % KV_PAGE)) * P.kv_dim + (size_t)hk * P.d_head;
@@ -437,6 +437,47 @@ __device__ __noinline__ void mg_attn_prefetch(const MegaParams& P, int layer, in
     cp_async_commit();
 }
 
+// scaled scores of ONE tile (rows [0, cn) of s.k = tokens a.t0 + c0 ..) against the gq query heads in s.q: 8 lanes per token,
+// dh / 8 dims each.  keep: into s.sc (the CTA's own soft-max); publish: as LL words (legacy form, statistics over the whole row)
+template <int GQ>
+__device__ __forceinline__ void mg_scores_tile(const MegaParams& P, const MgAttn& a, const MgAttnSmem& s, int c0, int cn, int gq, int dh,
+                                               bool publish, uint32_t tag_out, bool keep) {
+    const int tid = threadIdx.x;
+    const int ld = tid & 7, tl = tid >> 3;
+    const int DL = dh >> 3;
+    float sc[GQ];
+#pragma unroll
+    for (int gI = 0; gI < GQ; gI++) sc[gI] = 0.0f;
+    if (tl < cn) {
+        for (int c = 0; c < DL; c += 8) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(s.k + (size_t)tl * dh + ld * DL + c);
+            const __half2* kh = reinterpret_cast<const __half2*>(&kv);
+            float kf[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float2 f = __half22float2(kh[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
+#pragma unroll
+            for (int gI = 0; gI < GQ; gI++) if (gI < gq) {
+                const uint4 qq = *reinterpret_cast<const uint4*>(s.q + gI * dh + ld * DL + c);
+                const __half2* qh = reinterpret_cast<const __half2*>(&qq);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const float2 f = __half22float2(qh[i]); sc[gI] += kf[2 * i] * f.x; sc[gI] += kf[2 * i + 1] * f.y; }
+            }
+        }
+    }
+#pragma unroll
+    for (int gI = 0; gI < GQ; gI++) if (gI < gq) {
+        float v = sc[gI];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v = __fmul_rn(v, P.attn_scale);
+        if (tl < cn && ld == 0) {
+            if (publish) ll_st(P.sc2 + (size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl, v, tag_out);
+            if (keep) s.sc[gI * P.ts_cap + tl] = v;
+        }
+    }
+}
+
 // stage 1: scaled scores of this CTA's token slice for the gq query heads of its KV head -> LL words (+ shared for tile 0)
 template <int GQ>
 __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int phi, int n_kv, const MgSmem& S) {
@@ -474,103 +515,122 @@ __device__ __noinline__ void mg_attn_scores(const MegaParams& P, int layer, int 
         }
     }
     cp_async_wait_all();
-    const int ld = tid & 7, tl = tid >> 3;                          // 8 lanes per token, dh / 8 dims each
-    const int DL = dh >> 3;
     for (int c0 = 0; c0 < a.nt; c0 += P.ts_cap) {
         const int cn = min(P.ts_cap, a.nt - c0);
-        if (c0 > 0) {       // long context: further tiles are fetched synchronously
+        if (c0 > 0) {       // legacy form, long context: further tiles are fetched synchronously (the local form walks them in stage 2)
+            if (S.misc[8]) break;
             __syncthreads();
             mg_attn_load_rows<false>(P, a, S.kp[layer], s.k, c0, cn, n_kv - 1);
             if (tl_new >= c0 && tl_new < c0 + cn) for (int j = tid; j < dh; j += MG_THREADS) s.k[(size_t)(tl_new - c0) * dh + j] = __float2half_rn(__uint_as_float(ll_ld(P.kvn2 + a.hk * dh + j).x));
         }
         __syncthreads();
-        float sc[GQ];
-#pragma unroll
-        for (int gI = 0; gI < GQ; gI++) sc[gI] = 0.0f;
-        if (tl < cn) {
-            for (int c = 0; c < DL; c += 8) {
-                const uint4 kv = *reinterpret_cast<const uint4*>(s.k + (size_t)tl * dh + ld * DL + c);
-                const __half2* kh = reinterpret_cast<const __half2*>(&kv);
-                float kf[8];
-#pragma unroll
-                for (int i = 0; i < 4; i++) { const float2 f = __half22float2(kh[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
-#pragma unroll
-                for (int gI = 0; gI < GQ; gI++) if (gI < gq) {
-                    const uint4 qq = *reinterpret_cast<const uint4*>(s.q + gI * dh + ld * DL + c);
-                    const __half2* qh = reinterpret_cast<const __half2*>(&qq);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { const float2 f = __half22float2(qh[i]); sc[gI] += kf[2 * i] * f.x; sc[gI] += kf[2 * i + 1] * f.y; }
-                }
-            }
-        }
-#pragma unroll
-        for (int gI = 0; gI < GQ; gI++) if (gI < gq) {
-            float v = sc[gI];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v = __fmul_rn(v, P.attn_scale);
-            if (tl < cn && ld == 0) {
-                if (!S.misc[8]) ll_st(P.sc2 + (size_t)(a.hk * gq + gI) * P.score_stride + a.t0 + c0 + tl, v, tag_out);
-                if (c0 == 0) s.sc[gI * P.ts_cap + tl] = v;
-            }
-        }
+        mg_scores_tile<GQ>(P, a, s, c0, cn, gq, dh, !S.misc[8], tag_out, c0 == 0);
     }
 }
 
-// stage 2, local form (every context slice is one shared-memory tile): soft-max over the CTA's OWN scores.
+// stage 2, local form: soft-max over the CTA's OWN scores.
 //   one slice (n_split == 1): that is the whole row -- ggml's order exactly (max -> expf -> sum in double -> p * (1/sum) -> f16 -> V.p),
 //     the result goes straight to the attention output;
-//   several slices: flash-style -- p = f16(expf(s - m_local)), o = sum p v, and (m_local, l_local) travel with the partial; the CTA of
-//     split 0 merges: M = max m_s, w_s = expf(m_s - M), out = (sum_s w_s o_s) / (sum_s w_s l_s).  Against ggml this moves the f16
+//   several slices: flash-style -- p = f16(expf(s - m_local)), o = sum p v, and (m_local, l_local) travel with the partial; the CTAs
+//     of the head merge: M = max m_s, w_s = expf(m_s - M), out = (sum_s w_s o_s) / (sum_s w_s l_s).  Against ggml this moves the f16
 //     rounding of the probabilities in front of the normalisation (a 2^-11 relative change per probability, the size of every other
 //     rounding difference between two implementations of this arithmetic); it removes the all-to-all exchange of the scores and the
-//     statistics pass over the whole row (measured on the 8B model: the partials are published 1.9 us earlier per layer; the split
-//     merge then waits on two dependent L2 round trips, statistics and partials.  Fetching both as one batch of 8 / 12 slices per
-//     thread made the kernel 3 % SLOWER overall -- the wider register footprint of this function costs the caller three spilled
-//     registers -- so the two-step merge stays; profiles/r2_decode_experiments.md).
+//     statistics pass over the whole row.
+//   a slice longer than one shared-memory tile (contexts beyond max_split x ts_cap = 1152 tokens on the 8B model) is walked tile by
+//     tile with a running maximum: the later tiles' K / V rows are fetched synchronously, their scores computed here, and the
+//     accumulator rescaled by expf(m_old - m_new) -- the same flash order, now inside the CTA too.  (Before, such contexts fell back to
+//     the round-1 form with every score exchanged between the CTAs: 496 tok/s at 1024 tokens of context, 440 at 1152, 404 at 2048.)
 template <int GQ, bool TR>
-__device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, const MgSmem& S) {
+__device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int layer, int phi, int n_kv, const MgSmem& S) {
     const MgAttn a = mg_attn_get(S);
     if (!a.on) return;
     const MgAttnSmem s = mg_attn_carve(P, S.attn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, dh = P.d_head, gq = P.n_head / P.n_head_kv;
-    const uint32_t tag_po = mg_tag(P.seq, phi, 2), tag_ao = mg_tag(P.seq, phi, 3);
+    const uint32_t tag_in = mg_tag(P.seq, phi, 0), tag_po = mg_tag(P.seq, phi, 2), tag_ao = mg_tag(P.seq, phi, 3);
     const int TG = MG_THREADS / dh;
     const int d = tid & (dh - 1), tg = dh == 128 ? tid >> 7 : tid >> 6;
-    const int cn = a.nt;
     const bool single = a.n_split == 1;
+    const bool multi = a.nt > P.ts_cap;                    // more than one tile in this slice (never with a single slice)
+    float m_run = -INFINITY, l_run = 0.0f;                 // warps < gq: running statistics of their query head
     float acc[GQ];
 #pragma unroll
     for (int gI = 0; gI < GQ; gI++) acc[gI] = 0.0f;
     __syncthreads();                                       // the scores of stage 1 (written by the token's lane group) are in shared memory
-    if (cn > 0) {
-        if (warp < gq) {                                   // warp g: statistics and probabilities of query head g
-            float* row = s.sc + warp * P.ts_cap;
-            float m = -INFINITY;
-            for (int tl = lane; tl < cn; tl += 32) m = fmaxf(m, row[tl]);
-            m = warp_max(m);
-            double sum = 0.0;
-            for (int tl = lane; tl < cn; tl += 32) { const float e = expf(row[tl] - m); row[tl] = e; sum += (double)e; }
+    if (a.nt > 0) {
+        // later tiles travel behind the computation: K of tile c + 1 is requested when the scores of tile c are done (the K rows are
+        // dead), V of tile c + 1 when P.V of tile c is (cp.async groups in that order)
+        if (multi) { mg_attn_load_rows<true>(P, a, S.kp[layer], s.k, P.ts_cap, min(P.ts_cap, a.nt - P.ts_cap), n_kv - 1); cp_async_commit(); }
+        for (int c0 = 0; c0 < a.nt; c0 += P.ts_cap) {
+            const int cn = min(P.ts_cap, a.nt - c0);
+            const bool more = c0 + P.ts_cap < a.nt;
+            const int tl_new = n_kv - 1 - a.t0 - c0;       // the token being decoded: its rows are this layer's LL words (polled: other CTAs than q's)
+            const bool new_here = c0 > 0 && tl_new >= 0 && tl_new < cn;
+            if (c0 > 0) {
+                __syncthreads();                           // P.V of the previous tile has read its V rows and probabilities
+                mg_attn_load_rows<true>(P, a, S.vp[layer], s.v, c0, cn, n_kv - 1);
+                cp_async_commit();
+                cp_async_wait_group<1>();                  // this tile's K rows have landed (its V rows may still fly)
+                if (new_here && tid < dh) {
+                    const uint2* src = P.kvn2 + a.hk * dh + tid;
+                    uint2 w = ll_ld(src);
+                    int spins = 0;
+                    while (w.y != tag_in) { if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 1); break; } w = ll_ld(src); }
+                    s.k[(size_t)tl_new * dh + tid] = __float2half_rn(__uint_as_float(w.x));
+                }
+                __syncthreads();
+                mg_scores_tile<GQ>(P, a, s, c0, cn, gq, dh, false, 0u, true);
+                __syncthreads();
+                if (more) { mg_attn_load_rows<true>(P, a, S.kp[layer], s.k, c0 + P.ts_cap, min(P.ts_cap, a.nt - c0 - P.ts_cap), n_kv - 1); cp_async_commit(); }
+            }
+            if (warp < gq) {                               // warp g: statistics and probabilities of query head g
+                float* row = s.sc + warp * P.ts_cap;
+                float m = -INFINITY;
+                for (int tl = lane; tl < cn; tl += 32) m = fmaxf(m, row[tl]);
+                m = warp_max(m);
+                if (multi) m = fmaxf(m, m_run);
+                double sum = 0.0;
+                for (int tl = lane; tl < cn; tl += 32) { const float e = expf(row[tl] - m); row[tl] = e; sum += (double)e; }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            __syncwarp();
-            if (single) {
-                const float inv = (float)(1.0 / sum);
-                for (int tl = lane; tl < cn; tl += 32) row[tl] = __half2float(__float2half_rn(__fmul_rn(row[tl], inv)));
-            } else {
-                for (int tl = lane; tl < cn; tl += 32) row[tl] = __half2float(__float2half_rn(row[tl]));
-                if (lane == 0) ll_st2(P.st2 + ((size_t)(a.hk * gq + warp) * P.max_split + a.split) * 2, m, (float)sum, tag_po);
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                __syncwarp();
+                if (single) {
+                    const float inv = (float)(1.0 / sum);
+                    for (int tl = lane; tl < cn; tl += 32) row[tl] = __half2float(__float2half_rn(__fmul_rn(row[tl], inv)));
+                } else {
+                    for (int tl = lane; tl < cn; tl += 32) row[tl] = __half2float(__float2half_rn(row[tl]));
+                    if (!multi) { if (lane == 0) ll_st2(P.st2 + ((size_t)(a.hk * gq + warp) * P.max_split + a.split) * 2, m, (float)sum, tag_po); }
+                    else {
+                        const float corr = expf(m_run - m);                 // 0 on the first tile
+                        l_run = l_run * corr + (float)sum; m_run = m;
+                        if (lane == 0) S.stat[16 + warp] = corr;
+                    }
+                }
+            }
+            if (c0 > 0) {
+                if (more) cp_async_wait_group<1>(); else cp_async_wait_all();      // this tile's V rows have landed
+                if (new_here && tid >= dh && tid < 2 * dh) {
+                    const int j = tid - dh;
+                    const uint2* src = P.kvn2 + P.kv_dim + a.hk * dh + j;
+                    uint2 w = ll_ld(src);
+                    int spins = 0;
+                    while (w.y != tag_in) { if (mg_spin_out(S, spins)) { mg_poll_timeout(P, S, 1); break; } w = ll_ld(src); }
+                    s.v[(size_t)tl_new * dh + j] = __float2half_rn(__uint_as_float(w.x));
+                }
+            }
+            __syncthreads();
+            if (c0 == 0) mg_tr<TR>(P, S, 13);
+            if (multi && c0 > 0) {
+#pragma unroll
+                for (int gI = 0; gI < GQ; gI++) if (gI < gq) acc[gI] *= S.stat[16 + gI];
+            }
+#pragma unroll 4
+            for (int tl = tg; tl < cn; tl += TG) {
+                const float v = __half2float(s.v[(size_t)tl * dh + d]);
+#pragma unroll
+                for (int gI = 0; gI < GQ; gI++) if (gI < gq) acc[gI] += s.sc[gI * P.ts_cap + tl] * v;
             }
         }
-        __syncthreads();
-        mg_tr<TR>(P, S, 13);
-#pragma unroll 4
-        for (int tl = tg; tl < cn; tl += TG) {
-            const float v = __half2float(s.v[(size_t)tl * dh + d]);
-#pragma unroll
-            for (int gI = 0; gI < GQ; gI++) if (gI < gq) acc[gI] += s.sc[gI * P.ts_cap + tl] * v;
-        }
+        if (multi && warp < gq && lane == 0) ll_st2(P.st2 + ((size_t)(a.hk * gq + warp) * P.max_split + a.split) * 2, m_run, l_run, tag_po);
     } else if (!single && warp < gq && lane == 0) {
         ll_st2(P.st2 + ((size_t)(a.hk * gq + warp) * P.max_split + a.split) * 2, -INFINITY, 0.0f, tag_po);
     }
@@ -642,7 +702,7 @@ __device__ __noinline__ void mg_attn_pv_local(const MegaParams& P, int phi, cons
 // partial V.p -> LL words; the CTA of split 0 sums the split partials in split order.
 template <int GQ, bool TR>
 __device__ __noinline__ void mg_attn_pv(const MegaParams& P, int layer, int phi, int n_kv, const MgSmem& S) {
-    if (S.misc[8]) { mg_attn_pv_local<GQ, TR>(P, phi, S); return; }      // slices of one tile: soft-max on the CTA's own scores
+    if (S.misc[8]) { mg_attn_pv_local<GQ, TR>(P, layer, phi, n_kv, S); return; }      // soft-max on the CTA's own scores
     const MgAttn a = mg_attn_get(S);
     if (!a.on) return;
     const MgAttnSmem s = mg_attn_carve(P, S.attn);

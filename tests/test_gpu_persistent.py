@@ -51,12 +51,14 @@ def test_f32_weights_take_the_per_op_path(gguf_path):
     c.close(); m.close()
 
 
-def test_long_context_several_attention_tiles(gguf_path, oracle, monkeypatch):
-    """n_head_kv = 2 -> 32 context splits of 64-token tiles: past 2048 tokens a CTA loops over several tiles (the first one is
-    prefetched with cp.async, the others are fetched synchronously); also crosses KV page boundaries."""
+@pytest.mark.parametrize("n_fill", [2200, 4500])
+def test_long_context_several_attention_tiles(n_fill, gguf_path, oracle, monkeypatch):
+    """n_head_kv = 2 -> 32 context splits of 64-token tiles: past 2048 tokens a CTA walks several tiles of its slice with a running
+    maximum (the first tile is prefetched with cp.async during the QKV phase, the later ones travel behind the computation; at 4500
+    tokens three tiles, the token being decoded in the last one); also crosses KV page boundaries."""
     name = "small-llama-q4km"
-    (m1, c1), (m0, c0) = _two_paths(gguf_path(name), 2400, monkeypatch)
-    fill = gs.synth_prompt(name, 2200, 11)
+    (m1, c1), (m0, c0) = _two_paths(gguf_path(name), n_fill + 200, monkeypatch)
+    fill = gs.synth_prompt(name, n_fill, 11)
     c1.decode(fill); c0.decode(fill)                      # tcgen05 prefill on both (identical kernels)
     assert np.array_equal(c1.logits(), c0.logits())
     toks = gs.synth_prompt(name, 12, 12)
