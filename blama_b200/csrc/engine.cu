@@ -1018,6 +1018,8 @@ void ensure_prefill_bufs(blk_ctx* c, int T) {
         c->pf_splitk_elems = (e && e[0] == '0') ? 0 : (size_t)sms * 65536;
         c->pf_splitk = c->pf_splitk_elems ? dalloc<float>(c, c->pf_splitk_elems) : nullptr;
     }
+    // opt-in (measured neutral: 28.0 against 27.4-28.3 ms per 2048-token verify): work items of the prefill GEMMs taken with atomicAdd
+    { const char* e = getenv("BLK_GEMM_DYNAMIC"); c->pf_sched = (e && e[0] == '1') ? dalloc<int>(c, blk_ctx::PF_SCHED_CAP) : nullptr; }
     c->pf_logit_rows = 512;     // rows of one lm_head chunk: two M tiles share every weight tile through L2
     c->pf_logits = dalloc<float>(c, (size_t)c->pf_logit_rows * m->n_vocab);
     if (prefill_attn_tc_supported(dh, m->n_head, m->n_head_kv)) {      // transposed-V scratch of the tcgen05 attention (one layer at a time)
@@ -1144,7 +1146,9 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     auto after_gemm = [&](int) {};
     if (panel && !res_op(0)) { BLK_CUDA(cudaEventRecord(c->pn_start[0], st)); BLK_CUDA(cudaStreamWaitEvent(c->pf_stream, c->pn_start[0], 0)); }   // after whatever ran before
     fill_op(0);
-    const SplitKWs sk{c->pf_splitk, c->pf_splitk_elems};
+    int sched_next = 0;
+    if (c->pf_sched) BLK_CUDA(cudaMemsetAsync(c->pf_sched, 0, blk_ctx::PF_SCHED_CAP * sizeof(int), st));
+    const SplitKWs sk{c->pf_splitk, c->pf_splitk_elems, c->pf_sched, &sched_next, blk_ctx::PF_SCHED_CAP};
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
         rmsnorm_bf16_launch(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn, n, st);

@@ -88,6 +88,8 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     // the SMs; partial sums go to the workspace and are added in split order by a second kernel (deterministic).  Every split gets
     // at least 8 K blocks (hence never an empty one); a wave that is at least half full is left alone.
     a.k_splits = 1; a.n_whole = tiles; a.ws = nullptr;
+    a.sched = nullptr;
+    if (sk && sk->sched && sk->sched_next && *sk->sched_next < sk->sched_cap && tiles > sms) a.sched = sk->sched + (*sk->sched_next)++;      // more items than CTAs: dynamic
     if (sk && sk->ws && sms > 0) {
         const int n_whole = (tiles / sms) * sms, rem = tiles - n_whole;
         if (rem > 0 && 2 * rem <= sms && n_whole <= 2 * sms) {      // (after many whole waves the partial one is a small share: not worth a second kernel)

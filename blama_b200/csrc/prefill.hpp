@@ -14,7 +14,9 @@ namespace blk {
 // tiles from there by TMA -- for many-token batches, where the fused form would dequantise every weight tile T / 256 times.
 // sk != nullptr: workspace for the deterministic split-K of the last, partial wave of tiles (all tiles when the batch has fewer
 // tiles than SMs); n_sm * 65536 floats always suffice (split tiles * splits never exceeds the SM count)
-struct SplitKWs { float* ws; size_t elems; };
+// split-K workspace + the pool of zeroed work-distribution counters of a prefill pass (one per GEMM launch: sched_next counts them on the
+// host; exhausted or absent -> that launch uses the static schedule)
+struct SplitKWs { float* ws; size_t elems; int* sched = nullptr; int* sched_next = nullptr; int sched_cap = 0; };
 cudaError_t prefill_gemm(const QMat& W, const __nv_bfloat16* X, int T, float* C, long long ldc, const float* bias, int mode, cudaStream_t st,
                          __nv_bfloat16* panel = nullptr, bool panel_fill = true, const SplitKWs* sk = nullptr);
 // rows a matrix of N rows occupies in a panel (tile aligned)
