@@ -68,9 +68,15 @@ def test_qkv_post_rope_and_cache_rows(n_head, n_head_kv, d_head, neox, pos0, ff)
     print(f"\n[qkv_post heads {n_head}/{n_head_kv} d {d_head} neox {neox} pos0 {pos0}] max rel err {worst:.3g} (f16 ulp {F16_ULP:.3g})")
 
 
-@pytest.mark.parametrize("n_head,n_head_kv,d_head,T,pos0", [(4, 1, 128, 200, 0), (8, 2, 128, 64, 100), (7, 1, 128, 130, 31), (8, 1, 128, 96, 64), (1, 1, 128, 40, 5),
-                                                             (4, 2, 64, 100, 20)])
-def test_prefill_attention(n_head, n_head_kv, d_head, T, pos0):
+@pytest.mark.parametrize("n_head,n_head_kv,d_head,T,pos0,scores", [
+    (4, 1, 128, 200, 0, "random"), (8, 2, 128, 64, 100, "random"), (7, 1, 128, 130, 31, "random"), (8, 1, 128, 96, 64, "random"),
+    (1, 1, 128, 40, 5, "random"), (4, 2, 64, 100, 20, "random"),
+    # many key tiles (the K ring runs ahead of the V ring, both wrap several times)
+    (8, 2, 128, 700, 333, "random"), (2, 1, 128, 1100, 0, "random"),
+    # scores that grow by ~13 per 128-key tile: the one-pass kernel raises its reference maximum and rescales O in TMEM at EVERY tile;
+    # falling scores: it never does after the first tile and the late probabilities underflow
+    (4, 1, 128, 600, 100, "rising"), (8, 1, 128, 300, 77, "rising"), (4, 2, 128, 500, 0, "falling")])
+def test_prefill_attention(n_head, n_head_kv, d_head, T, pos0, scores):
     from blama_b200 import capi
 
     capi.init()
@@ -79,6 +85,12 @@ def test_prefill_attention(n_head, n_head_kv, d_head, T, pos0):
     q = rng.standard_normal((T, n_head * d_head)).astype(np.float32) * 1.5
     k = rng.standard_normal((n_keys, n_head_kv * d_head)).astype(np.float32)
     v = rng.standard_normal((n_keys, n_head_kv * d_head)).astype(np.float32)
+    if scores != "random":
+        # every query = sqrt(d) e + noise, key j = (+-0.1 j) e + noise: score_j ~ +-0.1 j (+ O(1) noise)
+        e = np.zeros(d_head, dtype=np.float32); e[::2] = 1.0; e /= np.linalg.norm(e)
+        q = (0.3 * q.reshape(T, n_head, d_head) + np.sqrt(d_head) * e).reshape(T, -1).astype(np.float32)
+        ramp = (0.1 if scores == "rising" else -0.1) * np.arange(n_keys, dtype=np.float32)
+        k = (k.reshape(n_keys, n_head_kv, d_head) + ramp[:, None, None] * e).reshape(n_keys, -1).astype(np.float32)
     got, used_tc = capi.test_prefill_attn(q, k, v, pos0, n_head, n_head_kv, d_head)
     assert used_tc == (d_head == 128)
     qh = q.astype(np.float16).astype(np.float64).reshape(T, n_head, d_head)
@@ -95,7 +107,7 @@ def test_prefill_attention(n_head, n_head_kv, d_head, T, pos0):
     scale = np.abs(ref).max(axis=1, keepdims=True)
     err = np.abs(got - ref)
     rel = float((err / scale).max())
-    print(f"\n[prefill attention heads {n_head}/{n_head_kv} d {d_head} T {T} pos0 {pos0} tc {used_tc}] max err / row max = {rel:.3g}")
+    print(f"\n[prefill attention heads {n_head}/{n_head_kv} d {d_head} T {T} pos0 {pos0} {scores} tc {used_tc}] max err / row max = {rel:.3g}")
     # bf16 output (half ulp 2^-9 of the value) + f16 probabilities (2^-11 each, averaged over the row): bounded by 1e-3 of the row's
     # largest value beside the output rounding
     assert np.all(err <= BF16_ULP * 0.51 * np.abs(ref) + 1e-3 * scale), rel
