@@ -36,6 +36,11 @@ class StepStats:
         self.floor_max_abs: List[float] = []
         self.floor_rms: List[float] = []
         self.ids_equal: List[bool] = []
+        self.top1_equal: List[bool] = []
+        self.overlap: List[float] = []           # |top-10 set of the device row  ∩  top-10 set of the reference row| / 10
+        self.floor_ids_equal: List[bool] = []    # the same three, for the second faithful implementation of the reference arithmetic
+        self.floor_top1_equal: List[bool] = []
+        self.floor_overlap: List[float] = []
         self.gap_ranks = 0          # ranks whose reference gap demanded an identical id ...
         self.gap_ok = 0             # ... and got it
         self.gaps: List[float] = []
@@ -45,6 +50,10 @@ class StepStats:
         d = alt - want
         self.floor_max_abs.append(float(np.abs(d).max()))
         self.floor_rms.append(float(np.sqrt(np.mean(d.astype(np.float64) ** 2))))
+        a10, w10 = top_sorted(alt, 10)[0], top_sorted(want, 10)[0]
+        self.floor_ids_equal.append(bool(np.array_equal(a10, w10)))
+        self.floor_top1_equal.append(bool(a10[0] == w10[0]))
+        self.floor_overlap.append(len(set(a10.tolist()) & set(w10.tolist())) / 10.0)
 
     def add(self, got: np.ndarray, want: np.ndarray, got_top_ids: np.ndarray):
         d = got - want
@@ -53,6 +62,8 @@ class StepStats:
         self.rms.append(float(np.sqrt(np.mean(d.astype(np.float64) ** 2))))
         ids11, val11 = top_sorted(want, 11)
         self.ids_equal.append(bool(np.array_equal(got_top_ids[:10], ids11[:10])))
+        self.top1_equal.append(bool(int(got_top_ids[0]) == int(ids11[0])))
+        self.overlap.append(len(set(int(i) for i in got_top_ids[:10]) & set(int(i) for i in ids11[:10])) / 10.0)
         gaps = val11[:10] - val11[1:11]
         self.gaps += [float(g) for g in gaps]
         bad = []
@@ -74,10 +85,16 @@ class StepStats:
         if self.floor_max_abs:
             floor = {"floor_max_abs": max(self.floor_max_abs), "floor_rms": max(self.floor_rms),
                      "within_floor": bool(max(self.max_abs) <= FLOOR_FACTOR * max(self.floor_max_abs) + 0.02 and
-                                          max(self.rms) <= FLOOR_FACTOR * max(self.floor_rms) + 1e-3)}
+                                          max(self.rms) <= FLOOR_FACTOR * max(self.floor_rms) + 1e-3),
+                     # what the reference arithmetic reproduces of ITS OWN top-10 when only the fp32 summation order changes
+                     "floor_top10_id_match_frac": sum(self.floor_ids_equal) / max(1, len(self.floor_ids_equal)),
+                     "floor_top1_match_frac": sum(self.floor_top1_equal) / max(1, len(self.floor_top1_equal)),
+                     "floor_top10_overlap_mean": float(np.mean(self.floor_overlap)) if self.floor_overlap else 0.0}
         return {"steps": len(self.max_abs), "max_abs": max(self.max_abs) if self.max_abs else 0.0, "rms": max(self.rms) if self.rms else 0.0, **floor,
                 "clean_frac": sum(e <= CLEAN_TOL for e in self.max_abs) / n,
                 "top10_id_match_frac": sum(self.ids_equal) / n,
+                "top1_match_frac": sum(self.top1_equal) / n,
+                "top10_overlap_mean": float(np.mean(self.overlap)) if self.overlap else 0.0,
                 "pinned_ranks": self.gap_ranks, "pinned_ranks_ok": self.gap_ok,
                 "gap_median": float(np.median(self.gaps)) if self.gaps else 0.0,
                 "gap_p10": float(np.percentile(self.gaps, 10)) if self.gaps else 0.0}
