@@ -1148,10 +1148,13 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     fill_op(0);
     int sched_next = 0;
     if (c->pf_sched) BLK_CUDA(cudaMemsetAsync(c->pf_sched, 0, blk_ctx::PF_SCHED_CAP * sizeof(int), st));
-    const SplitKWs sk{c->pf_splitk, c->pf_splitk_elems, c->pf_sched, &sched_next, blk_ctx::PF_SCHED_CAP};
+    // few-token batches: the split-K reduce of Wo / down (accumulates onto the residual stream) is folded into the RMSNorm that follows
+    PendingReduce pend;
+    const SplitKWs sk{c->pf_splitk, c->pf_splitk_elems, c->pf_sched, &sched_next, blk_ctx::PF_SCHED_CAP, &pend};
+    SplitKWs sk_last = sk; sk_last.defer = nullptr;      // the last down GEMM of a pass that is not followed by the final RMSNorm kernel
     for (int l = 0; l < m->n_layer; l++) {
         const LayerWeights& L = m->layers[l];
-        rmsnorm_bf16_launch(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn, n, st);
+        rmsnorm_bf16_launch(c->pf_x, L.attn_norm, d, m->rms_eps, c->pf_xn, n, st, &pend);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
@@ -1173,13 +1176,13 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         BLK_CUDA(prefill_gemm(L.wo, c->pf_ao, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 1), false, &sk));
         after_gemm(4 * l + 1);
         prof_mark(c, "gemm_wo");
-        rmsnorm_bf16_launch(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn, n, st);
+        rmsnorm_bf16_launch(c->pf_x, L.ffn_norm, d, m->rms_eps, c->pf_xn, n, st, &pend);
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "rmsnorm_bf16");
         BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, c->pf_xn, n, c->pf_h, ff, st, before_gemm(4 * l + 2), false, &sk));
         after_gemm(4 * l + 2);
         prof_mark(c, "gemm_gate_up_swiglu");
-        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 3), false, &sk));
+        BLK_CUDA(prefill_gemm(L.down, c->pf_h, n, c->pf_x, d, nullptr, 1, st, before_gemm(4 * l + 3), false, (l + 1 < m->n_layer || verify) ? &sk : &sk_last));
         after_gemm(4 * l + 3);
         prof_mark(c, "gemm_down");
         c->launches += 12;
@@ -1189,7 +1192,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     if (verify) {
         BLK_CUDA(cudaMemcpyAsync(c->pf_claimed, verify->claimed + (size_t)verify_row0 * 10, (size_t)n * 10 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         BLK_CUDA(cudaMemcpyAsync(c->pf_nclaimed, verify->n_claimed + verify_row0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        rmsnorm_bf16_launch(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn, n, st);
+        rmsnorm_bf16_launch(c->pf_x, m->out_norm, d, m->rms_eps, c->pf_xn, n, st, &pend);
         BLK_CUDA(cudaGetLastError()); c->launches++;
         __nv_bfloat16* head_panel = nullptr;
         if (sparse_head) {
@@ -1660,14 +1663,15 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
         embed_rows_kernel<<<n, 256, 0, st>>>(m->tok_embd, dv->tokens, dv->rpos, ws->pf_x, ws->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
         BLK_CUDA(cudaGetLastError()); ws->launches++;
         const long long ldq = dq + 2 * dkv;
-        const SplitKWs sk{ws->pf_splitk, ws->pf_splitk_elems};
+        PendingReduce pend;      // split-K reduce of Wo / down folded into the RMSNorm that follows
+        const SplitKWs sk{ws->pf_splitk, ws->pf_splitk_elems, nullptr, nullptr, 0, &pend};
         // matrices with a resident bf16 panel (model cache) take the TMA-fed GEMM: the step then streams the panels at HBM speed
         // instead of waiting for the de-quantising producers of the fused form
         const std::vector<__nv_bfloat16*>& res = model_panels(ws);
         auto res_op = [&](int i) -> __nv_bfloat16* { return i < (int)res.size() ? res[i] : nullptr; };
         for (int l = 0; l < m->n_layer; l++) {
             const LayerWeights& L = m->layers[l];
-            rmsnorm_bf16_launch(ws->pf_x, L.attn_norm, d, m->rms_eps, ws->pf_xn, n, st);
+            rmsnorm_bf16_launch(ws->pf_x, L.attn_norm, d, m->rms_eps, ws->pf_xn, n, st, &pend);
             const GemmPart qkv_parts[3] = {{&L.wq, L.bq, 0}, {&L.wk, L.bk, dq}, {&L.wv, L.bv, dq + dkv}};
             BLK_CUDA(prefill_gemm_multi(qkv_parts, 3, ws->pf_xn, n, ws->pf_qkv, ldq, st, res_op(4 * l), false, &sk));
             QkvPostBatchArgs qa{};
@@ -1682,12 +1686,12 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
             else decode_attn_batch_kernel<64><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
             BLK_CUDA(cudaGetLastError());
             BLK_CUDA(prefill_gemm(L.wo, ws->pf_ao, n, ws->pf_x, d, nullptr, 1, st, res_op(4 * l + 1), false, &sk));
-            rmsnorm_bf16_launch(ws->pf_x, L.ffn_norm, d, m->rms_eps, ws->pf_xn, n, st);
+            rmsnorm_bf16_launch(ws->pf_x, L.ffn_norm, d, m->rms_eps, ws->pf_xn, n, st, &pend);
             BLK_CUDA(prefill_gemm_swiglu(L.gate, L.up, ws->pf_xn, n, ws->pf_h, ff, st, res_op(4 * l + 2), false, &sk));
             BLK_CUDA(prefill_gemm(L.down, ws->pf_h, n, ws->pf_x, d, nullptr, 1, st, res_op(4 * l + 3), false, &sk));
             ws->launches += 8;
         }
-        rmsnorm_bf16_launch(ws->pf_x, m->out_norm, d, m->rms_eps, ws->pf_xn, n, st);
+        rmsnorm_bf16_launch(ws->pf_x, m->out_norm, d, m->rms_eps, ws->pf_xn, n, st, &pend);
         BLK_CUDA(prefill_gemm(m->output, ws->pf_xn, n, ws->pf_logits, V, nullptr, 0, st, res_op(4 * m->n_layer), false));
         ws->launches += 2;
         // threshold top-64 of every row (the selector of the batch-1 path, blockIdx.y = row): two launches for the whole batch

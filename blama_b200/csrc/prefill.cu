@@ -106,6 +106,12 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, tmap_w, a);
     e = cudaGetLastError();
     if (e != cudaSuccess || a.k_splits == 1) return e;
+    if (sk && sk->defer && a.mode == PG_ACCUM && a.n_whole == 0 && a.nseg == 1 && a.seg[0].col0 == 0 && !a.seg[0].bias &&
+        a.seg[0].W.N % PG_BN == 0 && a.ldc == a.seg[0].W.N) {
+        // every tile is split and full width: the caller's next RMSNorm over C adds the partial sums (same order: splits, then the residual)
+        *sk->defer = PendingReduce{a.ws, a.k_splits, (a.T + PG_BM - 1) / PG_BM};
+        return cudaSuccess;
+    }
     splitk_reduce_kernel<<<dim3((unsigned)(tiles - a.n_whole), 32), 256, 0, st>>>(a);
     return cudaGetLastError();
 }

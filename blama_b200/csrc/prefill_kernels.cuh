@@ -8,12 +8,12 @@
 #include "tma_ptx.cuh"
 
 #include "decode_kernels.cuh"
+#include "prefill.hpp"          // PendingReduce
 
 namespace blk {
 
 // ---- RMSNorm * weight -> bf16 (one CTA per token row) -------------------------------------------------------------------
 // The row is read ONCE with 16-byte loads and stays in registers between the two passes (K <= 8192; longer rows re-read it).
-__host__ inline void rmsnorm_bf16_launch(const float* x, const float* w, int K, float eps, __nv_bfloat16* y, int rows, cudaStream_t st);
 __device__ __forceinline__ double rms_sq4(float4 v) {
     return ((double)__fmul_rn(v.x, v.x) + (double)__fmul_rn(v.y, v.y)) + ((double)__fmul_rn(v.z, v.z) + (double)__fmul_rn(v.w, v.w));
 }
@@ -24,23 +24,38 @@ __device__ __forceinline__ uint2 rms_out4(float4 v, float scale, float4 w) {
     return o;
 }
 template <int NV>     // 16-byte words of the row a thread keeps in registers: rows up to NV * 1024 elements are read once
-__global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, int K, float eps,
-                                                          __nv_bfloat16* __restrict__ y) {
+__global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(float* __restrict__ x, const float* __restrict__ w, int K, float eps,
+                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ ws, int S, int m_tiles) {
+    // ws != nullptr: the row's pending split-K partial sums (256 x 256 f32 tiles at ws + ((nt * m_tiles + mt) * S + s) * 65536, the layout
+    // prefill_gemm_kernel writes) are added first -- splits in order, then the residual, as splitk_reduce_kernel does -- and the new
+    // residual row is written back
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * K);
+    float4* x4 = reinterpret_cast<float4*>(x + (size_t)row * K);
     const float4* w4 = reinterpret_cast<const float4*>(w);
     uint2* y2 = reinterpret_cast<uint2*>(y + (size_t)row * K);
     const int n4 = K >> 2;                               // K % 4 == 0 (checked at load: every row length is a multiple of 32)
     const bool in_regs = n4 <= NV * 256;
     __shared__ double red[8];
     __shared__ float s_scale;
+    auto fetch = [&](int i) -> float4 {
+        float4 v = x4[i];
+        if (ws) {
+            const int col = i << 2;
+            const float* p = ws + ((size_t)((col >> 8) * m_tiles + (row >> 8)) * S) * 65536 + (size_t)(row & 255) * 256 + (col & 255);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < S; s++) { const float4 q = __ldcg(reinterpret_cast<const float4*>(p + (size_t)s * 65536)); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+            v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+            x4[i] = v;
+        }
+        return v;
+    };
     float4 v[NV];
     double sum = 0.0;
     if (in_regs) {
 #pragma unroll
-        for (int j = 0; j < NV; j++) { const int i = tid + j * 256; if (i < n4) { v[j] = x4[i]; sum += rms_sq4(v[j]); } }
+        for (int j = 0; j < NV; j++) { const int i = tid + j * 256; if (i < n4) { v[j] = fetch(i); sum += rms_sq4(v[j]); } }
     } else {
-        for (int i = tid; i < n4; i += 256) sum += rms_sq4(x4[i]);
+        for (int i = tid; i < n4; i += 256) sum += rms_sq4(fetch(i));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -57,13 +72,17 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < NV; j++) { const int i = tid + j * 256; if (i < n4) y2[i] = rms_out4(v[j], scale, __ldg(w4 + i)); }
     } else {
-        for (int i = tid; i < n4; i += 256) y2[i] = rms_out4(x4[i], scale, __ldg(w4 + i));
+        for (int i = tid; i < n4; i += 256) y2[i] = rms_out4(x4[i], scale, __ldg(w4 + i));      // (the row was written back above)
     }
 }
 
-__host__ inline void rmsnorm_bf16_launch(const float* x, const float* w, int K, float eps, __nv_bfloat16* y, int rows, cudaStream_t st) {
-    if (K <= 4096) rmsnorm_bf16_kernel<4><<<rows, 256, 0, st>>>(x, w, K, eps, y);
-    else rmsnorm_bf16_kernel<8><<<rows, 256, 0, st>>>(x, w, K, eps, y);
+// pend: a deferred split-K accumulate over x (launch_gemm, SplitKWs::defer); consumed here
+__host__ inline void rmsnorm_bf16_launch(float* x, const float* w, int K, float eps, __nv_bfloat16* y, int rows, cudaStream_t st, PendingReduce* pend = nullptr) {
+    const float* ws = pend ? pend->ws : nullptr;
+    const int S = pend ? pend->S : 0, mt = pend ? pend->m_tiles : 0;
+    if (pend) *pend = PendingReduce{};
+    if (K <= 4096) rmsnorm_bf16_kernel<4><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
+    else rmsnorm_bf16_kernel<8><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
 }
 
 // ---- RoPE on q,k; q -> f16 [T][dq]; k,v -> f16 KV pages (one CTA per token, four elements per thread and step) --------------------
