@@ -14,7 +14,8 @@
 //   * blama's LogitComparer                reference inference/code/llama/LogitComparer.cpp:8-128
 // llama.cpp itself is NOT present in this container (no network); its algorithms are restated from
 // the published source at that tag ("upstream-recall" in SURVEY.md).  PARITY of the transformer forward is
-// therefore UNPINNED by reference fixtures; LogitComparer and dequantisation ARE pinned (tests/).
+// therefore UNPINNED by reference fixtures; LogitComparer and dequantisation ARE pinned (tests/), and the float path of the
+// forward is pinned to an independent implementation reading the same GGUF (Hugging Face transformers, tests/test_oracle_hf_pin.py).
 #include "oracle.h"
 
 #include <algorithm>

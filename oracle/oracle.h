@@ -14,6 +14,8 @@
  *   - block dequantisation              : PINNED against gguf-py's numpy dequantisers.
  *   - transformer forward               : PARITY UNPINNED by reference tests (the reference
  *     only ever tests GPT-2-117M fixtures that are not available); restates ggml-cpu.
+ *     Its float path (F32 mode) is pinned to an INDEPENDENT implementation instead: Hugging Face transformers
+ *     reading the same GGUF through its own loader (tests/golden/hf_forward_golden.npz, tools/gen_hf_forward_golden.py).
  */
 #pragma once
 #include <stdint.h>
