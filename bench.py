@@ -634,7 +634,7 @@ def main():
     ap.add_argument("--prompt", type=int, default=512)
     ap.add_argument("--new", type=int, default=256)
     ap.add_argument("--verify", type=int, default=2048, help="response tokens of the verify measurement (0 = skip)")
-    ap.add_argument("--verify-reps", type=int, default=5, help="timed repeats of the verify request (median reported)")
+    ap.add_argument("--verify-reps", type=int, default=9, help="timed repeats of the verify request (median reported)")
     ap.add_argument("--sequential-verify", action="store_true")
     ap.add_argument("--max-batch", type=int, default=1, help="--mode batch: /complete requests in flight per replica (continuous batching)")
     ap.add_argument("--mode", default="step", choices=["step", "stream", "mix", "batch"],
