@@ -23,7 +23,7 @@ __device__ __forceinline__ uint2 rms_out4(float4 v, float scale, float4 w) {
     uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
     return o;
 }
-template <int NV>     // 16-byte words of the row a thread keeps in registers: rows up to NV * 1024 elements are read once
+template <int NV, bool REDUCE>     // NV: 16-byte words of the row a thread keeps in registers: rows up to NV * 1024 elements are read once
 __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(float* __restrict__ x, const float* __restrict__ w, int K, float eps,
                                                           __nv_bfloat16* __restrict__ y, const float* __restrict__ ws, int S, int m_tiles) {
     // ws != nullptr: the row's pending split-K partial sums (256 x 256 f32 tiles at ws + ((nt * m_tiles + mt) * S + s) * 65536, the layout
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(float* __restrict__ x
     __shared__ double red[8];
     __shared__ float s_scale;
     auto fetch = [&](int i) -> float4 {
-        float4 v = x4[i];
-        if (ws) {
+        float4 v = REDUCE ? x4[i] : __ldg(reinterpret_cast<const float4*>(x4) + i);
+        if (REDUCE) {
             const int col = i << 2;
             const float* p = ws + ((size_t)((col >> 8) * m_tiles + (row >> 8)) * S) * 65536 + (size_t)(row & 255) * 256 + (col & 255);
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(float* __restrict__ x
 #pragma unroll
         for (int j = 0; j < NV; j++) { const int i = tid + j * 256; if (i < n4) y2[i] = rms_out4(v[j], scale, __ldg(w4 + i)); }
     } else {
-        for (int i = tid; i < n4; i += 256) y2[i] = rms_out4(x4[i], scale, __ldg(w4 + i));      // (the row was written back above)
+        for (int i = tid; i < n4; i += 256) y2[i] = rms_out4(x4[i], scale, __ldg(w4 + i));      // (REDUCE: the row was written back above)
     }
 }
 
@@ -81,8 +81,13 @@ __host__ inline void rmsnorm_bf16_launch(float* x, const float* w, int K, float 
     const float* ws = pend ? pend->ws : nullptr;
     const int S = pend ? pend->S : 0, mt = pend ? pend->m_tiles : 0;
     if (pend) *pend = PendingReduce{};
-    if (K <= 4096) rmsnorm_bf16_kernel<4><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
-    else rmsnorm_bf16_kernel<8><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
+    if (ws) {
+        if (K <= 4096) rmsnorm_bf16_kernel<4, true><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
+        else rmsnorm_bf16_kernel<8, true><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
+    } else {
+        if (K <= 4096) rmsnorm_bf16_kernel<4, false><<<rows, 256, 0, st>>>(x, w, K, eps, y, nullptr, 0, 0);
+        else rmsnorm_bf16_kernel<8, false><<<rows, 256, 0, st>>>(x, w, K, eps, y, nullptr, 0, 0);
+    }
 }
 
 // ---- RoPE on q,k; q -> f16 [T][dq]; k,v -> f16 KV pages (one CTA per token, four elements per thread and step) --------------------
