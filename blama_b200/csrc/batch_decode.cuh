@@ -30,6 +30,7 @@ struct QkvPostBatchArgs {
     int layer;
 };
 __global__ void __launch_bounds__(256) qkv_post_batch_kernel(const QkvPostBatchArgs b) {
+    pdl_launch_dependents(); pdl_wait();
     const int t = blockIdx.x;
     qkv_post_row(b.base, t, b.pos[t], b.k_pools[t][b.layer], b.v_pools[t][b.layer], b.page_table[t]);
 }
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) decode_attn_batch_kernel(const BatchAttnA
     __shared__ float red[MAX_GQ][8];
     __shared__ float m_run[MAX_GQ], l_run[MAX_GQ], corr[MAX_GQ];
     __shared__ float2 pv_red[TG][MAX_GQ][HP];
+    pdl_launch_dependents(); pdl_wait();
     const int hk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = a.n_head / a.n_head_kv, n_kv = a.pos[b] + 1;
     const int32_t* pt = a.page_table[b];

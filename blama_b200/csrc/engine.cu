@@ -1094,6 +1094,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
     flush_pos_shift(c);
     note_new_cells(c, n);
     cudaStream_t st = c->stream;
+    const ChainPdl chain_scope(n);      // few-token passes: every kernel of the chain is a programmatic dependent of its predecessor
     BLK_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     embed_kernel<<<n, 256, 0, st>>>(m->tok_embd, c->pf_tokens, c->d_pos, c->pf_x, c->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
     BLK_CUDA(cudaGetLastError()); c->launches++;
@@ -1165,7 +1166,7 @@ void prefill_chunk(blk_ctx* c, const int32_t* tokens, int n, const VerifyIo* ver
         qa.qkv = c->pf_qkv; qa.ld = ldq; qa.rope_cs = c->pf_rope; qa.pos0 = c->d_pos; qa.q_out = c->pf_q;
         qa.k_pool = c->k_pool[l]; qa.v_pool = c->v_pool[l]; qa.page_table = c->page_table;
         qa.dq = dq; qa.dkv = dkv; qa.d_head = dh; qa.neox = m->neox ? 1 : 0;
-        qkv_post_kernel<<<n, 256, 0, st>>>(qa);
+        BLK_CUDA(launch_chain(qkv_post_kernel, dim3(n), dim3(256), 0, st, qa));
         BLK_CUDA(cudaGetLastError());
         prof_mark(c, "qkv_post(rope+kv)");
         PrefillAttnArgs pa{};
@@ -1663,6 +1664,7 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
         embed_rows_kernel<<<n, 256, 0, st>>>(m->tok_embd, dv->tokens, dv->rpos, ws->pf_x, ws->pf_rope, dh / 2, m->theta_scale, m->rope_freqs);
         BLK_CUDA(cudaGetLastError()); ws->launches++;
         const long long ldq = dq + 2 * dkv;
+        const ChainPdl chain_scope(n);
         PendingReduce pend;      // split-K reduce of Wo / down folded into the RMSNorm that follows
         const SplitKWs sk{ws->pf_splitk, ws->pf_splitk_elems, nullptr, nullptr, 0, &pend};
         // matrices with a resident bf16 panel (model cache) take the TMA-fed GEMM: the step then streams the panels at HBM speed
@@ -1678,12 +1680,12 @@ extern "C" blk_status blk_decode_batch(blk_ctx* ws, blk_ctx* const* ctxs, const 
             qa.base.qkv = ws->pf_qkv; qa.base.ld = ldq; qa.base.rope_cs = ws->pf_rope; qa.base.q_out = ws->pf_q;
             qa.base.dq = dq; qa.base.dkv = dkv; qa.base.d_head = dh; qa.base.neox = m->neox ? 1 : 0;
             qa.pos = dv->pos; qa.page_table = dv->page_table; qa.k_pools = dv->k_pools; qa.v_pools = dv->v_pools; qa.layer = l;
-            qkv_post_batch_kernel<<<n, 256, 0, st>>>(qa);
+            BLK_CUDA(launch_chain(qkv_post_batch_kernel, dim3(n), dim3(256), 0, st, qa));
             BatchAttnArgs aa{};
             aa.q = ws->pf_q; aa.pos = dv->pos; aa.page_table = dv->page_table; aa.k_pools = dv->k_pools; aa.v_pools = dv->v_pools; aa.out = ws->pf_ao;
             aa.layer = l; aa.n_head = m->n_head; aa.n_head_kv = m->n_head_kv; aa.kv_dim = dkv; aa.scale = 1.0f / sqrtf((float)dh);
-            if (dh == 128) decode_attn_batch_kernel<128><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
-            else decode_attn_batch_kernel<64><<<dim3(m->n_head_kv, n), 256, 0, st>>>(aa);
+            if (dh == 128) BLK_CUDA(launch_chain(decode_attn_batch_kernel<128>, dim3(m->n_head_kv, n), dim3(256), 0, st, aa));
+            else BLK_CUDA(launch_chain(decode_attn_batch_kernel<64>, dim3(m->n_head_kv, n), dim3(256), 0, st, aa));
             BLK_CUDA(cudaGetLastError());
             BLK_CUDA(prefill_gemm(L.wo, ws->pf_ao, n, ws->pf_x, d, nullptr, 1, st, res_op(4 * l + 1), false, &sk));
             rmsnorm_bf16_launch(ws->pf_x, L.ffn_norm, d, m->rms_eps, ws->pf_xn, n, st, &pend);

@@ -103,8 +103,8 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     }
     const int items = a.n_whole + (tiles - a.n_whole) * a.k_splits;
     const int grid = items < sms ? items : sms;
-    kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, st>>>(tmap, tmap_w, a);
-    e = cudaGetLastError();
+    e = launch_chain(kernel, dim3((unsigned)grid), dim3(PG_THREADS), PG_SMEM_BYTES, st, tmap, tmap_w, a);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess || a.k_splits == 1) return e;
     if (sk && sk->defer && a.mode == PG_ACCUM && a.n_whole == 0 && a.nseg == 1 && a.seg[0].col0 == 0 && !a.seg[0].bias &&
         a.seg[0].W.N % PG_BN == 0 && a.ldc == a.seg[0].W.N) {
@@ -112,8 +112,8 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
         *sk->defer = PendingReduce{a.ws, a.k_splits, (a.T + PG_BM - 1) / PG_BM};
         return cudaSuccess;
     }
-    splitk_reduce_kernel<<<dim3((unsigned)(tiles - a.n_whole), 32), 256, 0, st>>>(a);
-    return cudaGetLastError();
+    e = launch_chain(splitk_reduce_kernel, dim3((unsigned)(tiles - a.n_whole), 32), dim3(256), 0, st, a);
+    return e == cudaSuccess ? cudaGetLastError() : e;
 }
 
 // first pass of the two-pass form: W -> panel rows [row0, row0 + W.N)
@@ -253,7 +253,7 @@ cudaError_t launch_attn_tc(const CUtensorMap& mq, const CUtensorMap& mk, const C
         if (e != cudaSuccess) return e;
     }
     constexpr int BQ = 128 / GQS;
-    prefill_attn_tc_kernel<GQ, GQS><<<dim3((a.T + BQ - 1) / BQ, n_head_kv), AT_THREADS, AT_SMEM_BYTES, st>>>(mq, mk, mv, a);
+    (void)launch_chain(prefill_attn_tc_kernel<GQ, GQS>, dim3((a.T + BQ - 1) / BQ, n_head_kv), dim3(AT_THREADS), AT_SMEM_BYTES, st, mq, mk, mv, a);
     return cudaGetLastError();
 }
 int attn_tc_slots(int gq) { return gq <= 1 ? 1 : gq <= 2 ? 2 : gq <= 4 ? 4 : 8; }
@@ -313,7 +313,7 @@ cudaError_t prefill_attn_tc(const __half* q, const __half* k_pool, const __half*
     const int gq = n_head / n_head_kv, dq = n_head * 128, n_keys = pos0 + T;
     if (n_keys > ctx_pad || ctx_pad % 128) return cudaErrorInvalidValue;
     // V^T of every key this chunk can see (zero padded to the key tile)
-    vt_transpose_kernel<<<dim3((n_keys + 127) / 128 * 2, n_head_kv), 256, 0, st>>>(v_pool, page_table, kv_dim, n_keys, ctx_pad, vt);
+    (void)launch_chain(vt_transpose_kernel, dim3((n_keys + 127) / 128 * 2, n_head_kv), dim3(256), 0, st, v_pool, page_table, kv_dim, n_keys, ctx_pad, vt);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap mq, mk, mv;

@@ -57,6 +57,7 @@ struct AttnTcArgs {
 __global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restrict__ v_pool, const int32_t* __restrict__ page_table,
                                                            int kv_dim, int n_keys, int ctx_pad, __half* __restrict__ vt) {
     __shared__ __half tile[64][128 + 2];
+    pdl_launch_dependents(); pdl_wait();
     const int k0 = blockIdx.x * 64, hk = blockIdx.y, tid = threadIdx.x;
     for (int i = tid; i < 64 * 16; i += 256) {
         const int r = i >> 4, c = i & 15, key = k0 + r;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) prefill_attn_tc_kernel(const __
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS[2] = {tmem, tmem + 128}, tO = tmem + 256;
+    pdl_launch_dependents(); pdl_wait();      // the prologue touched no global memory
 
     if (warp == 0) {
         // ===================== TMA: K0 K1 V0 K2 V1 K3 ... (the order in which the MMA warp frees the slots) =====================

@@ -381,6 +381,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // the prologue above touched no global memory: from here on the kernel reads what the previous kernel of the stream wrote
+    pdl_launch_dependents(); pdl_wait();
 
     const int m_tiles = (a.T + PG_BM - 1) / PG_BM, n_tiles = a.n_tiles;
     const int k_blocks_all = a.K / PG_BK;
@@ -638,6 +640,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) prefill_gemm_kernel(const __gri
 // ---- second step of a split-K GEMM: the split tiles' partial sums are added in split order, then the tile's epilogue runs --------
 // grid = (split tiles, 32): block (i, y) finishes rows 8 y .. 8 y + 7 of tile n_whole + i
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const PrefillGemmArgs a) {
+    pdl_launch_dependents(); pdl_wait();
     const int m_tiles = (a.T + PG_BM - 1) / PG_BM;
     const int tile = a.n_whole + blockIdx.x, S = a.k_splits;
     const int m0 = (tile % m_tiles) * PG_BM, nt = tile / m_tiles;

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(float* __restrict__ x
     // ws != nullptr: the row's pending split-K partial sums (256 x 256 f32 tiles at ws + ((nt * m_tiles + mt) * S + s) * 65536, the layout
     // prefill_gemm_kernel writes) are added first -- splits in order, then the residual, as splitk_reduce_kernel does -- and the new
     // residual row is written back
+    pdl_launch_dependents(); pdl_wait();
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float4* x4 = reinterpret_cast<float4*>(x + (size_t)row * K);
     const float4* w4 = reinterpret_cast<const float4*>(w);
@@ -82,11 +83,11 @@ __host__ inline void rmsnorm_bf16_launch(float* x, const float* w, int K, float 
     const int S = pend ? pend->S : 0, mt = pend ? pend->m_tiles : 0;
     if (pend) *pend = PendingReduce{};
     if (ws) {
-        if (K <= 4096) rmsnorm_bf16_kernel<4, true><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
-        else rmsnorm_bf16_kernel<8, true><<<rows, 256, 0, st>>>(x, w, K, eps, y, ws, S, mt);
+        if (K <= 4096) (void)launch_chain(rmsnorm_bf16_kernel<4, true>, dim3(rows), dim3(256), 0, st, x, w, K, eps, y, ws, S, mt);
+        else (void)launch_chain(rmsnorm_bf16_kernel<8, true>, dim3(rows), dim3(256), 0, st, x, w, K, eps, y, ws, S, mt);
     } else {
-        if (K <= 4096) rmsnorm_bf16_kernel<4, false><<<rows, 256, 0, st>>>(x, w, K, eps, y, nullptr, 0, 0);
-        else rmsnorm_bf16_kernel<8, false><<<rows, 256, 0, st>>>(x, w, K, eps, y, nullptr, 0, 0);
+        if (K <= 4096) (void)launch_chain(rmsnorm_bf16_kernel<4, false>, dim3(rows), dim3(256), 0, st, x, w, K, eps, y, (const float*)nullptr, 0, 0);
+        else (void)launch_chain(rmsnorm_bf16_kernel<8, false>, dim3(rows), dim3(256), 0, st, x, w, K, eps, y, (const float*)nullptr, 0, 0);
     }
 }
 
@@ -144,6 +145,7 @@ __device__ __forceinline__ void qkv_post_row(const QkvPostArgs& a, int t, int po
     }
 }
 __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
+    pdl_launch_dependents(); pdl_wait();
     qkv_post_row(a, blockIdx.x, a.pos0[0] + (int)blockIdx.x, a.k_pool, a.v_pool, a.page_table);
 }
 
