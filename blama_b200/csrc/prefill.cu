@@ -109,6 +109,7 @@ cudaError_t launch_gemm(PrefillGemmArgs& a, int ta, int tb, const __nv_bfloat16*
     if (sk && sk->defer && a.mode == PG_ACCUM && a.n_whole == 0 && a.nseg == 1 && a.seg[0].col0 == 0 && !a.seg[0].bias &&
         a.seg[0].W.N % PG_BN == 0 && a.ldc == a.seg[0].W.N) {
         // every tile is split and full width: the caller's next RMSNorm over C adds the partial sums (same order: splits, then the residual)
+        if (sk->defer->ws) return cudaErrorInvalidValue;      // an earlier deferred reduce was never consumed: fail loudly, never drop partial sums
         *sk->defer = PendingReduce{a.ws, a.k_splits, (a.T + PG_BM - 1) / PG_BM};
         return cudaSuccess;
     }
